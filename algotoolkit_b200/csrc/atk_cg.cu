@@ -1,0 +1,342 @@
+// atk_cg.cu -- ConjugateGrad::solve on the device (reference src/LinearAlgebra/Krylov/ConjugateGradient.hpp:36-84).
+//
+// Reference loop (no tolerance test - it is commented out at :44-47,75-77):
+//     rs_old = r.r ; if ||b|| < 1e-12 return
+//     for i < maxIter:  Ap = A p ; pAp = p.Ap ; if |pAp| < 1e-12 return
+//                       alpha = rs_old/pAp ; x = x + p*alpha ; r = r - Ap*alpha
+//                       rs_new = r.r ; p = r + p*(rs_new/rs_old) ; rs_old = rs_new
+//
+// Device formulation: three kernels per iteration, no host round trip.
+//   K1  operator apply fused with the p.Ap partial sums                (stencil: 16 B/row, CSR: +12 B/nnz)
+//   K2  x += p*alpha ; r -= Ap*alpha ; partial sums of r.r              (48 B/row)
+//   K3  p = r + p*beta                                                  (24 B/row)
+// alpha, beta and the |pAp| < 1e-12 exit are evaluated ON THE DEVICE from the reduction slots (every CTA derives
+// the same scalars in its prologue; the CTA that finishes last commits the state).  Once the exit fires, a device
+// flag turns every later kernel into a no-op, so the host can enqueue iterations ahead and still stop at exactly
+// the reference's iteration.  The iteration is captured once in a CUDA graph and replayed.
+//
+// Element arithmetic keeps the reference's two roundings (`p*alpha` is rounded, then added; VectorObj.hpp:64-68,
+// 89-102).  Only the summation order of the two dot products differs (block tree vs. sequential), unless the
+// context is in ATK_REDUCE_SEQUENTIAL mode.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "atk_internal.cuh"
+
+namespace atk {
+
+namespace {
+
+struct CgState {
+    double rs_old;
+    double last_pAp;
+    double b_norm2;
+    int it;          // iterations completed (== loop index of the iteration in flight)
+    int done;        // 1 once an exit condition fired
+    int stopped_on_pAp;
+    int zero_rhs;
+    int trace_cap;
+    int pad;
+};
+
+// rs_old = r.r and the ||b|| < 1e-12 test (:37-42).  One CTA; the two dots were left in the slots by dot kernels.
+__global__ void cg_begin_kernel(CgState* st, const double* slot_rr, const double* slot_bb, int world) {
+    if (threadIdx.x != 0) return;
+    const double rr = slot_sum(slot_rr, world);
+    const double bb = slot_sum(slot_bb, world);
+    st->rs_old = rr;
+    st->b_norm2 = bb;
+    st->last_pAp = 0.0;
+    st->it = 0;
+    st->stopped_on_pAp = 0;
+    const int zero = (sqrt(bb) < 1e-12) ? 1 : 0;
+    st->zero_rhs = zero;
+    st->done = zero;
+}
+
+// K2: x = x + p*alpha ; r = r - Ap*alpha ; rs_new partial.   (:59-63)
+template <bool VEC2>
+__global__ void __launch_bounds__(kReduceBlock) cg_update_xr_kernel(int64_t n, CgState* st, const double* __restrict__ slot_pAp,
+                                                                    int world, double* __restrict__ x, double* __restrict__ r,
+                                                                    const double* __restrict__ p, const double* __restrict__ Ap,
+                                                                    double* partials, unsigned* ticket, double* rr_out,
+                                                                    double* pAp_trace) {
+    if (st->done) return;
+    const double pAp = slot_sum(slot_pAp, world);
+    if (fabs(pAp) < 1e-12) {  // :53-57 - leave x, r, p untouched; benign identical write from every CTA's thread 0
+        if (threadIdx.x == 0 && blockIdx.x == 0) {
+            st->last_pAp = pAp;
+            if (pAp_trace && st->it < st->trace_cap) pAp_trace[st->it] = pAp;
+            st->stopped_on_pAp = 1;
+            __threadfence();
+            st->done = 1;
+        }
+        return;
+    }
+    const double alpha = __ddiv_rn(st->rs_old, pAp);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc = 0.0;
+    if constexpr (VEC2) {
+        const int64_t n2 = n >> 1;
+        double2* x2 = reinterpret_cast<double2*>(x);
+        double2* r2 = reinterpret_cast<double2*>(r);
+        const double2* p2 = reinterpret_cast<const double2*>(p);
+        const double2* a2 = reinterpret_cast<const double2*>(Ap);
+        double acc1 = 0.0;
+        for (int64_t i = t; i < n2; i += stride) {
+            double2 xv = x2[i], rv = r2[i];
+            const double2 pv = p2[i], av = a2[i];
+            xv.x = add_rn(xv.x, mul_rn(pv.x, alpha));
+            xv.y = add_rn(xv.y, mul_rn(pv.y, alpha));
+            rv.x = sub_rn(rv.x, mul_rn(av.x, alpha));
+            rv.y = sub_rn(rv.y, mul_rn(av.y, alpha));
+            x2[i] = xv;
+            r2[i] = rv;
+            acc = add_rn(acc, mul_rn(rv.x, rv.x));
+            acc1 = add_rn(acc1, mul_rn(rv.y, rv.y));
+        }
+        acc = add_rn(acc, acc1);
+        if (t == 0 && (n & 1)) {
+            const int64_t i = n - 1;
+            x[i] = add_rn(x[i], mul_rn(p[i], alpha));
+            const double rn = sub_rn(r[i], mul_rn(Ap[i], alpha));
+            r[i] = rn;
+            acc = add_rn(acc, mul_rn(rn, rn));
+        }
+    } else {
+        for (int64_t i = t; i < n; i += stride) {
+            x[i] = add_rn(x[i], mul_rn(p[i], alpha));
+            const double rn = sub_rn(r[i], mul_rn(Ap[i], alpha));
+            r[i] = rn;
+            acc = add_rn(acc, mul_rn(rn, rn));
+        }
+    }
+    double total;
+    if (grid_sum_last_block<kReduceBlock>(acc, partials, ticket, &total)) {
+        if (threadIdx.x == 0) {
+            *rr_out = total;
+            st->last_pAp = pAp;
+            if (pAp_trace && st->it < st->trace_cap) pAp_trace[st->it] = pAp;
+        }
+    }
+}
+
+// Sequential-order variant of the r.r sum for ATK_REDUCE_SEQUENTIAL: K2 without the reduction, followed by the
+// one-CTA sequential dot kernel (atk_vector.cu).
+template <bool VEC2>
+__global__ void __launch_bounds__(kReduceBlock) cg_update_xr_nosum_kernel(int64_t n, CgState* st, const double* __restrict__ slot_pAp,
+                                                                          int world, double* __restrict__ x, double* __restrict__ r,
+                                                                          const double* __restrict__ p, const double* __restrict__ Ap,
+                                                                          double* pAp_trace) {
+    if (st->done) return;
+    const double pAp = slot_sum(slot_pAp, world);
+    if (fabs(pAp) < 1e-12) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) {
+            st->last_pAp = pAp;
+            if (pAp_trace && st->it < st->trace_cap) pAp_trace[st->it] = pAp;
+            st->stopped_on_pAp = 1;
+            __threadfence();
+            st->done = 1;
+        }
+        return;
+    }
+    const double alpha = __ddiv_rn(st->rs_old, pAp);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        x[i] = add_rn(x[i], mul_rn(p[i], alpha));
+        r[i] = sub_rn(r[i], mul_rn(Ap[i], alpha));
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        st->last_pAp = pAp;  // racing readers only read rs_old / done / it
+        if (pAp_trace && st->it < st->trace_cap) pAp_trace[st->it] = pAp;
+    }
+}
+
+// K3: p = r + p*(rs_new/rs_old) ; rs_old = rs_new.   (:79-80)
+template <bool VEC2>
+__global__ void __launch_bounds__(kReduceBlock) cg_update_p_kernel(int64_t n, CgState* st, const double* __restrict__ slot_rr,
+                                                                   int world, const double* __restrict__ r, double* __restrict__ p,
+                                                                   unsigned* ticket, double* rs_trace) {
+    if (st->done) return;
+    const double rs_new = slot_sum(slot_rr, world);
+    const double beta = __ddiv_rn(rs_new, st->rs_old);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if constexpr (VEC2) {
+        const int64_t n2 = n >> 1;
+        const double2* r2 = reinterpret_cast<const double2*>(r);
+        double2* p2 = reinterpret_cast<double2*>(p);
+        for (int64_t i = t; i < n2; i += stride) {
+            const double2 rv = r2[i];
+            double2 pv = p2[i];
+            pv.x = add_rn(rv.x, mul_rn(pv.x, beta));
+            pv.y = add_rn(rv.y, mul_rn(pv.y, beta));
+            p2[i] = pv;
+        }
+        if (t == 0 && (n & 1)) p[n - 1] = add_rn(r[n - 1], mul_rn(p[n - 1], beta));
+    } else {
+        for (int64_t i = t; i < n; i += stride) p[i] = add_rn(r[i], mul_rn(p[i], beta));
+    }
+    if (last_block_done(ticket)) {
+        if (threadIdx.x == 0) {
+            if (rs_trace && st->it < st->trace_cap) rs_trace[st->it] = rs_new;
+            st->rs_old = rs_new;
+            st->it = st->it + 1;
+        }
+    }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r, double* p, int max_iter,
+              atk_cg_info* info) {
+    ATK_REQUIRE(op && b && x && r && p && info, ATK_ERR_INVALID_ARGUMENT, "null argument to cg_solve");
+    ATK_REQUIRE(op->n_cols == op->n_rows_local * 1 || ctx->world > 1, ATK_ERR_INVALID_ARGUMENT, "Dimension mismatch");
+    const int64_t n = op->n_rows_local;
+    cudaStream_t st = ctx->stream;
+    const int64_t launches0 = ctx->launches;
+    const int trace_cap = (info->pAp_trace || info->rs_trace) ? std::max(0, info->trace_capacity) : 0;
+
+    CgState* d_state = nullptr;
+    double *Ap = nullptr, *d_ptrace = nullptr, *d_rtrace = nullptr;
+    int* h_done = nullptr;  // pinned: done flag of every poll
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    std::vector<cudaEvent_t> poll_events;
+    auto cleanup = [&]() {
+        if (gexec) cudaGraphExecDestroy(gexec);
+        if (graph) cudaGraphDestroy(graph);
+        for (auto e : poll_events) cudaEventDestroy(e);
+        cudaFree(d_state); cudaFree(Ap); cudaFree(d_ptrace); cudaFree(d_rtrace);
+        if (h_done) cudaFreeHost(h_done);
+    };
+    try {
+        ATK_CUDA_CHECK(cudaMalloc(&d_state, sizeof(CgState)));
+        ATK_CUDA_CHECK(cudaMalloc(&Ap, sizeof(double) * std::max<int64_t>(n, 1)));
+        if (trace_cap > 0) {
+            ATK_CUDA_CHECK(cudaMalloc(&d_ptrace, sizeof(double) * trace_cap));
+            ATK_CUDA_CHECK(cudaMalloc(&d_rtrace, sizeof(double) * trace_cap));
+            ATK_CUDA_CHECK(cudaMemsetAsync(d_ptrace, 0xff, sizeof(double) * trace_cap, st));  // NaN fill
+            ATK_CUDA_CHECK(cudaMemsetAsync(d_rtrace, 0xff, sizeof(double) * trace_cap, st));
+        }
+        CgState h0{};
+        h0.trace_cap = trace_cap;
+        ATK_CUDA_CHECK(cudaMemcpyAsync(d_state, &h0, sizeof(CgState), cudaMemcpyHostToDevice, st));
+
+        const bool vec = aligned16(x) && aligned16(r) && aligned16(p) && aligned16(Ap);
+        const int64_t work = vec ? (n + 1) / 2 : n;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((work + kReduceBlock - 1) / kReduceBlock, ctx->reduce_grid()));
+        const bool seq = ctx->reduction == ATK_REDUCE_SEQUENTIAL;
+        const int* done_flag = &d_state->done;
+
+        auto enqueue_iteration = [&]() {
+            op->apply(p, Ap, seq ? -1 : kSlotPAp, done_flag);  // K1 (+ all-gather of the partial)
+            if (seq) {
+                // the fused tree sum is replaced by strictly ordered sums
+                launch_dot(ctx, n, p, Ap, kSlotPAp, done_flag);
+                cg_update_xr_nosum_kernel<false><<<grid, kReduceBlock, 0, st>>>(n, d_state, ctx->slot(kSlotPAp), ctx->world, x, r,
+                                                                                p, Ap, d_ptrace);
+                count_launch(ctx);
+                launch_dot(ctx, n, r, r, kSlotRR, done_flag);
+            } else {
+                if (vec)
+                    cg_update_xr_kernel<true><<<grid, kReduceBlock, 0, st>>>(n, d_state, ctx->slot(kSlotPAp), ctx->world, x, r, p,
+                                                                             Ap, ctx->d_partials, ctx->d_tickets + 3,
+                                                                             ctx->slot(kSlotRR) + ctx->rank, d_ptrace);
+                else
+                    cg_update_xr_kernel<false><<<grid, kReduceBlock, 0, st>>>(n, d_state, ctx->slot(kSlotPAp), ctx->world, x, r, p,
+                                                                              Ap, ctx->d_partials, ctx->d_tickets + 3,
+                                                                              ctx->slot(kSlotRR) + ctx->rank, d_ptrace);
+                count_launch(ctx);
+                allgather_slot(ctx, kSlotRR, st);
+            }
+            if (vec)
+                cg_update_p_kernel<true><<<grid, kReduceBlock, 0, st>>>(n, d_state, ctx->slot(kSlotRR), ctx->world, r, p,
+                                                                        ctx->d_tickets + 4, d_rtrace);
+            else
+                cg_update_p_kernel<false><<<grid, kReduceBlock, 0, st>>>(n, d_state, ctx->slot(kSlotRR), ctx->world, r, p,
+                                                                         ctx->d_tickets + 4, d_rtrace);
+            count_launch(ctx);
+        };
+
+        // ---- capture one iteration, replay it
+        int launches_per_iter = 0;
+        if (max_iter > 0) {
+            const int64_t l0 = ctx->launches;
+            ATK_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            try {
+                enqueue_iteration();
+            } catch (...) {
+                cudaGraph_t g2 = nullptr;
+                cudaStreamEndCapture(st, &g2);
+                if (g2) cudaGraphDestroy(g2);
+                throw;
+            }
+            ATK_CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+            ATK_CUDA_CHECK(cudaGraphInstantiate(&gexec, graph, 0));
+            launches_per_iter = (int)(ctx->launches - l0);
+            ctx->launches = l0;  // capture did not launch anything
+        }
+
+        ATK_CUDA_CHECK(cudaEventRecord(ctx->ev_t0, st));
+        // rs_old = r.r ; ||b||   (:37-38)
+        launch_dot(ctx, n, r, r, kSlotRR);
+        launch_dot(ctx, n, b, b, kSlotBnorm);
+        cg_begin_kernel<<<1, 32, 0, st>>>(d_state, ctx->slot(kSlotRR), ctx->slot(kSlotBnorm), ctx->world);
+        count_launch(ctx);
+
+        // ---- run: iterations are enqueued in batches; the exit flag is read back after every batch and examined
+        // two batches later (a blocking wait on that batch's event, so every rank of a distributed run takes the
+        // same decision after the same batch and enqueues the same number of collectives).
+        constexpr int kBatch = 16, kLag = 2;
+        const int n_batches = (max_iter + kBatch - 1) / kBatch;
+        ATK_CUDA_CHECK(cudaMallocHost(&h_done, sizeof(int) * std::max(n_batches, 1)));
+        poll_events.resize(std::max(n_batches, 1), nullptr);
+        int enq = 0;
+        for (int bt = 0; bt < n_batches; ++bt) {
+            if (bt >= kLag) {
+                ATK_CUDA_CHECK(cudaEventSynchronize(poll_events[bt - kLag]));
+                if (h_done[bt - kLag]) break;
+            }
+            const int cnt = std::min(kBatch, max_iter - enq);
+            for (int q = 0; q < cnt; ++q) {
+                ATK_CUDA_CHECK(cudaGraphLaunch(gexec, st));
+                ctx->launches += launches_per_iter;
+            }
+            enq += cnt;
+            ATK_CUDA_CHECK(cudaMemcpyAsync(h_done + bt, &d_state->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+            ATK_CUDA_CHECK(cudaEventCreateWithFlags(&poll_events[bt], cudaEventDisableTiming));
+            ATK_CUDA_CHECK(cudaEventRecord(poll_events[bt], st));
+        }
+        ATK_CUDA_CHECK(cudaEventRecord(ctx->ev_t1, st));
+
+        CgState hs{};
+        ATK_CUDA_CHECK(cudaMemcpyAsync(&hs, d_state, sizeof(CgState), cudaMemcpyDeviceToHost, st));
+        if (trace_cap > 0) {
+            if (info->pAp_trace)
+                ATK_CUDA_CHECK(cudaMemcpyAsync(info->pAp_trace, d_ptrace, sizeof(double) * trace_cap, cudaMemcpyDeviceToHost, st));
+            if (info->rs_trace)
+                ATK_CUDA_CHECK(cudaMemcpyAsync(info->rs_trace, d_rtrace, sizeof(double) * trace_cap, cudaMemcpyDeviceToHost, st));
+        }
+        ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        ATK_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
+        info->iterations = hs.it;
+        info->stopped_on_pAp = hs.stopped_on_pAp;
+        info->zero_rhs = hs.zero_rhs;
+        info->last_pAp = hs.last_pAp;
+        info->rs = hs.rs_old;
+        info->device_ms = ms;
+        info->kernel_launches = (int)(ctx->launches - launches0);
+    } catch (...) {
+        cleanup();
+        throw;
+    }
+    cleanup();
+}
+
+}  // namespace atk

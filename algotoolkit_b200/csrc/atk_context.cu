@@ -1,0 +1,191 @@
+// atk_context.cu -- context, scratch buffers, memory entry points and the NCCL plumbing.
+//
+// NCCL is resolved with dlopen() the first time a distributed context is created, so the single-GPU
+// library has no link-time dependency on it.  Inside a torch process the already-loaded (torch-bundled)
+// libnccl.so.2 is picked up by SONAME; in a plain C++ program the system library is.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+#include <mutex>
+
+#include "atk_internal.cuh"
+
+namespace atk {
+
+// ------------------------------------------------------------------------------------------ NCCL via dlopen
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+
+void load_nccl() {
+    std::call_once(g_nccl_once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (g_nccl.handle) break;
+        }
+        if (!g_nccl.handle) return;
+#define ATK_SYM(field, sym) g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(g_nccl.handle, sym))
+        ATK_SYM(GetUniqueId, "ncclGetUniqueId");
+        ATK_SYM(CommInitRank, "ncclCommInitRank");
+        ATK_SYM(CommDestroy, "ncclCommDestroy");
+        ATK_SYM(AllGather, "ncclAllGather");
+        ATK_SYM(Send, "ncclSend");
+        ATK_SYM(Recv, "ncclRecv");
+        ATK_SYM(GroupStart, "ncclGroupStart");
+        ATK_SYM(GroupEnd, "ncclGroupEnd");
+        ATK_SYM(GetErrorString, "ncclGetErrorString");
+#undef ATK_SYM
+    });
+    ATK_REQUIRE(g_nccl.handle && g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllGather && g_nccl.Send &&
+                    g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd,
+                ATK_ERR_NCCL, "libnccl.so.2 could not be loaded (needed for a distributed context)");
+}
+
+void nccl_check(ncclResult_t r, const char* what) {
+    if (r != ncclSuccess) {
+        std::string m = std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error");
+        throw Error(ATK_ERR_NCCL, m);
+    }
+}
+}  // namespace
+
+void allgather_slot(Context* ctx, int slot, cudaStream_t stream) {
+    if (ctx->world == 1) return;
+    double* base = ctx->slot(slot);
+    nccl_check(g_nccl.AllGather(base + ctx->rank, base, 1, ncclDouble, (ncclComm_t)ctx->nccl_comm, stream),
+               "ncclAllGather");
+}
+
+void exchange_halo(Context* ctx, const double* first_plane, const double* last_plane, double* halo_lo, double* halo_hi,
+                   size_t plane_elems, cudaStream_t stream) {
+    if (ctx->world == 1) return;
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    const int lo = ctx->rank - 1, hi = ctx->rank + 1;
+    nccl_check(g_nccl.GroupStart(), "ncclGroupStart");
+    if (lo >= 0) {
+        nccl_check(g_nccl.Send(first_plane, plane_elems, ncclDouble, lo, comm, stream), "ncclSend");
+        nccl_check(g_nccl.Recv(halo_lo, plane_elems, ncclDouble, lo, comm, stream), "ncclRecv");
+    }
+    if (hi < ctx->world) {
+        nccl_check(g_nccl.Send(last_plane, plane_elems, ncclDouble, hi, comm, stream), "ncclSend");
+        nccl_check(g_nccl.Recv(halo_hi, plane_elems, ncclDouble, hi, comm, stream), "ncclRecv");
+    }
+    nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd");
+}
+
+double read_slot(Context* ctx, int slot) {
+    ATK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pinned, ctx->slot(slot), sizeof(double) * ctx->world, cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+    ATK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    // rank-ordered sum; volatile keeps the host compiler from reassociating (it may not anyway)
+    volatile double s = ctx->h_pinned[0];
+    for (int q = 1; q < ctx->world; ++q) s = s + ctx->h_pinned[q];
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------ context
+static void init_context(Context& c, int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        throw Error(ATK_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                      "); libatk_cuda has no CPU fallback");
+    ATK_REQUIRE(device >= 0 && device < count, ATK_ERR_INVALID_ARGUMENT, "device index out of range");
+    c.device = device;
+    ATK_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    ATK_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    c.sm_count = prop.multiProcessorCount;
+    ATK_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    ATK_CUDA_CHECK(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
+    ATK_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+    ATK_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
+    ATK_CUDA_CHECK(cudaEventCreate(&c.ev_t0));
+    ATK_CUDA_CHECK(cudaEventCreate(&c.ev_t1));
+    ATK_CUDA_CHECK(cudaMalloc(&c.d_partials, sizeof(double) * kMaxPartials));
+    ATK_CUDA_CHECK(cudaMalloc(&c.d_tickets, sizeof(unsigned) * kNumTickets));
+    ATK_CUDA_CHECK(cudaMalloc(&c.d_gather, sizeof(double) * kNumSlots * kMaxRanks));
+    ATK_CUDA_CHECK(cudaMemset(c.d_tickets, 0, sizeof(unsigned) * kNumTickets));
+    ATK_CUDA_CHECK(cudaMemset(c.d_gather, 0, sizeof(double) * kNumSlots * kMaxRanks));
+    ATK_CUDA_CHECK(cudaMallocHost(&c.h_pinned, sizeof(double) * 64));
+    ATK_CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+atk_context_s* context_create(int device) {
+    auto* h = new atk_context_s();
+    try {
+        init_context(h->c, device);
+    } catch (...) {
+        delete h;
+        throw;
+    }
+    return h;
+}
+
+atk_context_s* context_create_distributed(int device, int rank, int world, const void* uid, size_t uid_bytes) {
+    ATK_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, ATK_ERR_INVALID_ARGUMENT,
+                "bad rank / world size");
+    auto* h = new atk_context_s();
+    try {
+        init_context(h->c, device);
+        h->c.rank = rank;
+        h->c.world = world;
+        if (world > 1) {
+            load_nccl();
+            ATK_REQUIRE(uid && uid_bytes == sizeof(ncclUniqueId), ATK_ERR_INVALID_ARGUMENT, "bad NCCL unique id blob");
+            ncclUniqueId id;
+            std::memcpy(&id, uid, sizeof(id));
+            ncclComm_t comm;
+            nccl_check(g_nccl.CommInitRank(&comm, world, id, rank), "ncclCommInitRank");
+            h->c.nccl_comm = comm;
+        }
+    } catch (...) {
+        delete h;
+        throw;
+    }
+    return h;
+}
+
+void nccl_unique_id(void* buf, size_t cap, size_t* bytes) {
+    load_nccl();
+    ATK_REQUIRE(buf && cap >= sizeof(ncclUniqueId), ATK_ERR_INVALID_ARGUMENT, "unique-id buffer too small (need 128 bytes)");
+    ncclUniqueId id;
+    nccl_check(g_nccl.GetUniqueId(&id), "ncclGetUniqueId");
+    std::memcpy(buf, &id, sizeof(id));
+    if (bytes) *bytes = sizeof(id);
+}
+
+void context_destroy(atk_context_s* h) {
+    if (!h) return;
+    Context& c = h->c;
+    cudaSetDevice(c.device);
+    cudaDeviceSynchronize();
+    if (c.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c.nccl_comm);
+    cudaFree(c.d_partials);
+    cudaFree(c.d_tickets);
+    cudaFree(c.d_gather);
+    cudaFreeHost(c.h_pinned);
+    cudaEventDestroy(c.ev_fork);
+    cudaEventDestroy(c.ev_join);
+    cudaEventDestroy(c.ev_t0);
+    cudaEventDestroy(c.ev_t1);
+    cudaStreamDestroy(c.stream);
+    cudaStreamDestroy(c.comm_stream);
+    delete h;
+}
+
+}  // namespace atk

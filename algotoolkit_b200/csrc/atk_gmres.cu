@@ -1,0 +1,292 @@
+// atk_gmres.cu -- GMRES::solve on the device (reference src/LinearAlgebra/Krylov/GMRES.hpp:27-171, the
+// unpreconditioned branch), keeping the reference's behaviour:
+//   * the Arnoldi projection runs over i < j only (:73) - w is never orthogonalised against V[j];
+//   * H is allocated once per solve() and never cleared between restarts (:55), so from the second cycle on the
+//     Givens step starts from the previous cycle's rho[j] left in H(j,j) (:89-94);
+//   * no inner convergence test; `tol` is an absolute residual threshold tested once per restart (:107) and against
+//     ||w|| inside the cycle (:81-85);
+//   * x = x + V[i]*y[i] is added for i ascending with two roundings per term (:167-170).
+//
+// Device data: V is one (K+1) x n column-major array, w/r/t are work vectors; the (K+1)^2 Hessenberg, the Givens
+// coefficients and e1 live on the HOST (O(K^2) scalar work per cycle, negligible bytes) and are computed with the
+// reference's formulae in the reference's order.  The host needs ||w|| and the column of H after every Arnoldi step,
+// so there is one small D2H per step; everything else stays on the device.
+//
+// Orthogonalisation modes:
+//   MGS  (parity path)  per i: dot kernel -> h in a reduction slot; axmy kernel reads h from the slot: w = w - V[i]*h.
+//        Algorithmic traffic per (i) pair 40 B/row.
+//   CGS2 (throughput)   h = V[0:j]^T w as one multi-dot kernel, w -= V[0:j] h as one multi-axpy kernel, twice.
+//        16*j + ... B/row per pass; different rounding, never used for parity.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
+#include "atk_internal.cuh"
+
+namespace atk {
+
+namespace {
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// w = w - v*h, h read from a reduction slot (sum over ranks in rank order); thread 0 also records h.
+__global__ void __launch_bounds__(256) mgs_axmy_kernel(int64_t n, const double* __restrict__ v, double* __restrict__ w,
+                                                       const double* __restrict__ slot, int world, double* __restrict__ h_out) {
+    const double h = slot_sum(slot, world);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) *h_out = h;
+    for (int64_t i = t; i < n; i += stride) w[i] = sub_rn(w[i], mul_rn(v[i], h));
+}
+
+// out = w / sqrt(slot)  (V[j+1] = w / H(j+1,j), :86) - skipped when the norm is zero (the host raises the error).
+__global__ void __launch_bounds__(256) normalize_kernel(int64_t n, const double* __restrict__ w, double* __restrict__ out,
+                                                        const double* __restrict__ slot, int world, double* __restrict__ norm_out) {
+    const double nrm = sqrt(slot_sum(slot, world));
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) *norm_out = nrm;
+    if (nrm == 0.0) return;
+    for (int64_t i = t; i < n; i += stride) out[i] = __ddiv_rn(w[i], nrm);
+}
+
+// x[e] = (((x[e] + V0[e]*y0) + V1[e]*y1) + ...), i ascending: bit-identical to k successive x = x + V[i]*y[i].
+__global__ void __launch_bounds__(256) update_solution_kernel(int64_t n, int k, const double* __restrict__ V, int64_t ldv,
+                                                              const double* __restrict__ y, double* __restrict__ x) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        double acc = x[e];
+        for (int i = 0; i < k; ++i) acc = add_rn(acc, mul_rn(V[(int64_t)i * ldv + e], __ldg(y + i)));
+        x[e] = acc;
+    }
+}
+
+// ---- CGS2 kernels -------------------------------------------------------------------------------------------------
+// h[i] = V[i].w for i < j in one pass over w: each CTA owns a contiguous chunk of rows, keeps its w chunk in registers
+// and streams the j columns; per-CTA partials go to part[i*gridDim.x + block], a second kernel adds them in block order.
+constexpr int kCgsBlock = 256;
+constexpr int kCgsPerThread = 4;
+__global__ void __launch_bounds__(kCgsBlock) multi_dot_kernel(int64_t n, int j, const double* __restrict__ V, int64_t ldv,
+                                                              const double* __restrict__ w, double* __restrict__ part) {
+    const int64_t chunk = (int64_t)kCgsBlock * kCgsPerThread;
+    const int64_t base = (int64_t)blockIdx.x * chunk;
+    double wv[kCgsPerThread];
+#pragma unroll
+    for (int q = 0; q < kCgsPerThread; ++q) {
+        const int64_t e = base + (int64_t)q * kCgsBlock + threadIdx.x;
+        wv[q] = (e < n) ? w[e] : 0.0;
+    }
+    for (int i = 0; i < j; ++i) {
+        const double* v = V + (int64_t)i * ldv;
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < kCgsPerThread; ++q) {
+            const int64_t e = base + (int64_t)q * kCgsBlock + threadIdx.x;
+            if (e < n) acc = add_rn(acc, mul_rn(v[e], wv[q]));
+        }
+        const double bs = block_sum<kCgsBlock>(acc);
+        if (threadIdx.x == 0) part[(int64_t)i * gridDim.x + blockIdx.x] = bs;
+    }
+}
+__global__ void __launch_bounds__(256) multi_dot_final_kernel(int j, int nblocks, const double* __restrict__ part,
+                                                              double* __restrict__ h_local) {
+    const int i = blockIdx.x;
+    if (i >= j) return;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) s = add_rn(s, part[(int64_t)i * nblocks + b]);
+    const double t = block_sum<256>(s);
+    if (threadIdx.x == 0) h_local[i] = t;
+}
+// w -= sum_i V[i]*h[i] (i ascending, two roundings per term); h_acc[i] += h[i] for the Hessenberg column
+__global__ void __launch_bounds__(256) multi_axmy_kernel(int64_t n, int j, const double* __restrict__ V, int64_t ldv,
+                                                         const double* __restrict__ h, double* __restrict__ w) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        double acc = w[e];
+        for (int i = 0; i < j; ++i) acc = sub_rn(acc, mul_rn(V[(int64_t)i * ldv + e], __ldg(h + i)));
+        w[e] = acc;
+    }
+}
+
+struct Givens {
+    // reference GMRES.hpp:139-151
+    static void generate(double dx, double dy, double& cs, double& sn, double& rho) {
+        rho = std::sqrt(dx * dx + dy * dy);
+        if (std::fabs(rho) < DBL_EPSILON) {
+            cs = 1.0;
+            sn = 0.0;
+            rho = 0.0;
+        } else {
+            cs = dx / rho;
+            sn = dy / rho;
+        }
+    }
+};
+
+}  // namespace
+
+void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t n_x, int max_iter, int krylov_dim,
+                 double tol, atk_gmres_ortho ortho, atk_gmres_callback cb, void* user, atk_gmres_info* info) {
+    ATK_REQUIRE(op && b && x && info, ATK_ERR_INVALID_ARGUMENT, "null argument to gmres_solve");
+    const int64_t n = op->n_rows_local;
+    const int64_t n_global = op->n_cols;
+    // GMRES.hpp:28-37
+    ATK_REQUIRE(n_x == n, ATK_ERR_INVALID_ARGUMENT, "Initial guess vector must match system size");
+    ATK_REQUIRE(krylov_dim > 0 && krylov_dim <= n_global, ATK_ERR_INVALID_ARGUMENT, "Invalid Krylov subspace dimension");
+    ATK_REQUIRE(ortho == ATK_GMRES_MGS || ctx->world == 1, ATK_ERR_INVALID_ARGUMENT, "CGS2 is single-GPU in this version");
+    const int K = krylov_dim;
+    const int64_t ld = K + 1;
+    cudaStream_t st = ctx->stream;
+    const int64_t launches0 = ctx->launches;
+    auto notify = [&](int ev, double v) { if (cb) cb(ev, v, user); };
+
+    double *V = nullptr, *w = nullptr, *r = nullptr, *t = nullptr, *d_h = nullptr, *d_y = nullptr, *d_part = nullptr;
+    double* h_col = nullptr;  // pinned: H column + norm coming back each Arnoldi step
+    auto cleanup = [&]() {
+        cudaFree(V); cudaFree(w); cudaFree(r); cudaFree(t); cudaFree(d_h); cudaFree(d_y); cudaFree(d_part);
+        if (h_col) cudaFreeHost(h_col);
+    };
+    info->restarts = 0;
+    info->status = 0;
+    info->arnoldi_steps = 0;
+    info->trace_count = 0;
+    auto trace = [&](double v) {
+        if (info->residual_trace && info->trace_count < info->trace_capacity) info->residual_trace[info->trace_count] = v;
+        info->trace_count++;
+    };
+    try {
+        const size_t nn = (size_t)std::max<int64_t>(n, 1);
+        ATK_CUDA_CHECK(cudaMalloc(&V, sizeof(double) * nn * (size_t)ld));
+        ATK_CUDA_CHECK(cudaMalloc(&w, sizeof(double) * nn));
+        ATK_CUDA_CHECK(cudaMalloc(&r, sizeof(double) * nn));
+        ATK_CUDA_CHECK(cudaMalloc(&t, sizeof(double) * nn));
+        ATK_CUDA_CHECK(cudaMalloc(&d_h, sizeof(double) * (size_t)(ld + 1)));
+        ATK_CUDA_CHECK(cudaMalloc(&d_y, sizeof(double) * (size_t)ld));
+        ATK_CUDA_CHECK(cudaMallocHost(&h_col, sizeof(double) * (size_t)(ld + 1)));
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8));
+        const int cgs_blocks = (int)std::max<int64_t>(1, (n + kCgsBlock * kCgsPerThread - 1) / (kCgsBlock * kCgsPerThread));
+        if (ortho == ATK_GMRES_CGS2) ATK_CUDA_CHECK(cudaMalloc(&d_part, sizeof(double) * (size_t)cgs_blocks * (size_t)K));
+
+        std::vector<double> H((size_t)ld * ld, 0.0);  // :55 - allocated once, never cleared
+        std::vector<double> cs(K, 1.0), sn(K, 0.0), rho(K, 0.0), e1(ld, 0.0), y(ld, 0.0);
+        auto Hm = [&](int i, int j) -> double& { return H[(size_t)i + (size_t)j * ld]; };
+
+        ATK_CUDA_CHECK(cudaEventRecord(ctx->ev_t0, st));
+        auto residual = [&]() -> double {  // r = b - A*x ; ||r||   (:42,47 / :99,104)
+            op->apply(x, t, -1, nullptr);
+            launch_sub(ctx, n, b, t, r);
+            launch_dot(ctx, n, r, r, kSlotNorm);
+            return std::sqrt(read_slot(ctx, kSlotNorm));
+        };
+        double beta = residual();
+        info->initial_residual = beta;
+        info->final_residual = beta;
+        trace(beta);
+        notify(ATK_GMRES_INITIAL_RESIDUAL, beta);
+        if (beta < tol) {  // :49-52
+            notify(ATK_GMRES_INITIAL_GOOD, 0.0);
+            info->status = 2;
+        } else {
+            e1[0] = beta;
+            bool finished = false;
+            for (int iter = 0; iter < max_iter && !finished; ++iter) {
+                ATK_REQUIRE(beta != 0.0, ATK_ERR_RUNTIME, "Division by zero.");  // V[0] = r / beta (:63)
+                launch_div(ctx, n, r, beta, V);
+                int kry = K;
+                for (int j = 0; j < K; ++j) {
+                    const double* vj = V + (size_t)j * nn;
+                    op->apply(vj, w, -1, nullptr);  // :70
+                    if (ortho == ATK_GMRES_MGS) {
+                        for (int i = 0; i < j; ++i) {  // :73-77
+                            const double* vi = V + (size_t)i * nn;
+                            launch_dot(ctx, n, vi, w, kSlotH);
+                            mgs_axmy_kernel<<<grid, 256, 0, st>>>(n, vi, w, ctx->slot(kSlotH), ctx->world, d_h + i);
+                            count_launch(ctx);
+                        }
+                    } else if (j > 0) {
+                        for (int pass = 0; pass < 2; ++pass) {
+                            multi_dot_kernel<<<cgs_blocks, kCgsBlock, 0, st>>>(n, j, V, (int64_t)nn, w, d_part);
+                            multi_dot_final_kernel<<<j, 256, 0, st>>>(j, cgs_blocks, d_part, pass == 0 ? d_h : d_y);
+                            multi_axmy_kernel<<<grid, 256, 0, st>>>(n, j, V, (int64_t)nn, pass == 0 ? d_h : d_y, w);
+                            count_launch(ctx, 3);
+                        }
+                        // H(0:j, j) = h(pass 0) + h(pass 1)
+                        launch_add(ctx, j, d_h, d_y, d_h);
+                    }
+                    launch_dot(ctx, n, w, w, kSlotNorm);  // :79
+                    normalize_kernel<<<grid, 256, 0, st>>>(n, w, V + (size_t)(j + 1) * nn, ctx->slot(kSlotNorm), ctx->world,
+                                                           d_h + j);  // :86 (skipped on the device when the norm is 0)
+                    count_launch(ctx);
+                    ATK_CUDA_CHECK(cudaGetLastError());
+                    ATK_CUDA_CHECK(cudaMemcpyAsync(h_col, d_h, sizeof(double) * (size_t)(j + 1), cudaMemcpyDeviceToHost, st));
+                    ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+                    info->arnoldi_steps++;
+                    for (int i = 0; i < j; ++i) Hm(i, j) = h_col[i];  // :75
+                    const double w_norm = h_col[j];
+                    Hm(j + 1, j) = w_norm;  // :80
+                    if (w_norm < tol) {     // :81-85
+                        kry = j;
+                        notify(ATK_GMRES_KRYLOV_UPDATE, (double)kry);
+                        break;
+                    }
+                    ATK_REQUIRE(w_norm != 0.0, ATK_ERR_RUNTIME, "Division by zero.");  // VectorObj.hpp:76 via :86
+                    for (int i = 0; i < j; ++i) {  // :89-91 / :134-137
+                        const double tmp = Hm(i, j);
+                        Hm(i, j) = cs[i] * Hm(i, j) + sn[i] * Hm(i + 1, j);
+                        Hm(i + 1, j) = -sn[i] * tmp + cs[i] * Hm(i + 1, j);
+                    }
+                    Givens::generate(Hm(j, j), Hm(j + 1, j), cs[j], sn[j], rho[j]);  // :92
+                    Hm(j, j) = rho[j];      // :93
+                    Hm(j + 1, j) = 0.0;     // :94
+                    {                       // :95 / :128-132
+                        const double tmp = e1[j];
+                        e1[j] = cs[j] * tmp + sn[j] * e1[j + 1];
+                        e1[j + 1] = -sn[j] * tmp + cs[j] * e1[j + 1];
+                    }
+                }
+                // updateSolution (:153-171)
+                for (int i = kry - 1; i >= 0; --i) {
+                    y[i] = e1[i];
+                    for (int jj = i + 1; jj < kry; ++jj) y[i] = y[i] - Hm(i, jj) * y[jj];
+                    ATK_REQUIRE(!(std::fabs(Hm(i, i)) < DBL_EPSILON), ATK_ERR_RUNTIME,
+                                "GMRES updateSolution: Zero diagonal element encountered in H.");
+                    y[i] = y[i] / Hm(i, i);
+                }
+                if (kry > 0) {
+                    ATK_CUDA_CHECK(cudaMemcpyAsync(d_y, y.data(), sizeof(double) * (size_t)kry, cudaMemcpyHostToDevice, st));
+                    update_solution_kernel<<<grid, 256, 0, st>>>(n, kry, V, (int64_t)nn, d_y, x);
+                    count_launch(ctx);
+                    ATK_CUDA_CHECK(cudaStreamSynchronize(st));  // y (pageable) must stay valid until the copy ran
+                }
+                beta = residual();  // :99-104
+                info->restarts = iter + 1;
+                info->final_residual = beta;
+                trace(beta);
+                notify(ATK_GMRES_RESTART_RESIDUAL, beta);
+                if (beta < tol) {  // :107-110
+                    notify(ATK_GMRES_CONVERGED, (double)iter);
+                    info->status = 1;
+                    finished = true;
+                    break;
+                }
+                std::fill(e1.begin(), e1.end(), 0.0);  // :111-112
+                e1[0] = beta;
+            }
+            if (!finished) notify(ATK_GMRES_MAX_ITER, 0.0);  // :114
+        }
+        ATK_CUDA_CHECK(cudaEventRecord(ctx->ev_t1, st));
+        ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        ATK_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
+        info->device_ms = ms;
+        info->kernel_launches = (int)(ctx->launches - launches0);
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        cleanup();
+        throw;
+    }
+    cleanup();
+}
+
+}  // namespace atk

@@ -1,0 +1,209 @@
+// atk_internal.cuh -- shared declarations of libatk_cuda.so (not part of the public ABI).
+//
+// Layout of the library:
+//   atk_context.cu   context, streams, scratch, memory entry points, NCCL (dlopen'ed lazily)
+//   atk_vector.cu    VectorObj kernels: dot / nrm2 / scale / div / add / sub / axpy
+//   atk_spmv.cu      CSC -> CSR -> SELL-32 conversion on the device, SELL and CSR-vector SpMV
+//   atk_stencil.cu   matrix-free 7-point Poisson operator (+ fused p.Ap), device-side assembly
+//   atk_cg.cu        ConjugateGrad::solve device loop
+//   atk_gmres.cu     GMRES::solve device loop
+//   atk_api.cu       extern "C" wrappers (exceptions -> status codes)
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <exception>
+#include <string>
+#include <vector>
+
+#include "../../include/atk_cuda.h"
+
+namespace atk {
+
+// ------------------------------------------------------------------------------------------ errors
+struct Error : public std::exception {
+    int code;
+    std::string msg;
+    Error(int c, std::string m) : code(c), msg(std::move(m)) {}
+    const char* what() const noexcept override { return msg.c_str(); }
+};
+
+#define ATK_CUDA_CHECK(expr)                                                                             \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            throw ::atk::Error(ATK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + \
+                                                 __FILE__ + ":" + std::to_string(__LINE__) + ")");       \
+    } while (0)
+
+#define ATK_REQUIRE(cond, code, text)                    \
+    do {                                                 \
+        if (!(cond)) throw ::atk::Error((code), (text)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ constants
+constexpr int kMaxRanks = 16;          // ranks per communicator (one box: <= 8)
+constexpr int kReduceBlock = 256;      // block size of every kernel that ends in a grid-wide sum
+constexpr int kMaxPartials = 1 << 16;  // per-block partial sums a single kernel may produce
+constexpr int kNumSlots = 8;           // independent reduction result slots
+constexpr int kNumTickets = 16;
+
+// Reduction slots: slot s lives at gather[s*kMaxRanks + q], q = rank.  Each rank writes its
+// own entry; on a distributed context an in-place all-gather fills the others; consumers add
+// the entries in rank order, so every rank derives bit-identical scalars.
+enum Slot : int { kSlotPAp = 0, kSlotRR = 1, kSlotGeneric = 2, kSlotBnorm = 3, kSlotH = 4, kSlotNorm = 5 };
+
+struct Context {
+    int device = 0;
+    int rank = 0, world = 1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t comm_stream = nullptr;  // halo exchange
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    atk_reduction reduction = ATK_REDUCE_TREE;
+    double* d_partials = nullptr;  // [kMaxPartials]
+    unsigned* d_tickets = nullptr; // [kNumTickets], self-resetting (atomicInc wrap)
+    double* d_gather = nullptr;    // [kNumSlots * kMaxRanks]
+    double* h_pinned = nullptr;    // [64] pinned scratch for scalar read-back
+    int64_t launches = 0;
+    void* nccl_comm = nullptr;
+
+    double* slot(int s) const { return d_gather + (size_t)s * kMaxRanks; }
+    int reduce_grid() const { return sm_count * 4; }
+};
+
+inline void count_launch(Context* c, int n = 1) { c->launches += n; }
+
+// In-place all-gather of one reduction slot across ranks (no-op when world == 1).
+void allgather_slot(Context* ctx, int slot, cudaStream_t stream);
+// Exchange one xy-plane with the z-neighbours: sends `first_plane` down / `last_plane` up, receives into
+// halo_lo / halo_hi.  Runs on `stream`.
+void exchange_halo(Context* ctx, const double* first_plane, const double* last_plane, double* halo_lo, double* halo_hi,
+                   size_t plane_elems, cudaStream_t stream);
+// Host value of a reduction slot (sum over ranks in rank order); synchronises the compute stream.
+double read_slot(Context* ctx, int slot);
+
+// ------------------------------------------------------------------------------------------ operators
+struct Operator {
+    Context* ctx = nullptr;
+    int64_t n_rows_local = 0;  // rows owned by this rank
+    int64_t n_cols = 0;        // global columns
+    int64_t row_begin = 0;     // first global row owned
+    int64_t nnz = 0;
+    virtual ~Operator() {}
+    // y = A x on the compute stream; if dot_slot >= 0 also leaves this rank's partial of x.y in that slot
+    // (and all-gathers it).  `skip_flag` (device int, may be null): when *skip_flag != 0 the kernels return at once.
+    virtual void apply(const double* x, double* y, int dot_slot, const int* skip_flag) = 0;
+    virtual bool has_csr() const { return false; }
+    virtual void export_csr(int*, int*, double*) const { throw Error(ATK_ERR_INVALID_ARGUMENT, "operator has no CSR arrays"); }
+};
+
+Operator* make_operator_from_csc(Context* ctx, int n_rows, int n_cols, int64_t nnz, const int* col_ptr, const int* row_idx,
+                                 const double* vals, bool on_device, atk_format format);
+Operator* make_stencil7(Context* ctx, int nx, int ny, int nz, double cx, double cy, double cz);
+Operator* make_poisson_assembled(Context* ctx, int nx, int ny, int nz, double cx, double cy, double cz, atk_format format);
+Operator* make_stencil27_assembled(Context* ctx, int nx, int ny, int nz, const double* coef, atk_format format);
+
+// ------------------------------------------------------------------------------------------ vector kernels (host launchers)
+void launch_dot(Context* ctx, int64_t n, const double* x, const double* y, int slot, const int* skip_flag = nullptr);
+void launch_scale(Context* ctx, int64_t n, const double* x, double s, double* out);
+void launch_div(Context* ctx, int64_t n, const double* x, double s, double* out);
+void launch_add(Context* ctx, int64_t n, const double* x, const double* y, double* out);
+void launch_sub(Context* ctx, int64_t n, const double* x, const double* y, double* out);
+void launch_axpy(Context* ctx, int64_t n, const double* x, const double* y, double a, double* out);
+void launch_axmy(Context* ctx, int64_t n, const double* x, const double* y, double a, double* out);
+
+// ------------------------------------------------------------------------------------------ solvers
+void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r, double* p, int max_iter, atk_cg_info* info);
+void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t n_x, int max_iter, int krylov_dim,
+                 double tol, atk_gmres_ortho ortho, atk_gmres_callback cb, void* user, atk_gmres_info* info);
+
+// ------------------------------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+
+// Multiply and add that can never be contracted into an FMA (the reference is built without FMA).
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+
+__device__ __forceinline__ unsigned linear_block_id() {
+    return blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+}
+__device__ __forceinline__ unsigned total_blocks() { return gridDim.x * gridDim.y * gridDim.z; }
+__device__ __forceinline__ unsigned linear_thread_id() {
+    return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+}
+
+// Fixed-shape block sum: xor-shuffle tree inside each warp, then the warp results added in warp order.
+// Every thread returns the same value.  BLOCK = threads per block (multiple of 32).
+template <int BLOCK>
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double warp_part[BLOCK / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = add_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const unsigned tid = linear_thread_id();
+    __syncthreads();  // protect warp_part against a previous use
+    if ((tid & 31) == 0) warp_part[tid >> 5] = v;
+    __syncthreads();
+    double t = warp_part[0];
+#pragma unroll
+    for (int w = 1; w < BLOCK / 32; ++w) t = add_rn(t, warp_part[w]);
+    return t;
+}
+
+// Grid-wide deterministic sum: each block leaves its partial in partials[block]; the block that arrives last adds
+// all partials in a fixed order.  Returns true (for every thread) in that last block, with the total in *total.
+// The ticket wraps back to 0 by itself (atomicInc), so it is ready for the next launch.
+template <int BLOCK>
+__device__ __forceinline__ bool grid_sum_last_block(double v, double* partials, unsigned* ticket, double* total) {
+    __shared__ bool is_last;
+    const double bs = block_sum<BLOCK>(v);
+    const unsigned nb = total_blocks();
+    if (linear_thread_id() == 0) {
+        partials[linear_block_id()] = bs;
+        __threadfence();
+        const unsigned t = atomicInc(ticket, nb - 1);
+        is_last = (t == nb - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    double s = 0.0;
+    for (unsigned i = linear_thread_id(); i < nb; i += BLOCK) s = add_rn(s, __ldcg(partials + i));
+    *total = block_sum<BLOCK>(s);
+    return true;
+}
+
+// Election without a sum: true in the block that finishes last.
+__device__ __forceinline__ bool last_block_done(unsigned* ticket) {
+    __shared__ bool is_last_e;
+    __syncthreads();
+    if (linear_thread_id() == 0) {
+        __threadfence();
+        const unsigned nb = total_blocks();
+        const unsigned t = atomicInc(ticket, nb - 1);
+        is_last_e = (t == nb - 1);
+    }
+    __syncthreads();
+    return is_last_e;
+}
+
+// Sum of a reduction slot over ranks, in rank order (what every consumer kernel does in its prologue).
+__device__ __forceinline__ double slot_sum(const double* slot, int world) {
+    double s = __ldcg(slot);
+    for (int q = 1; q < world; ++q) s = add_rn(s, __ldcg(slot + q));
+    return s;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace atk
+
+struct atk_context_s {
+    atk::Context c;
+};
+struct atk_operator_s {
+    atk::Operator* op;
+};

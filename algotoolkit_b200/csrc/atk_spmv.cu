@@ -1,0 +1,612 @@
+// atk_spmv.cu -- SparseMatrixCSC<double> on the device (reference src/Obj/SparseObj.hpp).
+//
+//   finished CSC arrays (col_ptr,row_indices,values after finalize(), :76-100)
+//        |  count rows (atomics) -> exclusive scan -> scatter -> per-row sort by CSC position
+//        v
+//   CSR with each row's entries in ascending (column, CSC position) order
+//        |  row lengths -> (optional sigma-window sort) -> slice widths -> scan -> fill
+//        v
+//   SELL-32-sigma: slices of 32 rows stored column-major, one thread per row
+//
+// Why SELL and one thread per row: the reference matvec (:131-152) adds val*x[col] into y[row] for col ascending,
+// starting from 0.0, so the bit pattern of y[row] is fixed by a strictly sequential sum over the row.  A thread
+// that walks its own row in order reproduces it exactly, and the column-major slice makes those walks coalesced.
+// The CSR-vector kernel (several lanes per row + shuffle tree) is kept as the throughput alternative for long,
+// irregular rows; it is deterministic but sums in a different order.
+//
+// Algorithmic traffic per SpMV: 12*nnz + 4*(n+1) + 8*m + 8*n bytes.
+#include <algorithm>
+
+#include "atk_internal.cuh"
+
+namespace atk {
+
+namespace {
+
+constexpr int kSliceRows = 32;
+
+// ------------------------------------------------------------------------------------------ int32 exclusive scan
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_kernel(const int* __restrict__ in, int* __restrict__ out,
+                                                                 int* __restrict__ tile_sums, int64_t n) {
+    __shared__ int warp_sums[kScanThreads / 32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int v[kScanItems];
+    int local = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        local += v[k];
+    }
+    // inclusive scan of `local` across the block
+    int incl = local;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    int warp_off = 0;
+    for (int w = 0; w < warp; ++w) warp_off += warp_sums[w];
+    int run = warp_off + incl - local;  // exclusive prefix of this thread inside the tile
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < n) out[base + k] = run;
+        run += v[k];
+    }
+    if (threadIdx.x == kScanThreads - 1) tile_sums[blockIdx.x] = warp_off + incl;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_add_kernel(int* __restrict__ out, const int* __restrict__ tile_prefix,
+                                                                int64_t n) {
+    const int add = tile_prefix[blockIdx.x];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile;
+    for (int k = threadIdx.x; k < kScanTile; k += kScanThreads)
+        if (base + k < n) out[base + k] += add;
+}
+
+// out[i] = sum_{t<i} in[t], i in [0,n).  in and out may alias.
+void exclusive_scan_i32(Context* ctx, const int* in, int* out, int64_t n) {
+    if (n <= 0) return;
+    const int64_t tiles = (n + kScanTile - 1) / kScanTile;
+    int* tile_sums = nullptr;
+    ATK_CUDA_CHECK(cudaMalloc(&tile_sums, sizeof(int) * (size_t)tiles));
+    scan_tile_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(in, out, tile_sums, n);
+    ATK_CUDA_CHECK(cudaGetLastError());
+    count_launch(ctx);
+    if (tiles > 1) {
+        exclusive_scan_i32(ctx, tile_sums, tile_sums, tiles);
+        scan_add_kernel<<<(unsigned)tiles, kScanThreads, 0, ctx->stream>>>(out, tile_sums, n);
+        ATK_CUDA_CHECK(cudaGetLastError());
+        count_launch(ctx);
+    }
+    ATK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ATK_CUDA_CHECK(cudaFree(tile_sums));
+}
+
+// ------------------------------------------------------------------------------------------ CSC -> CSR
+__global__ void count_rows_kernel(int64_t nnz, const int* __restrict__ row_idx, int* __restrict__ row_cnt, int n_rows,
+                                  int* __restrict__ bad) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += stride) {
+        const int r = row_idx[p];
+        if (r < 0 || r >= n_rows) { *bad = 1; continue; }
+        atomicAdd(row_cnt + r, 1);
+    }
+}
+
+// column index of every CSC position: 8 lanes per column
+__global__ void expand_cols_kernel(int n_cols, const int* __restrict__ col_ptr, int* __restrict__ col_of_pos) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t c = g >> 3;
+    const int sub = (int)(g & 7);
+    if (c >= n_cols) return;
+    const int e = col_ptr[c + 1];
+    for (int k = col_ptr[c] + sub; k < e; k += 8) col_of_pos[k] = (int)c;
+}
+
+__global__ void scatter_pos_kernel(int64_t nnz, const int* __restrict__ row_idx, const int* __restrict__ row_ptr,
+                                   int* __restrict__ fill, int* __restrict__ pos_of_slot) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += stride) {
+        const int r = row_idx[p];
+        const int s = atomicAdd(fill + r, 1);
+        pos_of_slot[row_ptr[r] + s] = (int)p;
+    }
+}
+
+// One warp per row: order the row's CSC positions ascending (= ascending column, ties in stored order) by rank
+// counting, then gather column and value.  Rows of <= 32 entries are ranked with shuffles.
+__global__ void __launch_bounds__(256) order_rows_kernel(int n_rows, const int* __restrict__ row_ptr,
+                                                         const int* __restrict__ pos_of_slot,
+                                                         const int* __restrict__ col_of_pos, const double* __restrict__ vals,
+                                                         int* __restrict__ csr_col, double* __restrict__ csr_val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = warp0; row < n_rows; row += nwarps) {
+        const int s = row_ptr[row], e = row_ptr[row + 1], len = e - s;
+        if (len <= 32) {
+            const int key = (lane < len) ? pos_of_slot[s + lane] : 0x7fffffff;
+            int rank = 0;
+#pragma unroll
+            for (int m = 0; m < 32; ++m) {
+                const int other = __shfl_sync(0xffffffffu, key, m);
+                rank += (other < key) ? 1 : 0;
+            }
+            if (lane < len) {
+                csr_col[s + rank] = col_of_pos[key];
+                csr_val[s + rank] = vals[key];
+            }
+        } else {
+            for (int a = lane; a < len; a += 32) {
+                const int key = pos_of_slot[s + a];
+                int rank = 0;
+                for (int b = 0; b < len; ++b) rank += (pos_of_slot[s + b] < key) ? 1 : 0;
+                csr_col[s + rank] = col_of_pos[key];
+                csr_val[s + rank] = vals[key];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ CSR -> SELL-32-sigma
+// rank of every row inside its sigma-window, longer rows first, ties by row index (a deterministic permutation)
+constexpr int kSigma = 1024;
+__global__ void __launch_bounds__(kSigma) sigma_rank_kernel(int n_rows, const int* __restrict__ row_ptr,
+                                                            int* __restrict__ perm) {
+    __shared__ int len[kSigma];
+    const int base = blockIdx.x * kSigma;
+    const int r = base + threadIdx.x;
+    const int cnt = min(kSigma, n_rows - base);
+    len[threadIdx.x] = (r < n_rows) ? row_ptr[r + 1] - row_ptr[r] : -1;
+    __syncthreads();
+    if (r >= n_rows) return;
+    const int mine = len[threadIdx.x];
+    int rank = 0;
+    for (int t = 0; t < cnt; ++t) {
+        const int o = len[t];
+        rank += (o > mine || (o == mine && t < (int)threadIdx.x)) ? 1 : 0;
+    }
+    perm[base + rank] = r;
+}
+
+__global__ void slice_width_kernel(int n_rows, int n_slices, const int* __restrict__ row_ptr, const int* __restrict__ perm,
+                                   int* __restrict__ width) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slices) return;
+    int w = 0;
+    for (int l = 0; l < kSliceRows; ++l) {
+        const int t = s * kSliceRows + l;
+        if (t >= n_rows) break;
+        const int r = perm ? perm[t] : t;
+        w = max(w, row_ptr[r + 1] - row_ptr[r]);
+    }
+    width[s] = w;
+}
+
+__global__ void sell_fill_kernel(int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ csr_col,
+                                 const double* __restrict__ csr_val, const int* __restrict__ perm,
+                                 const int* __restrict__ wscan, int* __restrict__ sell_col, double* __restrict__ sell_val) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t padded_rows = ((int64_t)n_rows + kSliceRows - 1) / kSliceRows * kSliceRows;
+    if (t >= padded_rows) return;
+    const int s = (int)(t / kSliceRows), lane = (int)(t % kSliceRows);
+    const int w = wscan[s + 1] - wscan[s];
+    const int64_t off = (int64_t)wscan[s] * kSliceRows + lane;
+    int rs = 0, len = 0;
+    if (t < n_rows) {
+        const int r = perm ? perm[t] : (int)t;
+        rs = row_ptr[r];
+        len = row_ptr[r + 1] - rs;
+    }
+    for (int k = 0; k < w; ++k) {
+        const bool real = k < len;
+        sell_col[off + (int64_t)k * kSliceRows] = real ? csr_col[rs + k] : -1;  // -1: padding, never multiplied
+        sell_val[off + (int64_t)k * kSliceRows] = real ? csr_val[rs + k] : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ SpMV kernels
+// SELL: one warp per slice (persistent, grid-stride over slices), one thread per row.
+// acc starts at 0.0 and takes val*x[col] in ascending column order; a column whose x is exactly 0 is skipped,
+// as the reference does (SparseObj.hpp:141).
+template <bool DOT>
+__global__ void __launch_bounds__(kReduceBlock) sell_spmv_kernel(int n_rows, int n_slices, const int* __restrict__ wscan,
+                                                                 const int* __restrict__ sell_col,
+                                                                 const double* __restrict__ sell_val,
+                                                                 const int* __restrict__ perm, const double* __restrict__ x,
+                                                                 double* __restrict__ y, double* partials, unsigned* ticket,
+                                                                 double* dot_out, const int* skip_flag) {
+    if (skip_flag && *skip_flag) return;
+    const int lane = threadIdx.x & 31;
+    const int warp0 = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+    double dacc = 0.0;
+    for (int s = warp0; s < n_slices; s += nwarps) {
+        const int w0 = wscan[s], w = wscan[s + 1] - w0;
+        const int64_t off = (int64_t)w0 * kSliceRows + lane;
+        double acc = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < w; ++k) {
+            const int c = __ldg(sell_col + off + (int64_t)k * kSliceRows);
+            const double v = __ldg(sell_val + off + (int64_t)k * kSliceRows);
+            if (c >= 0) {
+                const double xv = x[c];
+                if (xv != 0.0) acc = add_rn(acc, mul_rn(v, xv));
+            }
+        }
+        const int t = s * kSliceRows + lane;
+        if (t < n_rows) {
+            const int r = perm ? perm[t] : t;
+            y[r] = acc;
+            if constexpr (DOT) dacc = add_rn(dacc, mul_rn(x[r], acc));
+        }
+    }
+    if constexpr (DOT) {
+        double total;
+        if (grid_sum_last_block<kReduceBlock>(dacc, partials, ticket, &total)) {
+            if (linear_thread_id() == 0) *dot_out = total;
+        }
+    }
+}
+
+// CSR-vector: LANES lanes cooperate on a row; fixed shuffle tree.
+template <int LANES, bool DOT>
+__global__ void __launch_bounds__(kReduceBlock) csr_vector_spmv_kernel(int n_rows, const int* __restrict__ row_ptr,
+                                                                       const int* __restrict__ csr_col,
+                                                                       const double* __restrict__ csr_val,
+                                                                       const double* __restrict__ x, double* __restrict__ y,
+                                                                       double* partials, unsigned* ticket, double* dot_out,
+                                                                       const int* skip_flag) {
+    if (skip_flag && *skip_flag) return;
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int sub = (int)(gt % LANES);
+    const int64_t group0 = gt / LANES, ngroups = ((int64_t)gridDim.x * blockDim.x) / LANES;
+    // whole warps must iterate together for the shuffles: round the trip count up per warp
+    const int64_t rows_per_pass = ngroups;
+    double dacc = 0.0;
+    for (int64_t base = 0; base < n_rows; base += rows_per_pass) {
+        const int64_t row = base + group0;
+        double acc = 0.0;
+        if (row < n_rows) {
+            const int e = row_ptr[row + 1];
+            for (int k = row_ptr[row] + sub; k < e; k += LANES) {
+                const double xv = x[__ldg(csr_col + k)];
+                if (xv != 0.0) acc = add_rn(acc, mul_rn(__ldg(csr_val + k), xv));
+            }
+        }
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) acc = add_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+        if (row < n_rows && sub == 0) {
+            y[row] = acc;
+            if constexpr (DOT) dacc = add_rn(dacc, mul_rn(x[row], acc));
+        }
+    }
+    if constexpr (DOT) {
+        double total;
+        if (grid_sum_last_block<kReduceBlock>(dacc, partials, ticket, &total)) {
+            if (linear_thread_id() == 0) *dot_out = total;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ the operator
+struct AssembledMatrix : public Operator {
+    int n_rows = 0;
+    atk_format format = ATK_FORMAT_SELL;
+    // CSR
+    int* row_ptr = nullptr;
+    int* csr_col = nullptr;
+    double* csr_val = nullptr;
+    // SELL
+    int n_slices = 0;
+    int* wscan = nullptr;  // [n_slices+1] exclusive scan of slice widths
+    int* perm = nullptr;   // sorted position -> row, or null (identity)
+    int* sell_col = nullptr;
+    double* sell_val = nullptr;
+    int64_t sell_elems = 0;
+    int lanes = 8;
+
+    ~AssembledMatrix() override {
+        cudaFree(row_ptr); cudaFree(csr_col); cudaFree(csr_val);
+        cudaFree(wscan); cudaFree(perm); cudaFree(sell_col); cudaFree(sell_val);
+    }
+    bool has_csr() const override { return true; }
+    void export_csr(int* h_row_ptr, int* h_col, double* h_val) const override {
+        ATK_CUDA_CHECK(cudaMemcpy(h_row_ptr, row_ptr, sizeof(int) * ((size_t)n_rows + 1), cudaMemcpyDeviceToHost));
+        if (nnz > 0) {
+            ATK_CUDA_CHECK(cudaMemcpy(h_col, csr_col, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost));
+            ATK_CUDA_CHECK(cudaMemcpy(h_val, csr_val, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost));
+        }
+    }
+
+    void apply(const double* x, double* y, int dot_slot, const int* skip_flag) override {
+        Context* c = ctx;
+        double* dot_out = dot_slot >= 0 ? c->slot(dot_slot) + c->rank : nullptr;
+        const int grid = c->sm_count * 8;
+        if (format == ATK_FORMAT_SELL) {
+            const int g = (int)std::max<int64_t>(1, std::min<int64_t>(grid, ((int64_t)n_slices * 32 + kReduceBlock - 1) / kReduceBlock));
+            if (dot_slot >= 0)
+                sell_spmv_kernel<true><<<g, kReduceBlock, 0, c->stream>>>(n_rows, n_slices, wscan, sell_col, sell_val, perm, x,
+                                                                          y, c->d_partials, c->d_tickets + 1, dot_out, skip_flag);
+            else
+                sell_spmv_kernel<false><<<g, kReduceBlock, 0, c->stream>>>(n_rows, n_slices, wscan, sell_col, sell_val, perm,
+                                                                           x, y, nullptr, nullptr, nullptr, skip_flag);
+        } else {
+            const int g = (int)std::max<int64_t>(1, std::min<int64_t>(grid, ((int64_t)n_rows * lanes + kReduceBlock - 1) / kReduceBlock));
+#define ATK_CSRV(L)                                                                                                      \
+    if (dot_slot >= 0)                                                                                                   \
+        csr_vector_spmv_kernel<L, true><<<g, kReduceBlock, 0, c->stream>>>(n_rows, row_ptr, csr_col, csr_val, x, y,        \
+                                                                           c->d_partials, c->d_tickets + 1, dot_out,      \
+                                                                           skip_flag);                                    \
+    else                                                                                                                 \
+        csr_vector_spmv_kernel<L, false><<<g, kReduceBlock, 0, c->stream>>>(n_rows, row_ptr, csr_col, csr_val, x, y,       \
+                                                                            nullptr, nullptr, nullptr, skip_flag);
+            switch (lanes) {
+                case 2: ATK_CSRV(2) break;
+                case 4: ATK_CSRV(4) break;
+                case 8: ATK_CSRV(8) break;
+                case 16: ATK_CSRV(16) break;
+                default: ATK_CSRV(32) break;
+            }
+#undef ATK_CSRV
+        }
+        ATK_CUDA_CHECK(cudaGetLastError());
+        count_launch(c);
+        if (dot_slot >= 0) allgather_slot(c, dot_slot, c->stream);
+    }
+};
+
+template <typename T>
+T* dalloc(size_t n) {
+    T* p = nullptr;
+    ATK_CUDA_CHECK(cudaMalloc(&p, sizeof(T) * std::max<size_t>(n, 1)));
+    return p;
+}
+
+inline int grid_for(int64_t work, int block, int cap) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>((work + block - 1) / block, cap));
+}
+
+}  // namespace
+
+// Takes DEVICE CSC arrays and builds the operator.  The CSC arrays are not retained.
+static Operator* build_from_device_csc(Context* ctx, int n_rows, int n_cols, int64_t nnz, const int* d_col_ptr,
+                                       const int* d_row_idx, const double* d_vals, atk_format format) {
+    ATK_REQUIRE(nnz >= 0 && nnz < (int64_t)0x7fffffff, ATK_ERR_INVALID_ARGUMENT, "nnz must be below 2^31");
+    ATK_REQUIRE(ctx->world == 1, ATK_ERR_INVALID_ARGUMENT,
+                "assembled operators are single-GPU in this version (use the stencil operators on a distributed context)");
+    auto* A = new AssembledMatrix();
+    try {
+        A->ctx = ctx;
+        A->n_rows = n_rows;
+        A->n_rows_local = n_rows;
+        A->n_cols = n_cols;
+        A->nnz = nnz;
+        A->format = format;
+        cudaStream_t st = ctx->stream;
+        const int cap = ctx->sm_count * 16;
+
+        // ---- CSC -> CSR
+        A->row_ptr = dalloc<int>((size_t)n_rows + 1);
+        A->csr_col = dalloc<int>((size_t)nnz);
+        A->csr_val = dalloc<double>((size_t)nnz);
+        int* fill = dalloc<int>((size_t)n_rows + 1);
+        int* col_of_pos = dalloc<int>((size_t)nnz);
+        int* pos_of_slot = dalloc<int>((size_t)nnz);
+        int* bad = dalloc<int>(1);
+        ATK_CUDA_CHECK(cudaMemsetAsync(A->row_ptr, 0, sizeof(int) * ((size_t)n_rows + 1), st));
+        ATK_CUDA_CHECK(cudaMemsetAsync(fill, 0, sizeof(int) * ((size_t)n_rows + 1), st));
+        ATK_CUDA_CHECK(cudaMemsetAsync(bad, 0, sizeof(int), st));
+        if (nnz > 0) {
+            count_rows_kernel<<<grid_for(nnz, 256, cap), 256, 0, st>>>(nnz, d_row_idx, A->row_ptr, n_rows, bad);
+            count_launch(ctx);
+        }
+        int h_bad = 0;
+        ATK_CUDA_CHECK(cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+        ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (h_bad) {
+            cudaFree(fill); cudaFree(col_of_pos); cudaFree(pos_of_slot); cudaFree(bad);
+            throw Error(ATK_ERR_OUT_OF_RANGE, "Index out of range");
+        }
+        exclusive_scan_i32(ctx, A->row_ptr, A->row_ptr, (int64_t)n_rows + 1);
+        if (nnz > 0) {
+            expand_cols_kernel<<<(unsigned)(((int64_t)n_cols * 8 + 255) / 256), 256, 0, st>>>(n_cols, d_col_ptr, col_of_pos);
+            scatter_pos_kernel<<<grid_for(nnz, 256, cap), 256, 0, st>>>(nnz, d_row_idx, A->row_ptr, fill, pos_of_slot);
+            order_rows_kernel<<<grid_for((int64_t)n_rows * 32, 256, cap), 256, 0, st>>>(n_rows, A->row_ptr, pos_of_slot,
+                                                                                      col_of_pos, d_vals, A->csr_col, A->csr_val);
+            count_launch(ctx, 3);
+        }
+        ATK_CUDA_CHECK(cudaGetLastError());
+        ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+        cudaFree(fill); cudaFree(col_of_pos); cudaFree(pos_of_slot); cudaFree(bad);
+
+        // lanes per row for the CSR-vector kernel: next power of two >= mean row length, in [2,32]
+        const double mean = n_rows > 0 ? (double)nnz / n_rows : 0.0;
+        int lanes = 2;
+        while (lanes < 32 && lanes < mean) lanes <<= 1;
+        A->lanes = lanes;
+
+        // ---- CSR -> SELL-32-sigma
+        if (format == ATK_FORMAT_SELL) {
+            const int n_slices = (n_rows + kSliceRows - 1) / kSliceRows;
+            A->n_slices = n_slices;
+            A->wscan = dalloc<int>((size_t)n_slices + 1);
+            ATK_CUDA_CHECK(cudaMemsetAsync(A->wscan, 0, sizeof(int) * ((size_t)n_slices + 1), st));
+            auto total_width = [&](const int* perm) -> int64_t {
+                if (n_slices == 0) return 0;
+                slice_width_kernel<<<(n_slices + 255) / 256, 256, 0, st>>>(n_rows, n_slices, A->row_ptr, perm, A->wscan);
+                count_launch(ctx);
+                exclusive_scan_i32(ctx, A->wscan, A->wscan, (int64_t)n_slices + 1);
+                int tot = 0;
+                ATK_CUDA_CHECK(cudaMemcpy(&tot, A->wscan + n_slices, sizeof(int), cudaMemcpyDeviceToHost));
+                return tot;
+            };
+            int64_t tw = total_width(nullptr);
+            // padding above 25 %: sort rows by length inside windows of 1024 rows
+            if (nnz > 0 && (double)tw * kSliceRows > 1.25 * (double)nnz && n_rows > kSliceRows) {
+                A->perm = dalloc<int>((size_t)n_rows);
+                sigma_rank_kernel<<<(n_rows + kSigma - 1) / kSigma, kSigma, 0, st>>>(n_rows, A->row_ptr, A->perm);
+                count_launch(ctx);
+                ATK_CUDA_CHECK(cudaMemsetAsync(A->wscan, 0, sizeof(int) * ((size_t)n_slices + 1), st));
+                tw = total_width(A->perm);
+            }
+            A->sell_elems = tw * kSliceRows;
+            ATK_REQUIRE(A->sell_elems < (int64_t)0x7fffffff * 8, ATK_ERR_NOMEM, "SELL storage too large");
+            A->sell_col = dalloc<int>((size_t)A->sell_elems);
+            A->sell_val = dalloc<double>((size_t)A->sell_elems);
+            if (n_slices > 0) {
+                const int64_t padded = (int64_t)n_slices * kSliceRows;
+                sell_fill_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, st>>>(n_rows, A->row_ptr, A->csr_col, A->csr_val,
+                                                                                  A->perm, A->wscan, A->sell_col, A->sell_val);
+                count_launch(ctx);
+            }
+            ATK_CUDA_CHECK(cudaGetLastError());
+            ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+        }
+    } catch (...) {
+        delete A;
+        throw;
+    }
+    return A;
+}
+
+Operator* make_operator_from_csc(Context* ctx, int n_rows, int n_cols, int64_t nnz, const int* col_ptr, const int* row_idx,
+                                 const double* vals, bool on_device, atk_format format) {
+    ATK_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0, ATK_ERR_INVALID_ARGUMENT, "negative matrix dimension");
+    ATK_REQUIRE(col_ptr != nullptr, ATK_ERR_INVALID_ARGUMENT, "col_ptr is null");
+    if (on_device) return build_from_device_csc(ctx, n_rows, n_cols, nnz, col_ptr, row_idx, vals, format);
+    int* d_cp = dalloc<int>((size_t)n_cols + 1);
+    int* d_ri = dalloc<int>((size_t)nnz);
+    double* d_v = dalloc<double>((size_t)nnz);
+    Operator* op = nullptr;
+    try {
+        ATK_CUDA_CHECK(cudaMemcpyAsync(d_cp, col_ptr, sizeof(int) * ((size_t)n_cols + 1), cudaMemcpyHostToDevice, ctx->stream));
+        if (nnz > 0) {
+            ATK_CUDA_CHECK(cudaMemcpyAsync(d_ri, row_idx, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+            ATK_CUDA_CHECK(cudaMemcpyAsync(d_v, vals, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        op = build_from_device_csc(ctx, n_rows, n_cols, nnz, d_cp, d_ri, d_v, format);
+    } catch (...) {
+        cudaFree(d_cp); cudaFree(d_ri); cudaFree(d_v);
+        throw;
+    }
+    cudaFree(d_cp); cudaFree(d_ri); cudaFree(d_v);
+    return op;
+}
+
+// ------------------------------------------------------------------------------------------ device-side assembly
+// The CSC arrays Poisson3DSolver::buildLaplacianMatrix + finalize() would leave (Poisson.hpp:49-95), generated
+// column by column: column c=(i,j,k) holds its diagonal plus one entry from every INTERIOR row adjacent to it.
+namespace {
+__device__ __forceinline__ bool on_shell(int i, int j, int k, int nx, int ny, int nz) {
+    return i == 0 || i == nx - 1 || j == 0 || j == ny - 1 || k == 0 || k == nz - 1;
+}
+template <bool FILL>
+__global__ void poisson_csc_kernel(int nx, int ny, int nz, double cx, double cy, double cz, double cc, int* __restrict__ col_ptr,
+                                   int* __restrict__ row_idx, double* __restrict__ vals) {
+    const int64_t n = (int64_t)nx * ny * nz;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int i = (int)(c % nx), j = (int)((c / nx) % ny), k = (int)(c / ((int64_t)nx * ny));
+    const int64_t sxy = (int64_t)nx * ny;
+    int p = FILL ? col_ptr[c] : 0;
+    auto emit = [&](int64_t row, double v) {
+        if (FILL) { row_idx[p] = (int)row; vals[p] = v; }
+        ++p;
+    };
+    if (k - 1 >= 0 && !on_shell(i, j, k - 1, nx, ny, nz)) emit(c - sxy, cz);
+    if (j - 1 >= 0 && !on_shell(i, j - 1, k, nx, ny, nz)) emit(c - nx, cy);
+    if (i - 1 >= 0 && !on_shell(i - 1, j, k, nx, ny, nz)) emit(c - 1, cx);
+    emit(c, on_shell(i, j, k, nx, ny, nz) ? 1.0 : cc);
+    if (i + 1 < nx && !on_shell(i + 1, j, k, nx, ny, nz)) emit(c + 1, cx);
+    if (j + 1 < ny && !on_shell(i, j + 1, k, nx, ny, nz)) emit(c + nx, cy);
+    if (k + 1 < nz && !on_shell(i, j, k + 1, nx, ny, nz)) emit(c + sxy, cz);
+    if (!FILL) col_ptr[c] = p;
+}
+
+struct Coef27 { double v[27]; };
+template <bool FILL>
+__global__ void op27_csc_kernel(int nx, int ny, int nz, Coef27 coef, int* __restrict__ col_ptr, int* __restrict__ row_idx,
+                                double* __restrict__ vals) {
+    const int64_t n = (int64_t)nx * ny * nz;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int ic = (int)(c % nx), jc = (int)((c / nx) % ny), kc = (int)(c / ((int64_t)nx * ny));
+    const int64_t sxy = (int64_t)nx * ny;
+    int p = FILL ? col_ptr[c] : 0;
+    for (int dk = 1; dk >= -1; --dk)
+        for (int dj = 1; dj >= -1; --dj)
+            for (int di = 1; di >= -1; --di) {
+                const int ir = ic - di, jr = jc - dj, kr = kc - dk;
+                if (ir < 0 || ir >= nx || jr < 0 || jr >= ny || kr < 0 || kr >= nz) continue;
+                if (FILL) {
+                    row_idx[p] = (int)(ir + (int64_t)jr * nx + (int64_t)kr * sxy);
+                    vals[p] = coef.v[(dk + 1) * 9 + (dj + 1) * 3 + (di + 1)];
+                }
+                ++p;
+            }
+    if (!FILL) col_ptr[c] = p;
+}
+}  // namespace
+
+template <typename CountK, typename FillK>
+static Operator* assemble_on_device(Context* ctx, int64_t n, atk_format format, CountK count, FillK fill) {
+    ATK_REQUIRE(n > 0 && n < (int64_t)0x7fffffff, ATK_ERR_INVALID_ARGUMENT, "grid too large for int32 indices");
+    int* d_cp = dalloc<int>((size_t)n + 1);
+    int* d_ri = nullptr;
+    double* d_v = nullptr;
+    Operator* op = nullptr;
+    try {
+        ATK_CUDA_CHECK(cudaMemsetAsync(d_cp, 0, sizeof(int) * ((size_t)n + 1), ctx->stream));
+        count(d_cp);
+        count_launch(ctx);
+        exclusive_scan_i32(ctx, d_cp, d_cp, n + 1);
+        int nnz = 0;
+        ATK_CUDA_CHECK(cudaMemcpy(&nnz, d_cp + n, sizeof(int), cudaMemcpyDeviceToHost));
+        ATK_REQUIRE(nnz >= 0, ATK_ERR_INVALID_ARGUMENT, "nnz overflows int32");
+        d_ri = dalloc<int>((size_t)nnz);
+        d_v = dalloc<double>((size_t)nnz);
+        fill(d_cp, d_ri, d_v);
+        count_launch(ctx);
+        ATK_CUDA_CHECK(cudaGetLastError());
+        op = build_from_device_csc(ctx, (int)n, (int)n, nnz, d_cp, d_ri, d_v, format);
+    } catch (...) {
+        cudaFree(d_cp); cudaFree(d_ri); cudaFree(d_v);
+        throw;
+    }
+    cudaFree(d_cp); cudaFree(d_ri); cudaFree(d_v);
+    return op;
+}
+
+Operator* make_poisson_assembled(Context* ctx, int nx, int ny, int nz, double cx, double cy, double cz, atk_format format) {
+    ATK_REQUIRE(nx > 0 && ny > 0 && nz > 0, ATK_ERR_INVALID_ARGUMENT, "grid dimensions must be positive");
+    const int64_t n = (int64_t)nx * ny * nz;
+    const double cc = -2.0 * (cx + cy + cz);  // Poisson.hpp:57
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    cudaStream_t st = ctx->stream;
+    return assemble_on_device(
+        ctx, n, format,
+        [&](int* cp) { poisson_csc_kernel<false><<<grid, 256, 0, st>>>(nx, ny, nz, cx, cy, cz, cc, cp, nullptr, nullptr); },
+        [&](int* cp, int* ri, double* v) { poisson_csc_kernel<true><<<grid, 256, 0, st>>>(nx, ny, nz, cx, cy, cz, cc, cp, ri, v); });
+}
+
+Operator* make_stencil27_assembled(Context* ctx, int nx, int ny, int nz, const double* coef, atk_format format) {
+    ATK_REQUIRE(nx > 0 && ny > 0 && nz > 0 && coef, ATK_ERR_INVALID_ARGUMENT, "bad 27-point operator arguments");
+    const int64_t n = (int64_t)nx * ny * nz;
+    Coef27 cf;
+    for (int t = 0; t < 27; ++t) cf.v[t] = coef[t];
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    cudaStream_t st = ctx->stream;
+    return assemble_on_device(
+        ctx, n, format, [&](int* cp) { op27_csc_kernel<false><<<grid, 256, 0, st>>>(nx, ny, nz, cf, cp, nullptr, nullptr); },
+        [&](int* cp, int* ri, double* v) { op27_csc_kernel<true><<<grid, 256, 0, st>>>(nx, ny, nz, cf, cp, ri, v); });
+}
+
+}  // namespace atk

@@ -1,0 +1,211 @@
+/* include/atk_cuda.h -- C ABI of libatk_cuda.so: the B200 (sm_100a) device path behind
+ * AlgoToolkit's sparse iterative-solver hot path.
+ *
+ * The reference (Yin169/AlgoToolkit) has no FFI seam: its "operator API" is a set of C++17
+ * templates plus a pybind11 module.  The seam is created here: the double instantiations of
+ * the reference's L0 operators and its three solve() loops become calls into this library,
+ * and the reference-named host classes in algotoolkit_b200/host/ (VectorObj, SparseMatrixCSC,
+ * ConjugateGrad, GMRES, Poisson3DSolver, utils::readMatrixMarket, the `fastsolver` module)
+ * are thin owners of host std::vectors above it.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C, opaque handles, caller-owned buffers, no exceptions, no C++/torch types;
+ *   - every function returns an atk_status; the codes 1..3 map 1:1 onto the exception types
+ *     the reference throws (std::invalid_argument / std::runtime_error / std::out_of_range);
+ *     atk_last_error() returns the message of the last failure on the calling thread;
+ *   - `const double* x` style vector arguments are DEVICE pointers (from atk_malloc, or any
+ *     CUDA allocation such as a torch tensor's data_ptr()) unless the function name ends in
+ *     `_host`, in which case they are host pointers and the call does its own H2D/D2H;
+ *   - all arithmetic is IEEE fp64, multiply and add rounded separately (the reference is
+ *     built without FMA), indices are int32 (nnz < 2^31 at every BASELINE config);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     ATK_ERR_CUDA.
+ *
+ * Reference paths below are relative to the reference root (/root/reference).
+ */
+#ifndef ATK_CUDA_H
+#define ATK_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATK_ABI_VERSION 1
+
+typedef enum atk_status {
+    ATK_OK = 0,
+    ATK_ERR_INVALID_ARGUMENT = 1, /* std::invalid_argument: SparseObj.hpp:133, GMRES.hpp:30-36, VectorObj.hpp:90,98,106 */
+    ATK_ERR_RUNTIME = 2,          /* std::runtime_error:    VectorObj.hpp:76,83 (divide by zero), GMRES.hpp:163 */
+    ATK_ERR_OUT_OF_RANGE = 3,     /* std::out_of_range:     VectorObj.hpp:38,43, SparseObj.hpp:69,107, Poisson.hpp:162 */
+    ATK_ERR_CUDA = 4,             /* CUDA runtime failure, or no device */
+    ATK_ERR_NCCL = 5,             /* NCCL failure / libnccl not loadable */
+    ATK_ERR_NOMEM = 6
+} atk_status;
+
+typedef struct atk_context_s* atk_context_t;   /* device, streams, reduction scratch, NCCL communicator */
+typedef struct atk_operator_s* atk_operator_t; /* a device-resident linear operator (row block of it when distributed) */
+
+/* How dot / norm reductions are ordered. */
+typedef enum atk_reduction {
+    ATK_REDUCE_TREE = 0,       /* fixed-shape block tree + fixed-order final pass: deterministic run to run */
+    ATK_REDUCE_SEQUENTIAL = 1  /* strictly sequential from 0.0 in index order: bit-identical to std::inner_product
+                                  (VectorObj.hpp:52-54,105-108); one thread does the adds, for parity runs only */
+} atk_reduction;
+
+/* Device storage format of an assembled matrix. */
+typedef enum atk_format {
+    ATK_FORMAT_SELL = 0,       /* SELL-32-sigma, one thread per row, taps added in ascending column order from 0.0:
+                                  bit-identical to the CSC matvec of SparseObj.hpp:131-152 */
+    ATK_FORMAT_CSR_VECTOR = 1  /* CSR, 2..32 lanes per row + shuffle tree: deterministic, not reference-ordered */
+} atk_format;
+
+/* ------------------------------------------------------------------------------------------------ context */
+int atk_abi_version(void);
+const char* atk_last_error(void);
+int atk_device_count(int* count);
+
+/* One context per process and GPU. */
+int atk_context_create(int device, atk_context_t* out);
+/* Distributed context: `world` processes, one GPU each, row-slab partition.  `nccl_uid` is the blob produced by
+ * atk_nccl_unique_id() on rank 0 and broadcast by the caller (torch.distributed, MPI, a file...). */
+int atk_nccl_unique_id(void* buf, size_t capacity, size_t* bytes);
+int atk_context_create_distributed(int device, int rank, int world, const void* nccl_uid, size_t uid_bytes,
+                                   atk_context_t* out);
+int atk_context_destroy(atk_context_t ctx);
+int atk_context_rank(atk_context_t ctx, int* rank, int* world);
+int atk_context_set_reduction(atk_context_t ctx, atk_reduction mode);
+int atk_context_synchronize(atk_context_t ctx);
+/* Number of kernels this library has launched on the context since creation (for bench.py's gpu_launches). */
+int atk_context_launch_count(atk_context_t ctx, int64_t* launches);
+
+/* ------------------------------------------------------------------------------------------------ memory */
+int atk_malloc(atk_context_t ctx, size_t bytes, void** dptr);
+int atk_free(atk_context_t ctx, void* dptr);
+int atk_memcpy_h2d(atk_context_t ctx, void* dst_device, const void* src_host, size_t bytes);
+int atk_memcpy_d2h(atk_context_t ctx, void* dst_host, const void* src_device, size_t bytes);
+int atk_memcpy_d2d(atk_context_t ctx, void* dst_device, const void* src_device, size_t bytes);
+int atk_memset_zero(atk_context_t ctx, void* dptr, size_t bytes);
+int atk_host_alloc(size_t bytes, void** hptr); /* pinned */
+int atk_host_free(void* hptr);
+
+/* ------------------------------------------------------------------------------------------------ VectorObj ops
+ * Replaces src/Obj/VectorObj.hpp for T=double.  n is the LOCAL length; on a distributed context dot/nrm2 return
+ * the global value (rank-ordered sum of the per-rank partials, identical on every rank). */
+int atk_dot(atk_context_t ctx, int64_t n, const double* x, const double* y, double* result_host);   /* :105-108 */
+int atk_nrm2(atk_context_t ctx, int64_t n, const double* x, double* result_host);                   /* :52-54   */
+int atk_vec_scale(atk_context_t ctx, int64_t n, const double* x, double s, double* out);            /* :64-68  x*s */
+int atk_vec_div(atk_context_t ctx, int64_t n, const double* x, double s, double* out);              /* :75-80  x/s; s==0 -> ATK_ERR_RUNTIME */
+int atk_vec_add(atk_context_t ctx, int64_t n, const double* x, const double* y, double* out);       /* :89-94   */
+int atk_vec_sub(atk_context_t ctx, int64_t n, const double* x, const double* y, double* out);       /* :97-102  */
+/* out = x + y*a with the product rounded first (the `x + p*alpha` idiom of ConjugateGradient.hpp:60,79) */
+int atk_vec_axpy(atk_context_t ctx, int64_t n, const double* x, const double* y, double a, double* out);
+/* out = x - y*a (ConjugateGradient.hpp:61, GMRES.hpp:76) */
+int atk_vec_axmy(atk_context_t ctx, int64_t n, const double* x, const double* y, double a, double* out);
+
+/* ------------------------------------------------------------------------------------------------ operators */
+/* SparseMatrixCSC<double> (src/Obj/SparseObj.hpp:22-39): takes the finished CSC arrays (values, row_indices,
+ * col_ptr after finalize(), :76-100) and converts them ON THE DEVICE to CSR (stable in column order) and then to
+ * the requested format.  `on_device` != 0 means the three arrays are already device pointers. */
+int atk_operator_from_csc(atk_context_t ctx, int n_rows, int n_cols, int64_t nnz, const int* col_ptr,
+                          const int* row_idx, const double* vals, int on_device, atk_format format,
+                          atk_operator_t* out);
+/* Matrix-free operator of Poisson3DSolver::buildLaplacianMatrix (src/PDEs/FDM/Poisson.hpp:49-95): identity on the
+ * Dirichlet shell, 7 taps (cz,cy,cx,cc=-2(cx+cy+cz),cx,cy,cz) inside, idx = i + j*nx + k*nx*ny (:98-100).
+ * On a distributed context the operator is the rank's z-slab (planes [k_begin,k_end) of nz, balanced split). */
+int atk_operator_stencil7(atk_context_t ctx, int nx, int ny, int nz, double cx, double cy, double cz,
+                          atk_operator_t* out);
+/* The same Poisson operator ASSEMBLED: the CSC arrays buildLaplacianMatrix+finalize would produce are generated on
+ * the device (never on the host) and sent through the same CSC->CSR->format conversion as atk_operator_from_csc. */
+int atk_operator_poisson_assembled(atk_context_t ctx, int nx, int ny, int nz, double cx, double cy, double cz,
+                                   atk_format format, atk_operator_t* out);
+/* Synthetic 27-point operator of BASELINE config 5: open boundaries, coef[13] on the diagonal and
+ * coef[(dk+1)*9+(dj+1)*3+(di+1)] for neighbour (i+di,j+dj,k+dk); generated on the device. */
+int atk_operator_stencil27_assembled(atk_context_t ctx, int nx, int ny, int nz, const double coef[27],
+                                     atk_format format, atk_operator_t* out);
+int atk_operator_destroy(atk_operator_t op);
+/* local rows, columns (global), stored entries (without padding) */
+int atk_operator_shape(atk_operator_t op, int64_t* n_rows_local, int64_t* n_cols, int64_t* nnz);
+/* first global row owned by this rank and the local row count (0, n_rows on a single-GPU context) */
+int atk_operator_row_range(atk_operator_t op, int64_t* row_begin, int64_t* n_rows_local);
+/* CSR arrays of an assembled operator copied to HOST buffers (row_ptr[n_rows+1], col_idx[nnz], vals[nnz]); lets
+ * tests check the device conversion against the oracle. */
+int atk_operator_export_csr(atk_operator_t op, int* row_ptr, int* col_idx, double* vals);
+/* y = A*x  (SparseMatrixCSC::operator*(VectorObj), SparseObj.hpp:131-152).  x and y are local row blocks. */
+int atk_operator_apply(atk_context_t ctx, atk_operator_t op, const double* x, double* y);
+
+/* ------------------------------------------------------------------------------------------------ ConjugateGrad */
+typedef struct atk_cg_info {
+    int iterations;        /* loop index at which the solver stopped: == max_iter, or the i at which |p.Ap| < 1e-12 */
+    int stopped_on_pAp;    /* 1 if the |p.Ap| < 1e-12 exit fired (ConjugateGradient.hpp:53-57) */
+    int zero_rhs;          /* 1 if ||b|| < 1e-12 returned immediately (:38-42) */
+    double last_pAp;       /* p.Ap of the last iteration entered */
+    double rs;             /* r.r at exit */
+    float device_ms;       /* CUDA-event time of the device loop, excluding any host<->device copies */
+    int kernel_launches;   /* kernels this call launched */
+    /* optional per-iteration traces (host pointers, may be NULL), filled up to trace_capacity entries */
+    double* pAp_trace;
+    double* rs_trace;
+    int trace_capacity;
+} atk_cg_info;
+
+/* ConjugateGrad::solve (src/LinearAlgebra/Krylov/ConjugateGradient.hpp:36-84).  The solver state x, r, p lives in
+ * caller-owned device vectors and is updated in place, so a second call continues where the first stopped, as the
+ * reference's public members do.  A fresh solver is x=0, r=b, p=b (what the ctor leaves, :26-30).  There is no
+ * tolerance test (the reference's is commented out, :44-47,75-77). */
+int atk_cg_solve(atk_context_t ctx, atk_operator_t op, const double* b, double* x, double* r, double* p,
+                 int max_iter, atk_cg_info* info);
+/* Same through HOST buffers: uploads b and the state, runs, downloads x (and r, p when non-NULL).
+ * `fresh` != 0 ignores the incoming x/r/p contents and starts from x=0, r=p=b. */
+int atk_cg_solve_host(atk_context_t ctx, atk_operator_t op, const double* b, double* x, double* r, double* p,
+                      int fresh, int max_iter, atk_cg_info* info);
+
+/* ------------------------------------------------------------------------------------------------ GMRES */
+typedef enum atk_gmres_event {
+    ATK_GMRES_INITIAL_RESIDUAL = 0, /* GMRES.hpp:48  "Initial residual norm: " */
+    ATK_GMRES_INITIAL_GOOD = 1,     /* :50           "Initial guess is good enough." */
+    ATK_GMRES_KRYLOV_UPDATE = 2,    /* :83           "KrylovUpdate : " (value = j) */
+    ATK_GMRES_RESTART_RESIDUAL = 3, /* :105          "Residual norm after restart: " */
+    ATK_GMRES_CONVERGED = 4,        /* :108          "Converged after restart at iteration " (value = iter) */
+    ATK_GMRES_MAX_ITER = 5          /* :114          "Reached maximum iterations without convergence." */
+} atk_gmres_event;
+/* progress callback: the host class turns these into the reference's exact std::cout lines */
+typedef void (*atk_gmres_callback)(int event, double value, void* user);
+
+typedef enum atk_gmres_ortho {
+    ATK_GMRES_MGS = 0,   /* the reference's loop: for i<j { h = V[i].w; w = w - V[i]*h } (GMRES.hpp:73-77) */
+    ATK_GMRES_CGS2 = 1   /* batched: h = V[0:j]^T w; w -= V[0:j] h, twice; 4 reductions per step instead of j.
+                            Different rounding - a throughput option, never the parity path */
+} atk_gmres_ortho;
+
+typedef struct atk_gmres_info {
+    int restarts;          /* restart cycles run */
+    int status;            /* 0 reached max_iter, 1 converged after a restart, 2 initial guess good enough */
+    int arnoldi_steps;     /* total Arnoldi steps executed */
+    double initial_residual;
+    double final_residual;
+    float device_ms;
+    int kernel_launches;
+    double* residual_trace; /* optional host buffer: [0]=initial, then one per restart */
+    int trace_capacity;
+    int trace_count;
+} atk_gmres_info;
+
+/* GMRES::solve (src/LinearAlgebra/Krylov/GMRES.hpp:27-115), unpreconditioned, with the reference's behaviour:
+ * projection against V[0..j-1] only (:73), H allocated once per call and never cleared (:55), no inner convergence
+ * test, absolute tolerance, Givens from the current H(j,j) (:89-94), x += V[i]*y[i] added in ascending i (:167-170).
+ * x is the initial guess and the result.  Errors: ATK_ERR_INVALID_ARGUMENT for the checks at :28-37,
+ * ATK_ERR_RUNTIME for a zero pivot (:162-164) or a division by zero (VectorObj.hpp:76). */
+int atk_gmres_solve(atk_context_t ctx, atk_operator_t op, const double* b, double* x, int64_t n_x, int max_iter,
+                    int krylov_dim, double tol, atk_gmres_ortho ortho, atk_gmres_callback cb, void* user,
+                    atk_gmres_info* info);
+int atk_gmres_solve_host(atk_context_t ctx, atk_operator_t op, const double* b, double* x, int64_t n_x, int max_iter,
+                         int krylov_dim, double tol, atk_gmres_ortho ortho, atk_gmres_callback cb, void* user,
+                         atk_gmres_info* info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATK_CUDA_H */
