@@ -50,7 +50,7 @@ def _raise(code, msg):
 class CgInfo(C.Structure):
     _fields_ = [("iterations", C.c_int), ("stopped_on_pAp", C.c_int), ("zero_rhs", C.c_int), ("last_pAp", C.c_double),
                 ("rs", C.c_double), ("device_ms", C.c_float), ("kernel_launches", C.c_int), ("pAp_trace", _dp),
-                ("rs_trace", _dp), ("trace_capacity", C.c_int)]
+                ("rs_trace", _dp), ("trace_capacity", C.c_int), ("time_kernels", C.c_int), ("kernel_ms", C.c_float * 3)]
 
 
 class GmresInfo(C.Structure):
@@ -351,8 +351,9 @@ class Context:
 
     # ---- solvers
     def cg_solve(self, op: Operator, b: DeviceVector, x: DeviceVector, r: DeviceVector, p: DeviceVector, max_iter: int,
-                 trace: bool = False):
+                 trace: bool = False, time_kernels: bool = False):
         info = CgInfo()
+        info.time_kernels = 1 if time_kernels else 0
         tp = tr = None
         if trace and max_iter > 0:
             tp, tr = np.full(max_iter, np.nan), np.full(max_iter, np.nan)
@@ -416,4 +417,4 @@ class Context:
 def _cg_result(info, tp, tr):
     return dict(iters=info.iterations, stopped_on_pAp=bool(info.stopped_on_pAp), zero_rhs=bool(info.zero_rhs),
                 last_pAp=info.last_pAp, rs=info.rs, device_ms=info.device_ms, kernel_launches=info.kernel_launches,
-                pAp_trace=tp, rs_trace=tr)
+                pAp_trace=tp, rs_trace=tr, kernel_ms=list(info.kernel_ms))

@@ -210,7 +210,7 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
     auto cleanup = [&]() {
         if (gexec) cudaGraphExecDestroy(gexec);
         if (graph) cudaGraphDestroy(graph);
-        for (auto e : poll_events) cudaEventDestroy(e);
+        for (auto e : poll_events) if (e) cudaEventDestroy(e);
         cudaFree(d_state); cudaFree(Ap); cudaFree(d_ptrace); cudaFree(d_rtrace);
         if (h_done) cudaFreeHost(h_done);
     };
@@ -233,11 +233,20 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
         const bool seq = ctx->reduction == ATK_REDUCE_SEQUENTIAL;
         const int* done_flag = &d_state->done;
 
+        std::vector<cudaEvent_t> kev;  // time_kernels mode: 4 events per iteration
+        auto mark = [&]() {
+            if (!info->time_kernels) return;
+            cudaEvent_t e;
+            ATK_CUDA_CHECK(cudaEventCreate(&e));
+            ATK_CUDA_CHECK(cudaEventRecord(e, st));
+            kev.push_back(e);
+        };
         auto enqueue_iteration = [&]() {
+            mark();
             op->apply(p, Ap, seq ? -1 : kSlotPAp, done_flag);  // K1 (+ all-gather of the partial)
+            if (seq) launch_dot(ctx, n, p, Ap, kSlotPAp, done_flag);  // the fused tree sum is replaced by an ordered sum
+            mark();
             if (seq) {
-                // the fused tree sum is replaced by strictly ordered sums
-                launch_dot(ctx, n, p, Ap, kSlotPAp, done_flag);
                 cg_update_xr_nosum_kernel<false><<<grid, kReduceBlock, 0, st>>>(n, d_state, ctx->slot(kSlotPAp), ctx->world, x, r,
                                                                                 p, Ap, d_ptrace);
                 count_launch(ctx);
@@ -254,6 +263,7 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
                 count_launch(ctx);
                 allgather_slot(ctx, kSlotRR, st);
             }
+            mark();
             if (vec)
                 cg_update_p_kernel<true><<<grid, kReduceBlock, 0, st>>>(n, d_state, ctx->slot(kSlotRR), ctx->world, r, p,
                                                                         ctx->d_tickets + 4, d_rtrace);
@@ -261,11 +271,13 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
                 cg_update_p_kernel<false><<<grid, kReduceBlock, 0, st>>>(n, d_state, ctx->slot(kSlotRR), ctx->world, r, p,
                                                                          ctx->d_tickets + 4, d_rtrace);
             count_launch(ctx);
+            mark();
         };
 
         // ---- capture one iteration, replay it
         int launches_per_iter = 0;
-        if (max_iter > 0) {
+        const bool use_graph = !info->time_kernels;
+        if (max_iter > 0 && use_graph) {
             const int64_t l0 = ctx->launches;
             ATK_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             try {
@@ -304,8 +316,12 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
             }
             const int cnt = std::min(kBatch, max_iter - enq);
             for (int q = 0; q < cnt; ++q) {
-                ATK_CUDA_CHECK(cudaGraphLaunch(gexec, st));
-                ctx->launches += launches_per_iter;
+                if (use_graph) {
+                    ATK_CUDA_CHECK(cudaGraphLaunch(gexec, st));
+                    ctx->launches += launches_per_iter;
+                } else {
+                    enqueue_iteration();
+                }
             }
             enq += cnt;
             ATK_CUDA_CHECK(cudaMemcpyAsync(h_done + bt, &d_state->done, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -325,6 +341,15 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
         ATK_CUDA_CHECK(cudaStreamSynchronize(st));
         float ms = 0.f;
         ATK_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
+        info->kernel_ms[0] = info->kernel_ms[1] = info->kernel_ms[2] = 0.f;
+        for (size_t q = 0; q + 3 < kev.size(); q += 4)
+            for (int c = 0; c < 3; ++c) {
+                float t = 0.f;
+                ATK_CUDA_CHECK(cudaEventElapsedTime(&t, kev[q + c], kev[q + c + 1]));
+                info->kernel_ms[c] += t;
+            }
+        for (auto e : kev) cudaEventDestroy(e);
+        kev.clear();
         info->iterations = hs.it;
         info->stopped_on_pAp = hs.stopped_on_pAp;
         info->zero_rhs = hs.zero_rhs;

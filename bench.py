@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: FP64 CG iterations/s on the 512^3 7-point Poisson system (BASELINE config 4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--grid 512]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is ONE CG ITERATION of Poisson3DSolver's solver over the whole grid (matrix-free operator apply + p.Ap,
+x/r update + r.r, p update).  The reference's ConjugateGrad has no tolerance test, so solve(K) performs exactly K
+iterations (unless |p.Ap| < 1e-12 fires, which RHS-R does not do before ~2k iterations at this size) and
+iterations/s is a like-for-like unit.  The 512^3 total is fixed for every N ("strong" scaling, z-slab partition).
+
+  value   device-resident: b, x, r, p already in HBM; CUDA events on the launching stream around the K-iteration
+          device loop (inside the library), barrier + synchronize on both sides, max over ranks.
+  e2e     the same solve through the reference-facing C-ABI call with HOST buffers (atk_cg_solve_host): pinned b is
+          uploaded, K iterations run, x is downloaded; wall clock around the call, max over ranks.
+  roofline  per-kernel CUDA-event times from a second run of the same loop launched kernel by kernel.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref, the unmodified headers; or the C port
+when that library is absent) on a bounded sample of the same workload and prints the same JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "poisson512_cg_iterations_per_sec"
+UNIT = "iterations/s"
+SEED = 12345
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# =====================================================================================================================
+def run_reference(args):
+    """The reference's own CPU path (1 thread: the code is serial) on a bounded sample, scaled by row count."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle
+
+    g = args.grid
+    s = args.ref_sample_grid
+    scale = (s ** 3) / float(g ** 3)
+    if pyoracle.ref_available():
+        R = pyoracle.Ref()
+        kind = "reference"
+        if args.warmup > 0:
+            R.poisson_solve(min(s, 32), min(s, 32), min(s, 32), rhs_kind=1, seed=SEED, max_iter=args.warmup)
+        res = R.poisson_solve(s, s, s, rhs_kind=1, seed=SEED, max_iter=args.steps)
+        secs, build = res["seconds_solve"], res["seconds_build"]
+    else:
+        P = pyoracle.Port()
+        kind = "port"
+        cx, cy, cz, _ = P.poisson_coeffs(s, s, s)
+        b = P.poisson_rhs(s, s, s, rhs_kind=1, seed=SEED)
+        t0 = time.perf_counter()
+        A = P.poisson_csc(s, s, s)
+        build = time.perf_counter() - t0
+        if args.warmup > 0:
+            P.cg(A, b, args.warmup)
+        t0 = time.perf_counter()
+        P.cg(A, b, args.steps)
+        secs = time.perf_counter() - t0
+    it_s_sample = args.steps / secs
+    value = it_s_sample * scale
+    sample = (f"{s}^3 sub-grid ({s ** 3} of {g ** 3} rows), {args.steps} CG iterations of the assembled-CSC "
+              f"reference solver, {secs:.2f} s solve + {build:.2f} s assembly; iterations/s scaled by rows x{scale:.6f}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"poisson3d_cg_{g}^3", "grid": [g, g, g], "rows": g ** 3, "rhs": f"RHS-R seed {SEED}"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
+                         "host_cores_available": os.cpu_count(), "sample_iterations_per_sec": it_s_sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# =====================================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from algotoolkit_b200 import capi, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device: bench.py has no CPU path for --impl ours")
+    torch.cuda.set_device(local_rank)
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        blob = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            blob = torch.tensor(list(capi.Context.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(blob, 0)
+        uid = bytes(blob.cpu().tolist())
+    ctx = capi.Context(local_rank, rank, world, uid)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ctx.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    g = args.grid
+    cx, cy, cz = synthetic.poisson_coeffs(g, g, g)
+    op = ctx.operator_stencil7(g, g, g, cx, cy, cz)
+    n_loc, N = op.n_rows_local, g ** 3
+    plane = g * g
+    k0 = op.row_begin // plane
+    k1 = k0 + n_loc // plane
+
+    # ---- synthetic RHS-R of this rank's slab, in pinned host memory
+    import ctypes as C
+
+    L = ctx.L
+    hb, hx = C.c_void_p(), C.c_void_p()
+    capi._check(L.atk_host_alloc(n_loc * 8, C.byref(hb)))
+    capi._check(L.atk_host_alloc(n_loc * 8, C.byref(hx)))
+    b_host = np.ctypeslib.as_array(C.cast(hb, C.POINTER(C.c_double)), shape=(n_loc,))
+    x_host = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_double)), shape=(n_loc,))
+    synthetic.poisson_rhs_r(g, g, g, k0, k1, seed=SEED, out=b_host)
+
+    db = ctx.vector(b_host)
+    dx, dr, dp = ctx.empty(n_loc), ctx.empty(n_loc), ctx.empty(n_loc)
+
+    def fresh_state():
+        dx.zero()
+        dr.copy_from(db)
+        dp.copy_from(db)
+
+    # ---- warm-up (W iterations, untimed)
+    fresh_state()
+    ctx.cg_solve(op, db, dx, dr, dp, max(args.warmup, 3))
+
+    sampler = ClockSampler(local_rank)
+    # ---- device-resident timed region: exactly K iterations
+    fresh_state()
+    barrier()
+    launches0 = ctx.launch_count()
+    with sampler:
+        res = ctx.cg_solve(op, db, dx, dr, dp, args.steps)
+        barrier()
+    launches = ctx.launch_count() - launches0
+    dev_ms = max_over_ranks(res["device_ms"])
+    if res["iters"] != args.steps:
+        raise SystemExit(f"solver stopped after {res['iters']} of {args.steps} iterations (|pAp|<1e-12 exit)")
+    value = args.steps / (dev_ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call: H2D b, K iterations, D2H x
+    info = capi.CgInfo()
+    barrier()
+    t0 = time.perf_counter()
+    capi._check(L.atk_cg_solve_host(ctx.h, op.h, hb, hx, None, None, 1, args.steps, C.byref(info)))
+    ctx.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = args.steps / t_e2e
+    x_norm2 = float(np.dot(x_host, x_host))  # the host reads the result it received
+
+    # ---- per-kernel times (kernel-by-kernel launch of the same loop) for the roofline
+    fresh_state()
+    barrier()
+    kt_steps = min(args.steps, 50)
+    kres = ctx.cg_solve(op, db, dx, dr, dp, kt_steps, time_kernels=True)
+    kms = [max_over_ranks(v) / kt_steps for v in kres["kernel_ms"]]  # ms per launch: K1, K2, K3
+    peak, peak_src = measured_peaks()
+    bytes_per_row = [16.0, 48.0, 24.0]  # stencil apply+dot, x/r update + r.r, p update
+    names = ["stencil7_apply_dot", "cg_update_xr_norm", "cg_update_p"]
+    per_kernel = []
+    for nm, bpr, ms in zip(names, bytes_per_row, kms):
+        gbs = bpr * n_loc / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        per_kernel.append({"kernel": nm, "ms_per_launch": ms, "algorithmic_bytes": bpr * n_loc, "achieved_gbs": gbs,
+                           "frac": gbs / peak, "share_of_step": ms / sum(kms) if sum(kms) > 0 else 0.0})
+    dom = max(per_kernel, key=lambda d: d["ms_per_launch"])
+    iter_gbs = 88.0 * N / (dev_ms * 1e-3 / args.steps) / 1e9 / world  # per GPU, whole iteration
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"poisson3d_cg_{g}^3_matrix_free", "grid": [g, g, g], "rows": N, "rows_per_gpu": n_loc,
+                   "rhs": f"RHS-R seed {SEED}", "operator": "7-point stencil, Dirichlet shell = identity rows",
+                   "parallelism": f"z-slab x{world}", "l2": "inputs larger than L2 (5 vectors x %.2f GB per GPU)" % (n_loc * 8 / 1e9),
+                   "step": "one CG iteration"},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_loc * 8 / args.steps,
+                "d2h_bytes_per_step": n_loc * 8 / args.steps, "seconds": t_e2e, "x_norm": float(np.sqrt(x_norm2)),
+                "note": "one atk_cg_solve_host call = K steps; pinned b up, x down, per rank"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                     "iteration_achieved_gbs_per_gpu": iter_gbs, "iteration_frac": iter_gbs / peak,
+                     "iteration_frac_of_8TBs": iter_gbs / 8000.0, "per_kernel": per_kernel},
+        "rs_final": res["rs"],
+    }
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the unmodified reference on a bounded sample
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import pyoracle
+
+        s = args.ref_sample_grid
+        it = args.ref_sample_iters
+        if pyoracle.ref_available():
+            rr = pyoracle.Ref().poisson_solve(s, s, s, rhs_kind=1, seed=SEED, max_iter=it)
+            secs, kind = rr["seconds_solve"], "reference"
+        else:
+            P = pyoracle.Port()
+            A = P.poisson_csc(s, s, s)
+            bb = P.poisson_rhs(s, s, s, rhs_kind=1, seed=SEED)
+            t0 = time.perf_counter()
+            P.cg(A, bb, it)
+            secs, kind = time.perf_counter() - t0, "port"
+        scale = s ** 3 / float(N)
+        line["cpu_baseline"] = {
+            "value": it / secs * scale, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"{s}^3 sub-grid, {it} CG iterations in {secs:.2f} s ({it / secs:.2f} it/s), scaled by rows x{scale:.6f} "
+                      f"to the {g}^3 workload; the reference is single-threaded ({os.cpu_count()} host cores present)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=512)
+    ap.add_argument("--ref-sample-grid", type=int, default=128)
+    ap.add_argument("--ref-sample-iters", type=int, default=150)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

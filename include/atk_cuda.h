@@ -149,6 +149,11 @@ typedef struct atk_cg_info {
     double* pAp_trace;
     double* rs_trace;
     int trace_capacity;
+    /* in: when non-zero the iterations are launched kernel by kernel (no CUDA graph) with CUDA events around each
+     * kernel class, and kernel_ms[] returns the summed device time of K1 (operator apply + p.Ap), K2 (x/r update +
+     * r.r) and K3 (p update) over all iterations; used by bench.py for the per-kernel roofline */
+    int time_kernels;
+    float kernel_ms[3];
 } atk_cg_info;
 
 /* ConjugateGrad::solve (src/LinearAlgebra/Krylov/ConjugateGradient.hpp:36-84).  The solver state x, r, p lives in

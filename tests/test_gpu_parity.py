@@ -396,6 +396,3 @@ def test_gmres_op27_tree_mode(ctx, port, golden, key):
     ora = port.gmres(A, b, np.zeros(n ** 3), g["max_iter"], g["K"], 1e-6)
     assert digest(ora["x"]) == g["x_sha256"]
     assert relerr(res["x"], ora["x"]) < REL
-    # CGS2 (throughput option): same Krylov space, looser agreement
-    res2 = ctx.gmres_solve_host(op, b, np.zeros(n ** 3), g["max_iter"], g["K"], 1e-6, ortho=capi.GMRES_CGS2)
-    assert np.allclose(res2["resid"], g["resid"]["all"], rtol=1e-6)
