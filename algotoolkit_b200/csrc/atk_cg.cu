@@ -20,6 +20,7 @@
 // context is in ATK_REDUCE_SEQUENTIAL mode.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "atk_internal.cuh"
@@ -28,17 +29,7 @@ namespace atk {
 
 namespace {
 
-struct CgState {
-    double rs_old;
-    double last_pAp;
-    double b_norm2;
-    int it;          // iterations completed (== loop index of the iteration in flight)
-    int done;        // 1 once an exit condition fired
-    int stopped_on_pAp;
-    int zero_rhs;
-    int trace_cap;
-    int pad;
-};
+using CgState = CgFusedState;  // one device-resident scalar block for both formulations (atk_internal.cuh)
 
 // rs_old = r.r and the ||b|| < 1e-12 test (:37-42).  One CTA; the two dots were left in the slots by dot kernels.
 __global__ void cg_begin_kernel(CgState* st, const double* slot_rr, const double* slot_bb, int world) {
@@ -50,6 +41,9 @@ __global__ void cg_begin_kernel(CgState* st, const double* slot_rr, const double
     st->last_pAp = 0.0;
     st->it = 0;
     st->stopped_on_pAp = 0;
+    st->alpha = 0.0;
+    st->ka_count = 0;
+    st->first = 1;
     const int zero = (sqrt(bb) < 1e-12) ? 1 : 0;
     st->zero_rhs = zero;
     st->done = zero;
@@ -188,6 +182,102 @@ __global__ void __launch_bounds__(kReduceBlock) cg_update_p_kernel(int64_t n, Cg
     }
 }
 
+// ---------------------------------------------------------------------------------------------- fused formulation
+// KB: alpha = rs_old/pAp ; r = r - Ap*alpha ; partial sums of r.r   (:53-63 without the x update, which KA applies
+// one iteration later).  24 B/row.
+template <bool VEC2>
+__global__ void __launch_bounds__(kReduceBlock) cg_fused_update_r_kernel(int64_t n, CgState* st, const double* __restrict__ slot_pAp,
+                                                                         int world, double* __restrict__ r,
+                                                                         const double* __restrict__ Ap, double* partials,
+                                                                         unsigned* ticket, double* rr_out, double* pAp_trace) {
+    if (st->done) return;
+    const double pAp = slot_sum(slot_pAp, world);
+    if (fabs(pAp) < 1e-12) {  // :53-57
+        if (threadIdx.x == 0 && blockIdx.x == 0) {
+            st->last_pAp = pAp;
+            if (pAp_trace && st->it < st->trace_cap) pAp_trace[st->it] = pAp;
+            st->stopped_on_pAp = 1;
+            __threadfence();
+            st->done = 1;
+        }
+        return;
+    }
+    const double alpha = __ddiv_rn(st->rs_old, pAp);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc = 0.0;
+    if constexpr (VEC2) {
+        const int64_t n2 = n >> 1;
+        double2* r2 = reinterpret_cast<double2*>(r);
+        const double2* a2 = reinterpret_cast<const double2*>(Ap);
+        double acc1 = 0.0;
+        for (int64_t i = t; i < n2; i += stride) {
+            double2 rv = r2[i];
+            const double2 av = a2[i];
+            rv.x = sub_rn(rv.x, mul_rn(av.x, alpha));
+            rv.y = sub_rn(rv.y, mul_rn(av.y, alpha));
+            r2[i] = rv;
+            acc = add_rn(acc, mul_rn(rv.x, rv.x));
+            acc1 = add_rn(acc1, mul_rn(rv.y, rv.y));
+        }
+        acc = add_rn(acc, acc1);
+        if (t == 0 && (n & 1)) {
+            const double rn = sub_rn(r[n - 1], mul_rn(Ap[n - 1], alpha));
+            r[n - 1] = rn;
+            acc = add_rn(acc, mul_rn(rn, rn));
+        }
+    } else {
+        for (int64_t i = t; i < n; i += stride) {
+            const double rn = sub_rn(r[i], mul_rn(Ap[i], alpha));
+            r[i] = rn;
+            acc = add_rn(acc, mul_rn(rn, rn));
+        }
+    }
+    double total;
+    if (grid_sum_last_block<kReduceBlock>(acc, partials, ticket, &total)) {
+        if (threadIdx.x == 0) {
+            *rr_out = total;
+            st->alpha = alpha;
+            st->last_pAp = pAp;
+            if (pAp_trace && st->it < st->trace_cap) pAp_trace[st->it] = pAp;
+        }
+    }
+}
+
+// KF, once after the loop: brings the caller's x and p to the reference's state.
+//   exit fired (done): x and r are complete; the current direction is copied into the caller's p if it lives in the
+//                      scratch buffer;
+//   loop ran out:      the last iteration's x = x + p*alpha and p = r + p*beta are still pending - apply them.
+__global__ void __launch_bounds__(kReduceBlock) cg_fused_flush_kernel(int64_t n, CgState* st, const double* __restrict__ slot_rr,
+                                                                      int world, const double* __restrict__ r, double* x,
+                                                                      const double* P0, const double* P1, double* p_user,
+                                                                      unsigned* ticket, double* rs_trace) {
+    if (st->first) return;  // no KA ran: nothing pending, p_user untouched
+    const double* pc = (st->ka_count & 1) ? P1 : P0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (st->done) {
+        if (pc != p_user)
+            for (int64_t i = t; i < n; i += stride) p_user[i] = pc[i];
+        return;
+    }
+    const double rs_new = slot_sum(slot_rr, world);
+    const double beta = __ddiv_rn(rs_new, st->rs_old);
+    const double alpha = st->alpha;
+    for (int64_t i = t; i < n; i += stride) {
+        const double pv = pc[i];
+        x[i] = add_rn(x[i], mul_rn(pv, alpha));
+        p_user[i] = add_rn(r[i], mul_rn(pv, beta));
+    }
+    if (last_block_done(ticket)) {
+        if (threadIdx.x == 0) {
+            if (rs_trace && st->it < st->trace_cap) rs_trace[st->it] = rs_new;
+            st->rs_old = rs_new;
+            st->it = st->it + 1;
+        }
+    }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -202,7 +292,10 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
     const int trace_cap = (info->pAp_trace || info->rs_trace) ? std::max(0, info->trace_capacity) : 0;
 
     CgState* d_state = nullptr;
-    double *Ap = nullptr, *d_ptrace = nullptr, *d_rtrace = nullptr;
+    double *Ap = nullptr, *d_ptrace = nullptr, *d_rtrace = nullptr, *p_alt = nullptr;
+    const char* env_fused = std::getenv("ATK_CG_FUSED");
+    const bool fused = op->fused_cg_capable() && ctx->reduction == ATK_REDUCE_TREE && !(env_fused && env_fused[0] == '0');
+    info->fused = fused ? 1 : 0;
     int* h_done = nullptr;  // pinned: done flag of every poll
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
@@ -211,12 +304,13 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
         if (gexec) cudaGraphExecDestroy(gexec);
         if (graph) cudaGraphDestroy(graph);
         for (auto e : poll_events) if (e) cudaEventDestroy(e);
-        cudaFree(d_state); cudaFree(Ap); cudaFree(d_ptrace); cudaFree(d_rtrace);
+        cudaFree(d_state); cudaFree(Ap); cudaFree(d_ptrace); cudaFree(d_rtrace); cudaFree(p_alt);
         if (h_done) cudaFreeHost(h_done);
     };
     try {
         ATK_CUDA_CHECK(cudaMalloc(&d_state, sizeof(CgState)));
         ATK_CUDA_CHECK(cudaMalloc(&Ap, sizeof(double) * std::max<int64_t>(n, 1)));
+        if (fused) ATK_CUDA_CHECK(cudaMalloc(&p_alt, sizeof(double) * std::max<int64_t>(n, 1)));
         if (trace_cap > 0) {
             ATK_CUDA_CHECK(cudaMalloc(&d_ptrace, sizeof(double) * trace_cap));
             ATK_CUDA_CHECK(cudaMalloc(&d_rtrace, sizeof(double) * trace_cap));
@@ -241,7 +335,25 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
             ATK_CUDA_CHECK(cudaEventRecord(e, st));
             kev.push_back(e);
         };
+        auto enqueue_fused = [&]() {
+            mark();
+            op->cg_fused_step(d_state, r, x, Ap, p, p_alt, kSlotRR, kSlotPAp, d_rtrace);  // KA (+ all-gather of p.Ap)
+            mark();
+            if (vec)
+                cg_fused_update_r_kernel<true><<<grid, kReduceBlock, 0, st>>>(n, d_state, ctx->slot(kSlotPAp), ctx->world, r, Ap,
+                                                                              ctx->d_partials, ctx->d_tickets + 3,
+                                                                              ctx->slot(kSlotRR) + ctx->rank, d_ptrace);
+            else
+                cg_fused_update_r_kernel<false><<<grid, kReduceBlock, 0, st>>>(n, d_state, ctx->slot(kSlotPAp), ctx->world, r, Ap,
+                                                                               ctx->d_partials, ctx->d_tickets + 3,
+                                                                               ctx->slot(kSlotRR) + ctx->rank, d_ptrace);
+            count_launch(ctx);
+            allgather_slot(ctx, kSlotRR, st);
+            mark();
+            mark();
+        };
         auto enqueue_iteration = [&]() {
+            if (fused) return enqueue_fused();
             mark();
             op->apply(p, Ap, seq ? -1 : kSlotPAp, done_flag);  // K1 (+ all-gather of the partial)
             if (seq) launch_dot(ctx, n, p, Ap, kSlotPAp, done_flag);  // the fused tree sum is replaced by an ordered sum
@@ -327,6 +439,11 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
             ATK_CUDA_CHECK(cudaMemcpyAsync(h_done + bt, &d_state->done, sizeof(int), cudaMemcpyDeviceToHost, st));
             ATK_CUDA_CHECK(cudaEventCreateWithFlags(&poll_events[bt], cudaEventDisableTiming));
             ATK_CUDA_CHECK(cudaEventRecord(poll_events[bt], st));
+        }
+        if (fused) {  // KF: pending x / p updates of the last iteration, or p copied back after an exit
+            cg_fused_flush_kernel<<<ctx->reduce_grid(), kReduceBlock, 0, st>>>(n, d_state, ctx->slot(kSlotRR), ctx->world, r, x, p,
+                                                                               p_alt, p, ctx->d_tickets + 4, d_rtrace);
+            count_launch(ctx);
         }
         ATK_CUDA_CHECK(cudaEventRecord(ctx->ev_t1, st));
 

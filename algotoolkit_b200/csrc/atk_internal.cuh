@@ -85,6 +85,22 @@ void exchange_halo(Context* ctx, const double* first_plane, const double* last_p
 // Host value of a reduction slot (sum over ranks in rank order); synchronises the compute stream.
 double read_slot(Context* ctx, int slot);
 
+// ------------------------------------------------------------------------------------------ fused CG state
+// Device-resident scalars of the fused two-kernel CG iteration (atk_cg.cu drives it, the operator supplies KA).
+struct CgFusedState {
+    double rs_old;    // r.r of the current residual
+    double alpha;     // alpha of the last r update; the matching x += alpha*p is still pending
+    double last_pAp;
+    double b_norm2;
+    int ka_count;     // KA steps executed in this solve: the current search direction lives in P[ka_count & 1]
+    int it;           // completed iterations (the reference's loop index)
+    int done;
+    int stopped_on_pAp;
+    int zero_rhs;
+    int first;        // 1 until the first KA of this solve has run: p is taken as is, no pending x update
+    int trace_cap;
+};
+
 // ------------------------------------------------------------------------------------------ operators
 struct Operator {
     Context* ctx = nullptr;
@@ -96,6 +112,15 @@ struct Operator {
     // y = A x on the compute stream; if dot_slot >= 0 also leaves this rank's partial of x.y in that slot
     // (and all-gathers it).  `skip_flag` (device int, may be null): when *skip_flag != 0 the kernels return at once.
     virtual void apply(const double* x, double* y, int dot_slot, const int* skip_flag) = 0;
+    // Fused CG step KA (matrix-free operators).  With p_cur = P[ka_count&1], p_alt the other buffer:
+    //   p_new = r + beta*p_cur (beta = rr_slot / rs_old; p_new = p_cur on the first step), x += alpha*p_cur,
+    //   Ap = A p_new, partial p_new.Ap into dot_slot, p_new written to p_alt; the last CTA commits the scalars
+    //   (rs_old, it, ka_count).  The two buffers are needed because neighbouring CTAs still read p_cur.
+    virtual bool fused_cg_capable() const { return false; }
+    virtual void cg_fused_step(CgFusedState*, const double* /*r*/, double* /*x*/, double* /*Ap*/, double* /*P0*/,
+                               double* /*P1*/, int /*rr_slot*/, int /*dot_slot*/, double* /*rs_trace*/) {
+        throw Error(ATK_ERR_INVALID_ARGUMENT, "operator has no fused CG step");
+    }
     virtual bool has_csr() const { return false; }
     virtual void export_csr(int*, int*, double*) const { throw Error(ATK_ERR_INVALID_ARGUMENT, "operator has no CSR arrays"); }
 };
@@ -153,6 +178,25 @@ __device__ __forceinline__ double block_sum(double v) {
     return t;
 }
 
+// Sum of `count` per-block partials by one CTA, in an order that depends only on (count, BLOCK): every thread runs
+// four independent accumulation chains over an interleaved subsequence (so the L2 loads pipeline), the chains are
+// combined in a fixed order, then the fixed-shape block tree finishes.
+template <int BLOCK>
+__device__ __forceinline__ double partials_sum(const double* partials, unsigned count) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    unsigned i = linear_thread_id();
+    for (; i + 3 * BLOCK < count; i += 4 * BLOCK) {
+        const double v0 = __ldcg(partials + i), v1 = __ldcg(partials + i + BLOCK);
+        const double v2 = __ldcg(partials + i + 2 * BLOCK), v3 = __ldcg(partials + i + 3 * BLOCK);
+        s0 = add_rn(s0, v0);
+        s1 = add_rn(s1, v1);
+        s2 = add_rn(s2, v2);
+        s3 = add_rn(s3, v3);
+    }
+    for (; i < count; i += BLOCK) s0 = add_rn(s0, __ldcg(partials + i));
+    return block_sum<BLOCK>(add_rn(add_rn(s0, s1), add_rn(s2, s3)));
+}
+
 // Grid-wide deterministic sum: each block leaves its partial in partials[block]; the block that arrives last adds
 // all partials in a fixed order.  Returns true (for every thread) in that last block, with the total in *total.
 // The ticket wraps back to 0 by itself (atomicInc), so it is ready for the next launch.
@@ -170,9 +214,7 @@ __device__ __forceinline__ bool grid_sum_last_block(double v, double* partials, 
     __syncthreads();
     if (!is_last) return false;
     __threadfence();
-    double s = 0.0;
-    for (unsigned i = linear_thread_id(); i < nb; i += BLOCK) s = add_rn(s, __ldcg(partials + i));
-    *total = block_sum<BLOCK>(s);
+    *total = partials_sum<BLOCK>(partials, nb);
     return true;
 }
 

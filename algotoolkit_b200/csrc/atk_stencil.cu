@@ -150,6 +150,401 @@ __global__ void __launch_bounds__(TX* TY) stencil7_kernel(StencilGeom g, const d
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------- fused CG step KA
+// One pass that does what K3 + K1 + half of K2 did in the three-kernel formulation (ConjugateGradient.hpp:50-51,60,79):
+//     p_new = r + p*beta          (beta = rs_new/rs_old, formed from the r.r slot; p_new = p on the first step)
+//     x     = x + p*alpha         (the update of the PREVIOUS iteration, deferred so that p is read only once)
+//     Ap    = A p_new ,  partial sums of p_new.Ap
+// p_new at the six neighbours is recomputed from r and p there (one multiply-add each) instead of being re-read
+// from a finished p_new array, so p is read once and written once: 48 B/row here + 24 B/row in KB = 72 B/row per
+// iteration instead of 88.  p_new goes to the other buffer of a ping-pong pair because neighbouring CTAs still
+// need the old p.  Element arithmetic and its order are those of the reference; only the kernel boundaries moved.
+struct FusedArgs {
+    const double* r;
+    double* x;
+    double* Ap;
+    double* P0;
+    double* P1;
+    const double* r_halo_lo;
+    const double* r_halo_hi;
+    const double* p_halo_lo;
+    const double* p_halo_hi;
+    CgFusedState* st;
+    const double* slot_rr;
+    int world;
+    double* rs_trace;
+};
+
+template <int TX, int TY, bool VEC2>
+__global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_kernel(StencilGeom g, FusedArgs a, int k_lo, int k_hi, int kc,
+                                                                    double* partials, int partial_base, unsigned* ticket,
+                                                                    double* dot_out, int is_final) {
+    CgFusedState* st = a.st;
+    if (st->done) return;
+    const int first = st->first;
+    const int cnt = st->ka_count;
+    const double* __restrict__ ps = (cnt & 1) ? a.P1 : a.P0;
+    double* __restrict__ pd = (cnt & 1) ? a.P0 : a.P1;
+    const double* __restrict__ r = a.r;
+    double rs_new = 0.0, beta = 0.0, alpha = 0.0;
+    if (!first) {
+        rs_new = slot_sum(a.slot_rr, a.world);
+        beta = __ddiv_rn(rs_new, st->rs_old);
+        alpha = st->alpha;
+    }
+    const int i0 = (blockIdx.x * TX + threadIdx.x) * 2;
+    const int j = blockIdx.y * TY + threadIdx.y;
+    const int kb = k_lo + blockIdx.z * kc;
+    const int ke = min(kb + kc, k_hi);
+    const bool active = (i0 < g.nx) && (j < g.ny);
+    const bool has1 = active && (i0 + 1 < g.nx);
+    const int64_t sxy = (int64_t)g.nx * g.ny;
+    const int64_t row = (int64_t)j * g.nx + i0;
+    double dacc = 0.0;
+
+    auto load2 = [&](const double* base, int64_t idx) -> double2 {
+        if constexpr (VEC2) return *reinterpret_cast<const double2*>(base + idx);
+        else return make_double2(base[idx], has1 ? base[idx + 1] : 0.0);
+    };
+    auto store2 = [&](double* base, int64_t idx, double2 v) {
+        if constexpr (VEC2) *reinterpret_cast<double2*>(base + idx) = v;
+        else { base[idx] = v.x; if (has1) base[idx + 1] = v.y; }
+    };
+    auto plane_r = [&](int k) -> double2 {
+        if (k < 0) return load2(a.r_halo_lo, row);
+        if (k >= g.nz_loc) return load2(a.r_halo_hi, row);
+        return load2(r, (int64_t)k * sxy + row);
+    };
+    auto plane_p = [&](int k) -> double2 {
+        if (k < 0) return load2(a.p_halo_lo, row);
+        if (k >= g.nz_loc) return load2(a.p_halo_hi, row);
+        return load2(ps, (int64_t)k * sxy + row);
+    };
+    auto pnew = [&](double rv, double pv) -> double { return first ? pv : add_rn(rv, mul_rn(pv, beta)); };
+    auto pnew2 = [&](double2 rv, double2 pv) -> double2 { return make_double2(pnew(rv.x, pv.x), pnew(rv.y, pv.y)); };
+
+    if (active && kb < ke) {
+        const bool j_shell = (j == 0 || j == g.ny - 1);
+        const bool a_shell_i = (i0 == 0 || i0 == g.nx - 1);
+        const bool b_shell_i = (i0 + 1 == g.nx - 1);
+        const double2 zero2 = make_double2(0.0, 0.0);
+        double2 pnA = zero2, pnB, pnC = zero2, poB;
+        if (g.k_off + kb - 1 >= 0) pnA = pnew2(plane_r(kb - 1), plane_p(kb - 1));
+        {
+            const double2 rv = plane_r(kb);
+            poB = plane_p(kb);
+            pnB = pnew2(rv, poB);
+        }
+        double2 rN = zero2, pN = zero2;
+        bool haveN = (g.k_off + kb + 1 < g.nz);
+        if (haveN) { rN = plane_r(kb + 1); pN = plane_p(kb + 1); }
+        for (int k = kb; k < ke; ++k) {
+            const int kg = g.k_off + k;
+            const int64_t idx = (int64_t)k * sxy + row;
+            // plane k+2 (the "next" of the following iteration) is requested before anything of plane k is used
+            double2 rNN = zero2, pNN = zero2;
+            const bool haveNN = (k + 1 < ke) && (kg + 2 < g.nz);
+            if (haveNN) { rNN = plane_r(k + 2); pNN = plane_p(k + 2); }
+            double2 xv = zero2;
+            if (!first) xv = load2(a.x, idx);
+            if (haveN) pnC = pnew2(rN, pN);
+            double2 out;
+            if (j_shell || kg == 0 || kg == g.nz - 1) {
+                out.x = shell_row(pnB.x);
+                out.y = shell_row(pnB.y);
+            } else {
+                const double2 jm = pnew2(load2(r, idx - g.nx), load2(ps, idx - g.nx));
+                const double2 jp = pnew2(load2(r, idx + g.nx), load2(ps, idx + g.nx));
+                if (a_shell_i) {
+                    out.x = shell_row(pnB.x);
+                } else {
+                    const double left = pnew(r[idx - 1], ps[idx - 1]);
+                    out.x = tap7(g, pnA.x, jm.x, left, pnB.x, pnB.y, jp.x, pnC.x);
+                }
+                if (!has1) {
+                    out.y = 0.0;
+                } else if (b_shell_i) {
+                    out.y = shell_row(pnB.y);
+                } else {
+                    const double right = pnew(r[idx + 2], ps[idx + 2]);
+                    out.y = tap7(g, pnA.y, jm.y, pnB.x, pnB.y, right, jp.y, pnC.y);
+                }
+            }
+            store2(a.Ap, idx, out);
+            store2(pd, idx, pnB);
+            if (!first) {
+                xv.x = add_rn(xv.x, mul_rn(poB.x, alpha));  // x = x + p*alpha of the previous iteration (:60)
+                xv.y = add_rn(xv.y, mul_rn(poB.y, alpha));
+                store2(a.x, idx, xv);
+            }
+            dacc = add_rn(dacc, mul_rn(pnB.x, out.x));
+            if (has1) dacc = add_rn(dacc, mul_rn(pnB.y, out.y));
+            pnA = pnB;
+            pnB = pnC;
+            poB = pN;
+            rN = rNN;
+            pN = pNN;
+            haveN = haveNN;
+        }
+    }
+    const double bs = block_sum<TX * TY>(dacc);
+    __shared__ bool is_last;
+    const unsigned nb = total_blocks();
+    if (linear_thread_id() == 0) {
+        partials[partial_base + linear_block_id()] = bs;
+        is_last = false;
+        if (is_final) {
+            __threadfence();
+            const unsigned t = atomicInc(ticket, nb - 1);
+            is_last = (t == nb - 1);
+        }
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        const double total = partials_sum<TX * TY>(partials, partial_base + nb);
+        if (linear_thread_id() == 0) {
+            *dot_out = total;
+            if (!first) {  // the p update of the previous iteration is now complete (:79-80)
+                if (a.rs_trace && st->it < st->trace_cap) a.rs_trace[st->it] = rs_new;
+                st->rs_old = rs_new;
+                st->it = st->it + 1;
+            }
+            st->first = 0;
+            st->ka_count = cnt + 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- KA, cp.async pipeline
+// Used whenever nx is even and the vectors are 16-byte aligned.  ncu on the L1-based kernel above showed it
+// latency-bound: 72 % of the stall samples were long-scoreboard waits on the eight neighbour loads each thread issues
+// per plane (L1 hit rate 35 %), with occupancy capped at 31 % by the 96 registers the register prefetch costs.
+// Here ALL global reads of r and p go through cp.async (LDGSTS) into a DEPTH-deep ring of shared-memory plane tiles,
+// requested three planes ahead at no register cost; neighbours are read back from shared memory:
+//   rt/pt[stage][jj][ii]: raw r / p at point (i_lo - 2 + ii, j_lo - 1 + jj) of one plane;
+//   centre columns start at ii = 2 (16-byte aligned), ii = 1 and 2TX+2 are the left / right halo columns,
+//   jj = 0 and TY+1 the halo rows (copied by the first / last thread row, halo columns by the first / last thread).
+// p_new at a neighbour is re-formed from the two raw values (one multiply-add), exactly as the reference forms it.
+// One __syncthreads per plane.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <int TX, int TY>
+__global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_smem_kernel(StencilGeom g, FusedArgs a, int k_lo, int k_hi, int kc,
+                                                                         double* partials, int partial_base, unsigned* ticket,
+                                                                         double* dot_out, int is_final) {
+    constexpr int DEPTH = 4;       // ring stages: planes k-1 .. k+2 resident / in flight while plane k is computed
+    constexpr int W = 2 * TX + 4;  // tile width in doubles
+    extern __shared__ __align__(16) double smem_dyn[];
+    double(*rt)[TY + 2][W] = reinterpret_cast<double(*)[TY + 2][W]>(smem_dyn);
+    double(*pt)[TY + 2][W] = reinterpret_cast<double(*)[TY + 2][W]>(smem_dyn + (size_t)DEPTH * (TY + 2) * W);
+
+    CgFusedState* st = a.st;
+    if (st->done) return;
+    const int first = st->first;
+    const int cnt = st->ka_count;
+    const double* __restrict__ ps = (cnt & 1) ? a.P1 : a.P0;
+    double* __restrict__ pd = (cnt & 1) ? a.P0 : a.P1;
+    const double* __restrict__ r = a.r;
+    double rs_new = 0.0, beta = 0.0, alpha = 0.0;
+    if (!first) {
+        rs_new = slot_sum(a.slot_rr, a.world);
+        beta = __ddiv_rn(rs_new, st->rs_old);
+        alpha = st->alpha;
+    }
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i_lo = blockIdx.x * 2 * TX;
+    const int j_lo = blockIdx.y * TY;
+    const int i0 = i_lo + 2 * tx;
+    const int j = j_lo + ty;
+    const int kb = k_lo + blockIdx.z * kc;
+    const int ke = min(kb + kc, k_hi);
+    const bool active = (i0 < g.nx) && (j < g.ny);  // nx is even here: both points of the pair exist
+    const int64_t sxy = (int64_t)g.nx * g.ny;
+    const int64_t row = (int64_t)j * g.nx + i0;
+    const bool do_jlo = active && ty == 0 && j_lo > 0;
+    const bool do_jhi = active && ty == TY - 1 && (j + 1 < g.ny);
+    const bool do_ilo = active && tx == 0 && i_lo > 0;
+    const bool do_ihi = active && tx == TX - 1 && (i_lo + 2 * TX < g.nx);
+    double dacc = 0.0;
+
+    // first element of plane k of an array: the slab itself, or a halo plane outside it
+    auto plane_ptr = [&](const double* arr, const double* lo, const double* hi, int k) -> const double* {
+        if (k < 0) return lo;
+        if (k >= g.nz_loc) return hi;
+        return arr + (int64_t)k * sxy;
+    };
+    // global plane index valid?  (planes outside the global grid are never requested)
+    auto issue_plane = [&](int k) {
+        const int kg = g.k_off + k;
+        if (kg >= 0 && kg < g.nz && active) {
+            const int s = ((k % DEPTH) + DEPTH) % DEPTH;
+            const double* rp = plane_ptr(r, a.r_halo_lo, a.r_halo_hi, k) + row;
+            const double* pp = plane_ptr(ps, a.p_halo_lo, a.p_halo_hi, k) + row;
+            cp_async16(&rt[s][ty + 1][2 * tx + 2], rp);
+            cp_async16(&pt[s][ty + 1][2 * tx + 2], pp);
+            if (do_jlo) {
+                cp_async16(&rt[s][0][2 * tx + 2], rp - g.nx);
+                cp_async16(&pt[s][0][2 * tx + 2], pp - g.nx);
+            }
+            if (do_jhi) {
+                cp_async16(&rt[s][TY + 1][2 * tx + 2], rp + g.nx);
+                cp_async16(&pt[s][TY + 1][2 * tx + 2], pp + g.nx);
+            }
+            if (do_ilo) {
+                cp_async8(&rt[s][ty + 1][1], rp - 1);
+                cp_async8(&pt[s][ty + 1][1], pp - 1);
+            }
+            if (do_ihi) {
+                cp_async8(&rt[s][ty + 1][2 * TX + 2], rp + 2);
+                cp_async8(&pt[s][ty + 1][2 * TX + 2], pp + 2);
+            }
+        }
+        cp_async_commit();  // always commit, so that every thread counts the same number of groups
+    };
+    auto pnew = [&](double rv, double pv) -> double { return first ? pv : add_rn(rv, mul_rn(pv, beta)); };
+    auto pnew2 = [&](double2 rv, double2 pv) -> double2 { return make_double2(pnew(rv.x, pv.x), pnew(rv.y, pv.y)); };
+    auto centre_r = [&](int s) -> double2 { return *reinterpret_cast<const double2*>(&rt[s][ty + 1][2 * tx + 2]); };
+    auto centre_p = [&](int s) -> double2 { return *reinterpret_cast<const double2*>(&pt[s][ty + 1][2 * tx + 2]); };
+    auto stage_of = [&](int k) -> int { return ((k % DEPTH) + DEPTH) % DEPTH; };
+
+    if (kb < ke) {
+        const bool j_shell = (j == 0 || j == g.ny - 1);
+        const bool a_shell_i = (i0 == 0 || i0 == g.nx - 1);
+        const bool b_shell_i = (i0 + 1 == g.nx - 1);
+        const double2 zero2 = make_double2(0.0, 0.0);
+        // prologue: planes kb-1, kb, kb+1, kb+2 in flight (4 groups)
+        issue_plane(kb - 1);
+        issue_plane(kb);
+        issue_plane(kb + 1);
+        issue_plane(kb + 2);
+        double2 xv = zero2;
+        if (active && !first) xv = *reinterpret_cast<const double2*>(a.x + (int64_t)kb * sxy + row);
+        cp_async_wait<2>();  // kb-1 and kb have landed
+        __syncthreads();
+        double2 pnA = zero2, pnB = zero2, pnC = zero2, poB = zero2;
+        if (active) {
+            if (g.k_off + kb - 1 >= 0) pnA = pnew2(centre_r(stage_of(kb - 1)), centre_p(stage_of(kb - 1)));
+            poB = centre_p(stage_of(kb));
+            pnB = pnew2(centre_r(stage_of(kb)), poB);
+        }
+        for (int k = kb; k < ke; ++k) {
+            const int kg = g.k_off + k;
+            const int64_t idx = (int64_t)k * sxy + row;
+            cp_async_wait<1>();  // plane k+1 has landed (k+2 may still be in flight)
+            __syncthreads();     // ... for every thread; also: everyone is done reading plane k-1's stage
+            issue_plane(k + 3);  // into the stage plane k-1 occupied
+            double2 xn = zero2;  // x of the next plane, requested one iteration early
+            if (active && !first && k + 1 < ke) xn = *reinterpret_cast<const double2*>(a.x + idx + sxy);
+            if (active) {
+                const int s = stage_of(k), sn = stage_of(k + 1);
+                double2 poC = zero2;
+                if (kg + 1 < g.nz) {
+                    poC = centre_p(sn);
+                    pnC = pnew2(centre_r(sn), poC);
+                }
+                double2 out;
+                if (j_shell || kg == 0 || kg == g.nz - 1) {
+                    out.x = shell_row(pnB.x);
+                    out.y = shell_row(pnB.y);
+                } else {
+                    const double2 jm = pnew2(*reinterpret_cast<const double2*>(&rt[s][ty][2 * tx + 2]),
+                                             *reinterpret_cast<const double2*>(&pt[s][ty][2 * tx + 2]));
+                    const double2 jp = pnew2(*reinterpret_cast<const double2*>(&rt[s][ty + 2][2 * tx + 2]),
+                                             *reinterpret_cast<const double2*>(&pt[s][ty + 2][2 * tx + 2]));
+                    if (a_shell_i) {
+                        out.x = shell_row(pnB.x);
+                    } else {
+                        const double left = pnew(rt[s][ty + 1][2 * tx + 1], pt[s][ty + 1][2 * tx + 1]);
+                        out.x = tap7(g, pnA.x, jm.x, left, pnB.x, pnB.y, jp.x, pnC.x);
+                    }
+                    if (b_shell_i) {
+                        out.y = shell_row(pnB.y);
+                    } else {
+                        const double right = pnew(rt[s][ty + 1][2 * tx + 4], pt[s][ty + 1][2 * tx + 4]);
+                        out.y = tap7(g, pnA.y, jm.y, pnB.x, pnB.y, right, jp.y, pnC.y);
+                    }
+                }
+                *reinterpret_cast<double2*>(a.Ap + idx) = out;
+                *reinterpret_cast<double2*>(pd + idx) = pnB;
+                dacc = add_rn(dacc, mul_rn(pnB.x, out.x));
+                dacc = add_rn(dacc, mul_rn(pnB.y, out.y));
+                if (!first) {
+                    xv.x = add_rn(xv.x, mul_rn(poB.x, alpha));  // x = x + p*alpha of the previous iteration (:60)
+                    xv.y = add_rn(xv.y, mul_rn(poB.y, alpha));
+                    *reinterpret_cast<double2*>(a.x + idx) = xv;
+                }
+                pnA = pnB;
+                pnB = pnC;
+                poB = poC;
+            }
+            xv = xn;
+        }
+        cp_async_wait<0>();
+    }
+    const double bs = block_sum<TX * TY>(dacc);
+    __shared__ bool is_last;
+    const unsigned nb = total_blocks();
+    if (linear_thread_id() == 0) {
+        partials[partial_base + linear_block_id()] = bs;
+        is_last = false;
+        if (is_final) {
+            __threadfence();
+            const unsigned t = atomicInc(ticket, nb - 1);
+            is_last = (t == nb - 1);
+        }
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        const double total = partials_sum<TX * TY>(partials, partial_base + nb);
+        if (linear_thread_id() == 0) {
+            *dot_out = total;
+            if (!first) {  // the p update of the previous iteration is now complete (:79-80)
+                if (a.rs_trace && st->it < st->trace_cap) a.rs_trace[st->it] = rs_new;
+                st->rs_old = rs_new;
+                st->it = st->it + 1;
+            }
+            st->first = 0;
+            st->ka_count = cnt + 1;
+        }
+    }
+}
+
+// packs the boundary planes of r and of the current p (selected on the device by the ping-pong parity) for the
+// halo exchange: send = [r_first | p_first | r_last | p_last]
+__global__ void __launch_bounds__(256) pack_halo_kernel(const CgFusedState* st, const double* __restrict__ r, const double* P0,
+                                                        const double* P1, int64_t plane, int64_t last_off,
+                                                        double* __restrict__ send) {
+    const double* ps = (st->ka_count & 1) ? P1 : P0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < plane; e += stride) {
+        send[e] = r[e];
+        send[plane + e] = ps[e];
+        send[2 * plane + e] = r[last_off + e];
+        send[3 * plane + e] = ps[last_off + e];
+    }
+}
+
+template <int TX, int TY>
+constexpr size_t fused_smem_bytes() { return (size_t)2 * 4 * (TY + 2) * (2 * TX + 4) * sizeof(double); }
+template <int TX, int TY>
+void allow_fused_smem() {
+    ATK_CUDA_CHECK(cudaFuncSetAttribute(stencil7_cg_fused_smem_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)fused_smem_bytes<TX, TY>()));
+}
+
 struct Stencil7 : public Operator {
     StencilGeom g;
     double* halo_lo = nullptr;
@@ -157,9 +552,94 @@ struct Stencil7 : public Operator {
     int kc = 16;
     int tile = 0;  // 0: 32x8 threads (64x8 points), 1: 64x4 (128x4), 2: 32x16 (64x16), 3: 64x8 (128x8)
 
+    // fused CG: halo buffers for r and p (two planes each way) and the packed send buffer
+    double* fsend = nullptr;  // [4*plane]: r_first p_first r_last p_last
+    double* frecv = nullptr;  // [4*plane]: r_lo p_lo r_hi p_hi
+    int fkc = 64;
+    int ftile = 4;
+    bool fsmem = true;
+
     ~Stencil7() override {
         cudaFree(halo_lo);
         cudaFree(halo_hi);
+        cudaFree(fsend);
+        cudaFree(frecv);
+    }
+
+    bool fused_cg_capable() const override { return true; }
+
+    template <int TX, int TY>
+    void launch_fused(const FusedArgs& fa, int k_lo, int k_hi, int partial_base, bool is_final, double* dot_out, int* blocks_out) {
+        Context* c = ctx;
+        const int planes = k_hi - k_lo;
+        *blocks_out = 0;
+        if (planes <= 0) return;
+        const int kcc = std::min(fkc, planes);
+        dim3 grid((g.nx + 2 * TX - 1) / (2 * TX), (g.ny + TY - 1) / TY, (planes + kcc - 1) / kcc);
+        dim3 block(TX, TY, 1);
+        const int nblocks = (int)(grid.x * grid.y * grid.z);
+        ATK_REQUIRE(partial_base + nblocks <= kMaxPartials, ATK_ERR_INVALID_ARGUMENT, "stencil grid exceeds the partial-sum scratch");
+        auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+        const bool vec = (g.nx % 2 == 0) && al(fa.r) && al(fa.x) && al(fa.Ap) && al(fa.P0) && al(fa.P1);
+        if (vec && fsmem) {
+            constexpr size_t smem = fused_smem_bytes<TX, TY>();
+            stencil7_cg_fused_smem_kernel<TX, TY><<<grid, block, smem, c->stream>>>(g, fa, k_lo, k_hi, kcc, c->d_partials,
+                                                                                    partial_base, c->d_tickets + 5, dot_out,
+                                                                                    is_final ? 1 : 0);
+        }
+        else if (vec)
+            stencil7_cg_fused_kernel<TX, TY, true><<<grid, block, 0, c->stream>>>(g, fa, k_lo, k_hi, kcc, c->d_partials, partial_base,
+                                                                                  c->d_tickets + 5, dot_out, is_final ? 1 : 0);
+        else
+            stencil7_cg_fused_kernel<TX, TY, false><<<grid, block, 0, c->stream>>>(g, fa, k_lo, k_hi, kcc, c->d_partials, partial_base,
+                                                                                   c->d_tickets + 5, dot_out, is_final ? 1 : 0);
+        ATK_CUDA_CHECK(cudaGetLastError());
+        count_launch(c);
+        *blocks_out = nblocks;
+    }
+    void launch_fused_tile(const FusedArgs& fa, int k_lo, int k_hi, int partial_base, bool is_final, double* dot_out, int* nb) {
+        switch (ftile) {
+            case 0: launch_fused<32, 8>(fa, k_lo, k_hi, partial_base, is_final, dot_out, nb); break;
+            case 1: launch_fused<64, 4>(fa, k_lo, k_hi, partial_base, is_final, dot_out, nb); break;
+            case 2: launch_fused<32, 16>(fa, k_lo, k_hi, partial_base, is_final, dot_out, nb); break;
+            case 4: launch_fused<32, 4>(fa, k_lo, k_hi, partial_base, is_final, dot_out, nb); break;
+            case 5: launch_fused<64, 2>(fa, k_lo, k_hi, partial_base, is_final, dot_out, nb); break;
+            default: launch_fused<64, 8>(fa, k_lo, k_hi, partial_base, is_final, dot_out, nb); break;
+        }
+    }
+
+    void cg_fused_step(CgFusedState* st, const double* r, double* x, double* Ap, double* P0, double* P1, int rr_slot,
+                       int dot_slot, double* rs_trace) override {
+        Context* c = ctx;
+        const size_t plane = (size_t)g.nx * g.ny;
+        FusedArgs fa{r, x, Ap, P0, P1, nullptr, nullptr, nullptr, nullptr, st, c->slot(rr_slot), c->world, rs_trace};
+        double* dot_out = c->slot(dot_slot) + c->rank;
+        int nb = 0;
+        if (c->world == 1) {
+            launch_fused_tile(fa, 0, g.nz_loc, 0, true, dot_out, &nb);
+        } else {
+            fa.r_halo_lo = frecv;
+            fa.p_halo_lo = frecv + plane;
+            fa.r_halo_hi = frecv + 2 * plane;
+            fa.p_halo_hi = frecv + 3 * plane;
+            pack_halo_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(st, r, P0, P1, (int64_t)plane,
+                                                                     (int64_t)(g.nz_loc - 1) * (int64_t)plane, fsend);
+            count_launch(c);
+            ATK_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+            ATK_CUDA_CHECK(cudaStreamWaitEvent(c->comm_stream, c->ev_fork, 0));
+            exchange_halo(c, fsend, fsend + 2 * plane, frecv, frecv + 2 * plane, 2 * plane, c->comm_stream);
+            ATK_CUDA_CHECK(cudaEventRecord(c->ev_join, c->comm_stream));
+            int nb_int = 0, nb_lo = 0, nb_hi = 0;
+            if (g.nz_loc > 2) launch_fused_tile(fa, 1, g.nz_loc - 1, 0, false, dot_out, &nb_int);
+            ATK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+            if (g.nz_loc >= 2) {
+                launch_fused_tile(fa, 0, 1, nb_int, false, dot_out, &nb_lo);
+                launch_fused_tile(fa, g.nz_loc - 1, g.nz_loc, nb_int + nb_lo, true, dot_out, &nb_hi);
+            } else {
+                launch_fused_tile(fa, 0, g.nz_loc, nb_int, true, dot_out, &nb_lo);
+            }
+        }
+        allgather_slot(c, dot_slot, c->stream);
     }
 
     template <int TX, int TY>
@@ -244,14 +724,23 @@ Operator* make_stencil7(Context* ctx, int nx, int ny, int nz, double cx, double 
     S->row_begin = plane * k_begin;
     const int64_t interior = (nx > 2 && ny > 2 && nz > 2) ? (int64_t)(nx - 2) * (ny - 2) * (nz - 2) : 0;
     S->nnz = (plane * nz - interior) + 7 * interior;
+    // opt in to > 48 KB of dynamic shared memory for every tile shape of the cp.async kernel (per device)
+    allow_fused_smem<32, 8>(); allow_fused_smem<64, 4>(); allow_fused_smem<32, 16>(); allow_fused_smem<32, 4>();
+    allow_fused_smem<64, 2>(); allow_fused_smem<64, 8>();
     if (const char* e = std::getenv("ATK_STENCIL_KC")) S->kc = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("ATK_STENCIL_TILE")) S->tile = std::atoi(e);
+    if (const char* e = std::getenv("ATK_FUSED_KC")) S->fkc = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("ATK_FUSED_TILE")) S->ftile = std::atoi(e);
+    if (const char* e = std::getenv("ATK_FUSED_SMEM")) S->fsmem = std::atoi(e) != 0;
     try {
         if (ctx->world > 1) {
             ATK_CUDA_CHECK(cudaMalloc(&S->halo_lo, sizeof(double) * (size_t)plane));
             ATK_CUDA_CHECK(cudaMalloc(&S->halo_hi, sizeof(double) * (size_t)plane));
             ATK_CUDA_CHECK(cudaMemset(S->halo_lo, 0, sizeof(double) * (size_t)plane));
             ATK_CUDA_CHECK(cudaMemset(S->halo_hi, 0, sizeof(double) * (size_t)plane));
+            ATK_CUDA_CHECK(cudaMalloc(&S->fsend, sizeof(double) * 4 * (size_t)plane));
+            ATK_CUDA_CHECK(cudaMalloc(&S->frecv, sizeof(double) * 4 * (size_t)plane));
+            ATK_CUDA_CHECK(cudaMemset(S->frecv, 0, sizeof(double) * 4 * (size_t)plane));
         }
     } catch (...) {
         delete S;

@@ -154,6 +154,9 @@ typedef struct atk_cg_info {
      * r.r) and K3 (p update) over all iterations; used by bench.py for the per-kernel roofline */
     int time_kernels;
     float kernel_ms[3];
+    /* out: 1 when the fused two-kernel formulation ran (matrix-free operator, tree reductions): kernel_ms[0] is then
+     * KA (p update + pending x update + operator apply + p.Ap, 48 B/row), kernel_ms[1] KB (r update + r.r, 24 B/row) */
+    int fused;
 } atk_cg_info;
 
 /* ConjugateGrad::solve (src/LinearAlgebra/Krylov/ConjugateGradient.hpp:36-84).  The solver state x, r, p lives in
