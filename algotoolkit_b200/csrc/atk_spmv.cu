@@ -546,9 +546,11 @@ __global__ void op27_csc_kernel(int nx, int ny, int nz, Coef27 coef, int* __rest
             for (int di = 1; di >= -1; --di) {
                 const int ir = ic - di, jr = jc - dj, kr = kc - dk;
                 if (ir < 0 || ir >= nx || jr < 0 || jr >= ny || kr < 0 || kr >= nz) continue;
+                const double v = coef.v[(dk + 1) * 9 + (dj + 1) * 3 + (di + 1)];
+                if (v == 0.0) continue;  // addValue never stores an explicit zero (SparseObj.hpp:71-73)
                 if (FILL) {
                     row_idx[p] = (int)(ir + (int64_t)jr * nx + (int64_t)kr * sxy);
-                    vals[p] = coef.v[(dk + 1) * 9 + (dj + 1) * 3 + (di + 1)];
+                    vals[p] = v;
                 }
                 ++p;
             }
