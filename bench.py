@@ -267,6 +267,14 @@ def run_ours(args):
         per_kernel.append({"kernel": nm, "ms_per_launch": ms, "algorithmic_bytes": bpr * n_loc, "achieved_gbs": gbs,
                            "frac": gbs / peak, "share_of_step": ms / sum(kms) if sum(kms) > 0 else 0.0})
     dom = max(per_kernel, key=lambda d: d["ms_per_launch"])
+    traffic = None
+    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same grid, N=1)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ent = json.load(f).get(dom["kernel"])
+        if ent and ent["grid"] == g and ent["n_gpus"] == world:
+            traffic = ent["dram_bytes_per_launch"]
+    except Exception:
+        pass
     t_it = dev_ms * 1e-3 / args.steps
     iter_gbs = iter_bytes_per_row * N / t_it / 1e9 / world      # bytes this formulation must move, per GPU
     iter_gbs_88 = 88.0 * N / t_it / 1e9 / world                 # SURVEY 8(d) three-kernel figure, for comparison
@@ -285,7 +293,7 @@ def run_ours(args):
                 "note": "one atk_cg_solve_host call = K steps; pinned b up, x down, per rank"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                     "frac": dom["frac"], "traffic": traffic, "algorithmic_bytes": dom["algorithmic_bytes"], "peak_source": peak_src,
                      "formulation": "fused KA+KB, 72 B/row" if kres["fused"] else "K1+K2+K3, 88 B/row",
                      "iteration_bytes_per_row": iter_bytes_per_row,
                      "iteration_achieved_gbs_per_gpu": iter_gbs, "iteration_frac": iter_gbs / peak,
