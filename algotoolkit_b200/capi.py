@@ -68,7 +68,8 @@ EXPORTS = [
     "atk_context_synchronize", "atk_context_launch_count", "atk_malloc", "atk_free", "atk_memcpy_h2d", "atk_memcpy_d2h",
     "atk_memcpy_d2d", "atk_memset_zero", "atk_host_alloc", "atk_host_free", "atk_dot", "atk_nrm2", "atk_vec_scale",
     "atk_vec_div", "atk_vec_add", "atk_vec_sub", "atk_vec_axpy", "atk_vec_axmy", "atk_operator_from_csc",
-    "atk_operator_stencil7", "atk_operator_poisson_assembled", "atk_operator_stencil27_assembled", "atk_operator_destroy",
+    "atk_operator_stencil7", "atk_operator_poisson_assembled", "atk_operator_stencil27_assembled", "atk_slab_partition",
+    "atk_operator_destroy",
     "atk_operator_shape", "atk_operator_row_range", "atk_operator_export_csr", "atk_operator_apply", "atk_cg_solve",
     "atk_cg_solve_host", "atk_gmres_solve", "atk_gmres_solve_host",
 ]
@@ -118,6 +119,7 @@ def load():
         "atk_operator_poisson_assembled": [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                            C.POINTER(_vp)],
         "atk_operator_stencil27_assembled": [_vp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.POINTER(_vp)],
+        "atk_slab_partition": [C.c_int, C.c_int, C.c_int, _ip, _ip],
         "atk_operator_destroy": [_vp],
         "atk_operator_shape": [_vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)],
         "atk_operator_row_range": [_vp, C.POINTER(i64), C.POINTER(i64)],
@@ -147,6 +149,13 @@ def device_count() -> int:
     n = C.c_int(0)
     _check(load().atk_device_count(C.byref(n)))
     return n.value
+
+
+def slab_partition(nz: int, rank: int, world: int):
+    """Planes [k_begin, k_end) owned by `rank` (host arithmetic of the library, no device needed)."""
+    a, b = C.c_int(), C.c_int()
+    _check(load().atk_slab_partition(nz, rank, world, C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def _np_ptr(a):

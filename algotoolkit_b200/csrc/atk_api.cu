@@ -244,6 +244,13 @@ int atk_operator_stencil27_assembled(atk_context_t ctx, int nx, int ny, int nz, 
         wrap_operator(out, atk::make_stencil27_assembled(C(ctx), nx, ny, nz, coef, format));
     });
 }
+int atk_slab_partition(int nz, int rank, int world, int* k_begin, int* k_end) {
+    return guarded([&] {
+        ATK_REQUIRE(k_begin && k_end && world >= 1 && rank >= 0 && rank < world && nz >= world, ATK_ERR_INVALID_ARGUMENT,
+                    "bad slab partition arguments");
+        atk::slab_partition(nz, rank, world, k_begin, k_end);
+    });
+}
 int atk_operator_destroy(atk_operator_t op) {
     return guarded([&] {
         if (!op) return;

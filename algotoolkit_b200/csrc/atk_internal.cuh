@@ -125,6 +125,13 @@ struct Operator {
     virtual void export_csr(int*, int*, double*) const { throw Error(ATK_ERR_INVALID_ARGUMENT, "operator has no CSR arrays"); }
 };
 
+// balanced split of nz planes over `world` ranks: the first nz % world ranks get one extra plane
+inline void slab_partition(int nz, int rank, int world, int* k_begin, int* k_end) {
+    const int base = nz / world, rem = nz % world;
+    *k_begin = rank * base + (rank < rem ? rank : rem);
+    *k_end = *k_begin + base + (rank < rem ? 1 : 0);
+}
+
 Operator* make_operator_from_csc(Context* ctx, int n_rows, int n_cols, int64_t nnz, const int* col_ptr, const int* row_idx,
                                  const double* vals, bool on_device, atk_format format);
 Operator* make_stencil7(Context* ctx, int nx, int ny, int nz, double cx, double cy, double cz);

@@ -714,9 +714,9 @@ Operator* make_stencil7(Context* ctx, int nx, int ny, int nz, double cx, double 
     auto* S = new Stencil7();
     S->ctx = ctx;
     // balanced z-slab split: the first (nz % world) ranks get one extra plane
-    const int base = nz / ctx->world, rem = nz % ctx->world;
-    const int k_begin = ctx->rank * base + std::min(ctx->rank, rem);
-    const int nz_loc = base + (ctx->rank < rem ? 1 : 0);
+    int k_begin = 0, k_end = 0;
+    slab_partition(nz, ctx->rank, ctx->world, &k_begin, &k_end);
+    const int nz_loc = k_end - k_begin;
     S->g = StencilGeom{nx, ny, nz, k_begin, nz_loc, cx, cy, cz, -2.0 * (cx + cy + cz)};  // cc: Poisson.hpp:57
     const int64_t plane = (int64_t)nx * ny;
     S->n_rows_local = plane * nz_loc;

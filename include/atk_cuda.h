@@ -125,6 +125,9 @@ int atk_operator_poisson_assembled(atk_context_t ctx, int nx, int ny, int nz, do
  * coef[(dk+1)*9+(dj+1)*3+(di+1)] for neighbour (i+di,j+dj,k+dk); generated on the device. */
 int atk_operator_stencil27_assembled(atk_context_t ctx, int nx, int ny, int nz, const double coef[27],
                                      atk_format format, atk_operator_t* out);
+/* The balanced z-slab split used by the distributed stencil operators: planes [k_begin, k_end) of nz for `rank` of
+ * `world` (the first nz % world ranks own one extra plane).  Pure host arithmetic, needs no device. */
+int atk_slab_partition(int nz, int rank, int world, int* k_begin, int* k_end);
 int atk_operator_destroy(atk_operator_t op);
 /* local rows, columns (global), stored entries (without padding) */
 int atk_operator_shape(atk_operator_t op, int64_t* n_rows_local, int64_t* n_cols, int64_t* nnz);

@@ -1,0 +1,95 @@
+"""CPU-side checks of the drop-in boundary: the library loads, exports every symbol include/atk_cuda.h declares,
+fails loudly without a device, and the product never routes through the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "atk_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(atk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from algotoolkit_b200 import build as atk_build
+    from algotoolkit_b200 import capi
+
+    atk_build.build()
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    declared = header_symbols()
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/atk_cuda.h but not exported"
+    assert sorted(capi.EXPORTS) == declared
+    assert lib.atk_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert " T atk_cg_solve" in out and " T atk_gmres_solve" in out
+
+
+def test_no_cpu_fallback_without_device():
+    from algotoolkit_b200 import capi
+
+    if capi.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        capi.Context(0)
+
+
+def test_library_is_sm100a_and_has_cp_async_kernels():
+    from algotoolkit_b200 import capi
+
+    out = subprocess.run(["cuobjdump", "--list-elf", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "LDGSTS" in sass  # cp.async: the shared-memory plane pipeline of the fused CG kernel
+
+
+def test_product_never_touches_the_oracle():
+    """Nothing under algotoolkit_b200/ or include/ may import, link or call anything under oracle/."""
+    bad = []
+    for base in ("algotoolkit_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            if "build" in dirpath.split(os.sep):
+                continue
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                    continue
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                if re.search(r"(from|import)\s+oracle|liboracle|libatk_ref|krylov_oracle|pyoracle|oracle/|orc_[a-z]+\(|ref_[a-z_]+\(", txt):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+    deps = subprocess.run(["ldd", os.path.join(ROOT, "algotoolkit_b200", "libatk_cuda.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in deps and "atk_ref" not in deps
+
+
+def test_fastsolver_module_builds_and_imports():
+    import sys
+
+    from algotoolkit_b200 import build_host
+
+    build_host.build()
+    sys.path.insert(0, os.path.join(ROOT, "algotoolkit_b200"))
+    import fastsolver
+
+    for name in ("Vector", "SparseMatrix", "GMRES", "ConjugateGrad", "Poisson3DSolver", "read_matrix_market", "matvec_mul",
+                 "BoundaryType"):
+        assert hasattr(fastsolver, name)
+    A = fastsolver.SparseMatrix(3, 3)  # host-side container semantics need no GPU
+    A.addValue(0, 2, 3.0)
+    A.addValue(1, 0, 4.0)
+    A.addValue(2, 2, 0.0)  # explicit zero: not stored
+    A.finalize()
+    assert A(0, 2) == 3.0 and A(1, 0) == 4.0 and A(2, 2) == 0.0 and A.nnz() == 2
+    with pytest.raises(IndexError):
+        A(3, 0)
+    v = fastsolver.Vector(4)
+    v[1] = 2.5
+    assert v[1] == 2.5 and v.size() == 4
+    with pytest.raises(IndexError):
+        v[4]
