@@ -50,7 +50,7 @@ def _raise(code, msg):
 class CgInfo(C.Structure):
     _fields_ = [("iterations", C.c_int), ("stopped_on_pAp", C.c_int), ("zero_rhs", C.c_int), ("last_pAp", C.c_double),
                 ("rs", C.c_double), ("device_ms", C.c_float), ("kernel_launches", C.c_int), ("pAp_trace", _dp),
-                ("rs_trace", _dp), ("trace_capacity", C.c_int), ("time_kernels", C.c_int), ("kernel_ms", C.c_float * 3), ("fused", C.c_int)]
+                ("rs_trace", _dp), ("trace_capacity", C.c_int), ("time_kernels", C.c_int), ("kernel_ms", C.c_float * 3), ("fused", C.c_int), ("peer", C.c_int)]
 
 
 class GmresInfo(C.Structure):
@@ -426,4 +426,4 @@ class Context:
 def _cg_result(info, tp, tr):
     return dict(iters=info.iterations, stopped_on_pAp=bool(info.stopped_on_pAp), zero_rhs=bool(info.zero_rhs),
                 last_pAp=info.last_pAp, rs=info.rs, device_ms=info.device_ms, kernel_launches=info.kernel_launches,
-                pAp_trace=tp, rs_trace=tr, kernel_ms=list(info.kernel_ms), fused=bool(info.fused))
+                pAp_trace=tp, rs_trace=tr, kernel_ms=list(info.kernel_ms), fused=bool(info.fused), peer=bool(info.peer))

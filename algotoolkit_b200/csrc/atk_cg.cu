@@ -32,7 +32,8 @@ namespace {
 using CgState = CgFusedState;  // one device-resident scalar block for both formulations (atk_internal.cuh)
 
 // rs_old = r.r and the ||b|| < 1e-12 test (:37-42).  One CTA; the two dots were left in the slots by dot kernels.
-__global__ void cg_begin_kernel(CgState* st, const double* slot_rr, const double* slot_bb, int world) {
+__global__ void cg_begin_kernel(CgState* st, const double* slot_rr, const double* slot_bb, int world,
+                                unsigned long long epoch) {
     if (threadIdx.x != 0) return;
     const double rr = slot_sum(slot_rr, world);
     const double bb = slot_sum(slot_bb, world);
@@ -44,6 +45,7 @@ __global__ void cg_begin_kernel(CgState* st, const double* slot_rr, const double
     st->alpha = 0.0;
     st->ka_count = 0;
     st->first = 1;
+    st->epoch = epoch;
     const int zero = (sqrt(bb) < 1e-12) ? 1 : 0;
     st->zero_rhs = zero;
     st->done = zero;
@@ -183,14 +185,30 @@ __global__ void __launch_bounds__(kReduceBlock) cg_update_p_kernel(int64_t n, Cg
 }
 
 // ---------------------------------------------------------------------------------------------- fused formulation
+// Peer-memory mode of KB / KF (Context::p2p): partial sums and halo planes travel by stores into the other GPUs'
+// memory; sequence flags replace the NCCL all-gather.  `plane` doubles per xy-plane (even).
+struct PeerKb {
+    int on = 0;
+    int rank = 0;
+    const unsigned long long* flags = nullptr;
+    double* const* peer_gather = nullptr;
+    unsigned long long* const* peer_flags = nullptr;
+    double* lo_nb_r_hi = nullptr;
+    double* hi_nb_r_lo = nullptr;
+    int64_t plane = 0;
+};
+
 // KB: alpha = rs_old/pAp ; r = r - Ap*alpha ; partial sums of r.r   (:53-63 without the x update, which KA applies
 // one iteration later).  24 B/row.
 template <bool VEC2>
 __global__ void __launch_bounds__(kReduceBlock) cg_fused_update_r_kernel(int64_t n, CgState* st, const double* __restrict__ slot_pAp,
                                                                          int world, double* __restrict__ r,
                                                                          const double* __restrict__ Ap, double* partials,
-                                                                         unsigned* ticket, double* rr_out, double* pAp_trace) {
+                                                                         unsigned* ticket, double* rr_out, double* pAp_trace,
+                                                                         PeerKb pk) {
     if (st->done) return;
+    // peer mode: wait until every rank's p.Ap partial of this iteration has been stored into our slots
+    if (pk.on) wait_partials(pk.flags, world, kSlotPAp, st->epoch + (unsigned long long)st->ka_count);
     const double pAp = slot_sum(slot_pAp, world);
     if (fabs(pAp) < 1e-12) {  // :53-57
         if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -211,12 +229,17 @@ __global__ void __launch_bounds__(kReduceBlock) cg_fused_update_r_kernel(int64_t
         double2* r2 = reinterpret_cast<double2*>(r);
         const double2* a2 = reinterpret_cast<const double2*>(Ap);
         double acc1 = 0.0;
+        const int64_t plane2 = pk.plane >> 1;
         for (int64_t i = t; i < n2; i += stride) {
             double2 rv = r2[i];
             const double2 av = a2[i];
             rv.x = sub_rn(rv.x, mul_rn(av.x, alpha));
             rv.y = sub_rn(rv.y, mul_rn(av.y, alpha));
             r2[i] = rv;
+            if (pk.on) {  // mirror the first / last plane of the new r into the neighbours' halo planes (NVLink stores)
+                if (i < plane2 && pk.lo_nb_r_hi) reinterpret_cast<double2*>(pk.lo_nb_r_hi)[i] = rv;
+                if (i >= n2 - plane2 && pk.hi_nb_r_lo) reinterpret_cast<double2*>(pk.hi_nb_r_lo)[i - (n2 - plane2)] = rv;
+            }
             acc = add_rn(acc, mul_rn(rv.x, rv.x));
             acc1 = add_rn(acc1, mul_rn(rv.y, rv.y));
         }
@@ -233,10 +256,14 @@ __global__ void __launch_bounds__(kReduceBlock) cg_fused_update_r_kernel(int64_t
             acc = add_rn(acc, mul_rn(rn, rn));
         }
     }
+    if (pk.on) __threadfence_system();  // each thread orders its peer stores before its CTA's ticket
     double total;
     if (grid_sum_last_block<kReduceBlock>(acc, partials, ticket, &total)) {
+        if (pk.on && threadIdx.x < 32)
+            publish_partial_warp(pk.peer_gather, pk.peer_flags, world, pk.rank, kSlotRR, total,
+                                 st->epoch + (unsigned long long)st->ka_count);
         if (threadIdx.x == 0) {
-            *rr_out = total;
+            if (!pk.on) *rr_out = total;
             st->alpha = alpha;
             st->last_pAp = pAp;
             if (pAp_trace && st->it < st->trace_cap) pAp_trace[st->it] = pAp;
@@ -251,8 +278,9 @@ __global__ void __launch_bounds__(kReduceBlock) cg_fused_update_r_kernel(int64_t
 __global__ void __launch_bounds__(kReduceBlock) cg_fused_flush_kernel(int64_t n, CgState* st, const double* __restrict__ slot_rr,
                                                                       int world, const double* __restrict__ r, double* x,
                                                                       const double* P0, const double* P1, double* p_user,
-                                                                      unsigned* ticket, double* rs_trace) {
+                                                                      unsigned* ticket, double* rs_trace, PeerKb pk) {
     if (st->first) return;  // no KA ran: nothing pending, p_user untouched
+    if (pk.on && !st->done) wait_partials(pk.flags, world, kSlotRR, st->epoch + (unsigned long long)st->ka_count);
     const double* pc = (st->ka_count & 1) ? P1 : P0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,6 +324,26 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
     const char* env_fused = std::getenv("ATK_CG_FUSED");
     const bool fused = op->fused_cg_capable() && ctx->reduction == ATK_REDUCE_TREE && !(env_fused && env_fused[0] == '0');
     info->fused = fused ? 1 : 0;
+    // peer-memory mode: every rank must agree (it changes who waits for whom)
+    bool peer = false;
+    if (fused && ctx->world > 1) {
+        int mine = op->peer_capable() && (n % 2 == 0) && aligned16(x) && aligned16(r) && aligned16(p) ? 1 : 0;
+        std::vector<int> all((size_t)ctx->world);
+        allgather_host_bytes(ctx, &mine, all.data(), sizeof(int));
+        peer = true;
+        for (int v : all) peer = peer && v;
+    }
+    op->set_peer_mode(peer);
+    info->peer = peer ? 1 : 0;
+    PeerKb pk;
+    if (peer) {
+        pk.on = 1;
+        pk.rank = ctx->rank;
+        pk.flags = ctx->d_flags;
+        pk.peer_gather = ctx->d_peer_gather;
+        pk.peer_flags = ctx->d_peer_flags;
+        op->peer_r_targets(&pk.lo_nb_r_hi, &pk.hi_nb_r_lo, &pk.plane);
+    }
     int* h_done = nullptr;  // pinned: done flag of every poll
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
@@ -342,13 +390,13 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
             if (vec)
                 cg_fused_update_r_kernel<true><<<grid, kReduceBlock, 0, st>>>(n, d_state, ctx->slot(kSlotPAp), ctx->world, r, Ap,
                                                                               ctx->d_partials, ctx->d_tickets + 3,
-                                                                              ctx->slot(kSlotRR) + ctx->rank, d_ptrace);
+                                                                              ctx->slot(kSlotRR) + ctx->rank, d_ptrace, pk);
             else
                 cg_fused_update_r_kernel<false><<<grid, kReduceBlock, 0, st>>>(n, d_state, ctx->slot(kSlotPAp), ctx->world, r, Ap,
                                                                                ctx->d_partials, ctx->d_tickets + 3,
-                                                                               ctx->slot(kSlotRR) + ctx->rank, d_ptrace);
+                                                                               ctx->slot(kSlotRR) + ctx->rank, d_ptrace, pk);
             count_launch(ctx);
-            allgather_slot(ctx, kSlotRR, st);
+            if (!peer) allgather_slot(ctx, kSlotRR, st);
             mark();
             mark();
         };
@@ -410,8 +458,9 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
         // rs_old = r.r ; ||b||   (:37-38)
         launch_dot(ctx, n, r, r, kSlotRR);
         launch_dot(ctx, n, b, b, kSlotBnorm);
-        cg_begin_kernel<<<1, 32, 0, st>>>(d_state, ctx->slot(kSlotRR), ctx->slot(kSlotBnorm), ctx->world);
+        cg_begin_kernel<<<1, 32, 0, st>>>(d_state, ctx->slot(kSlotRR), ctx->slot(kSlotBnorm), ctx->world, ctx->epoch);
         count_launch(ctx);
+        if (peer) op->initial_halo_exchange(r, p);  // boundary planes of the incoming r and p, once, through NCCL
 
         // ---- run: iterations are enqueued in batches; the exit flag is read back after every batch and examined
         // two batches later (a blocking wait on that batch's event, so every rank of a distributed run takes the
@@ -442,9 +491,10 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
         }
         if (fused) {  // KF: pending x / p updates of the last iteration, or p copied back after an exit
             cg_fused_flush_kernel<<<ctx->reduce_grid(), kReduceBlock, 0, st>>>(n, d_state, ctx->slot(kSlotRR), ctx->world, r, x, p,
-                                                                               p_alt, p, ctx->d_tickets + 4, d_rtrace);
+                                                                               p_alt, p, ctx->d_tickets + 4, d_rtrace, pk);
             count_launch(ctx);
         }
+        if (peer) ctx->epoch += (unsigned long long)std::max(max_iter, 0) + 4ull;  // same advance on every rank
         ATK_CUDA_CHECK(cudaEventRecord(ctx->ev_t1, st));
 
         CgState hs{};
@@ -467,6 +517,7 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
             }
         for (auto e : kev) cudaEventDestroy(e);
         kev.clear();
+        op->set_peer_mode(false);
         info->iterations = hs.it;
         info->stopped_on_pAp = hs.stopped_on_pAp;
         info->zero_rhs = hs.zero_rhs;
@@ -475,6 +526,7 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
         info->device_ms = ms;
         info->kernel_launches = (int)(ctx->launches - launches0);
     } catch (...) {
+        op->set_peer_mode(false);
         cleanup();
         throw;
     }

@@ -6,6 +6,10 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -87,6 +91,85 @@ void exchange_halo(Context* ctx, const double* first_plane, const double* last_p
     nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd");
 }
 
+void allgather_host_bytes(Context* ctx, const void* send, void* recv, size_t bytes) {
+    if (ctx->world == 1) {
+        std::memcpy(recv, send, bytes);
+        return;
+    }
+    char* d = nullptr;
+    ATK_CUDA_CHECK(cudaMalloc(&d, bytes * (size_t)ctx->world));
+    try {
+        ATK_CUDA_CHECK(cudaMemcpyAsync(d + bytes * (size_t)ctx->rank, send, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        nccl_check(g_nccl.AllGather(d + bytes * (size_t)ctx->rank, d, bytes, ncclChar, (ncclComm_t)ctx->nccl_comm, ctx->stream),
+                   "ncclAllGather(setup)");
+        ATK_CUDA_CHECK(cudaMemcpyAsync(recv, d, bytes * (size_t)ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
+        ATK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+        cudaFree(d);
+        throw;
+    }
+    cudaFree(d);
+}
+
+void ipc_share(Context* ctx, void* local, std::vector<void*>& peers, const std::vector<int>& want) {
+    peers.assign((size_t)ctx->world, nullptr);
+    peers[(size_t)ctx->rank] = local;
+    if (ctx->world == 1) return;
+    cudaIpcMemHandle_t mine;
+    ATK_CUDA_CHECK(cudaIpcGetMemHandle(&mine, local));
+    std::vector<cudaIpcMemHandle_t> all((size_t)ctx->world);
+    allgather_host_bytes(ctx, &mine, all.data(), sizeof(mine));
+    for (int q = 0; q < ctx->world; ++q) {
+        if (q == ctx->rank) continue;
+        if (!want.empty() && std::find(want.begin(), want.end(), q) == want.end()) continue;
+        void* p = nullptr;
+        ATK_CUDA_CHECK(cudaIpcOpenMemHandle(&p, all[(size_t)q], cudaIpcMemLazyEnablePeerAccess));
+        peers[(size_t)q] = p;
+        ctx->ipc_opened.push_back(p);
+    }
+}
+
+// Decide collectively whether peer-memory signalling can be used and set it up.
+static void setup_p2p(Context& c) {
+    c.p2p = false;
+    if (c.world == 1) return;
+    const char* env = std::getenv("ATK_COMM");
+    int ok = !(env && std::string(env) == "nccl");
+    // ranks are assumed to be one per device of this node, device index = local rank; check the mapping is possible
+    int ndev = 0;
+    cudaGetDeviceCount(&ndev);
+    // all ranks exchange (device, hostname hash) and everyone checks peer access to every other device
+    struct Info { int device; unsigned long long host; } mine{c.device, 0ull};
+    char hn[256] = {0};
+    gethostname(hn, sizeof(hn) - 1);
+    for (const char* q = hn; *q; ++q) mine.host = mine.host * 1315423911ull + (unsigned char)*q;
+    std::vector<Info> all((size_t)c.world);
+    allgather_host_bytes(&c, &mine, all.data(), sizeof(Info));
+    for (int q = 0; q < c.world && ok; ++q) {
+        if (q == c.rank) continue;
+        if (all[(size_t)q].host != mine.host || all[(size_t)q].device == c.device || all[(size_t)q].device >= ndev) { ok = 0; break; }
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, c.device, all[(size_t)q].device) != cudaSuccess || !can) ok = 0;
+    }
+    std::vector<int> oks((size_t)c.world);
+    allgather_host_bytes(&c, &ok, oks.data(), sizeof(int));
+    for (int v : oks) ok = ok && v;
+    if (!ok) return;
+    std::vector<void*> peers;
+    ipc_share(&c, c.d_gather, peers, {});  // d_gather and d_flags are one allocation (init_context)
+    std::vector<double*> pg((size_t)c.world);
+    std::vector<unsigned long long*> pf((size_t)c.world);
+    for (int q = 0; q < c.world; ++q) {
+        pg[(size_t)q] = static_cast<double*>(peers[(size_t)q]);
+        pf[(size_t)q] = reinterpret_cast<unsigned long long*>(pg[(size_t)q] + (size_t)kNumSlots * kMaxRanks);
+    }
+    ATK_CUDA_CHECK(cudaMalloc(&c.d_peer_gather, sizeof(double*) * (size_t)c.world));
+    ATK_CUDA_CHECK(cudaMalloc(&c.d_peer_flags, sizeof(unsigned long long*) * (size_t)c.world));
+    ATK_CUDA_CHECK(cudaMemcpy(c.d_peer_gather, pg.data(), sizeof(double*) * (size_t)c.world, cudaMemcpyHostToDevice));
+    ATK_CUDA_CHECK(cudaMemcpy(c.d_peer_flags, pf.data(), sizeof(unsigned long long*) * (size_t)c.world, cudaMemcpyHostToDevice));
+    c.p2p = true;
+}
+
 double read_slot(Context* ctx, int slot) {
     ATK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_pinned, ctx->slot(slot), sizeof(double) * ctx->world, cudaMemcpyDeviceToHost,
                                    ctx->stream));
@@ -118,9 +201,11 @@ static void init_context(Context& c, int device) {
     ATK_CUDA_CHECK(cudaEventCreate(&c.ev_t1));
     ATK_CUDA_CHECK(cudaMalloc(&c.d_partials, sizeof(double) * kMaxPartials));
     ATK_CUDA_CHECK(cudaMalloc(&c.d_tickets, sizeof(unsigned) * kNumTickets));
-    ATK_CUDA_CHECK(cudaMalloc(&c.d_gather, sizeof(double) * kNumSlots * kMaxRanks));
+    // reduction slots followed by their sequence flags: one allocation, so that one IPC handle shares both
+    ATK_CUDA_CHECK(cudaMalloc(&c.d_gather, (sizeof(double) + sizeof(unsigned long long)) * kNumSlots * kMaxRanks));
+    c.d_flags = reinterpret_cast<unsigned long long*>(c.d_gather + (size_t)kNumSlots * kMaxRanks);
     ATK_CUDA_CHECK(cudaMemset(c.d_tickets, 0, sizeof(unsigned) * kNumTickets));
-    ATK_CUDA_CHECK(cudaMemset(c.d_gather, 0, sizeof(double) * kNumSlots * kMaxRanks));
+    ATK_CUDA_CHECK(cudaMemset(c.d_gather, 0, (sizeof(double) + sizeof(unsigned long long)) * kNumSlots * kMaxRanks));
     ATK_CUDA_CHECK(cudaMallocHost(&c.h_pinned, sizeof(double) * 64));
     ATK_CUDA_CHECK(cudaDeviceSynchronize());
 }
@@ -152,6 +237,7 @@ atk_context_s* context_create_distributed(int device, int rank, int world, const
             ncclComm_t comm;
             nccl_check(g_nccl.CommInitRank(&comm, world, id, rank), "ncclCommInitRank");
             h->c.nccl_comm = comm;
+            setup_p2p(h->c);
         }
     } catch (...) {
         delete h;
@@ -174,6 +260,9 @@ void context_destroy(atk_context_s* h) {
     Context& c = h->c;
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
+    for (void* p : c.ipc_opened) cudaIpcCloseMemHandle(p);
+    cudaFree(c.d_peer_gather);
+    cudaFree(c.d_peer_flags);
     if (c.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c.nccl_comm);
     cudaFree(c.d_partials);
     cudaFree(c.d_tickets);

@@ -70,6 +70,17 @@ struct Context {
     int64_t launches = 0;
     void* nccl_comm = nullptr;
 
+    // ---- peer-memory signalling (distributed contexts whose GPUs can all map each other; NVLink / NVSwitch) ----
+    // d_gather and d_flags form one allocation that every peer maps through CUDA IPC.  A rank publishes a partial sum
+    // by storing it into EVERY rank's d_gather[slot][my_rank] and then releasing a sequence number into the matching
+    // d_flags entry; consumers spin on their LOCAL flags.  No NCCL call is needed inside an iteration.
+    bool p2p = false;
+    unsigned long long* d_flags = nullptr;       // [kNumSlots * kMaxRanks], local
+    double** d_peer_gather = nullptr;            // device array [world]: every rank's d_gather as mapped here
+    unsigned long long** d_peer_flags = nullptr; // device array [world]
+    std::vector<void*> ipc_opened;               // mappings to close at destruction
+    unsigned long long epoch = 1;                // sequence-number base, advanced identically on all ranks
+
     double* slot(int s) const { return d_gather + (size_t)s * kMaxRanks; }
     int reduce_grid() const { return sm_count * 4; }
 };
@@ -84,6 +95,11 @@ void exchange_halo(Context* ctx, const double* first_plane, const double* last_p
                    size_t plane_elems, cudaStream_t stream);
 // Host value of a reduction slot (sum over ranks in rank order); synchronises the compute stream.
 double read_slot(Context* ctx, int slot);
+// Collective: every rank passes a device allocation of its own (same size everywhere); on return peers[q] is rank q's
+// allocation mapped into this process (peers[rank] = local).  Only ranks listed in `want` are mapped (empty = all).
+void ipc_share(Context* ctx, void* local, std::vector<void*>& peers, const std::vector<int>& want);
+// Collective all-gather of `bytes` host bytes per rank (setup-time helper, goes through NCCL).
+void allgather_host_bytes(Context* ctx, const void* send, void* recv, size_t bytes);
 
 // ------------------------------------------------------------------------------------------ fused CG state
 // Device-resident scalars of the fused two-kernel CG iteration (atk_cg.cu drives it, the operator supplies KA).
@@ -99,6 +115,7 @@ struct CgFusedState {
     int zero_rhs;
     int first;        // 1 until the first KA of this solve has run: p is taken as is, no pending x update
     int trace_cap;
+    unsigned long long epoch;  // peer-signalling sequence base of this solve: flags carry epoch + ka_count
 };
 
 // ------------------------------------------------------------------------------------------ operators
@@ -121,6 +138,11 @@ struct Operator {
                                double* /*P1*/, int /*rr_slot*/, int /*dot_slot*/, double* /*rs_trace*/) {
         throw Error(ATK_ERR_INVALID_ARGUMENT, "operator has no fused CG step");
     }
+    // peer-memory mode of the fused step (distributed stencil operators on NVLink-connected GPUs)
+    virtual bool peer_capable() const { return false; }
+    virtual void set_peer_mode(bool) {}
+    virtual void peer_r_targets(double** lo, double** hi, int64_t* plane_elems) const { *lo = *hi = nullptr; *plane_elems = 0; }
+    virtual void initial_halo_exchange(const double* /*r*/, const double* /*p*/) {}
     virtual bool has_csr() const { return false; }
     virtual void export_csr(int*, int*, double*) const { throw Error(ATK_ERR_INVALID_ARGUMENT, "operator has no CSR arrays"); }
 };
@@ -237,6 +259,49 @@ __device__ __forceinline__ bool last_block_done(unsigned* ticket) {
     }
     __syncthreads();
     return is_last_e;
+}
+
+// ---- peer signalling primitives ----
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// Producer side, called by the first WARP of the CTA that finished last, after every CTA of the kernel has fenced its
+// stores at system scope: lane q stores `value` as this rank's partial of `slot` into rank q's slots, fences, then
+// releases sequence number `seq` into rank q's flag - all peers are served in parallel.
+__device__ __forceinline__ void publish_partial_warp(double* const* peer_gather, unsigned long long* const* peer_flags, int world,
+                                                     int rank, int slot, double value, unsigned long long seq) {
+    const int lane = threadIdx.x & 31;
+    const int off = slot * kMaxRanks + rank;
+    if (lane < world) {
+        peer_gather[lane][off] = value;
+        __threadfence_system();
+        st_release_sys(peer_flags[lane] + off, seq);
+    }
+}
+// Consumer side: returns once every rank's flag of `slot` has reached `seq`.  Lane q of the first warp polls rank q's
+// flag with relaxed loads (all flags in parallel); one system-scope fence afterwards gives the acquire ordering; the CTA
+// then synchronises.  Flags live in LOCAL memory (peers store into it), so polling costs only L2 hits.
+__device__ __forceinline__ void wait_partials(const unsigned long long* flags, int world, int slot, unsigned long long seq) {
+    if (linear_thread_id() < 32) {
+        const int lane = linear_thread_id();
+        if (lane < world) {
+            const unsigned long long* f = flags + slot * kMaxRanks + lane;
+            while (ld_relaxed_sys(f) < seq) __nanosleep(32);
+        }
+        __syncwarp();
+        __threadfence_system();
+    }
+    __syncthreads();
 }
 
 // Sum of a reduction slot over ranks, in rank order (what every consumer kernel does in its prologue).

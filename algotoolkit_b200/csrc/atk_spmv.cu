@@ -228,17 +228,27 @@ __global__ void __launch_bounds__(kReduceBlock) sell_spmv_kernel(int n_rows, int
     const int warp0 = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
     double dacc = 0.0;
+    constexpr int U = 8;  // entries of a row handled per batch: all 2U matrix loads are issued together, then all U gathers
     for (int s = warp0; s < n_slices; s += nwarps) {
         const int w0 = wscan[s], w = wscan[s + 1] - w0;
         const int64_t off = (int64_t)w0 * kSliceRows + lane;
         double acc = 0.0;
-#pragma unroll 4
-        for (int k = 0; k < w; ++k) {
-            const int c = __ldg(sell_col + off + (int64_t)k * kSliceRows);
-            const double v = __ldg(sell_val + off + (int64_t)k * kSliceRows);
-            if (c >= 0) {
-                const double xv = x[c];
-                if (xv != 0.0) acc = add_rn(acc, mul_rn(v, xv));
+        for (int kb = 0; kb < w; kb += U) {
+            int c[U];
+            double v[U], xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool in = kb + u < w;
+                c[u] = in ? __ldg(sell_col + off + (int64_t)(kb + u) * kSliceRows) : -1;
+                v[u] = in ? __ldg(sell_val + off + (int64_t)(kb + u) * kSliceRows) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = x[c[u] < 0 ? 0 : c[u]];  // unconditional (padding reads x[0], then ignored)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                // ascending column order; padding and exact-zero x entries contribute nothing (SparseObj.hpp:141)
+                const double t = add_rn(acc, mul_rn(v[u], xv[u]));
+                acc = (c[u] >= 0 && xv[u] != 0.0) ? t : acc;
             }
         }
         const int t = s * kSliceRows + lane;
@@ -256,7 +266,9 @@ __global__ void __launch_bounds__(kReduceBlock) sell_spmv_kernel(int n_rows, int
     }
 }
 
-// CSR-vector: LANES lanes cooperate on a row; fixed shuffle tree.
+// CSR-vector: LANES lanes cooperate on a row and a group of lanes works on R rows at a time, so that 2R matrix loads
+// and R gathers are in flight per lane before anything is consumed; fixed shuffle tree per row (deterministic, but not
+// the reference's summation order).
 template <int LANES, bool DOT>
 __global__ void __launch_bounds__(kReduceBlock) csr_vector_spmv_kernel(int n_rows, const int* __restrict__ row_ptr,
                                                                        const int* __restrict__ csr_col,
@@ -265,27 +277,57 @@ __global__ void __launch_bounds__(kReduceBlock) csr_vector_spmv_kernel(int n_row
                                                                        double* partials, unsigned* ticket, double* dot_out,
                                                                        const int* skip_flag) {
     if (skip_flag && *skip_flag) return;
+    constexpr int R = 4;
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int sub = (int)(gt % LANES);
     const int64_t group0 = gt / LANES, ngroups = ((int64_t)gridDim.x * blockDim.x) / LANES;
-    // whole warps must iterate together for the shuffles: round the trip count up per warp
-    const int64_t rows_per_pass = ngroups;
+    const int64_t rows_per_pass = ngroups * R;
+    const int64_t n_pass = ((int64_t)n_rows + rows_per_pass - 1) / rows_per_pass;  // same trip count for every lane
     double dacc = 0.0;
-    for (int64_t base = 0; base < n_rows; base += rows_per_pass) {
-        const int64_t row = base + group0;
-        double acc = 0.0;
-        if (row < n_rows) {
-            const int e = row_ptr[row + 1];
-            for (int k = row_ptr[row] + sub; k < e; k += LANES) {
-                const double xv = x[__ldg(csr_col + k)];
-                if (xv != 0.0) acc = add_rn(acc, mul_rn(__ldg(csr_val + k), xv));
+    for (int64_t pass = 0; pass < n_pass; ++pass) {
+        const int64_t r0 = pass * rows_per_pass + group0 * R;
+        double acc[R];
+        int kb[R], ke[R];
+        int maxlen = 0;
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const bool valid = r0 + q < n_rows;
+            kb[q] = valid ? row_ptr[r0 + q] : 0;
+            ke[q] = valid ? row_ptr[r0 + q + 1] : 0;
+            acc[q] = 0.0;
+            maxlen = max(maxlen, ke[q] - kb[q]);
+        }
+        for (int o = sub; o < maxlen; o += LANES) {
+            int c[R];
+            double v[R], xv[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const bool in = kb[q] + o < ke[q];
+                c[q] = in ? __ldg(csr_col + kb[q] + o) : -1;
+                v[q] = in ? __ldg(csr_val + kb[q] + o) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) xv[q] = x[c[q] < 0 ? 0 : c[q]];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const double t = add_rn(acc[q], mul_rn(v[q], xv[q]));
+                acc[q] = (c[q] >= 0 && xv[q] != 0.0) ? t : acc[q];
             }
         }
+        __syncwarp();
 #pragma unroll
-        for (int o = LANES / 2; o > 0; o >>= 1) acc = add_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-        if (row < n_rows && sub == 0) {
-            y[row] = acc;
-            if constexpr (DOT) dacc = add_rn(dacc, mul_rn(x[row], acc));
+        for (int q = 0; q < R; ++q) {
+#pragma unroll
+            for (int o = LANES / 2; o > 0; o >>= 1) acc[q] = add_rn(acc[q], __shfl_xor_sync(0xffffffffu, acc[q], o));
+        }
+        if (sub == 0) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                if (r0 + q < n_rows) {
+                    y[r0 + q] = acc[q];
+                    if constexpr (DOT) dacc = add_rn(dacc, mul_rn(x[r0 + q], acc[q]));
+                }
+            }
         }
     }
     if constexpr (DOT) {

@@ -174,6 +174,16 @@ struct FusedArgs {
     const double* slot_rr;
     int world;
     double* rs_trace;
+    // peer-memory mode (Context::p2p): no NCCL inside the iteration
+    int p2p;
+    int rank;
+    const unsigned long long* flags;             // local sequence flags
+    double* const* peer_gather;                  // every rank's reduction slots, mapped here
+    unsigned long long* const* peer_flags;
+    const double* my_p_lo[2];                    // local p halo planes, indexed by ping-pong parity
+    const double* my_p_hi[2];
+    double* nb_lo_p_hi[2];                       // lower neighbour's p_hi halo planes (null on rank 0)
+    double* nb_hi_p_lo[2];                       // upper neighbour's p_lo halo planes (null on the last rank)
 };
 
 template <int TX, int TY, bool VEC2>
@@ -358,6 +368,18 @@ __global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_smem_kernel(StencilG
     double* __restrict__ pd = (cnt & 1) ? a.P0 : a.P1;
     const double* __restrict__ r = a.r;
     double rs_new = 0.0, beta = 0.0, alpha = 0.0;
+    const double* p_halo_lo = a.p_halo_lo;
+    const double* p_halo_hi = a.p_halo_hi;
+    double* nb_lo = nullptr;  // where this step's boundary planes of p_new go on the neighbours
+    double* nb_hi = nullptr;
+    if (a.p2p) {
+        p_halo_lo = a.my_p_lo[cnt & 1];
+        p_halo_hi = a.my_p_hi[cnt & 1];
+        nb_lo = a.nb_lo_p_hi[(cnt + 1) & 1];
+        nb_hi = a.nb_hi_p_lo[(cnt + 1) & 1];
+        // every rank's r.r partial of the previous KB must have landed (this is also what orders the halo planes)
+        if (!first) wait_partials(a.flags, a.world, kSlotRR, st->epoch + (unsigned long long)cnt);
+    }
     if (!first) {
         rs_new = slot_sum(a.slot_rr, a.world);
         beta = __ddiv_rn(rs_new, st->rs_old);
@@ -391,7 +413,7 @@ __global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_smem_kernel(StencilG
         if (kg >= 0 && kg < g.nz && active) {
             const int s = ((k % DEPTH) + DEPTH) % DEPTH;
             const double* rp = plane_ptr(r, a.r_halo_lo, a.r_halo_hi, k) + row;
-            const double* pp = plane_ptr(ps, a.p_halo_lo, a.p_halo_hi, k) + row;
+            const double* pp = plane_ptr(ps, p_halo_lo, p_halo_hi, k) + row;
             cp_async16(&rt[s][ty + 1][2 * tx + 2], rp);
             cp_async16(&pt[s][ty + 1][2 * tx + 2], pp);
             if (do_jlo) {
@@ -478,6 +500,10 @@ __global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_smem_kernel(StencilG
                 }
                 *reinterpret_cast<double2*>(a.Ap + idx) = out;
                 *reinterpret_cast<double2*>(pd + idx) = pnB;
+                if (a.p2p) {  // boundary planes of p_new go straight into the neighbours' halo buffers over NVLink
+                    if (k == 0 && nb_lo) *reinterpret_cast<double2*>(nb_lo + row) = pnB;
+                    if (k == g.nz_loc - 1 && nb_hi) *reinterpret_cast<double2*>(nb_hi + row) = pnB;
+                }
                 dacc = add_rn(dacc, mul_rn(pnB.x, out.x));
                 dacc = add_rn(dacc, mul_rn(pnB.y, out.y));
                 if (!first) {
@@ -496,6 +522,10 @@ __global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_smem_kernel(StencilG
     const double bs = block_sum<TX * TY>(dacc);
     __shared__ bool is_last;
     const unsigned nb = total_blocks();
+    if (a.p2p) {
+        __threadfence_system();  // every thread orders its own peer stores at system scope ...
+        __syncthreads();         // ... before thread 0 takes the ticket below
+    }
     if (linear_thread_id() == 0) {
         partials[partial_base + linear_block_id()] = bs;
         is_last = false;
@@ -509,8 +539,11 @@ __global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_smem_kernel(StencilG
     if (is_last) {
         __threadfence();
         const double total = partials_sum<TX * TY>(partials, partial_base + nb);
+        if (a.p2p && linear_thread_id() < 32)
+            publish_partial_warp(a.peer_gather, a.peer_flags, a.world, a.rank, kSlotPAp, total,
+                                 st->epoch + (unsigned long long)cnt + 1ull);
         if (linear_thread_id() == 0) {
-            *dot_out = total;
+            if (!a.p2p) *dot_out = total;
             if (!first) {  // the p update of the previous iteration is now complete (:79-80)
                 if (a.rs_trace && st->it < st->trace_cap) a.rs_trace[st->it] = rs_new;
                 st->rs_old = rs_new;
@@ -518,6 +551,119 @@ __global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_smem_kernel(StencilG
             }
             st->first = 0;
             st->ka_count = cnt + 1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- plain apply, cp.async
+// y = A x (+ partial sums of x.y) with the same data path as KA: x planes stream through a 4-deep ring of
+// shared-memory tiles filled by cp.async three planes ahead; k-1 / k / k+1 centre values live in registers.
+// Used when nx is even and x, y are 16-byte aligned; the register-marching kernel above is the general fallback.
+template <int TX, int TY, bool DOT>
+__global__ void __launch_bounds__(TX* TY) stencil7_smem_kernel(StencilGeom g, const double* __restrict__ x, double* __restrict__ y,
+                                                                const double* __restrict__ halo_lo,
+                                                                const double* __restrict__ halo_hi, int k_lo, int k_hi, int kc,
+                                                                double* partials, int partial_base, unsigned* ticket,
+                                                                double* dot_out, int dot_final, const int* skip_flag) {
+    constexpr int DEPTH = 4;
+    constexpr int W = 2 * TX + 4;
+    extern __shared__ __align__(16) double smem_dyn[];
+    double(*xt)[TY + 2][W] = reinterpret_cast<double(*)[TY + 2][W]>(smem_dyn);
+    if (skip_flag && *skip_flag) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i_lo = blockIdx.x * 2 * TX;
+    const int j_lo = blockIdx.y * TY;
+    const int i0 = i_lo + 2 * tx;
+    const int j = j_lo + ty;
+    const int kb = k_lo + blockIdx.z * kc;
+    const int ke = min(kb + kc, k_hi);
+    const bool active = (i0 < g.nx) && (j < g.ny);
+    const int64_t sxy = (int64_t)g.nx * g.ny;
+    const int64_t row = (int64_t)j * g.nx + i0;
+    const bool do_jlo = active && ty == 0 && j_lo > 0;
+    const bool do_jhi = active && ty == TY - 1 && (j + 1 < g.ny);
+    const bool do_ilo = active && tx == 0 && i_lo > 0;
+    const bool do_ihi = active && tx == TX - 1 && (i_lo + 2 * TX < g.nx);
+    double dacc = 0.0;
+    auto stage_of = [&](int k) -> int { return ((k % DEPTH) + DEPTH) % DEPTH; };
+    auto issue_plane = [&](int k) {
+        const int kg = g.k_off + k;
+        if (kg >= 0 && kg < g.nz && active) {
+            const int s = stage_of(k);
+            const double* xp = (k < 0 ? halo_lo : (k >= g.nz_loc ? halo_hi : x + (int64_t)k * sxy)) + row;
+            cp_async16(&xt[s][ty + 1][2 * tx + 2], xp);
+            if (do_jlo) cp_async16(&xt[s][0][2 * tx + 2], xp - g.nx);
+            if (do_jhi) cp_async16(&xt[s][TY + 1][2 * tx + 2], xp + g.nx);
+            if (do_ilo) cp_async8(&xt[s][ty + 1][1], xp - 1);
+            if (do_ihi) cp_async8(&xt[s][ty + 1][2 * TX + 2], xp + 2);
+        }
+        cp_async_commit();
+    };
+    auto centre = [&](int s) -> double2 { return *reinterpret_cast<const double2*>(&xt[s][ty + 1][2 * tx + 2]); };
+    if (kb < ke) {
+        const bool j_shell = (j == 0 || j == g.ny - 1);
+        const bool a_shell_i = (i0 == 0 || i0 == g.nx - 1);
+        const bool b_shell_i = (i0 + 1 == g.nx - 1);
+        const double2 zero2 = make_double2(0.0, 0.0);
+        issue_plane(kb - 1);
+        issue_plane(kb);
+        issue_plane(kb + 1);
+        issue_plane(kb + 2);
+        cp_async_wait<2>();
+        __syncthreads();
+        double2 vA = zero2, vB = zero2, vC = zero2;
+        if (active) {
+            if (g.k_off + kb - 1 >= 0) vA = centre(stage_of(kb - 1));
+            vB = centre(stage_of(kb));
+        }
+        for (int k = kb; k < ke; ++k) {
+            const int kg = g.k_off + k;
+            const int64_t idx = (int64_t)k * sxy + row;
+            cp_async_wait<1>();
+            __syncthreads();
+            issue_plane(k + 3);
+            if (active) {
+                const int s = stage_of(k);
+                if (kg + 1 < g.nz) vC = centre(stage_of(k + 1));
+                double2 out;
+                if (j_shell || kg == 0 || kg == g.nz - 1) {
+                    out.x = shell_row(vB.x);
+                    out.y = shell_row(vB.y);
+                } else {
+                    const double2 jm = *reinterpret_cast<const double2*>(&xt[s][ty][2 * tx + 2]);
+                    const double2 jp = *reinterpret_cast<const double2*>(&xt[s][ty + 2][2 * tx + 2]);
+                    out.x = a_shell_i ? shell_row(vB.x) : tap7(g, vA.x, jm.x, xt[s][ty + 1][2 * tx + 1], vB.x, vB.y, jp.x, vC.x);
+                    out.y = b_shell_i ? shell_row(vB.y) : tap7(g, vA.y, jm.y, vB.x, vB.y, xt[s][ty + 1][2 * tx + 4], jp.y, vC.y);
+                }
+                *reinterpret_cast<double2*>(y + idx) = out;
+                if constexpr (DOT) {
+                    dacc = add_rn(dacc, mul_rn(vB.x, out.x));
+                    dacc = add_rn(dacc, mul_rn(vB.y, out.y));
+                }
+                vA = vB;
+                vB = vC;
+            }
+        }
+        cp_async_wait<0>();
+    }
+    if constexpr (DOT) {
+        const double bs = block_sum<TX * TY>(dacc);
+        __shared__ bool is_last;
+        const unsigned nb = total_blocks();
+        if (linear_thread_id() == 0) {
+            partials[partial_base + linear_block_id()] = bs;
+            is_last = false;
+            if (dot_final) {
+                __threadfence();
+                const unsigned t = atomicInc(ticket, nb - 1);
+                is_last = (t == nb - 1);
+            }
+        }
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            const double total = partials_sum<TX * TY>(partials, partial_base + nb);
+            if (linear_thread_id() == 0) *dot_out = total;
         }
     }
 }
@@ -549,12 +695,14 @@ struct Stencil7 : public Operator {
     StencilGeom g;
     double* halo_lo = nullptr;
     double* halo_hi = nullptr;
-    int kc = 16;
-    int tile = 0;  // 0: 32x8 threads (64x8 points), 1: 64x4 (128x4), 2: 32x16 (64x16), 3: 64x8 (128x8)
+    int kc = 64;
+    int tile = 4;  // 0: 32x8 threads (64x8 points), 1: 64x4 (128x4), 2: 32x16 (64x16), 3: 64x8 (128x8)
 
     // fused CG: halo buffers for r and p (two planes each way) and the packed send buffer
     double* fsend = nullptr;  // [4*plane]: r_first p_first r_last p_last
-    double* frecv = nullptr;  // [4*plane]: r_lo p_lo r_hi p_hi
+    double* frecv = nullptr;  // halo arena [6*plane]: r_lo p_lo[0] r_hi p_hi[0] p_lo[1] p_hi[1] (the last two: peer mode)
+    double* nb_lo_arena = nullptr;  // the neighbours' halo arenas mapped through CUDA IPC (peer mode)
+    double* nb_hi_arena = nullptr;
     int fkc = 64;
     int ftile = 4;
     bool fsmem = true;
@@ -567,6 +715,31 @@ struct Stencil7 : public Operator {
     }
 
     bool fused_cg_capable() const override { return true; }
+    bool peer_mode = false;  // set by the CG driver for the duration of a solve (all ranks agree)
+
+    // peer mode helpers for the CG driver
+    bool peer_capable() const override {
+        return ctx->world > 1 && ctx->p2p && fsmem && (g.nx % 2 == 0) && frecv != nullptr;
+    }
+    void set_peer_mode(bool on) override { peer_mode = on; }
+    // where KB must mirror the first / last plane of r: the neighbours' r_hi / r_lo halo planes
+    void peer_r_targets(double** lo_nb_r_hi, double** hi_nb_r_lo, int64_t* plane_elems) const override {
+        const size_t plane = (size_t)g.nx * g.ny;
+        *lo_nb_r_hi = nb_lo_arena ? nb_lo_arena + 2 * plane : nullptr;
+        *hi_nb_r_lo = nb_hi_arena ? nb_hi_arena : nullptr;
+        *plane_elems = (int64_t)plane;
+    }
+    // one NCCL exchange of the boundary planes of r and p (parity 0) at the start of a solve
+    void initial_halo_exchange(const double* r, const double* p) override {
+        Context* c = ctx;
+        const size_t plane = (size_t)g.nx * g.ny;
+        const size_t last = (size_t)(g.nz_loc - 1) * plane;
+        ATK_CUDA_CHECK(cudaMemcpyAsync(fsend, r, sizeof(double) * plane, cudaMemcpyDeviceToDevice, c->stream));
+        ATK_CUDA_CHECK(cudaMemcpyAsync(fsend + plane, p, sizeof(double) * plane, cudaMemcpyDeviceToDevice, c->stream));
+        ATK_CUDA_CHECK(cudaMemcpyAsync(fsend + 2 * plane, r + last, sizeof(double) * plane, cudaMemcpyDeviceToDevice, c->stream));
+        ATK_CUDA_CHECK(cudaMemcpyAsync(fsend + 3 * plane, p + last, sizeof(double) * plane, cudaMemcpyDeviceToDevice, c->stream));
+        exchange_halo(c, fsend, fsend + 2 * plane, frecv, frecv + 2 * plane, 2 * plane, c->stream);
+    }
 
     template <int TX, int TY>
     void launch_fused(const FusedArgs& fa, int k_lo, int k_hi, int partial_base, bool is_final, double* dot_out, int* blocks_out) {
@@ -615,8 +788,30 @@ struct Stencil7 : public Operator {
         FusedArgs fa{r, x, Ap, P0, P1, nullptr, nullptr, nullptr, nullptr, st, c->slot(rr_slot), c->world, rs_trace};
         double* dot_out = c->slot(dot_slot) + c->rank;
         int nb = 0;
+        fa.p2p = 0;
         if (c->world == 1) {
             launch_fused_tile(fa, 0, g.nz_loc, 0, true, dot_out, &nb);
+        } else if (peer_mode) {
+            // halo planes were written by the neighbours' previous KB (r) and KA (p); one launch over all planes
+            fa.p2p = 1;
+            fa.rank = c->rank;
+            fa.flags = c->d_flags;
+            fa.peer_gather = c->d_peer_gather;
+            fa.peer_flags = c->d_peer_flags;
+            fa.r_halo_lo = frecv;
+            fa.r_halo_hi = frecv + 2 * plane;
+            fa.my_p_lo[0] = frecv + plane;
+            fa.my_p_hi[0] = frecv + 3 * plane;
+            fa.my_p_lo[1] = frecv + 4 * plane;
+            fa.my_p_hi[1] = frecv + 5 * plane;
+            fa.p_halo_lo = fa.my_p_lo[0];
+            fa.p_halo_hi = fa.my_p_hi[0];
+            fa.nb_lo_p_hi[0] = nb_lo_arena ? nb_lo_arena + 3 * plane : nullptr;
+            fa.nb_lo_p_hi[1] = nb_lo_arena ? nb_lo_arena + 5 * plane : nullptr;
+            fa.nb_hi_p_lo[0] = nb_hi_arena ? nb_hi_arena + plane : nullptr;
+            fa.nb_hi_p_lo[1] = nb_hi_arena ? nb_hi_arena + 4 * plane : nullptr;
+            launch_fused_tile(fa, 0, g.nz_loc, 0, true, dot_out, &nb);
+            return;  // the p.Ap partials travel by peer stores: no all-gather
         } else {
             fa.r_halo_lo = frecv;
             fa.p_halo_lo = frecv + plane;
@@ -656,6 +851,21 @@ struct Stencil7 : public Operator {
         ATK_REQUIRE(partial_base + nblocks <= kMaxPartials, ATK_ERR_INVALID_ARGUMENT, "stencil grid exceeds the partial-sum scratch");
         const bool vec = (g.nx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) &&
                          ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
+        if (vec && fsmem) {
+            constexpr size_t smem = (size_t)4 * (TY + 2) * (2 * TX + 4) * sizeof(double);
+            if (dot)
+                stencil7_smem_kernel<TX, TY, true><<<grid, block, smem, c->stream>>>(g, x, y, halo_lo, halo_hi, k_lo, k_hi, kcc,
+                                                                                     c->d_partials, partial_base, c->d_tickets + 2,
+                                                                                     dot_out, dot_final ? 1 : 0, skip_flag);
+            else
+                stencil7_smem_kernel<TX, TY, false><<<grid, block, smem, c->stream>>>(g, x, y, halo_lo, halo_hi, k_lo, k_hi, kcc,
+                                                                                      c->d_partials, partial_base, c->d_tickets + 2,
+                                                                                      dot_out, dot_final ? 1 : 0, skip_flag);
+            ATK_CUDA_CHECK(cudaGetLastError());
+            count_launch(c);
+            *blocks_out = nblocks;
+            return;
+        }
 #define ATK_ST(V, D)                                                                                                     \
     stencil7_kernel<TX, TY, V, D><<<grid, block, 0, c->stream>>>(g, x, y, halo_lo, halo_hi, k_lo, k_hi, kcc, c->d_partials, \
                                                                  partial_base, c->d_tickets + 2, dot_out, dot_final ? 1 : 0, \
@@ -674,7 +884,9 @@ struct Stencil7 : public Operator {
             case 1: launch<64, 4>(x, y, k_lo, k_hi, dot, partial_base, dot_final, dot_out, skip_flag, blocks_out); break;
             case 2: launch<32, 16>(x, y, k_lo, k_hi, dot, partial_base, dot_final, dot_out, skip_flag, blocks_out); break;
             case 3: launch<64, 8>(x, y, k_lo, k_hi, dot, partial_base, dot_final, dot_out, skip_flag, blocks_out); break;
-            default: launch<32, 8>(x, y, k_lo, k_hi, dot, partial_base, dot_final, dot_out, skip_flag, blocks_out); break;
+            case 0: launch<32, 8>(x, y, k_lo, k_hi, dot, partial_base, dot_final, dot_out, skip_flag, blocks_out); break;
+            case 5: launch<64, 2>(x, y, k_lo, k_hi, dot, partial_base, dot_final, dot_out, skip_flag, blocks_out); break;
+            default: launch<32, 4>(x, y, k_lo, k_hi, dot, partial_base, dot_final, dot_out, skip_flag, blocks_out); break;
         }
     }
 
@@ -739,8 +951,17 @@ Operator* make_stencil7(Context* ctx, int nx, int ny, int nz, double cx, double 
             ATK_CUDA_CHECK(cudaMemset(S->halo_lo, 0, sizeof(double) * (size_t)plane));
             ATK_CUDA_CHECK(cudaMemset(S->halo_hi, 0, sizeof(double) * (size_t)plane));
             ATK_CUDA_CHECK(cudaMalloc(&S->fsend, sizeof(double) * 4 * (size_t)plane));
-            ATK_CUDA_CHECK(cudaMalloc(&S->frecv, sizeof(double) * 4 * (size_t)plane));
-            ATK_CUDA_CHECK(cudaMemset(S->frecv, 0, sizeof(double) * 4 * (size_t)plane));
+            ATK_CUDA_CHECK(cudaMalloc(&S->frecv, sizeof(double) * 6 * (size_t)plane));
+            ATK_CUDA_CHECK(cudaMemset(S->frecv, 0, sizeof(double) * 6 * (size_t)plane));
+            if (ctx->p2p) {  // collective: map the z-neighbours' halo arenas
+                std::vector<void*> peers;
+                std::vector<int> want;
+                if (ctx->rank > 0) want.push_back(ctx->rank - 1);
+                if (ctx->rank + 1 < ctx->world) want.push_back(ctx->rank + 1);
+                ipc_share(ctx, S->frecv, peers, want);
+                if (ctx->rank > 0) S->nb_lo_arena = static_cast<double*>(peers[(size_t)ctx->rank - 1]);
+                if (ctx->rank + 1 < ctx->world) S->nb_hi_arena = static_cast<double*>(peers[(size_t)ctx->rank + 1]);
+            }
         }
     } catch (...) {
         delete S;

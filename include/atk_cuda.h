@@ -160,6 +160,10 @@ typedef struct atk_cg_info {
     /* out: 1 when the fused two-kernel formulation ran (matrix-free operator, tree reductions): kernel_ms[0] is then
      * KA (p update + pending x update + operator apply + p.Ap, 48 B/row), kernel_ms[1] KB (r update + r.r, 24 B/row) */
     int fused;
+    /* out: 1 when the iteration ran in peer-memory mode on a distributed context: halo planes and partial sums move by
+     * direct stores into the neighbouring GPUs' memory (CUDA IPC over NVLink) and sequence flags, no NCCL call inside
+     * the loop.  0: NCCL send/recv + all-gather (also selectable with ATK_COMM=nccl). */
+    int peer;
 } atk_cg_info;
 
 /* ConjugateGrad::solve (src/LinearAlgebra/Krylov/ConjugateGradient.hpp:36-84).  The solver state x, r, p lives in

@@ -44,6 +44,12 @@ for fused in ("1", "0"):
     os.environ["ATK_CG_FUSED"] = fused
     res = ctx.cg_solve_host(op, b_loc, iters, trace=True)
     results[fused] = (gather(res["x"]), gather(res["r"]), gather(res["p"]), res)
+# a second fused solve on the same context (sequence-number epochs must advance), continuing from the first state
+os.environ["ATK_CG_FUSED"] = "1"
+x1, r1, p1, _ = [results["1"][q] for q in range(4)]
+sl = slice(op.row_begin, op.row_begin + op.n_rows_local)
+res2 = ctx.cg_solve_host(op, b_loc, 7, state=(x1[sl], r1[sl], p1[sl]))
+x_cont = gather(res2["x"])
 # plain operator apply with halo exchange
 xin = np.random.default_rng(3).standard_normal(nx * ny * nz)
 y_loc = op.apply_numpy(xin[op.row_begin: op.row_begin + op.n_rows_local])
@@ -65,9 +71,13 @@ if rank == 0:
         ex = np.linalg.norm(x - ora["x"]) / np.linalg.norm(ora["x"])
         er = np.linalg.norm(r - ora["r"]) / np.linalg.norm(ora["r"])
         ep = np.linalg.norm(p - ora["p"]) / np.linalg.norm(ora["p"])
-        print(f"fused={fused}: iters {res['iters']} (oracle {ora['iters']}) fusedflag {res['fused']}  relerr x {ex:.2e} r {er:.2e} p {ep:.2e} "
+        print(f"fused={fused}: iters {res['iters']} (oracle {ora['iters']}) fusedflag {res['fused']} peer {res['peer']}  relerr x {ex:.2e} r {er:.2e} p {ep:.2e} "
               f"launches {res['kernel_launches']} ms {res['device_ms']:.2f}")
         ok &= res["iters"] == ora["iters"] and ex < 1e-10 and er < 1e-8 and ep < 1e-8
+    ora2 = P.cg(None, b, 7, state=(ora["x"], ora["r"], ora["p"]), stencil=(nx, ny, nz, cx, cy, cz))
+    ec = np.linalg.norm(x_cont - ora2["x"]) / np.linalg.norm(ora2["x"])
+    print(f"continued solve (+7 iterations): iters {res2['iters']} peer {res2['peer']} relerr x {ec:.2e}")
+    ok &= res2["iters"] == 7 and ec < 1e-10
     print("DIST_CHECK", "PASS" if ok else "FAIL")
 dist.barrier()
 dist.destroy_process_group()
