@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "atk_internal.cuh"
@@ -109,6 +110,187 @@ __global__ void __launch_bounds__(256) multi_axmy_kernel(int64_t n, int j, const
     }
 }
 
+
+// ---- persistent Arnoldi-MGS step ----------------------------------------------------------------------------------
+// One cooperative launch performs the WHOLE projection loop of an Arnoldi step (GMRES.hpp:73-86):
+//     for i < j: h = V[i].w ; w = w - V[i]*h        then  ||w|| ; V[j+1] = w / ||w||
+// Each CTA owns a contiguous chunk of rows and keeps its slice of w in SHARED MEMORY for the whole step, so per
+// projection only V[i] streams in (8 B/row from HBM, the second pass hits L2) instead of the 40 B/row of separate dot and
+// axmy kernels, and the 2j kernel launches of the step collapse into one.  CTAs meet at one software grid barrier per
+// projection (cooperative launch guarantees co-residency); every CTA then adds the per-CTA partials in CTA order.
+// With a single CTA (small n, e.g. bcsstk08) the barrier degenerates to __syncthreads; that configuration also
+// implements ATK_REDUCE_SEQUENTIAL (thread 0 adds the rounded products strictly in index order).
+struct MgsArgs {
+    int64_t n;
+    int j;
+    const double* V;
+    int64_t ldv;
+    const double* w;     // A*V[j]
+    double* vnext;       // V[j+1]
+    double* h_out;       // [j+1]: H(0..j-1, j) and ||w||
+    double* partials;    // [2 * gridDim.x]
+    unsigned* bar;       // zero-initialised counter of this step
+    int64_t chunk;       // rows per CTA (multiple of 2)
+    int sequential;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
+    __syncthreads();
+    if (gridDim.x > 1) {
+        if (threadIdx.x == 0) {
+            target += gridDim.x;
+            __threadfence();
+            atomicAdd(counter, 1u);
+            while (*reinterpret_cast<volatile unsigned*>(counter) < target) {}
+            __threadfence();
+        }
+        __syncthreads();
+    }
+}
+
+// Strictly ordered sum (single CTA, ATK_REDUCE_SEQUENTIAL): all threads write the rounded products of the whole slice
+// into `stage`, one barrier, thread 0 adds them in index order from 0.0 (= std::inner_product), result broadcast.
+template <typename F>
+__device__ __forceinline__ double sequential_sum(int64_t len, double* stage, double* bcast, F product) {
+    for (int64_t e = threadIdx.x; e < len; e += blockDim.x) stage[e] = product(e);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double acc = 0.0;
+#pragma unroll 16
+        for (int64_t k = 0; k < len; ++k) acc = add_rn(acc, stage[k]);
+        *bcast = acc;
+    }
+    __syncthreads();
+    return *bcast;
+}
+
+constexpr int kMgsRegRows = 8;  // rows per thread the register variant can hold
+
+// REG = true (slices of at most 8*BLOCK rows): the thread's rows of w and of the current V column live in registers,
+// the next column is requested while the current one is being reduced, and nothing is re-read.
+// REG = false: the slice of w lives in shared memory and V[i] is streamed twice (the second pass hits L1/L2).
+template <int BLOCK, bool REG>
+__global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
+    extern __shared__ __align__(16) double wsm[];  // REG: products [chunk] (sequential mode only); else w [chunk] (+ products)
+    __shared__ double bcast;
+    const int64_t c0 = (int64_t)blockIdx.x * a.chunk;
+    const int64_t len = max((int64_t)0, min(a.chunk, a.n - c0));
+    unsigned target = 0;
+    const unsigned G = gridDim.x;
+
+    // h from a per-thread partial: fixed block tree, then (several CTAs) barrier + fixed-order sum of the CTA partials
+    auto finish_tree = [&](double acc, int i) -> double {
+        const double bs = block_sum<BLOCK>(acc);
+        if (G == 1) return bs;
+        double* part = a.partials + (size_t)(i & 1) * G;
+        if (threadIdx.x == 0) part[blockIdx.x] = bs;
+        grid_barrier(a.bar, target);
+        double s = 0.0;
+        for (unsigned q = threadIdx.x; q < G; q += BLOCK) s = add_rn(s, __ldcg(part + q));
+        return block_sum<BLOCK>(s);
+    };
+
+    if constexpr (REG) {
+        double wr[kMgsRegRows], vc[kMgsRegRows], vn[kMgsRegRows];
+#pragma unroll
+        for (int q = 0; q < kMgsRegRows; ++q) {
+            const int64_t e = threadIdx.x + (int64_t)q * BLOCK;
+            wr[q] = e < len ? a.w[c0 + e] : 0.0;
+            vc[q] = (e < len && a.j > 0) ? a.V[c0 + e] : 0.0;
+            vn[q] = 0.0;
+        }
+        for (int i = 0; i <= a.j; ++i) {
+            if (i + 1 < a.j) {  // request the next column before this one is reduced
+                const double* v = a.V + (int64_t)(i + 1) * a.ldv + c0;
+#pragma unroll
+                for (int q = 0; q < kMgsRegRows; ++q) {
+                    const int64_t e = threadIdx.x + (int64_t)q * BLOCK;
+                    vn[q] = e < len ? v[e] : 0.0;
+                }
+            }
+            double h;
+            if (a.sequential) {
+#pragma unroll
+                for (int q = 0; q < kMgsRegRows; ++q) {
+                    const int64_t e = threadIdx.x + (int64_t)q * BLOCK;
+                    if (e < len) wsm[e] = (i < a.j) ? mul_rn(vc[q], wr[q]) : mul_rn(wr[q], wr[q]);
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double acc = 0.0;
+#pragma unroll 16
+                    for (int64_t k = 0; k < len; ++k) acc = add_rn(acc, wsm[k]);
+                    bcast = acc;
+                }
+                __syncthreads();
+                h = bcast;
+            } else {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < kMgsRegRows; ++q)  // rows beyond len hold zeros: adding +0.0 products changes nothing
+                    acc = add_rn(acc, (i < a.j) ? mul_rn(vc[q], wr[q]) : mul_rn(wr[q], wr[q]));
+                h = finish_tree(acc, i);
+            }
+            if (i < a.j) {
+                if (blockIdx.x == 0 && threadIdx.x == 0) a.h_out[i] = h;  // H(i,j)   (:75)
+#pragma unroll
+                for (int q = 0; q < kMgsRegRows; ++q) {
+                    wr[q] = sub_rn(wr[q], mul_rn(vc[q], h));               // (:76)
+                    vc[q] = vn[q];
+                }
+            } else {
+                const double nrm = sqrt(h);                                // (:79)
+                if (blockIdx.x == 0 && threadIdx.x == 0) a.h_out[a.j] = nrm;
+                if (nrm != 0.0) {
+#pragma unroll
+                    for (int q = 0; q < kMgsRegRows; ++q) {
+                        const int64_t e = threadIdx.x + (int64_t)q * BLOCK;
+                        if (e < len) a.vnext[c0 + e] = __ddiv_rn(wr[q], nrm);  // (:86)
+                    }
+                }
+            }
+        }
+    } else {
+        double* stage = wsm + a.chunk;
+        for (int64_t e = threadIdx.x; e < len; e += BLOCK) wsm[e] = a.w[c0 + e];
+        __syncthreads();
+        for (int i = 0; i <= a.j; ++i) {
+            // i < j: projection against V[i];  i == j: the norm of what is left
+            const double* v = (i < a.j) ? a.V + (int64_t)i * a.ldv + c0 : nullptr;
+            double h;
+            if (a.sequential) {  // single CTA
+                if (i < a.j) h = sequential_sum(len, stage, &bcast, [&](int64_t e) { return mul_rn(v[e], wsm[e]); });
+                else h = sequential_sum(len, stage, &bcast, [&](int64_t e) { return mul_rn(wsm[e], wsm[e]); });
+            } else {
+                double acc = 0.0;
+                if (i < a.j) for (int64_t e = threadIdx.x; e < len; e += BLOCK) acc = add_rn(acc, mul_rn(v[e], wsm[e]));
+                else for (int64_t e = threadIdx.x; e < len; e += BLOCK) acc = add_rn(acc, mul_rn(wsm[e], wsm[e]));
+                h = finish_tree(acc, i);
+            }
+            if (i < a.j) {
+                if (blockIdx.x == 0 && threadIdx.x == 0) a.h_out[i] = h;                                          // H(i,j)   (:75)
+                for (int64_t e = threadIdx.x; e < len; e += BLOCK) wsm[e] = sub_rn(wsm[e], mul_rn(v[e], h));      // (:76)
+                __syncthreads();
+            } else {
+                const double nrm = sqrt(h);                                                                       // (:79)
+                if (blockIdx.x == 0 && threadIdx.x == 0) a.h_out[a.j] = nrm;
+                if (nrm != 0.0)
+                    for (int64_t e = threadIdx.x; e < len; e += BLOCK) a.vnext[c0 + e] = __ddiv_rn(wsm[e], nrm);  // (:86)
+            }
+        }
+    }
+}
+
+using MgsKernel = void (*)(MgsArgs);
+inline MgsKernel mgs_kernel_for(int block, bool reg) {
+    switch (block) {
+        case 64: return reg ? arnoldi_mgs_kernel<64, true> : arnoldi_mgs_kernel<64, false>;
+        case 128: return reg ? arnoldi_mgs_kernel<128, true> : arnoldi_mgs_kernel<128, false>;
+        case 256: return reg ? arnoldi_mgs_kernel<256, true> : arnoldi_mgs_kernel<256, false>;
+        default: return reg ? arnoldi_mgs_kernel<512, true> : arnoldi_mgs_kernel<512, false>;
+    }
+}
+
 struct Givens {
     // reference GMRES.hpp:139-151
     static void generate(double dx, double dy, double& cs, double& sn, double& rho) {
@@ -168,6 +350,43 @@ void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t
         const int cgs_blocks = (int)std::max<int64_t>(1, (n + kCgsBlock * kCgsPerThread - 1) / (kCgsBlock * kCgsPerThread));
         if (ortho == ATK_GMRES_CGS2) ATK_CUDA_CHECK(cudaMalloc(&d_part, sizeof(double) * (size_t)cgs_blocks * (size_t)K));
 
+        // ---- persistent MGS step: usable when every CTA's slice of w fits in shared memory (single-GPU contexts)
+        bool persistent = false;
+        int mgs_grid = 1, mgs_block = 512;
+        MgsKernel mgs_kernel = nullptr;
+        int64_t mgs_chunk = 0;
+        size_t mgs_smem = 0;
+        unsigned* d_bar = nullptr;
+        double* d_mgs_part = nullptr;
+        if (ortho == ATK_GMRES_MGS && ctx->world == 1 && n > 0 && !std::getenv("ATK_GMRES_NO_PERSISTENT")) {
+            const bool seq = ctx->reduction == ATK_REDUCE_SEQUENTIAL;
+            int64_t chunk = seq ? n : std::max<int64_t>(2048, (n + ctx->sm_count - 1) / ctx->sm_count);
+            chunk = (chunk + 1) & ~(int64_t)1;
+            // 8 rows per thread: small systems run on a few warps and pay almost nothing per barrier
+            const int64_t rows = std::min(chunk, n);
+            mgs_block = rows <= 64 * 8 ? 64 : rows <= 128 * 8 ? 128 : rows <= 256 * 8 ? 256 : 512;
+            const bool reg = rows <= (int64_t)mgs_block * kMgsRegRows;
+            const size_t smem = sizeof(double) * (size_t)chunk * (reg ? (seq ? 1 : 0) : (seq ? 2 : 1));
+            mgs_kernel = mgs_kernel_for(mgs_block, reg);
+            int max_smem = 0;
+            ATK_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+            if (smem + 1024 <= (size_t)max_smem) {
+                ATK_CUDA_CHECK(cudaFuncSetAttribute(mgs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int per_sm = 0;
+                ATK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mgs_kernel, mgs_block, smem));
+                const int g = (int)((n + chunk - 1) / chunk);
+                if (per_sm >= 1 && g <= per_sm * ctx->sm_count) {
+                    persistent = true;
+                    mgs_grid = g;
+                    mgs_chunk = chunk;
+                    mgs_smem = smem;
+                    ATK_CUDA_CHECK(cudaMalloc(&d_bar, sizeof(unsigned) * (size_t)(K + 1)));
+                    ATK_CUDA_CHECK(cudaMalloc(&d_mgs_part, sizeof(double) * 2 * (size_t)g));
+                }
+            }
+        }
+        struct BarFree { unsigned*& b; double*& p; ~BarFree() { cudaFree(b); cudaFree(p); } } bar_free{d_bar, d_mgs_part};
+
         std::vector<double> H((size_t)ld * ld, 0.0);  // :55 - allocated once, never cleared
         std::vector<double> cs(K, 1.0), sn(K, 0.0), rho(K, 0.0), e1(ld, 0.0), y(ld, 0.0);
         auto Hm = [&](int i, int j) -> double& { return H[(size_t)i + (size_t)j * ld]; };
@@ -193,11 +412,19 @@ void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t
             for (int iter = 0; iter < max_iter && !finished; ++iter) {
                 ATK_REQUIRE(beta != 0.0, ATK_ERR_RUNTIME, "Division by zero.");  // V[0] = r / beta (:63)
                 launch_div(ctx, n, r, beta, V);
+                if (persistent) ATK_CUDA_CHECK(cudaMemsetAsync(d_bar, 0, sizeof(unsigned) * (size_t)(K + 1), st));
                 int kry = K;
                 for (int j = 0; j < K; ++j) {
                     const double* vj = V + (size_t)j * nn;
                     op->apply(vj, w, -1, nullptr);  // :70
-                    if (ortho == ATK_GMRES_MGS) {
+                    if (persistent) {
+                        MgsArgs ma{n, j, V, (int64_t)nn, w, V + (size_t)(j + 1) * nn, d_h, d_mgs_part, d_bar + j, mgs_chunk,
+                                   ctx->reduction == ATK_REDUCE_SEQUENTIAL ? 1 : 0};
+                        void* kargs[] = {&ma};
+                        ATK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)mgs_kernel, dim3(mgs_grid), dim3(mgs_block), kargs, mgs_smem,
+                                                                   st));
+                        count_launch(ctx);
+                    } else if (ortho == ATK_GMRES_MGS) {
                         for (int i = 0; i < j; ++i) {  // :73-77
                             const double* vi = V + (size_t)i * nn;
                             launch_dot(ctx, n, vi, w, kSlotH);
@@ -214,10 +441,12 @@ void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t
                         // H(0:j, j) = h(pass 0) + h(pass 1)
                         launch_add(ctx, j, d_h, d_y, d_h);
                     }
-                    launch_dot(ctx, n, w, w, kSlotNorm);  // :79
-                    normalize_kernel<<<grid, 256, 0, st>>>(n, w, V + (size_t)(j + 1) * nn, ctx->slot(kSlotNorm), ctx->world,
-                                                           d_h + j);  // :86 (skipped on the device when the norm is 0)
-                    count_launch(ctx);
+                    if (!persistent) {
+                        launch_dot(ctx, n, w, w, kSlotNorm);  // :79
+                        normalize_kernel<<<grid, 256, 0, st>>>(n, w, V + (size_t)(j + 1) * nn, ctx->slot(kSlotNorm), ctx->world,
+                                                               d_h + j);  // :86 (skipped on the device when the norm is 0)
+                        count_launch(ctx);
+                    }
                     ATK_CUDA_CHECK(cudaGetLastError());
                     ATK_CUDA_CHECK(cudaMemcpyAsync(h_col, d_h, sizeof(double) * (size_t)(j + 1), cudaMemcpyDeviceToHost, st));
                     ATK_CUDA_CHECK(cudaStreamSynchronize(st));
