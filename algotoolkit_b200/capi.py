@@ -68,7 +68,7 @@ EXPORTS = [
     "atk_context_synchronize", "atk_context_launch_count", "atk_malloc", "atk_free", "atk_memcpy_h2d", "atk_memcpy_d2h",
     "atk_memcpy_d2d", "atk_memset_zero", "atk_host_alloc", "atk_host_free", "atk_dot", "atk_nrm2", "atk_vec_scale",
     "atk_vec_div", "atk_vec_add", "atk_vec_sub", "atk_vec_axpy", "atk_vec_axmy", "atk_operator_from_csc",
-    "atk_operator_stencil7", "atk_operator_poisson_assembled", "atk_operator_stencil27_assembled", "atk_slab_partition",
+    "atk_operator_stencil7", "atk_operator_poisson_assembled", "atk_operator_stencil27", "atk_operator_stencil27_assembled", "atk_slab_partition",
     "atk_operator_destroy",
     "atk_operator_shape", "atk_operator_row_range", "atk_operator_export_csr", "atk_operator_apply", "atk_cg_solve",
     "atk_cg_solve_host", "atk_gmres_solve", "atk_gmres_solve_host",
@@ -118,6 +118,7 @@ def load():
         "atk_operator_stencil7": [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(_vp)],
         "atk_operator_poisson_assembled": [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                            C.POINTER(_vp)],
+        "atk_operator_stencil27": [_vp, C.c_int, C.c_int, C.c_int, _dp, C.POINTER(_vp)],
         "atk_operator_stencil27_assembled": [_vp, C.c_int, C.c_int, C.c_int, _dp, C.c_int, C.POINTER(_vp)],
         "atk_slab_partition": [C.c_int, C.c_int, C.c_int, _ip, _ip],
         "atk_operator_destroy": [_vp],
@@ -349,6 +350,13 @@ class Context:
     def operator_poisson_assembled(self, nx, ny, nz, cx, cy, cz, fmt=FORMAT_SELL) -> Operator:
         h = _vp()
         _check(self.L.atk_operator_poisson_assembled(self.h, nx, ny, nz, cx, cy, cz, fmt, C.byref(h)))
+        return Operator(self, h)
+
+    def operator_stencil27(self, nx, ny, nz, coef) -> Operator:
+        coef = np.ascontiguousarray(coef, np.float64)
+        assert coef.size == 27
+        h = _vp()
+        _check(self.L.atk_operator_stencil27(self.h, nx, ny, nz, coef.ctypes.data_as(_dp), C.byref(h)))
         return Operator(self, h)
 
     def operator_stencil27_assembled(self, nx, ny, nz, coef, fmt=FORMAT_SELL) -> Operator:

@@ -237,6 +237,12 @@ int atk_operator_poisson_assembled(atk_context_t ctx, int nx, int ny, int nz, do
         wrap_operator(out, atk::make_poisson_assembled(C(ctx), nx, ny, nz, cx, cy, cz, format));
     });
 }
+int atk_operator_stencil27(atk_context_t ctx, int nx, int ny, int nz, const double coef[27], atk_operator_t* out) {
+    return guarded([&] {
+        ATK_REQUIRE(out, ATK_ERR_INVALID_ARGUMENT, "null pointer");
+        wrap_operator(out, atk::make_stencil27(C(ctx), nx, ny, nz, coef));
+    });
+}
 int atk_operator_stencil27_assembled(atk_context_t ctx, int nx, int ny, int nz, const double coef[27], atk_format format,
                                      atk_operator_t* out) {
     return guarded([&] {
@@ -313,10 +319,10 @@ int atk_cg_solve_host(atk_context_t ctx, atk_operator_t op, const double* b, dou
         ATK_REQUIRE(b && x && info, ATK_ERR_INVALID_ARGUMENT, "null argument");
         ATK_REQUIRE(fresh || (r && p), ATK_ERR_INVALID_ARGUMENT, "continuing a solve needs r and p");
         const size_t bytes = sizeof(double) * (size_t)o->n_rows_local;
-        double* d[4] = {nullptr, nullptr, nullptr, nullptr};  // b x r p
-        auto release = [&] { for (auto* q : d) cudaFree(q); };
+        double* d[4] = {nullptr, nullptr, nullptr, nullptr};  // b x r p (cached workspace, recycled between calls)
+        auto release = [&] { for (auto* q : d) if (q) c->ws_release(q); };
         try {
-            for (auto& q : d) ATK_CUDA_CHECK(cudaMalloc(&q, bytes ? bytes : 8));
+            for (auto& q : d) q = static_cast<double*>(c->ws_alloc(bytes ? bytes : 8));
             ATK_CUDA_CHECK(cudaMemcpyAsync(d[0], b, bytes, cudaMemcpyHostToDevice, c->stream));
             if (fresh) {  // what the ctor leaves: x = 0, r = b - A*0 = b, p = r  (ConjugateGradient.hpp:26-30)
                 ATK_CUDA_CHECK(cudaMemsetAsync(d[1], 0, bytes, c->stream));

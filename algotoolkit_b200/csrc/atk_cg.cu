@@ -327,7 +327,11 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
     // peer-memory mode: every rank must agree (it changes who waits for whom)
     bool peer = false;
     if (fused && ctx->world > 1) {
-        int mine = op->peer_capable() && (n % 2 == 0) && aligned16(x) && aligned16(r) && aligned16(p) ? 1 : 0;
+        const char* force_nccl = std::getenv("ATK_CG_FORCE_NCCL");
+        int mine = op->peer_capable() && (n % 2 == 0) && aligned16(x) && aligned16(r) && aligned16(p) &&
+                           !(force_nccl && force_nccl[0] == '1')
+                       ? 1
+                       : 0;
         std::vector<int> all((size_t)ctx->world);
         allgather_host_bytes(ctx, &mine, all.data(), sizeof(int));
         peer = true;
@@ -352,16 +356,16 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
         if (gexec) cudaGraphExecDestroy(gexec);
         if (graph) cudaGraphDestroy(graph);
         for (auto e : poll_events) if (e) cudaEventDestroy(e);
-        cudaFree(d_state); cudaFree(Ap); cudaFree(d_ptrace); cudaFree(d_rtrace); cudaFree(p_alt);
-        if (h_done) cudaFreeHost(h_done);
+        ctx->ws_release(d_state); ctx->ws_release(Ap); ctx->ws_release(d_ptrace); ctx->ws_release(d_rtrace); ctx->ws_release(p_alt);
+        if (h_done && h_done != ctx->h_flags) cudaFreeHost(h_done);
     };
     try {
-        ATK_CUDA_CHECK(cudaMalloc(&d_state, sizeof(CgState)));
-        ATK_CUDA_CHECK(cudaMalloc(&Ap, sizeof(double) * std::max<int64_t>(n, 1)));
-        if (fused) ATK_CUDA_CHECK(cudaMalloc(&p_alt, sizeof(double) * std::max<int64_t>(n, 1)));
+        d_state = static_cast<CgState*>(ctx->ws_alloc(sizeof(CgState)));
+        Ap = static_cast<double*>(ctx->ws_alloc(sizeof(double) * std::max<int64_t>(n, 1)));
+        if (fused) p_alt = static_cast<double*>(ctx->ws_alloc(sizeof(double) * std::max<int64_t>(n, 1)));
         if (trace_cap > 0) {
-            ATK_CUDA_CHECK(cudaMalloc(&d_ptrace, sizeof(double) * trace_cap));
-            ATK_CUDA_CHECK(cudaMalloc(&d_rtrace, sizeof(double) * trace_cap));
+            d_ptrace = static_cast<double*>(ctx->ws_alloc(sizeof(double) * trace_cap));
+            d_rtrace = static_cast<double*>(ctx->ws_alloc(sizeof(double) * trace_cap));
             ATK_CUDA_CHECK(cudaMemsetAsync(d_ptrace, 0xff, sizeof(double) * trace_cap, st));  // NaN fill
             ATK_CUDA_CHECK(cudaMemsetAsync(d_rtrace, 0xff, sizeof(double) * trace_cap, st));
         }
@@ -467,7 +471,8 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
         // same decision after the same batch and enqueues the same number of collectives).
         constexpr int kBatch = 16, kLag = 2;
         const int n_batches = (max_iter + kBatch - 1) / kBatch;
-        ATK_CUDA_CHECK(cudaMallocHost(&h_done, sizeof(int) * std::max(n_batches, 1)));
+        if (n_batches <= kHostFlags) h_done = ctx->h_flags;
+        else ATK_CUDA_CHECK(cudaMallocHost(&h_done, sizeof(int) * (size_t)n_batches));
         poll_events.resize(std::max(n_batches, 1), nullptr);
         int enq = 0;
         for (int bt = 0; bt < n_batches; ++bt) {

@@ -180,6 +180,49 @@ double read_slot(Context* ctx, int slot) {
     return s;
 }
 
+// ------------------------------------------------------------------------------------------ workspace cache
+void* Context::ws_alloc(size_t bytes) {
+    if (bytes == 0) bytes = 8;
+    int best = -1;
+    for (int i = 0; i < (int)ws_blocks.size(); ++i)
+        if (!ws_blocks[i].busy && ws_blocks[i].bytes >= bytes && ws_blocks[i].bytes <= 2 * bytes + (1u << 20) &&
+            (best < 0 || ws_blocks[i].bytes < ws_blocks[best].bytes))
+            best = i;
+    if (best >= 0) {
+        ws_blocks[best].busy = true;
+        return ws_blocks[best].ptr;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {  // give the idle cache back and retry once
+        cudaGetLastError();
+        ws_trim();
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        throw Error(ATK_ERR_NOMEM, "out of device memory");
+    }
+    ATK_CUDA_CHECK(e);
+    ws_blocks.push_back(WsBlock{p, bytes, true});
+    return p;
+}
+void Context::ws_release(void* ptr) {
+    for (auto& b : ws_blocks)
+        if (b.ptr == ptr) {
+            b.busy = false;
+            return;
+        }
+}
+void Context::ws_trim() {
+    std::vector<WsBlock> keep;
+    for (auto& b : ws_blocks) {
+        if (b.busy) keep.push_back(b);
+        else cudaFree(b.ptr);
+    }
+    ws_blocks.swap(keep);
+}
+
 // ------------------------------------------------------------------------------------------ context
 static void init_context(Context& c, int device) {
     int count = 0;
@@ -207,6 +250,7 @@ static void init_context(Context& c, int device) {
     ATK_CUDA_CHECK(cudaMemset(c.d_tickets, 0, sizeof(unsigned) * kNumTickets));
     ATK_CUDA_CHECK(cudaMemset(c.d_gather, 0, (sizeof(double) + sizeof(unsigned long long)) * kNumSlots * kMaxRanks));
     ATK_CUDA_CHECK(cudaMallocHost(&c.h_pinned, sizeof(double) * 64));
+    ATK_CUDA_CHECK(cudaMallocHost(&c.h_flags, sizeof(int) * kHostFlags));
     ATK_CUDA_CHECK(cudaDeviceSynchronize());
 }
 
@@ -260,6 +304,8 @@ void context_destroy(atk_context_s* h) {
     Context& c = h->c;
     cudaSetDevice(c.device);
     cudaDeviceSynchronize();
+    for (auto& b : c.ws_blocks) cudaFree(b.ptr);
+    c.ws_blocks.clear();
     for (void* p : c.ipc_opened) cudaIpcCloseMemHandle(p);
     cudaFree(c.d_peer_gather);
     cudaFree(c.d_peer_flags);
@@ -268,6 +314,7 @@ void context_destroy(atk_context_s* h) {
     cudaFree(c.d_tickets);
     cudaFree(c.d_gather);
     cudaFreeHost(c.h_pinned);
+    cudaFreeHost(c.h_flags);
     cudaEventDestroy(c.ev_fork);
     cudaEventDestroy(c.ev_join);
     cudaEventDestroy(c.ev_t0);

@@ -49,6 +49,7 @@ constexpr int kReduceBlock = 256;      // block size of every kernel that ends i
 constexpr int kMaxPartials = 1 << 16;  // per-block partial sums a single kernel may produce
 constexpr int kNumSlots = 8;           // independent reduction result slots
 constexpr int kNumTickets = 16;
+constexpr int kHostFlags = 1 << 16;
 
 // Reduction slots: slot s lives at gather[s*kMaxRanks + q], q = rank.  Each rank writes its
 // own entry; on a distributed context an in-place all-gather fills the others; consumers add
@@ -67,6 +68,7 @@ struct Context {
     unsigned* d_tickets = nullptr; // [kNumTickets], self-resetting (atomicInc wrap)
     double* d_gather = nullptr;    // [kNumSlots * kMaxRanks]
     double* h_pinned = nullptr;    // [64] pinned scratch for scalar read-back
+    int* h_flags = nullptr;        // [kHostFlags] pinned: exit flags read back by the CG driver
     int64_t launches = 0;
     void* nccl_comm = nullptr;
 
@@ -81,8 +83,28 @@ struct Context {
     std::vector<void*> ipc_opened;               // mappings to close at destruction
     unsigned long long epoch = 1;                // sequence-number base, advanced identically on all ranks
 
+    // ---- workspace cache: solver-internal device buffers are recycled between calls instead of going through
+    // cudaMalloc / cudaFree (each costs ~0.1-1 ms at GB sizes and synchronises the device) ----
+    struct WsBlock { void* ptr; size_t bytes; bool busy; };
+    std::vector<WsBlock> ws_blocks;
+    void* ws_alloc(size_t bytes);   // smallest free cached block that fits, else a new cudaMalloc
+    void ws_release(void* ptr);     // back to the cache
+    void ws_trim();                 // cudaFree every idle block
+
     double* slot(int s) const { return d_gather + (size_t)s * kMaxRanks; }
     int reduce_grid() const { return sm_count * 4; }
+};
+
+// RAII handle on a cached workspace block
+struct WsBuffer {
+    Context* ctx = nullptr;
+    void* ptr = nullptr;
+    WsBuffer() = default;
+    WsBuffer(Context* c, size_t bytes) : ctx(c), ptr(c->ws_alloc(bytes)) {}
+    WsBuffer(const WsBuffer&) = delete;
+    WsBuffer& operator=(const WsBuffer&) = delete;
+    ~WsBuffer() { if (ptr) ctx->ws_release(ptr); }
+    template <typename T> T* as() const { return static_cast<T*>(ptr); }
 };
 
 inline void count_launch(Context* c, int n = 1) { c->launches += n; }
@@ -158,6 +180,7 @@ Operator* make_operator_from_csc(Context* ctx, int n_rows, int n_cols, int64_t n
                                  const double* vals, bool on_device, atk_format format);
 Operator* make_stencil7(Context* ctx, int nx, int ny, int nz, double cx, double cy, double cz);
 Operator* make_poisson_assembled(Context* ctx, int nx, int ny, int nz, double cx, double cy, double cz, atk_format format);
+Operator* make_stencil27(Context* ctx, int nx, int ny, int nz, const double* coef);
 Operator* make_stencil27_assembled(Context* ctx, int nx, int ny, int nz, const double* coef, atk_format format);
 
 // ------------------------------------------------------------------------------------------ vector kernels (host launchers)

@@ -918,6 +918,85 @@ struct Stencil7 : public Operator {
     }
 };
 
+// ---------------------------------------------------------------------------------------------- 27-point operator
+// Matrix-free form of the synthetic operator of BASELINE config 5: open boundaries (neighbours outside
+// the grid are dropped), A(r, r+d) = coef[d].  Taps are added from 0.0 in ascending column order (dk, dj, di
+// ascending), which is the order the assembled CSC matvec uses, so the result is bit-identical to the SELL operator
+// built by atk_operator_stencil27_assembled.  Zero coefficients are skipped (they are never stored by addValue).
+// One thread per two adjacent x points; neighbours come through L1/L2.  In GMRES(300) this kernel is < 1 % of a
+// restart cycle (the projection loop is the cost), so it is kept simple.
+struct Coef27 {
+    double v[27];
+};
+__global__ void __launch_bounds__(256) stencil27_kernel(StencilGeom g, Coef27 cf, const double* __restrict__ x,
+                                                        double* __restrict__ y, const double* __restrict__ halo_lo,
+                                                        const double* __restrict__ halo_hi, int k_lo, int k_hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= g.nx || j >= g.ny) return;
+    const int64_t sxy = (int64_t)g.nx * g.ny;
+    for (int k = k_lo + blockIdx.z; k < k_hi; k += gridDim.z) {
+        const int kg = g.k_off + k;
+        double acc = 0.0;
+#pragma unroll
+        for (int dk = -1; dk <= 1; ++dk) {
+            const int kk = k + dk;
+            if (kg + dk < 0 || kg + dk >= g.nz) continue;
+            const double* pl = kk < 0 ? halo_lo : (kk >= g.nz_loc ? halo_hi : x + (int64_t)kk * sxy);
+#pragma unroll
+            for (int dj = -1; dj <= 1; ++dj) {
+                const int jj = j + dj;
+                if (jj < 0 || jj >= g.ny) continue;
+#pragma unroll
+                for (int di = -1; di <= 1; ++di) {
+                    const int ii = i + di;
+                    const double c = cf.v[(dk + 1) * 9 + (dj + 1) * 3 + (di + 1)];
+                    if (ii < 0 || ii >= g.nx || c == 0.0) continue;
+                    acc = add_rn(acc, mul_rn(c, pl[(int64_t)jj * g.nx + ii]));
+                }
+            }
+        }
+        y[(int64_t)k * sxy + (int64_t)j * g.nx + i] = acc;
+    }
+}
+
+struct Stencil27 : public Operator {
+    StencilGeom g;
+    Coef27 cf;
+    double* halo_lo = nullptr;
+    double* halo_hi = nullptr;
+    ~Stencil27() override {
+        cudaFree(halo_lo);
+        cudaFree(halo_hi);
+    }
+    void launch(const double* x, double* y, int k_lo, int k_hi) {
+        if (k_hi <= k_lo) return;
+        dim3 block(32, 8, 1);
+        dim3 grid((g.nx + 31) / 32, (g.ny + 7) / 8, std::min(k_hi - k_lo, 64));
+        stencil27_kernel<<<grid, block, 0, ctx->stream>>>(g, cf, x, y, halo_lo, halo_hi, k_lo, k_hi);
+        ATK_CUDA_CHECK(cudaGetLastError());
+        count_launch(ctx);
+    }
+    void apply(const double* x, double* y, int dot_slot, const int* skip_flag) override {
+        Context* c = ctx;
+        (void)skip_flag;  // only the CG loop passes a skip flag, and CG on this operator goes through launch_dot below
+        if (c->world == 1) {
+            launch(x, y, 0, g.nz_loc);
+        } else {
+            const size_t plane = (size_t)g.nx * g.ny;
+            ATK_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+            ATK_CUDA_CHECK(cudaStreamWaitEvent(c->comm_stream, c->ev_fork, 0));
+            exchange_halo(c, x, x + (size_t)(g.nz_loc - 1) * plane, halo_lo, halo_hi, plane, c->comm_stream);
+            ATK_CUDA_CHECK(cudaEventRecord(c->ev_join, c->comm_stream));
+            launch(x, y, 1, g.nz_loc - 1);  // planes that need no halo run while the exchange is in flight
+            ATK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+            launch(x, y, 0, 1);
+            if (g.nz_loc > 1) launch(x, y, g.nz_loc - 1, g.nz_loc);
+        }
+        if (dot_slot >= 0) launch_dot(c, n_rows_local, x, y, dot_slot, skip_flag);
+    }
+};
+
 }  // namespace
 
 Operator* make_stencil7(Context* ctx, int nx, int ny, int nz, double cx, double cy, double cz) {
@@ -962,6 +1041,41 @@ Operator* make_stencil7(Context* ctx, int nx, int ny, int nz, double cx, double 
                 if (ctx->rank > 0) S->nb_lo_arena = static_cast<double*>(peers[(size_t)ctx->rank - 1]);
                 if (ctx->rank + 1 < ctx->world) S->nb_hi_arena = static_cast<double*>(peers[(size_t)ctx->rank + 1]);
             }
+        }
+    } catch (...) {
+        delete S;
+        throw;
+    }
+    return S;
+}
+
+Operator* make_stencil27(Context* ctx, int nx, int ny, int nz, const double* coef) {
+    ATK_REQUIRE(nx > 0 && ny > 0 && nz > 0 && coef, ATK_ERR_INVALID_ARGUMENT, "bad 27-point operator arguments");
+    ATK_REQUIRE(nz >= ctx->world, ATK_ERR_INVALID_ARGUMENT, "fewer z-planes than ranks");
+    auto* S = new Stencil27();
+    S->ctx = ctx;
+    int k_begin = 0, k_end = 0;
+    slab_partition(nz, ctx->rank, ctx->world, &k_begin, &k_end);
+    S->g = StencilGeom{nx, ny, nz, k_begin, k_end - k_begin, 0.0, 0.0, 0.0, 0.0};
+    for (int t = 0; t < 27; ++t) S->cf.v[t] = coef[t];
+    const int64_t plane = (int64_t)nx * ny;
+    S->n_rows_local = plane * (k_end - k_begin);
+    S->n_cols = plane * nz;
+    S->row_begin = plane * k_begin;
+    // stored entries: for every non-zero coefficient d, the number of grid points whose neighbour +d is inside the grid
+    int64_t nnz = 0;
+    for (int dk = -1; dk <= 1; ++dk)
+        for (int dj = -1; dj <= 1; ++dj)
+            for (int di = -1; di <= 1; ++di)
+                if (coef[(dk + 1) * 9 + (dj + 1) * 3 + (di + 1)] != 0.0)
+                    nnz += (int64_t)(nx - std::abs(di)) * (ny - std::abs(dj)) * (nz - std::abs(dk));
+    S->nnz = nnz;
+    try {
+        if (ctx->world > 1) {
+            ATK_CUDA_CHECK(cudaMalloc(&S->halo_lo, sizeof(double) * (size_t)plane));
+            ATK_CUDA_CHECK(cudaMalloc(&S->halo_hi, sizeof(double) * (size_t)plane));
+            ATK_CUDA_CHECK(cudaMemset(S->halo_lo, 0, sizeof(double) * (size_t)plane));
+            ATK_CUDA_CHECK(cudaMemset(S->halo_hi, 0, sizeof(double) * (size_t)plane));
         }
     } catch (...) {
         delete S;

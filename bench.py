@@ -235,12 +235,15 @@ def run_ours(args):
     value = args.steps / (dev_ms * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call: H2D b, K iterations, D2H x
-    info = capi.CgInfo()
-    barrier()
-    t0 = time.perf_counter()
-    capi._check(L.atk_cg_solve_host(ctx.h, op.h, hb, hx, None, None, 1, args.steps, C.byref(info)))
-    ctx.synchronize()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_times = []
+    for rep in range(2):  # the first call also pays one-time workspace allocation; the second is the steady state reported
+        info = capi.CgInfo()
+        barrier()
+        t0 = time.perf_counter()
+        capi._check(L.atk_cg_solve_host(ctx.h, op.h, hb, hx, None, None, 1, args.steps, C.byref(info)))
+        ctx.synchronize()
+        e2e_times.append(max_over_ranks(time.perf_counter() - t0))
+    t_e2e = e2e_times[-1]
     e2e_value = args.steps / t_e2e
     x_norm2 = float(np.dot(x_host, x_host))  # the host reads the result it received
 
@@ -289,7 +292,8 @@ def run_ours(args):
                    "step": "one CG iteration"},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_loc * 8 / args.steps,
-                "d2h_bytes_per_step": n_loc * 8 / args.steps, "seconds": t_e2e, "x_norm": float(np.sqrt(x_norm2)),
+                "d2h_bytes_per_step": n_loc * 8 / args.steps, "seconds": t_e2e, "first_call_seconds": e2e_times[0],
+                "device_loop_seconds": info.device_ms * 1e-3, "x_norm": float(np.sqrt(x_norm2)),
                 "note": "one atk_cg_solve_host call = K steps; pinned b up, x down, per rank"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",

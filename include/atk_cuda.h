@@ -123,6 +123,9 @@ int atk_operator_poisson_assembled(atk_context_t ctx, int nx, int ny, int nz, do
                                    atk_format format, atk_operator_t* out);
 /* Synthetic 27-point operator of BASELINE config 5: open boundaries, coef[13] on the diagonal and
  * coef[(dk+1)*9+(dj+1)*3+(di+1)] for neighbour (i+di,j+dj,k+dk); generated on the device. */
+/* The same 27-point operator MATRIX-FREE (bit-identical results); on a distributed context it is the rank's z-slab with
+ * one halo plane exchanged per apply, like atk_operator_stencil7. */
+int atk_operator_stencil27(atk_context_t ctx, int nx, int ny, int nz, const double coef[27], atk_operator_t* out);
 int atk_operator_stencil27_assembled(atk_context_t ctx, int nx, int ny, int nz, const double coef[27],
                                      atk_format format, atk_operator_t* out);
 /* The balanced z-slab split used by the distributed stencil operators: planes [k_begin, k_end) of nz for `rank` of

@@ -50,11 +50,28 @@ x1, r1, p1, _ = [results["1"][q] for q in range(4)]
 sl = slice(op.row_begin, op.row_begin + op.n_rows_local)
 res2 = ctx.cg_solve_host(op, b_loc, 7, state=(x1[sl], r1[sl], p1[sl]))
 x_cont = gather(res2["x"])
+# latency floor of one iteration on this (small) grid, warm, per communication mode
+lat = {}
+for mode in ("peer", "nccl"):
+    os.environ["ATK_CG_FUSED"] = "1"
+    os.environ["ATK_CG_FORCE_NCCL"] = "1" if mode == "nccl" else "0"
+    for rep in range(2):
+        rr = ctx.cg_solve_host(op, b_loc, 200)
+    lat[mode] = (rr["device_ms"] / max(rr["iters"], 1) * 1e3, rr["peer"], rr["iters"])
+os.environ["ATK_CG_FORCE_NCCL"] = "0"
 # plain operator apply with halo exchange
 xin = np.random.default_rng(3).standard_normal(nx * ny * nz)
 y_loc = op.apply_numpy(xin[op.row_begin: op.row_begin + op.n_rows_local])
 y_all = gather(y_loc)
 d = ctx.dot(ctx.vector(b_loc), ctx.vector(b_loc))
+# 27-point operator of BASELINE config 5, matrix-free and sharded: apply + a short GMRES
+coef = synthetic.stencil27_coefficients()
+op27 = ctx.operator_stencil27(nx, ny, nz, coef)
+y27 = gather(op27.apply_numpy(xin[op27.row_begin: op27.row_begin + op27.n_rows_local]))
+x_ext = synthetic.u01_array(777, 0, nx * ny * nz)
+b27_loc = op27.apply_numpy(x_ext[op27.row_begin: op27.row_begin + op27.n_rows_local])
+g27 = ctx.gmres_solve_host(op27, b27_loc, np.zeros(op27.n_rows_local), 2, 20, 1e-6)
+x27 = gather(g27["x"])
 if rank == 0:
     from oracle.pyoracle import Port
 
@@ -64,9 +81,19 @@ if rank == 0:
     y_ref = P.poisson_apply(nx, ny, nz, cx, cy, cz, xin)
     print(f"world {world} grid {nx}x{ny}x{nz} iters {iters}")
     print("apply with halo exchange bit-exact:", np.array_equal(y_all, y_ref))
+    for mode, (us, peer, its) in lat.items():
+        print(f"iteration latency floor ({mode}): {us:.1f} us/iteration over {its} iterations (peer={peer})")
     ok &= np.array_equal(y_all, y_ref)
     print("global dot rel err:", abs(d - P.dot(b, b)) / P.dot(b, b))
     ok &= abs(d - P.dot(b, b)) <= 1e-13 * P.dot(b, b)
+    A27 = P.op27_csc(nx, ny, nz)
+    print("27-point apply with halo exchange bit-exact:", np.array_equal(y27, P.spmv(A27, xin)))
+    ok &= np.array_equal(y27, P.spmv(A27, xin))
+    o27 = P.gmres(A27, P.spmv(A27, x_ext), np.zeros(nx * ny * nz), 2, 20, 1e-6)
+    e27 = np.linalg.norm(x27 - o27["x"]) / np.linalg.norm(o27["x"])
+    print("distributed GMRES(20) x2 restarts on the 27-point operator: resid", g27["resid"].tolist(), "oracle", o27["resid"].tolist(),
+          f"relerr x {e27:.2e}")
+    ok &= e27 < 1e-10 and np.allclose(g27["resid"], o27["resid"], rtol=1e-10)
     for fused, (x, r, p, res) in results.items():
         ex = np.linalg.norm(x - ora["x"]) / np.linalg.norm(ora["x"])
         er = np.linalg.norm(r - ora["r"]) / np.linalg.norm(ora["r"])
