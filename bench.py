@@ -307,6 +307,10 @@ def run_ours(args):
         "rs_final": res["rs"],
     }
 
+    # ---- secondary measurements of the same hot path (N=1 only; a few seconds): SpMV GB/s and GMRES restarts/s
+    if world == 1 and not args.no_extra:
+        line["extra"] = secondary_measurements(ctx, capi, synthetic, op, g, peak)
+
     # ---- CPU baseline beside it (rank 0, N=1 only): the unmodified reference on a bounded sample
     if world == 1 and not args.no_cpu_baseline:
         from oracle import pyoracle
@@ -335,6 +339,65 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def secondary_measurements(ctx, capi, synthetic, stencil_op, g, peak):
+    """SpMV HBM GB/s (matrix-free stencil at the bench grid, SELL-32 / CSR-vector on the assembled 256^3 Poisson matrix)
+    and GMRES(300) on bcsstk08 (BASELINE config 1) in both reduction modes.  CUDA-event timed inside the library where
+    the call reports it, host-timed around synchronised launches otherwise."""
+    out = {}
+
+    def time_apply(op, reps=20):
+        x = ctx.vector(np.random.default_rng(0).standard_normal(op.n_cols))
+        y = ctx.empty(op.n_rows_local)
+        for _ in range(3):
+            op.apply(x, y)
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            op.apply(x, y)
+        ctx.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        x.free()
+        y.free()
+        return dt
+
+    n = g ** 3
+    t = time_apply(stencil_op)
+    out["spmv_stencil7_matrix_free"] = {"grid": g, "ms": t * 1e3, "algorithmic_bytes": 16.0 * n, "GBs": 16.0 * n / t / 1e9,
+                                        "frac_of_measured_peak": 16.0 * n / t / 1e9 / peak}
+    ga = 256
+    cx, cy, cz = synthetic.poisson_coeffs(ga, ga, ga)
+    for name, fmt in (("spmv_sell32_assembled", capi.FORMAT_SELL), ("spmv_csr_vector_assembled", capi.FORMAT_CSR_VECTOR)):
+        t0 = time.perf_counter()
+        op = ctx.operator_poisson_assembled(ga, ga, ga, cx, cy, cz, fmt)
+        ctx.synchronize()
+        t_build = time.perf_counter() - t0
+        t = time_apply(op)
+        alg = 12.0 * op.nnz + 4.0 * (ga ** 3 + 1) + 16.0 * ga ** 3
+        out[name] = {"grid": ga, "nnz": op.nnz, "ms": t * 1e3, "algorithmic_bytes": alg, "GBs": alg / t / 1e9,
+                     "frac_of_measured_peak": alg / t / 1e9 / peak, "device_assembly_and_conversion_s": t_build}
+        op.destroy()
+    # GMRES(300) on bcsstk08 as the reference loads it (lower triangle; the file header is ignored)
+    try:
+        from algotoolkit_b200 import mmio
+
+        A = mmio.read_matrix_market_csc(os.path.join(ROOT, "tests", "golden", "data", "bcsstk08.mtx"))
+        op = ctx.operator_from_csc(A["n_rows"], A["n_cols"], A["col_ptr"], A["row_idx"], A["vals"])
+        x_ext = synthetic.u01_array(777, 0, A["n_cols"])
+        b = op.apply_numpy(x_ext)
+        for mode, name in ((capi.REDUCE_TREE, "tree"), (capi.REDUCE_SEQUENTIAL, "sequential")):
+            ctx.set_reduction(mode)
+            res = ctx.gmres_solve_host(op, b, np.zeros(A["n_rows"]), 2, 300, 1e-6)
+            out[f"gmres300_bcsstk08_{name}"] = {"restarts": res["restarts"], "arnoldi_steps": res["arnoldi_steps"],
+                                                "restarts_per_s": res["restarts"] / (res["device_ms"] * 1e-3),
+                                                "arnoldi_steps_per_s": res["arnoldi_steps"] / (res["device_ms"] * 1e-3),
+                                                "residual_after_restart_1": float(res["resid"][1])}
+        ctx.set_reduction(capi.REDUCE_TREE)
+        op.destroy()
+    except Exception as e:  # the headline number must not depend on the secondary block
+        out["gmres300_bcsstk08_error"] = repr(e)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -345,6 +408,7 @@ def main():
     ap.add_argument("--ref-sample-grid", type=int, default=128)
     ap.add_argument("--ref-sample-iters", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

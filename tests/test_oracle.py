@@ -204,3 +204,14 @@ def test_port_vs_reference_gmres_random(port, ref):
         a = port.gmres(A, b, np.zeros(n), iters, K, 1e-9)
         g = ref.gmres(M, b, np.zeros(n), iters, K, 1e-9, dense_h=dense_h)
         assert a["resid"].tolist() == g["resid"].tolist() and np.array_equal(a["x"], g["x"]) and a["status"] == g["status"]
+
+
+def test_python_matrix_market_reader_matches_reference_semantics(port):
+    """algotoolkit_b200/mmio.py (input handling for Python drivers) gives the same CSC arrays as the reference reader."""
+    from algotoolkit_b200 import mmio
+
+    for name in ("bcsstk01", "bcsstk08"):
+        a, b = mmio.read_matrix_market_csc(mm_path(name)), port.read_matrix_market(mm_path(name))
+        assert (a["n_rows"], a["n_cols"]) == (b.n_rows, b.n_cols)
+        assert np.array_equal(a["col_ptr"], b.col_ptr) and np.array_equal(a["row_idx"], b.row_idx)
+        assert np.array_equal(a["vals"], b.vals)
