@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libatk_cuda.so")
 ATK_OK, ATK_ERR_INVALID_ARGUMENT, ATK_ERR_RUNTIME, ATK_ERR_OUT_OF_RANGE, ATK_ERR_CUDA, ATK_ERR_NCCL, ATK_ERR_NOMEM = range(7)
 REDUCE_TREE, REDUCE_SEQUENTIAL = 0, 1
 FORMAT_SELL, FORMAT_CSR_VECTOR = 0, 1
-GMRES_MGS, GMRES_CGS2 = 0, 1
+GMRES_MGS, GMRES_MGS_BATCHED = 0, 1
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

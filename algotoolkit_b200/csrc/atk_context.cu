@@ -74,6 +74,13 @@ void allgather_slot(Context* ctx, int slot, cudaStream_t stream) {
                "ncclAllGather");
 }
 
+// in-place all-gather of `count` doubles per rank: rank q's block lives at buf + q*count
+void allgather_doubles(Context* ctx, double* buf, size_t count, cudaStream_t stream) {
+    if (ctx->world == 1) return;
+    nccl_check(g_nccl.AllGather(buf + (size_t)ctx->rank * count, buf, count, ncclDouble, (ncclComm_t)ctx->nccl_comm, stream),
+               "ncclAllGather");
+}
+
 void exchange_halo(Context* ctx, const double* first_plane, const double* last_plane, double* halo_lo, double* halo_hi,
                    size_t plane_elems, cudaStream_t stream) {
     if (ctx->world == 1) return;

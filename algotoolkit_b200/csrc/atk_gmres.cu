@@ -15,8 +15,14 @@
 // Orthogonalisation modes:
 //   MGS  (parity path)  per i: dot kernel -> h in a reduction slot; axmy kernel reads h from the slot: w = w - V[i]*h.
 //        Algorithmic traffic per (i) pair 40 B/row.
-//   CGS2 (throughput)   h = V[0:j]^T w as one multi-dot kernel, w -= V[0:j] h as one multi-axpy kernel, twice.
-//        16*j + ... B/row per pass; different rounding, never used for parity.
+//   MGS_BATCHED (throughput)  the same projection evaluated with TWO passes over V[0:j] and two reductions per step:
+//        c = V[0:j]^T w and g = V[0:j]^T v_j in one pass (g extends the Gram matrix G = V^T V), the host solves the unit
+//        lower-triangular system (I + strict_lower(G)) h = c, then w -= V[0:j] h in the second pass.
+//        In exact arithmetic h_i = v_i.(w - sum_{m<i} h_m v_m) = c_i - sum_{m<i} G_im h_m, i.e. exactly the reference's
+//        sequential loop - also for the reference's NON-orthonormal basis (it never projects against v_j, :73), which is
+//        why plain classical Gram-Schmidt (h = c) is NOT equivalent and fails parity by orders of magnitude.
+//        Traffic 16*n*j B per step instead of 40*n*j; rounding differs from the sequential loop at the 1e-14 level on
+//        the BASELINE config-5 operator (tests/test_gpu_parity.py).
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -63,53 +69,111 @@ __global__ void __launch_bounds__(256) update_solution_kernel(int64_t n, int k, 
     }
 }
 
-// ---- CGS2 kernels -------------------------------------------------------------------------------------------------
-// h[i] = V[i].w for i < j in one pass over w: each CTA owns a contiguous chunk of rows, keeps its w chunk in registers
-// and streams the j columns; per-CTA partials go to part[i*gridDim.x + block], a second kernel adds them in block order.
-constexpr int kCgsBlock = 256;
-constexpr int kCgsPerThread = 4;
-__global__ void __launch_bounds__(kCgsBlock) multi_dot_kernel(int64_t n, int j, const double* __restrict__ V, int64_t ldv,
-                                                              const double* __restrict__ w, double* __restrict__ part) {
-    const int64_t chunk = (int64_t)kCgsBlock * kCgsPerThread;
-    const int64_t base = (int64_t)blockIdx.x * chunk;
-    double wv[kCgsPerThread];
+// ---- batched (low-synchronisation) MGS kernels -------------------------------------------------------------------------
+// Pass 1: partial sums of V[col].w (col < ncols_w) and V[col].vj (col < ncols_g) for every column, one pass over V.
+// A CTA owns kBdBlock*kBdRows consecutive rows, keeps its rows of w and vj in registers and walks the columns in tiles of
+// kBdTile, so kBdTile*kBdRows column loads are in flight per thread and the block reduction is paid once per tile.
+// part[(rhs*ncols_g + col) * gridDim.x + block]; a second kernel adds the per-CTA partials in CTA order.
+constexpr int kBdBlock = 256;
+constexpr int kBdRows = 4;
+constexpr int kBdTile = 8;
+__global__ void __launch_bounds__(kBdBlock) multi_dot2_kernel(int64_t n, int ncols_w, int ncols_g, const double* __restrict__ V,
+                                                              int64_t ldv, const double* __restrict__ w,
+                                                              const double* __restrict__ vj, double* __restrict__ part) {
+    __shared__ double red[2 * kBdTile][kBdBlock / 32];
+    const int64_t base = (int64_t)blockIdx.x * kBdBlock * kBdRows;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double wq[kBdRows], gq[kBdRows];
+    bool in[kBdRows];
 #pragma unroll
-    for (int q = 0; q < kCgsPerThread; ++q) {
-        const int64_t e = base + (int64_t)q * kCgsBlock + threadIdx.x;
-        wv[q] = (e < n) ? w[e] : 0.0;
+    for (int q = 0; q < kBdRows; ++q) {
+        const int64_t e = base + (int64_t)q * kBdBlock + threadIdx.x;
+        in[q] = e < n;
+        wq[q] = in[q] ? w[e] : 0.0;
+        gq[q] = in[q] ? vj[e] : 0.0;
     }
-    for (int i = 0; i < j; ++i) {
-        const double* v = V + (int64_t)i * ldv;
-        double acc = 0.0;
+    for (int c0 = 0; c0 < ncols_g; c0 += kBdTile) {
+        double vals[kBdTile][kBdRows];
 #pragma unroll
-        for (int q = 0; q < kCgsPerThread; ++q) {
-            const int64_t e = base + (int64_t)q * kCgsBlock + threadIdx.x;
-            if (e < n) acc = add_rn(acc, mul_rn(v[e], wv[q]));
+        for (int t = 0; t < kBdTile; ++t) {
+            const double* v = V + (int64_t)min(c0 + t, ncols_g - 1) * ldv + base + threadIdx.x;
+#pragma unroll
+            for (int q = 0; q < kBdRows; ++q) vals[t][q] = in[q] ? v[(int64_t)q * kBdBlock] : 0.0;
         }
-        const double bs = block_sum<kCgsBlock>(acc);
-        if (threadIdx.x == 0) part[(int64_t)i * gridDim.x + blockIdx.x] = bs;
+        double acc[2 * kBdTile];
+#pragma unroll
+        for (int t = 0; t < kBdTile; ++t) {
+            double aw = 0.0, ag = 0.0;
+#pragma unroll
+            for (int q = 0; q < kBdRows; ++q) {
+                aw = add_rn(aw, mul_rn(vals[t][q], wq[q]));
+                ag = add_rn(ag, mul_rn(vals[t][q], gq[q]));
+            }
+            acc[t] = aw;
+            acc[kBdTile + t] = ag;
+        }
+#pragma unroll
+        for (int a = 0; a < 2 * kBdTile; ++a) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[a] = add_rn(acc[a], __shfl_xor_sync(0xffffffffu, acc[a], o));
+        }
+        __syncthreads();  // red[] free again
+        if (lane == 0) {
+#pragma unroll
+            for (int a = 0; a < 2 * kBdTile; ++a) red[a][warp] = acc[a];
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * kBdTile) {
+            const int a = threadIdx.x, t = a % kBdTile, rhs = a / kBdTile, col = c0 + t;
+            if (col < ncols_g && (rhs == 1 || col < ncols_w)) {
+                double sum = red[a][0];
+#pragma unroll
+                for (int ww = 1; ww < kBdBlock / 32; ++ww) sum = add_rn(sum, red[a][ww]);
+                part[((int64_t)rhs * ncols_g + col) * gridDim.x + blockIdx.x] = sum;
+            }
+        }
     }
 }
-__global__ void __launch_bounds__(256) multi_dot_final_kernel(int j, int nblocks, const double* __restrict__ part,
-                                                              double* __restrict__ h_local) {
-    const int i = blockIdx.x;
-    if (i >= j) return;
-    double s = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += 256) s = add_rn(s, part[(int64_t)i * nblocks + b]);
-    const double t = block_sum<256>(s);
-    if (threadIdx.x == 0) h_local[i] = t;
+// out[rhs*ncols_g + col] = sum over CTAs (fixed order) of part[...]; one CTA per (rhs, col)
+__global__ void __launch_bounds__(256) multi_dot2_final_kernel(int ncols_w, int ncols_g, int nblocks, const double* __restrict__ part,
+                                                               double* __restrict__ out) {
+    const int idx = blockIdx.x, rhs = idx / ncols_g, col = idx % ncols_g;
+    if (rhs == 0 && col >= ncols_w) {
+        if (threadIdx.x == 0) out[idx] = 0.0;
+        return;
+    }
+    const double total = partials_sum<256>(part + (int64_t)idx * nblocks, (unsigned)nblocks);
+    if (threadIdx.x == 0) out[idx] = total;
 }
-// w -= sum_i V[i]*h[i] (i ascending, two roundings per term); h_acc[i] += h[i] for the Hessenberg column
-__global__ void __launch_bounds__(256) multi_axmy_kernel(int64_t n, int j, const double* __restrict__ V, int64_t ldv,
-                                                         const double* __restrict__ h, double* __restrict__ w) {
+// Pass 2: w = w - V[0]*h0 - V[1]*h1 - ... (i ascending, product rounded first: the reference's order per element, :76)
+// fused with the partial sums of w.w for the norm that follows (:79).
+__global__ void __launch_bounds__(kReduceBlock) multi_axmy_norm_kernel(int64_t n, int j, const double* __restrict__ V, int64_t ldv,
+                                                                       const double* __restrict__ h, double* __restrict__ w,
+                                                                       double* partials, unsigned* ticket, double* norm2_out) {
+    extern __shared__ double hs[];
+    for (int i = threadIdx.x; i < j; i += blockDim.x) hs[i] = h[i];
+    __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double nacc = 0.0;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
         double acc = w[e];
-        for (int i = 0; i < j; ++i) acc = sub_rn(acc, mul_rn(V[(int64_t)i * ldv + e], __ldg(h + i)));
+        int i = 0;
+        for (; i + 8 <= j; i += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = V[(int64_t)(i + u) * ldv + e];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = sub_rn(acc, mul_rn(v[u], hs[i + u]));
+        }
+        for (; i < j; ++i) acc = sub_rn(acc, mul_rn(V[(int64_t)i * ldv + e], hs[i]));
         w[e] = acc;
+        nacc = add_rn(nacc, mul_rn(acc, acc));
+    }
+    double total;
+    if (grid_sum_last_block<kReduceBlock>(nacc, partials, ticket, &total)) {
+        if (threadIdx.x == 0) *norm2_out = total;
     }
 }
-
 
 // ---- persistent Arnoldi-MGS step ----------------------------------------------------------------------------------
 // One cooperative launch performs the WHOLE projection loop of an Arnoldi step (GMRES.hpp:73-86):
@@ -316,17 +380,17 @@ void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t
     // GMRES.hpp:28-37
     ATK_REQUIRE(n_x == n, ATK_ERR_INVALID_ARGUMENT, "Initial guess vector must match system size");
     ATK_REQUIRE(krylov_dim > 0 && krylov_dim <= n_global, ATK_ERR_INVALID_ARGUMENT, "Invalid Krylov subspace dimension");
-    ATK_REQUIRE(ortho == ATK_GMRES_MGS || ctx->world == 1, ATK_ERR_INVALID_ARGUMENT, "CGS2 is single-GPU in this version");
+    ATK_REQUIRE(ortho == ATK_GMRES_MGS || ortho == ATK_GMRES_MGS_BATCHED, ATK_ERR_INVALID_ARGUMENT, "unknown orthogonalisation mode");
     const int K = krylov_dim;
     const int64_t ld = K + 1;
     cudaStream_t st = ctx->stream;
     const int64_t launches0 = ctx->launches;
     auto notify = [&](int ev, double v) { if (cb) cb(ev, v, user); };
 
-    double *V = nullptr, *w = nullptr, *r = nullptr, *t = nullptr, *d_h = nullptr, *d_y = nullptr, *d_part = nullptr;
+    double *V = nullptr, *w = nullptr, *r = nullptr, *t = nullptr, *d_h = nullptr, *d_y = nullptr, *d_part = nullptr, *d_cg = nullptr;
     double* h_col = nullptr;  // pinned: H column + norm coming back each Arnoldi step
     auto cleanup = [&]() {
-        cudaFree(V); cudaFree(w); cudaFree(r); cudaFree(t); cudaFree(d_h); cudaFree(d_y); cudaFree(d_part);
+        cudaFree(V); cudaFree(w); cudaFree(r); cudaFree(t); cudaFree(d_h); cudaFree(d_y); cudaFree(d_part); cudaFree(d_cg);
         if (h_col) cudaFreeHost(h_col);
     };
     info->restarts = 0;
@@ -347,8 +411,19 @@ void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t
         ATK_CUDA_CHECK(cudaMalloc(&d_y, sizeof(double) * (size_t)ld));
         ATK_CUDA_CHECK(cudaMallocHost(&h_col, sizeof(double) * (size_t)(ld + 1)));
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8));
-        const int cgs_blocks = (int)std::max<int64_t>(1, (n + kCgsBlock * kCgsPerThread - 1) / (kCgsBlock * kCgsPerThread));
-        if (ortho == ATK_GMRES_CGS2) ATK_CUDA_CHECK(cudaMalloc(&d_part, sizeof(double) * (size_t)cgs_blocks * (size_t)K));
+        // batched MGS: per-CTA partials of the two multi-dots, the reduced [c | g] vector (all ranks), Gram matrix on the host
+        const bool batched = ortho == ATK_GMRES_MGS_BATCHED;
+        const int bd_blocks = (int)std::max<int64_t>(1, (n + kBdBlock * kBdRows - 1) / (kBdBlock * kBdRows));
+        const int cg_len = 2 * (K + 1);
+        double* h_cg = nullptr;  // pinned [world * cg_len]
+        std::vector<double> G, hvec((size_t)K + 1, 0.0);
+        if (batched) {
+            ATK_CUDA_CHECK(cudaMalloc(&d_part, sizeof(double) * (size_t)bd_blocks * (size_t)cg_len));
+            ATK_CUDA_CHECK(cudaMalloc(&d_cg, sizeof(double) * (size_t)cg_len * (size_t)ctx->world));
+            ATK_CUDA_CHECK(cudaMallocHost(&h_cg, sizeof(double) * (size_t)cg_len * (size_t)ctx->world));
+            G.assign((size_t)ld * ld, 0.0);
+        }
+        struct PinFree { double*& p; ~PinFree() { if (p) cudaFreeHost(p); } } pin_free{h_cg};
 
         // ---- persistent MGS step: usable when every CTA's slice of w fits in shared memory (single-GPU contexts)
         bool persistent = false;
@@ -432,17 +507,38 @@ void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t
                             count_launch(ctx);
                         }
                     } else if (j > 0) {
-                        for (int pass = 0; pass < 2; ++pass) {
-                            multi_dot_kernel<<<cgs_blocks, kCgsBlock, 0, st>>>(n, j, V, (int64_t)nn, w, d_part);
-                            multi_dot_final_kernel<<<j, 256, 0, st>>>(j, cgs_blocks, d_part, pass == 0 ? d_h : d_y);
-                            multi_axmy_kernel<<<grid, 256, 0, st>>>(n, j, V, (int64_t)nn, pass == 0 ? d_h : d_y, w);
-                            count_launch(ctx, 3);
+                        // ---- batched MGS: pass 1 (c = V[0:j]^T w, g = V[0:j+1]^T v_j), triangular solve, pass 2
+                        const int ncw = j, ncg = j + 1, len = 2 * ncg;
+                        multi_dot2_kernel<<<bd_blocks, kBdBlock, 0, st>>>(n, ncw, ncg, V, (int64_t)nn, w, vj, d_part);
+                        multi_dot2_final_kernel<<<len, 256, 0, st>>>(ncw, ncg, bd_blocks, d_part, d_cg + (size_t)ctx->rank * len);
+                        count_launch(ctx, 2);
+                        allgather_doubles(ctx, d_cg, (size_t)len, st);
+                        ATK_CUDA_CHECK(cudaMemcpyAsync(h_cg, d_cg, sizeof(double) * (size_t)len * ctx->world, cudaMemcpyDeviceToHost, st));
+                        ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+                        auto Gm = [&](int a, int b) -> double& { return G[(size_t)a + (size_t)b * ld]; };
+                        for (int i = 0; i < ncg; ++i) {  // rank-ordered sums: identical on every rank
+                            double c = 0.0, g = 0.0;
+                            for (int q = 0; q < ctx->world; ++q) {
+                                c = c + h_cg[(size_t)q * len + i];
+                                g = g + h_cg[(size_t)q * len + ncg + i];
+                            }
+                            hvec[(size_t)i] = c;  // c_i for i < j (entry j unused)
+                            Gm(j, i) = g;         // G(j,i) = v_j . v_i
+                            Gm(i, j) = g;
                         }
-                        // H(0:j, j) = h(pass 0) + h(pass 1)
-                        launch_add(ctx, j, d_h, d_y, d_h);
+                        for (int i = 0; i < j; ++i) {  // (I + strict_lower(G)) h = c, forward substitution
+                            double hi = hvec[(size_t)i];
+                            for (int m = 0; m < i; ++m) hi = hi - Gm(i, m) * hvec[(size_t)m];
+                            hvec[(size_t)i] = hi;
+                        }
+                        ATK_CUDA_CHECK(cudaMemcpyAsync(d_h, hvec.data(), sizeof(double) * (size_t)j, cudaMemcpyHostToDevice, st));
+                        multi_axmy_norm_kernel<<<ctx->reduce_grid(), kReduceBlock, sizeof(double) * (size_t)j, st>>>(
+                            n, j, V, (int64_t)nn, d_h, w, ctx->d_partials, ctx->d_tickets + 6, ctx->slot(kSlotNorm) + ctx->rank);
+                        count_launch(ctx);
+                        allgather_slot(ctx, kSlotNorm, st);
                     }
                     if (!persistent) {
-                        launch_dot(ctx, n, w, w, kSlotNorm);  // :79
+                        if (!(batched && j > 0)) launch_dot(ctx, n, w, w, kSlotNorm);  // :79 (the batched pass 2 already summed w.w)
                         normalize_kernel<<<grid, 256, 0, st>>>(n, w, V + (size_t)(j + 1) * nn, ctx->slot(kSlotNorm), ctx->world,
                                                                d_h + j);  // :86 (skipped on the device when the norm is 0)
                         count_launch(ctx);

@@ -111,6 +111,7 @@ inline void count_launch(Context* c, int n = 1) { c->launches += n; }
 
 // In-place all-gather of one reduction slot across ranks (no-op when world == 1).
 void allgather_slot(Context* ctx, int slot, cudaStream_t stream);
+void allgather_doubles(Context* ctx, double* buf, size_t count, cudaStream_t stream);
 // Exchange one xy-plane with the z-neighbours: sends `first_plane` down / `last_plane` up, receives into
 // halo_lo / halo_hi.  Runs on `stream`.
 void exchange_halo(Context* ctx, const double* first_plane, const double* last_plane, double* halo_lo, double* halo_hi,

@@ -193,9 +193,13 @@ typedef enum atk_gmres_event {
 typedef void (*atk_gmres_callback)(int event, double value, void* user);
 
 typedef enum atk_gmres_ortho {
-    ATK_GMRES_MGS = 0,   /* the reference's loop: for i<j { h = V[i].w; w = w - V[i]*h } (GMRES.hpp:73-77) */
-    ATK_GMRES_CGS2 = 1   /* batched: h = V[0:j]^T w; w -= V[0:j] h, twice; 4 reductions per step instead of j.
-                            Different rounding - a throughput option, never the parity path */
+    ATK_GMRES_MGS = 0,         /* the reference's loop: for i<j { h = V[i].w; w = w - V[i]*h } (GMRES.hpp:73-77), evaluated
+                                  projection by projection (persistent on-chip kernel where the slices fit) - parity path */
+    ATK_GMRES_MGS_BATCHED = 1  /* the same projection with two passes over V[0:j] and two reductions per Arnoldi step:
+                                  c = V^T w, g = V^T v_j (Gram row), solve (I + strict_lower(G)) h = c, w -= V h.
+                                  Mathematically identical to the loop above even for the reference's non-orthonormal
+                                  basis; rounding differs at the 1e-14 level on well-conditioned operators.  Plain
+                                  classical Gram-Schmidt (h = c) is NOT equivalent to the reference and is not offered. */
 } atk_gmres_ortho;
 
 typedef struct atk_gmres_info {

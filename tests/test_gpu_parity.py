@@ -417,6 +417,26 @@ def test_gmres_op27_tree_mode(ctx, port, golden, key):
         res = ctx.gmres_solve_host(op, b, np.zeros(n ** 3), g["max_iter"], g["K"], 1e-6)
         assert np.allclose(res["resid"], g["resid"]["all"], rtol=REL)
         assert relerr(res["x"], ora["x"]) < REL
+        # batched (low-synchronisation) MGS: two passes over V and two reductions per step, same projection
+        res = ctx.gmres_solve_host(op, b, np.zeros(n ** 3), g["max_iter"], g["K"], 1e-6, ortho=capi.GMRES_MGS_BATCHED)
+        assert np.allclose(res["resid"], g["resid"]["all"], rtol=REL)
+        assert relerr(res["x"], ora["x"]) < REL
+
+
+def test_gmres_batched_mgs_k300(ctx, port):
+    """K = 300 (the BASELINE Krylov dimension) on the config-5 operator at 14^3: the batched projection tracks the
+    reference's sequential loop to 1e-10 over two restarts (numpy prototype: 2e-14)."""
+    from algotoolkit_b200 import synthetic
+
+    n = 14
+    A = port.op27_csc(n, n, n)
+    b = port.spmv(A, port.u01_array(777, n ** 3))
+    ora = port.gmres(A, b, np.zeros(n ** 3), 2, 300, 1e-6)
+    op = ctx.operator_stencil27(n, n, n, synthetic.stencil27_coefficients())
+    for ortho in (capi.GMRES_MGS, capi.GMRES_MGS_BATCHED):
+        res = ctx.gmres_solve_host(op, b, np.zeros(n ** 3), 2, 300, 1e-6, ortho=ortho)
+        assert np.allclose(res["resid"], ora["resid"], rtol=REL), ortho
+        assert relerr(res["x"], ora["x"]) < REL, ortho
 
 
 # ------------------------------------------------------------------------------------------------ full-size properties

@@ -92,4 +92,24 @@ mgs_bytes = 40.0 * n5 * K * (K - 1) / 2 + 24.0 * n5 * K + K * (12.0 * op5.nnz + 
 out[f"gmres{K}_op27_{g5}"] = {"s_per_restart": res["device_ms"] * 1e-3, "arnoldi_steps_per_s": res["arnoldi_steps"] / (res["device_ms"] * 1e-3),
                               "algorithmic_GBs": mgs_bytes / (res["device_ms"] * 1e-3) / 1e9, "resid": res["resid"].tolist(),
                               "x_err_vs_ext": float(np.linalg.norm(res["x"] - x_ext) / np.linalg.norm(x_ext))}
+for name, ortho in (("batched", capi.GMRES_MGS_BATCHED),):
+    res = ctx.gmres_solve_host(op5, b5, np.zeros(n5), 1, K, 1e-6, ortho=ortho)
+    out[f"gmres{K}_op27_{g5}_{name}"] = {"s_per_restart": res["device_ms"] * 1e-3, "arnoldi_steps_per_s": res["arnoldi_steps"] / (res["device_ms"] * 1e-3),
+                                          "resid": res["resid"].tolist()}
+os.environ["ATK_GMRES_NO_PERSISTENT"] = "1"
+res = ctx.gmres_solve_host(op5, b5, np.zeros(n5), 1, K, 1e-6)
+out[f"gmres{K}_op27_{g5}_per_projection"] = {"s_per_restart": res["device_ms"] * 1e-3, "resid": res["resid"].tolist()}
+del os.environ["ATK_GMRES_NO_PERSISTENT"]
+# a size whose slices do not fit on chip (persistent kernel not applicable): 256^3 = 16.7 M rows, K = 40
+if not quick:
+    g6 = 256
+    n6 = g6 ** 3
+    op6 = ctx.operator_stencil27(g6, g6, g6, synthetic.stencil27_coefficients())
+    b6 = op6.apply_numpy(synthetic.u01_array(777, 0, n6))
+    K6 = 40
+    for name, ortho in (("per_projection", capi.GMRES_MGS), ("batched", capi.GMRES_MGS_BATCHED)):
+        res = ctx.gmres_solve_host(op6, b6, np.zeros(n6), 1, K6, 1e-6, ortho=ortho)
+        byts = (40.0 if ortho == capi.GMRES_MGS else 16.0) * n6 * K6 * (K6 - 1) / 2
+        out[f"gmres{K6}_op27_{g6}_{name}"] = {"s_per_restart": res["device_ms"] * 1e-3, "projection_GBs": byts / (res["device_ms"] * 1e-3) / 1e9,
+                                              "resid": res["resid"].tolist()}
 print(json.dumps(out, indent=1))
