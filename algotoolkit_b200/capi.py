@@ -59,6 +59,11 @@ class GmresInfo(C.Structure):
                 ("residual_trace", _dp), ("trace_capacity", C.c_int), ("trace_count", C.c_int)]
 
 
+class GdInfo(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("residual_norm", C.c_double), ("change_norm", C.c_double), ("device_ms", C.c_float),
+                ("kernel_launches", C.c_int)]
+
+
 GMRES_CALLBACK = C.CFUNCTYPE(None, C.c_int, C.c_double, C.c_void_p)
 
 # every symbol include/atk_cuda.h declares (tests check the .so exports all of them)
@@ -71,7 +76,8 @@ EXPORTS = [
     "atk_operator_stencil7", "atk_operator_poisson_assembled", "atk_operator_stencil27", "atk_operator_stencil27_assembled", "atk_slab_partition",
     "atk_operator_destroy",
     "atk_operator_shape", "atk_operator_row_range", "atk_operator_export_csr", "atk_operator_apply", "atk_cg_solve",
-    "atk_cg_solve_host", "atk_gmres_solve", "atk_gmres_solve_host",
+    "atk_cg_solve_host", "atk_gmres_solve", "atk_gmres_solve_host", "atk_gd_solve", "atk_gd_solve_host", "atk_arnoldi",
+    "atk_arnoldi_host",
 ]
 
 _lib = None
@@ -133,6 +139,10 @@ def load():
         "atk_gmres_solve_host": [_vp, _vp, _vp, _vp, i64, C.c_int, C.c_int, C.c_double, C.c_int, GMRES_CALLBACK, _vp,
                                  C.POINTER(GmresInfo)],
     }
+    sig["atk_gd_solve"] = [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.POINTER(GdInfo)]
+    sig["atk_gd_solve_host"] = sig["atk_gd_solve"]
+    sig["atk_arnoldi"] = [_vp, _vp, _vp, i64, C.c_int, _dp, C.c_double, _ip]
+    sig["atk_arnoldi_host"] = sig["atk_arnoldi"]
     for name, args in sig.items():
         fn = getattr(L, name)
         fn.argtypes = args
@@ -429,6 +439,27 @@ class Context:
         return dict(x=x, rc=rc, error=err, resid=trace[: min(info.trace_count, cap)].copy(), status=info.status,
                     restarts=info.restarts, arnoldi_steps=info.arnoldi_steps, device_ms=info.device_ms,
                     kernel_launches=info.kernel_launches, events=events)
+
+
+def gd_solve_host(ctx: Context, op: Operator, b, x0, max_iter: int, tol: float):
+    """GradientDescent::solve through host buffers."""
+    b = np.ascontiguousarray(b, np.float64)
+    x = np.ascontiguousarray(x0, np.float64).copy()
+    info = GdInfo()
+    _check(ctx.L.atk_gd_solve_host(ctx.h, op.h, _np_ptr(b), _np_ptr(x), max_iter, tol, C.byref(info)))
+    return dict(x=x, iters=info.iterations, residual_norm=info.residual_norm, change_norm=info.change_norm,
+                device_ms=info.device_ms, kernel_launches=info.kernel_launches)
+
+
+def arnoldi_host(ctx: Context, op: Operator, q0, m: int, tol: float):
+    """Krylov::Arnoldi through host buffers: returns Q as an (m, n) array (row i = Q[i]) and H as (m, m-1)."""
+    n = op.n_rows_local
+    Q = np.zeros((m, n))
+    Q[0] = np.ascontiguousarray(q0, np.float64)
+    H = np.zeros((m - 1, m))  # column-major m x (m-1)
+    bd = C.c_int(-1)
+    _check(ctx.L.atk_arnoldi_host(ctx.h, op.h, _np_ptr(Q), n, m, H.ctypes.data_as(_dp), tol, C.byref(bd)))
+    return dict(Q=Q, H=H.T.copy(), breakdown=bd.value)
 
 
 def _cg_result(info, tp, tr):

@@ -397,4 +397,52 @@ int atk_gmres_solve_host(atk_context_t ctx, atk_operator_t op, const double* b, 
     });
 }
 
+// ------------------------------------------------------------------------------------------------ "next" rows
+int atk_gd_solve(atk_context_t ctx, atk_operator_t op, const double* b, double* x, int max_iter, double tol, atk_gd_info* info) {
+    return guarded([&] {
+        atk::Context* c = C(ctx);
+        atk::Operator* o = O(op);
+        ATK_REQUIRE(o->ctx == c, ATK_ERR_INVALID_ARGUMENT, "operator belongs to another context");
+        atk::gd_solve(c, o, b, x, max_iter, tol, info);
+    });
+}
+int atk_gd_solve_host(atk_context_t ctx, atk_operator_t op, const double* b, double* x, int max_iter, double tol,
+                      atk_gd_info* info) {
+    return guarded([&] {
+        atk::Context* c = C(ctx);
+        atk::Operator* o = O(op);
+        ATK_REQUIRE(o->ctx == c && b && x && info, ATK_ERR_INVALID_ARGUMENT, "bad argument to atk_gd_solve_host");
+        const size_t bytes = sizeof(double) * (size_t)o->n_rows_local;
+        atk::WsBuffer db(c, bytes), dx(c, bytes);
+        ATK_CUDA_CHECK(cudaMemcpyAsync(db.ptr, b, bytes, cudaMemcpyHostToDevice, c->stream));
+        ATK_CUDA_CHECK(cudaMemcpyAsync(dx.ptr, x, bytes, cudaMemcpyHostToDevice, c->stream));
+        atk::gd_solve(c, o, db.as<double>(), dx.as<double>(), max_iter, tol, info);
+        ATK_CUDA_CHECK(cudaMemcpyAsync(x, dx.ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+        ATK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+int atk_arnoldi(atk_context_t ctx, atk_operator_t op, double* Q, int64_t ldq, int m, double* H, double tol, int* breakdown_at) {
+    return guarded([&] {
+        atk::Context* c = C(ctx);
+        atk::Operator* o = O(op);
+        ATK_REQUIRE(o->ctx == c, ATK_ERR_INVALID_ARGUMENT, "operator belongs to another context");
+        atk::arnoldi(c, o, Q, ldq, m, H, tol, breakdown_at);
+    });
+}
+int atk_arnoldi_host(atk_context_t ctx, atk_operator_t op, double* Q, int64_t ldq, int m, double* H, double tol,
+                     int* breakdown_at) {
+    return guarded([&] {
+        atk::Context* c = C(ctx);
+        atk::Operator* o = O(op);
+        ATK_REQUIRE(o->ctx == c && Q && H && breakdown_at && m >= 1 && ldq >= o->n_rows_local, ATK_ERR_INVALID_ARGUMENT,
+                    "bad argument to atk_arnoldi_host");
+        const size_t bytes = sizeof(double) * (size_t)ldq * (size_t)m;
+        atk::WsBuffer dq(c, bytes);
+        ATK_CUDA_CHECK(cudaMemcpyAsync(dq.ptr, Q, bytes, cudaMemcpyHostToDevice, c->stream));
+        atk::arnoldi(c, o, dq.as<double>(), ldq, m, H, tol, breakdown_at);
+        ATK_CUDA_CHECK(cudaMemcpyAsync(Q, dq.ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+        ATK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    });
+}
+
 }  // extern "C"

@@ -136,6 +136,14 @@ void ipc_share(Context* ctx, void* local, std::vector<void*>& peers, const std::
     }
 }
 
+void Context::ipc_close(void* mapped) {
+    if (!mapped) return;
+    auto it = std::find(ipc_opened.begin(), ipc_opened.end(), mapped);
+    if (it == ipc_opened.end()) return;
+    cudaIpcCloseMemHandle(mapped);
+    ipc_opened.erase(it);
+}
+
 // Decide collectively whether peer-memory signalling can be used and set it up.
 static void setup_p2p(Context& c) {
     c.p2p = false;
@@ -314,6 +322,7 @@ void context_destroy(atk_context_s* h) {
     for (auto& b : c.ws_blocks) cudaFree(b.ptr);
     c.ws_blocks.clear();
     for (void* p : c.ipc_opened) cudaIpcCloseMemHandle(p);
+    for (void* p : c.ipc_exported) cudaFree(p);  // exported halo arenas: kept alive until now for the peers' sake
     cudaFree(c.d_peer_gather);
     cudaFree(c.d_peer_flags);
     if (c.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c.nccl_comm);

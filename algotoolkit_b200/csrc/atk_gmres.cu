@@ -49,12 +49,13 @@ __global__ void __launch_bounds__(256) mgs_axmy_kernel(int64_t n, const double* 
 
 // out = w / sqrt(slot)  (V[j+1] = w / H(j+1,j), :86) - skipped when the norm is zero (the host raises the error).
 __global__ void __launch_bounds__(256) normalize_kernel(int64_t n, const double* __restrict__ w, double* __restrict__ out,
-                                                        const double* __restrict__ slot, int world, double* __restrict__ norm_out) {
+                                                        const double* __restrict__ slot, int world, double* __restrict__ norm_out,
+                                                        double skip_below) {
     const double nrm = sqrt(slot_sum(slot, world));
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t == 0) *norm_out = nrm;
-    if (nrm == 0.0) return;
+    if (nrm == 0.0 || nrm < skip_below) return;  // the reference breaks before assigning the next basis vector
     for (int64_t i = t; i < n; i += stride) out[i] = __ddiv_rn(w[i], nrm);
 }
 
@@ -196,6 +197,7 @@ struct MgsArgs {
     unsigned* bar;       // zero-initialised counter of this step
     int64_t chunk;       // rows per CTA (multiple of 2)
     int sequential;
+    double skip_below;   // V[j+1] is left untouched when ||w|| < skip_below (the reference breaks before assigning it)
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
             } else {
                 const double nrm = sqrt(h);                                // (:79)
                 if (blockIdx.x == 0 && threadIdx.x == 0) a.h_out[a.j] = nrm;
-                if (nrm != 0.0) {
+                if (nrm != 0.0 && !(nrm < a.skip_below)) {
 #pragma unroll
                     for (int q = 0; q < kMgsRegRows; ++q) {
                         const int64_t e = threadIdx.x + (int64_t)q * BLOCK;
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
             } else {
                 const double nrm = sqrt(h);                                                                       // (:79)
                 if (blockIdx.x == 0 && threadIdx.x == 0) a.h_out[a.j] = nrm;
-                if (nrm != 0.0)
+                if (nrm != 0.0 && !(nrm < a.skip_below))
                     for (int64_t e = threadIdx.x; e < len; e += BLOCK) a.vnext[c0 + e] = __ddiv_rn(wsm[e], nrm);  // (:86)
             }
         }
@@ -354,6 +356,59 @@ inline MgsKernel mgs_kernel_for(int block, bool reg) {
         default: return reg ? arnoldi_mgs_kernel<512, true> : arnoldi_mgs_kernel<512, false>;
     }
 }
+
+// Launch configuration of the persistent step kernel for slices of a system of n rows (single-GPU contexts), or
+// usable == false when a slice does not fit on chip.
+struct PersistentMgs {
+    bool usable = false;
+    int grid = 1, block = 512;
+    MgsKernel kernel = nullptr;
+    int64_t chunk = 0;
+    size_t smem = 0;
+    unsigned* d_bar = nullptr;
+    double* d_part = nullptr;
+    int n_bars = 0;
+    ~PersistentMgs() {
+        cudaFree(d_bar);
+        cudaFree(d_part);
+    }
+    void setup(Context* ctx, int64_t n, int max_steps) {
+        if (ctx->world != 1 || n <= 0 || std::getenv("ATK_GMRES_NO_PERSISTENT")) return;
+        const bool seq = ctx->reduction == ATK_REDUCE_SEQUENTIAL;
+        int64_t c = seq ? n : std::max<int64_t>(2048, (n + ctx->sm_count - 1) / ctx->sm_count);
+        c = (c + 1) & ~(int64_t)1;
+        const int64_t rows = std::min(c, n);
+        block = rows <= 64 * 8 ? 64 : rows <= 128 * 8 ? 128 : rows <= 256 * 8 ? 256 : 512;
+        const bool reg = rows <= (int64_t)block * kMgsRegRows;
+        const size_t sm = sizeof(double) * (size_t)c * (reg ? (seq ? 1 : 0) : (seq ? 2 : 1));
+        kernel = mgs_kernel_for(block, reg);
+        int max_smem = 0;
+        ATK_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+        if (sm + 1024 > (size_t)max_smem) return;
+        ATK_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        int per_sm = 0;
+        ATK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, sm));
+        const int g = (int)((n + c - 1) / c);
+        if (per_sm < 1 || g > per_sm * ctx->sm_count) return;
+        grid = g;
+        chunk = c;
+        smem = sm;
+        n_bars = max_steps + 1;
+        ATK_CUDA_CHECK(cudaMalloc(&d_bar, sizeof(unsigned) * (size_t)n_bars));
+        ATK_CUDA_CHECK(cudaMalloc(&d_part, sizeof(double) * 2 * (size_t)g));
+        usable = true;
+    }
+    void reset_barriers(cudaStream_t st) { ATK_CUDA_CHECK(cudaMemsetAsync(d_bar, 0, sizeof(unsigned) * (size_t)n_bars, st)); }
+    // projections of w against columns [0, ncols) of V, then the norm and V_next = w / norm; h_out[0..ncols] on the device
+    void launch(Context* ctx, int64_t n, int ncols, int step, const double* V, int64_t ldv, const double* w, double* vnext,
+                double* h_out, double skip_below) {
+        MgsArgs ma{n, ncols, V, ldv, w, vnext, h_out, d_part, d_bar + step, chunk, ctx->reduction == ATK_REDUCE_SEQUENTIAL ? 1 : 0,
+                   skip_below};
+        void* kargs[] = {&ma};
+        ATK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(block), kargs, smem, ctx->stream));
+        count_launch(ctx);
+    }
+};
 
 struct Givens {
     // reference GMRES.hpp:139-151
@@ -494,7 +549,7 @@ void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t
                     op->apply(vj, w, -1, nullptr);  // :70
                     if (persistent) {
                         MgsArgs ma{n, j, V, (int64_t)nn, w, V + (size_t)(j + 1) * nn, d_h, d_mgs_part, d_bar + j, mgs_chunk,
-                                   ctx->reduction == ATK_REDUCE_SEQUENTIAL ? 1 : 0};
+                                   ctx->reduction == ATK_REDUCE_SEQUENTIAL ? 1 : 0, tol};
                         void* kargs[] = {&ma};
                         ATK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)mgs_kernel, dim3(mgs_grid), dim3(mgs_block), kargs, mgs_smem,
                                                                    st));
@@ -540,7 +595,7 @@ void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t
                     if (!persistent) {
                         if (!(batched && j > 0)) launch_dot(ctx, n, w, w, kSlotNorm);  // :79 (the batched pass 2 already summed w.w)
                         normalize_kernel<<<grid, 256, 0, st>>>(n, w, V + (size_t)(j + 1) * nn, ctx->slot(kSlotNorm), ctx->world,
-                                                               d_h + j);  // :86 (skipped on the device when the norm is 0)
+                                                               d_h + j, tol);  // :86 (skipped when the norm is 0 or below tol)
                         count_launch(ctx);
                     }
                     ATK_CUDA_CHECK(cudaGetLastError());
@@ -606,6 +661,69 @@ void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t
         ATK_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
         info->device_ms = ms;
         info->kernel_launches = (int)(ctx->launches - launches0);
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        cleanup();
+        throw;
+    }
+    cleanup();
+}
+
+// ---------------------------------------------------------------------------------------------- Krylov::Arnoldi
+// Reference src/LinearAlgebra/Krylov/KrylovSubspace.hpp:11-38 ("next" row): textbook MGS Arnoldi.
+//     for i = 1..m-1:  Av = A*Q[i-1];  for j<i { h = Q[j].Av; H(j,i-1) = h; Av -= Q[j]*h }
+//                      h = ||Av||; if h < tol { breakdown at i; stop }  H(i,i-1) = h;  Q[i] = Av/h
+// Same kernels as the GMRES step (persistent on-chip kernel where the slices fit, per-projection kernels otherwise).
+// Q: m columns (ldq apart) on the device, Q[0] given; H: host, m x (m-1) column-major - only the entries the reference
+// writes are touched.  *breakdown = i of the breakdown, or -1.
+void arnoldi(Context* ctx, Operator* op, double* Q, int64_t ldq, int m, double* H, double tol, int* breakdown) {
+    ATK_REQUIRE(op && Q && H && breakdown && m >= 1, ATK_ERR_INVALID_ARGUMENT, "bad argument to arnoldi");
+    const int64_t n = op->n_rows_local;
+    ATK_REQUIRE(ldq >= n, ATK_ERR_INVALID_ARGUMENT, "Q columns overlap");
+    cudaStream_t st = ctx->stream;
+    *breakdown = -1;
+    double *w = nullptr, *d_h = nullptr, *h_col = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(w);
+        cudaFree(d_h);
+        if (h_col) cudaFreeHost(h_col);
+    };
+    try {
+        ATK_CUDA_CHECK(cudaMalloc(&w, sizeof(double) * (size_t)std::max<int64_t>(n, 1)));
+        ATK_CUDA_CHECK(cudaMalloc(&d_h, sizeof(double) * (size_t)(m + 1)));
+        ATK_CUDA_CHECK(cudaMallocHost(&h_col, sizeof(double) * (size_t)(m + 1)));
+        PersistentMgs pm;
+        pm.setup(ctx, n, m);
+        if (pm.usable) pm.reset_barriers(st);
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8));
+        for (int i = 1; i < m; ++i) {
+            op->apply(Q + (size_t)(i - 1) * ldq, w, -1, nullptr);
+            double* qi = Q + (size_t)i * ldq;
+            if (pm.usable) {
+                pm.launch(ctx, n, i, i, Q, ldq, w, qi, d_h, tol);
+            } else {
+                for (int j = 0; j < i; ++j) {
+                    const double* qj = Q + (size_t)j * ldq;
+                    launch_dot(ctx, n, qj, w, kSlotH);
+                    mgs_axmy_kernel<<<grid, 256, 0, st>>>(n, qj, w, ctx->slot(kSlotH), ctx->world, d_h + j);
+                    count_launch(ctx);
+                }
+                launch_dot(ctx, n, w, w, kSlotNorm);
+                normalize_kernel<<<grid, 256, 0, st>>>(n, w, qi, ctx->slot(kSlotNorm), ctx->world, d_h + i, tol);
+                count_launch(ctx);
+            }
+            ATK_CUDA_CHECK(cudaGetLastError());
+            ATK_CUDA_CHECK(cudaMemcpyAsync(h_col, d_h, sizeof(double) * (size_t)(i + 1), cudaMemcpyDeviceToHost, st));
+            ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+            for (int j = 0; j < i; ++j) H[(size_t)j + (size_t)(i - 1) * (size_t)m] = h_col[j];
+            const double nrm = h_col[i];
+            if (nrm < tol) {
+                *breakdown = i;
+                break;
+            }
+            H[(size_t)i + (size_t)(i - 1) * (size_t)m] = nrm;
+            ATK_REQUIRE(nrm != 0.0, ATK_ERR_RUNTIME, "Division by zero.");
+        }
     } catch (...) {
         cudaStreamSynchronize(st);
         cleanup();

@@ -81,6 +81,8 @@ struct Context {
     double** d_peer_gather = nullptr;            // device array [world]: every rank's d_gather as mapped here
     unsigned long long** d_peer_flags = nullptr; // device array [world]
     std::vector<void*> ipc_opened;               // mappings to close at destruction
+    std::vector<void*> ipc_exported;             // allocations other ranks may still have mapped: freed with the context
+    void ipc_close(void* mapped);                // close one mapping early (operator destruction)
     unsigned long long epoch = 1;                // sequence-number base, advanced identically on all ranks
 
     // ---- workspace cache: solver-internal device buffers are recycled between calls instead of going through
@@ -195,6 +197,8 @@ void launch_axmy(Context* ctx, int64_t n, const double* x, const double* y, doub
 
 // ------------------------------------------------------------------------------------------ solvers
 void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r, double* p, int max_iter, atk_cg_info* info);
+void gd_solve(Context* ctx, Operator* op, const double* b, double* x, int max_iter, double tol, atk_gd_info* info);
+void arnoldi(Context* ctx, Operator* op, double* Q, int64_t ldq, int m, double* H, double tol, int* breakdown);
 void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t n_x, int max_iter, int krylov_dim,
                  double tol, atk_gmres_ortho ortho, atk_gmres_callback cb, void* user, atk_gmres_info* info);
 

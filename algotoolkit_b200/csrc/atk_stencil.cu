@@ -707,11 +707,17 @@ struct Stencil7 : public Operator {
     int ftile = 4;
     bool fsmem = true;
 
+    bool arena_exported = false;
+
     ~Stencil7() override {
         cudaFree(halo_lo);
         cudaFree(halo_hi);
         cudaFree(fsend);
-        cudaFree(frecv);
+        // the neighbours may still have this rank's halo arena mapped: unmap theirs now, free ours with the context
+        ctx->ipc_close(nb_lo_arena);
+        ctx->ipc_close(nb_hi_arena);
+        if (arena_exported) ctx->ipc_exported.push_back(frecv);
+        else cudaFree(frecv);
     }
 
     bool fused_cg_capable() const override { return true; }
@@ -1038,6 +1044,7 @@ Operator* make_stencil7(Context* ctx, int nx, int ny, int nz, double cx, double 
                 if (ctx->rank > 0) want.push_back(ctx->rank - 1);
                 if (ctx->rank + 1 < ctx->world) want.push_back(ctx->rank + 1);
                 ipc_share(ctx, S->frecv, peers, want);
+                S->arena_exported = true;
                 if (ctx->rank > 0) S->nb_lo_arena = static_cast<double*>(peers[(size_t)ctx->rank - 1]);
                 if (ctx->rank + 1 < ctx->world) S->nb_hi_arena = static_cast<double*>(peers[(size_t)ctx->rank + 1]);
             }

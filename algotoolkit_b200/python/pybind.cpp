@@ -20,6 +20,8 @@
 
 #include "../host/LinearAlgebra/Krylov/ConjugateGradient.hpp"
 #include "../host/LinearAlgebra/Krylov/GMRES.hpp"
+#include "../host/LinearAlgebra/Krylov/KrylovSubspace.hpp"
+#include "../host/LinearAlgebra/Solver/IterSolver.hpp"
 #include "../host/Obj/DenseObj.hpp"
 #include "../host/Obj/SparseObj.hpp"
 #include "../host/Obj/VectorObj.hpp"
@@ -119,6 +121,20 @@ PYBIND11_MODULE(fastsolver, m) {
         .def("solve", &Cg::solve, "Solve the linear system using the Conjugate Gradient method.", py::arg("x"))
         .def_property_readonly("iterations", [](const Cg& c) { return c.last.iterations; })
         .def_property_readonly("stopped_on_pAp", [](const Cg& c) { return c.last.stopped_on_pAp; });
+
+    using Gd = GradientDescent<double, Csc, Vec>;
+    py::class_<Gd>(m, "GradientDescent")
+        .def(py::init<const Csc&, const Vec&, int, double>(), py::arg("A"), py::arg("b"), py::arg("max_iter"), py::arg("tol"),
+             py::keep_alive<1, 2>(), py::keep_alive<1, 3>())  // the solver keeps references, as the reference class does
+        .def("solve", &Gd::solve, "Solve the linear system using Gradient Descent.", py::arg("x"))
+        .def_property_readonly("iterations", [](const Gd& g) { return g.last.iterations; });
+
+    m.def("arnoldi", [](Dense& A, std::vector<Vec>& Q, Dense& H, double tol) {
+        py::scoped_ostream_redirect out(std::cout, py::module_::import("sys").attr("stdout"));
+        Krylov::Arnoldi<double, Dense, Vec>(A, Q, H, tol);
+        return Q;  // pybind11 passes std::vector by value: hand the filled basis back as the result
+    }, "Arnoldi iteration for generating an orthogonal basis of the Krylov subspace (returns the filled basis).",
+       py::arg("A"), py::arg("Q"), py::arg("H"), py::arg("tol"));
 
     py::class_<Gm>(m, "GMRES")
         .def(py::init<>())

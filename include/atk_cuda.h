@@ -227,6 +227,30 @@ int atk_gmres_solve_host(atk_context_t ctx, atk_operator_t op, const double* b, 
                          int krylov_dim, double tol, atk_gmres_ortho ortho, atk_gmres_callback cb, void* user,
                          atk_gmres_info* info);
 
+/* ------------------------------------------------------------------------------------------------ "next" rows
+ * compositions of the same kernels. */
+typedef struct atk_gd_info {
+    int iterations;        /* iterations whose update was applied */
+    double residual_norm;  /* ||r|| after the last update */
+    double change_norm;    /* ||x - xOld|| of the last update */
+    float device_ms;
+    int kernel_launches;
+} atk_gd_info;
+/* GradientDescent::solve (src/LinearAlgebra/Solver/IterSolver.hpp:23-44): steepest descent with the reference's loop
+ * condition (residualNorm > tol) and early exit (||x - xOld|| < tol).  x is the initial guess and the result. */
+int atk_gd_solve(atk_context_t ctx, atk_operator_t op, const double* b, double* x, int max_iter, double tol,
+                 atk_gd_info* info);
+int atk_gd_solve_host(atk_context_t ctx, atk_operator_t op, const double* b, double* x, int max_iter, double tol,
+                      atk_gd_info* info);
+/* Krylov::Arnoldi (src/LinearAlgebra/Krylov/KrylovSubspace.hpp:11-38): textbook MGS Arnoldi (projects against ALL
+ * previous vectors).  Q holds m columns of the local length, `ldq` doubles apart, Q[0] given, the others written;
+ * H is a HOST array, m x (m-1) column-major, of which only the entries the reference writes are touched;
+ * *breakdown_at = i when ||A q_(i-1) - ...|| < tol stopped the recursion at step i (Q[i] untouched), else -1. */
+int atk_arnoldi(atk_context_t ctx, atk_operator_t op, double* Q, int64_t ldq, int m, double* H, double tol,
+                int* breakdown_at);
+int atk_arnoldi_host(atk_context_t ctx, atk_operator_t op, double* Q, int64_t ldq, int m, double* H, double tol,
+                     int* breakdown_at);
+
 #ifdef __cplusplus
 }
 #endif

@@ -422,3 +422,64 @@ done:
     free(r); free(w); free(t);
     return rc;
 }
+
+/* ------------------------------------------------------------------ GradientDescent */
+/* IterSolver.hpp:23-44 */
+int orc_gd_solve(int n, const int* col_ptr, const int* row_idx, const double* vals, const double* b, double* x, int max_iter,
+                 double tol, int* iters, double* residual_norm, double* change_norm) {
+    const size_t N = (size_t)(n > 0 ? n : 1);
+    double* r = (double*)malloc(sizeof(double) * N);
+    double* Ar = (double*)malloc(sizeof(double) * N);
+    double* t = (double*)malloc(sizeof(double) * N);
+    double* xold = (double*)malloc(sizeof(double) * N);
+    orc_spmv_csc(n, n, col_ptr, row_idx, vals, x, t);            /* :24 r = b - A*x */
+    orc_vec_sub(n, b, t, r);
+    double rn = orc_nrm2(n, r);                                   /* :25 */
+    double cn = 0.0;
+    memcpy(xold, x, sizeof(double) * (size_t)n);                  /* :26 */
+    int it = 0;
+    for (; it < max_iter && rn > tol; ++it) {                     /* :28 */
+        orc_spmv_csc(n, n, col_ptr, row_idx, vals, r, Ar);        /* :29 */
+        const double alpha = orc_dot(n, r, r) / orc_dot(n, r, Ar); /* :30 */
+        orc_vec_scale(n, r, alpha, t);                            /* :32 x = x + r*alpha */
+        orc_vec_add(n, x, t, x);
+        orc_vec_scale(n, Ar, alpha, t);                           /* :33 r = r - Ar*alpha */
+        orc_vec_sub(n, r, t, r);
+        rn = orc_nrm2(n, r);                                      /* :35 */
+        orc_vec_sub(n, x, xold, t);                               /* :38 */
+        cn = orc_nrm2(n, t);
+        if (cn < tol) { ++it; break; }                            /* :39-41 (the update of this iteration was applied) */
+        memcpy(xold, x, sizeof(double) * (size_t)n);              /* :42 */
+    }
+    *iters = it;
+    *residual_norm = rn;
+    *change_norm = cn;
+    free(r); free(Ar); free(t); free(xold);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ Krylov::Arnoldi */
+/* KrylovSubspace.hpp:11-38 */
+int orc_arnoldi(int n, const int* col_ptr, const int* row_idx, const double* vals, double* Q, int m, double* H, double tol,
+                int* breakdown) {
+    const size_t N = (size_t)(n > 0 ? n : 1);
+    double* av = (double*)malloc(sizeof(double) * N);
+    double* t = (double*)malloc(sizeof(double) * N);
+    *breakdown = -1;
+    for (int i = 1; i < m; ++i) {                                              /* :18 */
+        orc_spmv_csc(n, n, col_ptr, row_idx, vals, Q + (size_t)(i - 1) * N, av); /* :19 */
+        for (int j = 0; j < i; ++j) {                                          /* :22-26 */
+            const double* qj = Q + (size_t)j * N;
+            const double h = orc_dot(n, qj, av);
+            H[(size_t)j + (size_t)(i - 1) * (size_t)m] = h;
+            orc_vec_scale(n, qj, h, t);
+            orc_vec_sub(n, av, t, av);
+        }
+        const double h = orc_nrm2(n, av);                                      /* :29 */
+        if (h < tol) { *breakdown = i; break; }                                /* :30-33 */
+        H[(size_t)i + (size_t)(i - 1) * (size_t)m] = h;                        /* :35 */
+        orc_vec_div(n, av, h, Q + (size_t)i * N);                              /* :36 */
+    }
+    free(av); free(t);
+    return 0;
+}

@@ -96,6 +96,17 @@ int orc_gmres_solve(int n, const int* col_ptr, const int* row_idx, const double*
                     int n_x, int max_iter, int krylov_dim, double tol, double* resid, int resid_cap, int* n_resid,
                     int* status, int* last_kry_update);
 
+/* ---- "next" rows: compositions of the same kernels ---- */
+/* GradientDescent::solve (src/LinearAlgebra/Solver/IterSolver.hpp:23-44): steepest descent with the residual-norm loop
+ * condition and the change-norm early exit.  x in/out; iters = iterations whose update was applied. */
+int orc_gd_solve(int n, const int* col_ptr, const int* row_idx, const double* vals, const double* b, double* x, int max_iter,
+                 double tol, int* iters, double* residual_norm, double* change_norm);
+/* Krylov::Arnoldi (src/LinearAlgebra/Krylov/KrylovSubspace.hpp:11-38): textbook MGS Arnoldi (projects against ALL previous
+ * vectors, unlike the loop inside GMRES).  Q: m columns of n (column-major, Q[0] given); H: m x (m-1) column-major, only
+ * the entries the reference writes are touched.  breakdown = iteration index at which ||Av|| < tol stopped it, or -1. */
+int orc_arnoldi(int n, const int* col_ptr, const int* row_idx, const double* vals, double* Q, int m, double* H, double tol,
+                int* breakdown);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,6 +103,8 @@ class Port:
                                    _dp, C.c_int]
         L.orc_gmres_solve.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, _dp,
                                       C.c_int, _ip, _ip, _ip]
+        L.orc_gd_solve.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_int, C.c_double, _ip, _dp, _dp]
+        L.orc_arnoldi.argtypes = [C.c_int, _ip, _ip, _dp, _dp, C.c_int, _dp, C.c_double, _ip]
 
     # -- vectors
     def u01(self, s):
@@ -262,6 +264,24 @@ class Port:
         return dict(x=x, resid=resid[: nres.value].copy(), status=status.value, rc=rc, kry_update=kry.value)
 
 
+    def gd(self, A, b, x0, max_iter, tol):
+        b, x = _f64(b), _f64(x0).copy()
+        it, rn, cn = C.c_int(), C.c_double(), C.c_double()
+        self.L.orc_gd_solve(A.n_rows, _i(A.col_ptr), _i(A.row_idx), _d(A.vals), _d(b), _d(x), max_iter, tol, C.byref(it),
+                            C.byref(rn), C.byref(cn))
+        return dict(x=x, iters=it.value, residual_norm=rn.value, change_norm=cn.value)
+
+    def arnoldi(self, A, q0, m, tol):
+        """Q as (m, n) array (row i = Q[i]), H as (m, m-1) array."""
+        n = A.n_rows
+        Q = np.zeros((m, n))
+        Q[0] = _f64(q0)
+        H = np.zeros((m - 1, m))  # column-major m x (m-1): column c at H[c]
+        bd = C.c_int()
+        self.L.orc_arnoldi(n, _i(A.col_ptr), _i(A.row_idx), _d(A.vals), _d(Q), m, _d(H), tol, C.byref(bd))
+        return dict(Q=Q, H=H.T.copy(), breakdown=bd.value)
+
+
 # =============================================================================== reference
 def ref_available() -> bool:
     return os.path.exists(os.path.join(_HERE, "_ref", "libatk_ref.so"))
@@ -302,6 +322,8 @@ class Ref:
         L.ref_poisson_solve.argtypes = [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int, C.c_uint64, C.c_int, C.c_double,
                                                                            _dp, _dp, _dp, _dp]
         L.ref_poisson_rhs.argtypes = [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int, C.c_uint64, _dp]
+        L.ref_gd_solve.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_double]
+        L.ref_arnoldi.argtypes = [C.c_void_p, _dp, C.c_int, _dp, C.c_double, C.c_char_p, C.c_int]
 
     # -- vectors
     def dot(self, a, b):
@@ -413,6 +435,20 @@ class Ref:
         if rc == 1:
             raise ValueError("invalid argument")
         return dict(x=x, rc=rc, log=text, resid=parse_gmres_log(text)[0], status=parse_gmres_log(text)[1])
+
+    def gd(self, M, b, x0, max_iter, tol):
+        b, x = _f64(b), _f64(x0).copy()
+        self.L.ref_gd_solve(M.h, _d(b), _d(x), max_iter, tol)
+        return dict(x=x)
+
+    def arnoldi(self, M, q0, m, tol):
+        n = M.n_rows
+        Q = np.zeros((m, n))
+        Q[0] = _f64(q0)
+        H = np.zeros((m - 1, m))
+        log = C.create_string_buffer(4096)
+        self.L.ref_arnoldi(M.h, _d(Q), m, _d(H), tol, log, 4096)
+        return dict(Q=Q, H=H.T.copy(), log=log.value.decode())
 
     def poisson_solve(self, nx, ny, nz, lx=1.0, ly=1.0, lz=1.0, rhs_kind=0, seed=12345, max_iter=1000, tol=1e-6):
         n = nx * ny * nz

@@ -18,6 +18,8 @@
 //   src/LinearAlgebra/Krylov/GMRES.hpp:27-171
 //   src/PDEs/FDM/Poisson.hpp:30-170
 //   src/utils.hpp:30-71                 readMatrixMarket
+//   src/LinearAlgebra/Solver/IterSolver.hpp:23-44      GradientDescent   ("next" row)
+//   src/LinearAlgebra/Krylov/KrylovSubspace.hpp:11-38  Krylov::Arnoldi   ("next" row)
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -40,6 +42,8 @@
 #include "Obj/SparseObj.hpp"
 #include "LinearAlgebra/Krylov/ConjugateGradient.hpp"
 #include "LinearAlgebra/Krylov/GMRES.hpp"
+#include "LinearAlgebra/Krylov/KrylovSubspace.hpp"
+#include "LinearAlgebra/Solver/IterSolver.hpp"
 // Poisson3DSolver keeps A and b private; the checker needs to read them.
 #define private public
 #include "PDEs/FDM/Poisson.hpp"
@@ -287,6 +291,36 @@ int ref_gmres_solve(void* h, const double* b, double* x_inout, int n_x, int max_
     copy_log(cap.os.str(), log, log_cap);
     if (rc == 0 || rc == 2) copy_out(x, x_inout);
     return rc;
+}
+
+// ---------------------------------------------------------------- GradientDescent / Krylov::Arnoldi ("next" rows)
+int ref_gd_solve(void* h, const double* b, double* x_inout, int max_iter, double tol) {
+    Csc& A = *static_cast<Csc*>(h);
+    Vec bb = make_vec(b, A.getRows());
+    Vec x = make_vec(x_inout, A.getRows());
+    GradientDescent<double, Csc, Vec> gd(A, bb, max_iter, tol);
+    gd.solve(x);
+    copy_out(x, x_inout);
+    return 0;
+}
+// Q: m columns of n (column-major), Q[0] given; H: m x (m-1) column-major (DenseObj storage order).
+// The reference instantiation is the one its pybind module binds: Arnoldi<double, DenseObj, VectorObj> (pybind.cpp:47).
+int ref_arnoldi(void* h, double* Q, int m, double* H, double tol, char* log, int log_cap) {
+    Csc& A = *static_cast<Csc*>(h);
+    const int n = A.getRows();
+    Dense Ad(n, n);
+    for (int c = 0; c < A.getCols(); ++c)
+        for (int k = A.col_ptr[c]; k < A.col_ptr[c + 1]; ++k) Ad(A.row_indices[k], c) = A.values[k];
+    std::vector<Vec> Qv;
+    for (int i = 0; i < m; ++i) Qv.push_back(make_vec(Q + (size_t)i * n, n));
+    Dense Hd(m, m - 1);
+    for (int i = 0; i < m * (m - 1); ++i) Hd[i] = H[i];
+    CoutCapture cap(0);
+    Krylov::Arnoldi<double, Dense, Vec>(Ad, Qv, Hd, tol);
+    copy_log(cap.os.str(), log, log_cap);
+    for (int i = 0; i < m; ++i) copy_out(Qv[i], Q + (size_t)i * n);
+    for (int i = 0; i < m * (m - 1); ++i) H[i] = Hd[i];
+    return 0;
 }
 
 // ---------------------------------------------------------------- Poisson3DSolver

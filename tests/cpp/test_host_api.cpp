@@ -9,6 +9,8 @@
 
 #include "LinearAlgebra/Krylov/ConjugateGradient.hpp"
 #include "LinearAlgebra/Krylov/GMRES.hpp"
+#include "LinearAlgebra/Krylov/KrylovSubspace.hpp"
+#include "LinearAlgebra/Solver/IterSolver.hpp"
 #include "Obj/DenseObj.hpp"
 #include "Obj/SparseObj.hpp"
 #include "Obj/VectorObj.hpp"
@@ -196,6 +198,35 @@ static void gmres_tests() {  // GMRES_test.cpp:43-92 (DenseObj A, as in the refe
     CHECK(log.find("Initial guess is good enough.") != std::string::npos);
 }
 
+static void gd_arnoldi_tests() {  // tests/itersolver_test.cpp:5-39, tests/KrylovSubspace_test.cpp (orthogonality, A Q = Q H)
+    SparseMatrixCSC<double> A = tridiag3();
+    VectorObj<double> b(3), x(3, 0.0);
+    b[0] = 1.0; b[1] = 5.0; b[2] = 0.0;
+    GradientDescent<double, SparseMatrixCSC<double>, VectorObj<double>> gd(A, b, 1000, 1e-6);
+    gd.solve(x);
+    CHECK_NEAR(x[0], 0.625, 1e-5);
+    CHECK_NEAR(x[1], 1.5, 1e-5);
+    CHECK_NEAR(x[2], 0.375, 1e-5);
+    CHECK(gd.last.iterations == 15);  // the reference stops after 15 updates on this system (oracle)
+
+    const int n = 6, m = 4;
+    DenseObj<double> D(n, n);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) D(i, j) = (i == j) ? 4.0 + i : 1.0 / (1.0 + i + j);
+    std::vector<VectorObj<double>> Q(m, VectorObj<double>(n, 0.0));
+    Q[0][0] = 1.0;
+    DenseObj<double> H(m, m - 1);
+    Krylov::Arnoldi<double, DenseObj<double>, VectorObj<double>>(D, Q, H, 1e-10);
+    for (int a = 0; a < m; ++a)
+        for (int c = 0; c < m; ++c) CHECK_NEAR(Q[a] * Q[c], a == c ? 1.0 : 0.0, 1e-8);
+    for (int c = 0; c + 1 < m; ++c) {  // A q_c = sum_r H(r,c) q_r
+        VectorObj<double> lhs = D * Q[c];
+        VectorObj<double> rhs(n, 0.0);
+        for (int r = 0; r <= c + 1; ++r) rhs = rhs + Q[r] * H(r, c);
+        CHECK((lhs - rhs).L2norm() < 1e-8);
+    }
+}
+
 static void poisson_tests() {  // README / code/PDE.ipynb: 1 CG iteration, errors 8.529918e-04 / 2.886627e-04 at 32^3
     const int n = 32;
     Poisson3DSolver<double> s(n, n, n, 1.0, 1.0, 1.0);
@@ -228,6 +259,7 @@ int main(int argc, char** argv) {
     vector_tests();
     cg_tests();
     gmres_tests();
+    gd_arnoldi_tests();
     poisson_tests();
     if (argc > 1) {  // Matrix Market round trip: path to bcsstk01.mtx
         SparseMatrixCSC<double> A(1, 1);

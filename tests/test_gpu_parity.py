@@ -505,3 +505,54 @@ def test_assembled_equals_matrix_free_256(ctx):
         assert res["iters"] == 60
         sols.append(x)
     assert ctx.nrm2(ctx.sub(sols[0], sols[1])) <= 1e-10 * ctx.nrm2(sols[0])
+
+
+# ------------------------------------------------------------------------------------------------ "next" rows
+def test_gradient_descent(ctx, port):
+    A = port.csc_from_triplets(3, 3, [0, 1, 0, 1, 2, 1, 2], [0, 0, 1, 1, 1, 2, 2], [4.0, -1.0, -1.0, 4.0, -1.0, -1.0, 4.0])
+    op = ctx.operator_from_csc(3, 3, A.col_ptr, A.row_idx, A.vals)
+    o = port.gd(A, [1.0, 5.0, 0.0], np.zeros(3), 1000, 1e-6)
+    g = capi.gd_solve_host(ctx, op, [1.0, 5.0, 0.0], np.zeros(3), 1000, 1e-6)   # tests/itersolver_test.cpp:5-39
+    assert g["iters"] == o["iters"] == 15 and np.allclose(g["x"], [0.625, 1.5, 0.375], atol=1e-5)
+    assert relerr(g["x"], o["x"]) < REL
+    n = 20
+    cx, cy, cz, _ = port.poisson_coeffs(n, n, n)
+    b = port.poisson_rhs(n, n, n, rhs_kind=1, seed=12345)
+    Ap = port.poisson_csc(n, n, n)
+    st = ctx.operator_stencil7(n, n, n, cx, cy, cz)
+    for max_iter, tol in ((60, 1e-9), (200, 1e-3), (0, 1e-6)):
+        o = port.gd(Ap, b, np.zeros(n ** 3), max_iter, tol)
+        g = capi.gd_solve_host(ctx, st, b, np.zeros(n ** 3), max_iter, tol)
+        assert abs(g["iters"] - o["iters"]) <= 2 and relerr(g["x"], o["x"]) < 1e-9 if o["iters"] else np.array_equal(g["x"], o["x"])
+    ctx.set_reduction(capi.REDUCE_SEQUENTIAL)
+    try:
+        o = port.gd(Ap, b, np.zeros(n ** 3), 25, 1e-12)
+        g = capi.gd_solve_host(ctx, st, b, np.zeros(n ** 3), 25, 1e-12)
+        assert g["iters"] == o["iters"] == 25 and np.array_equal(g["x"], o["x"])   # reference-ordered sums: bit-exact
+    finally:
+        ctx.set_reduction(capi.REDUCE_TREE)
+
+
+def test_arnoldi(ctx, port):
+    rng = np.random.default_rng(0)
+    n = 300
+    D = rng.standard_normal((n, n)) * (rng.random((n, n)) < 0.05) + np.diag(5 + rng.random(n))
+    r, c = np.nonzero(D)
+    A = port.csc_from_triplets(n, n, r, c, D[r, c])
+    op = ctx.operator_from_csc(n, n, A.col_ptr, A.row_idx, A.vals)
+    q0 = rng.standard_normal(n)
+    q0 /= np.linalg.norm(q0)
+    o = port.arnoldi(A, q0, 12, 1e-10)
+    g = capi.arnoldi_host(ctx, op, q0, 12, 1e-10)
+    assert g["breakdown"] == -1 and np.abs(g["Q"] - o["Q"]).max() < 1e-10 and np.abs(g["H"] - o["H"]).max() < 1e-10
+    assert np.abs(g["Q"] @ g["Q"].T - np.eye(12)).max() < 1e-10
+    ctx.set_reduction(capi.REDUCE_SEQUENTIAL)
+    try:
+        g = capi.arnoldi_host(ctx, op, q0, 12, 1e-10)
+        assert np.array_equal(g["Q"], o["Q"]) and np.array_equal(g["H"], o["H"])   # bit-exact in reference-ordered mode
+    finally:
+        ctx.set_reduction(capi.REDUCE_TREE)
+    A2 = port.csc_from_triplets(4, 4, [0, 1, 2, 3], [0, 1, 2, 3], [1.0, 2.0, 3.0, 4.0])
+    op2 = ctx.operator_from_csc(4, 4, A2.col_ptr, A2.row_idx, A2.vals)
+    g2, o2 = capi.arnoldi_host(ctx, op2, [1.0, 0, 0, 0], 3, 1e-8), port.arnoldi(A2, [1.0, 0, 0, 0], 3, 1e-8)
+    assert g2["breakdown"] == o2["breakdown"] == 1 and np.array_equal(g2["Q"], o2["Q"]) and np.array_equal(g2["H"], o2["H"])

@@ -215,3 +215,32 @@ def test_python_matrix_market_reader_matches_reference_semantics(port):
         assert (a["n_rows"], a["n_cols"]) == (b.n_rows, b.n_cols)
         assert np.array_equal(a["col_ptr"], b.col_ptr) and np.array_equal(a["row_idx"], b.row_idx)
         assert np.array_equal(a["vals"], b.vals)
+
+
+def test_next_rows_gd_and_arnoldi_vs_reference(port, ref):
+    """SURVEY 8(f) rank 1: GradientDescent (IterSolver.hpp:23-44) and Krylov::Arnoldi (KrylovSubspace.hpp:11-38)."""
+    A = port.csc_from_triplets(3, 3, [0, 1, 0, 1, 2, 1, 2], [0, 0, 1, 1, 1, 2, 2], [4.0, -1.0, -1.0, 4.0, -1.0, -1.0, 4.0])
+    M = ref.mat_from_csc(A)
+    g = port.gd(A, [1.0, 5.0, 0.0], np.zeros(3), 1000, 1e-6)  # tests/itersolver_test.cpp:5-39
+    assert np.array_equal(g["x"], ref.gd(M, [1.0, 5.0, 0.0], np.zeros(3), 1000, 1e-6)["x"])
+    assert np.allclose(g["x"], [0.625, 1.5, 0.375], atol=1e-5) and g["iters"] == 15
+    rng = np.random.default_rng(0)
+    n = 40
+    D = rng.standard_normal((n, n)) * (rng.random((n, n)) < 0.2) + np.diag(5 + rng.random(n))
+    D = (D + D.T) / 2
+    r, c = np.nonzero(D)
+    A = port.csc_from_triplets(n, n, r, c, D[r, c])
+    M = ref.mat_from_csc(A)
+    b = rng.standard_normal(n)
+    for max_iter, tol in ((500, 1e-9), (7, 1e-12), (0, 1e-6)):
+        assert np.array_equal(port.gd(A, b, np.zeros(n), max_iter, tol)["x"], ref.gd(M, b, np.zeros(n), max_iter, tol)["x"])
+    q0 = rng.standard_normal(n)
+    q0 /= np.linalg.norm(q0)
+    a, ar = port.arnoldi(A, q0, 8, 1e-10), ref.arnoldi(M, q0, 8, 1e-10)
+    assert np.array_equal(a["Q"], ar["Q"]) and np.array_equal(a["H"], ar["H"]) and a["breakdown"] == -1
+    assert np.abs(a["Q"] @ a["Q"].T - np.eye(8)).max() < 1e-10      # tests/KrylovSubspace_test.cpp: orthonormal basis
+    assert np.abs(D @ a["Q"][:7].T - a["Q"].T @ a["H"]).max() < 1e-12  # A Q = Q H
+    A2 = port.csc_from_triplets(4, 4, [0, 1, 2, 3], [0, 1, 2, 3], [1.0, 2.0, 3.0, 4.0])
+    a2, r2 = port.arnoldi(A2, [1.0, 0, 0, 0], 3, 1e-8), ref.arnoldi(ref.mat_from_csc(A2), [1.0, 0, 0, 0], 3, 1e-8)
+    assert a2["breakdown"] == 1 and r2["log"] == "Breakdown: Norm below tolerance at iteration 1\n"
+    assert np.array_equal(a2["Q"], r2["Q"]) and np.array_equal(a2["H"], r2["H"])
