@@ -190,9 +190,8 @@ __global__ void __launch_bounds__(kReduceBlock) cg_update_p_kernel(int64_t n, Cg
 struct PeerKb {
     int on = 0;
     int rank = 0;
-    const unsigned long long* flags = nullptr;
-    double* const* peer_gather = nullptr;
-    unsigned long long* const* peer_flags = nullptr;
+    const unsigned long long* ll = nullptr;
+    unsigned long long* const* peer_ll = nullptr;
     double* lo_nb_r_hi = nullptr;
     double* hi_nb_r_lo = nullptr;
     int64_t plane = 0;
@@ -207,9 +206,9 @@ __global__ void __launch_bounds__(kReduceBlock) cg_fused_update_r_kernel(int64_t
                                                                          unsigned* ticket, double* rr_out, double* pAp_trace,
                                                                          PeerKb pk) {
     if (st->done) return;
-    // peer mode: wait until every rank's p.Ap partial of this iteration has been stored into our slots
-    if (pk.on) wait_partials(pk.flags, world, kSlotPAp, st->epoch + (unsigned long long)st->ka_count);
-    const double pAp = slot_sum(slot_pAp, world);
+    // peer mode: wait until every rank's p.Ap partial of this iteration has been stored into our packed words
+    const double pAp = pk.on ? peer_wait_sum(pk.ll, world, kSlotPAp, st->epoch + (unsigned long long)st->ka_count)
+                             : slot_sum(slot_pAp, world);
     if (fabs(pAp) < 1e-12) {  // :53-57
         if (threadIdx.x == 0 && blockIdx.x == 0) {
             st->last_pAp = pAp;
@@ -260,8 +259,7 @@ __global__ void __launch_bounds__(kReduceBlock) cg_fused_update_r_kernel(int64_t
     double total;
     if (grid_sum_last_block<kReduceBlock>(acc, partials, ticket, &total)) {
         if (pk.on && threadIdx.x < 32)
-            publish_partial_warp(pk.peer_gather, pk.peer_flags, world, pk.rank, kSlotRR, total,
-                                 st->epoch + (unsigned long long)st->ka_count);
+            publish_partial_warp(pk.peer_ll, world, pk.rank, kSlotRR, total, st->epoch + (unsigned long long)st->ka_count);
         if (threadIdx.x == 0) {
             if (!pk.on) *rr_out = total;
             st->alpha = alpha;
@@ -280,7 +278,8 @@ __global__ void __launch_bounds__(kReduceBlock) cg_fused_flush_kernel(int64_t n,
                                                                       const double* P0, const double* P1, double* p_user,
                                                                       unsigned* ticket, double* rs_trace, PeerKb pk) {
     if (st->first) return;  // no KA ran: nothing pending, p_user untouched
-    if (pk.on && !st->done) wait_partials(pk.flags, world, kSlotRR, st->epoch + (unsigned long long)st->ka_count);
+    double rs_peer = 0.0;
+    if (pk.on && !st->done) rs_peer = peer_wait_sum(pk.ll, world, kSlotRR, st->epoch + (unsigned long long)st->ka_count);
     const double* pc = (st->ka_count & 1) ? P1 : P0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,7 +288,7 @@ __global__ void __launch_bounds__(kReduceBlock) cg_fused_flush_kernel(int64_t n,
             for (int64_t i = t; i < n; i += stride) p_user[i] = pc[i];
         return;
     }
-    const double rs_new = slot_sum(slot_rr, world);
+    const double rs_new = pk.on ? rs_peer : slot_sum(slot_rr, world);
     const double beta = __ddiv_rn(rs_new, st->rs_old);
     const double alpha = st->alpha;
     for (int64_t i = t; i < n; i += stride) {
@@ -343,9 +342,8 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
     if (peer) {
         pk.on = 1;
         pk.rank = ctx->rank;
-        pk.flags = ctx->d_flags;
-        pk.peer_gather = ctx->d_peer_gather;
-        pk.peer_flags = ctx->d_peer_flags;
+        pk.ll = ctx->d_ll;
+        pk.peer_ll = ctx->d_peer_ll;
         op->peer_r_targets(&pk.lo_nb_r_hi, &pk.hi_nb_r_lo, &pk.plane);
     }
     int* h_done = nullptr;  // pinned: done flag of every poll

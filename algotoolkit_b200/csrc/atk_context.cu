@@ -173,11 +173,14 @@ static void setup_p2p(Context& c) {
     std::vector<void*> peers;
     ipc_share(&c, c.d_gather, peers, {});  // d_gather and d_flags are one allocation (init_context)
     std::vector<double*> pg((size_t)c.world);
-    std::vector<unsigned long long*> pf((size_t)c.world);
+    std::vector<unsigned long long*> pf((size_t)c.world), pl((size_t)c.world);
     for (int q = 0; q < c.world; ++q) {
         pg[(size_t)q] = static_cast<double*>(peers[(size_t)q]);
         pf[(size_t)q] = reinterpret_cast<unsigned long long*>(pg[(size_t)q] + (size_t)kNumSlots * kMaxRanks);
+        pl[(size_t)q] = pf[(size_t)q] + (size_t)kNumSlots * kMaxRanks;
     }
+    ATK_CUDA_CHECK(cudaMalloc(&c.d_peer_ll, sizeof(unsigned long long*) * (size_t)c.world));
+    ATK_CUDA_CHECK(cudaMemcpy(c.d_peer_ll, pl.data(), sizeof(unsigned long long*) * (size_t)c.world, cudaMemcpyHostToDevice));
     ATK_CUDA_CHECK(cudaMalloc(&c.d_peer_gather, sizeof(double*) * (size_t)c.world));
     ATK_CUDA_CHECK(cudaMalloc(&c.d_peer_flags, sizeof(unsigned long long*) * (size_t)c.world));
     ATK_CUDA_CHECK(cudaMemcpy(c.d_peer_gather, pg.data(), sizeof(double*) * (size_t)c.world, cudaMemcpyHostToDevice));
@@ -260,10 +263,13 @@ static void init_context(Context& c, int device) {
     ATK_CUDA_CHECK(cudaMalloc(&c.d_partials, sizeof(double) * kMaxPartials));
     ATK_CUDA_CHECK(cudaMalloc(&c.d_tickets, sizeof(unsigned) * kNumTickets));
     // reduction slots followed by their sequence flags: one allocation, so that one IPC handle shares both
-    ATK_CUDA_CHECK(cudaMalloc(&c.d_gather, (sizeof(double) + sizeof(unsigned long long)) * kNumSlots * kMaxRanks));
+    // [gather doubles | flags | packed value/sequence words x2]
+    const size_t arena = (sizeof(double) + 3 * sizeof(unsigned long long)) * kNumSlots * kMaxRanks;
+    ATK_CUDA_CHECK(cudaMalloc(&c.d_gather, arena));
     c.d_flags = reinterpret_cast<unsigned long long*>(c.d_gather + (size_t)kNumSlots * kMaxRanks);
+    c.d_ll = c.d_flags + (size_t)kNumSlots * kMaxRanks;
     ATK_CUDA_CHECK(cudaMemset(c.d_tickets, 0, sizeof(unsigned) * kNumTickets));
-    ATK_CUDA_CHECK(cudaMemset(c.d_gather, 0, (sizeof(double) + sizeof(unsigned long long)) * kNumSlots * kMaxRanks));
+    ATK_CUDA_CHECK(cudaMemset(c.d_gather, 0, arena));
     ATK_CUDA_CHECK(cudaMallocHost(&c.h_pinned, sizeof(double) * 64));
     ATK_CUDA_CHECK(cudaMallocHost(&c.h_flags, sizeof(int) * kHostFlags));
     ATK_CUDA_CHECK(cudaDeviceSynchronize());
@@ -325,6 +331,7 @@ void context_destroy(atk_context_s* h) {
     for (void* p : c.ipc_exported) cudaFree(p);  // exported halo arenas: kept alive until now for the peers' sake
     cudaFree(c.d_peer_gather);
     cudaFree(c.d_peer_flags);
+    cudaFree(c.d_peer_ll);
     if (c.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)c.nccl_comm);
     cudaFree(c.d_partials);
     cudaFree(c.d_tickets);

@@ -78,8 +78,10 @@ struct Context {
     // d_flags entry; consumers spin on their LOCAL flags.  No NCCL call is needed inside an iteration.
     bool p2p = false;
     unsigned long long* d_flags = nullptr;       // [kNumSlots * kMaxRanks], local
+    unsigned long long* d_ll = nullptr;          // [kNumSlots * kMaxRanks * 2], local: value halves packed with their sequence
     double** d_peer_gather = nullptr;            // device array [world]: every rank's d_gather as mapped here
     unsigned long long** d_peer_flags = nullptr; // device array [world]
+    unsigned long long** d_peer_ll = nullptr;    // device array [world]
     std::vector<void*> ipc_opened;               // mappings to close at destruction
     std::vector<void*> ipc_exported;             // allocations other ranks may still have mapped: freed with the context
     void ipc_close(void* mapped);                // close one mapping early (operator destruction)
@@ -303,33 +305,51 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// Producer side, called by the first WARP of the CTA that finished last, after every CTA of the kernel has fenced its
-// stores at system scope: lane q stores `value` as this rank's partial of `slot` into rank q's slots, fences, then
-// releases sequence number `seq` into rank q's flag - all peers are served in parallel.
-__device__ __forceinline__ void publish_partial_warp(double* const* peer_gather, unsigned long long* const* peer_flags, int world,
-                                                     int rank, int slot, double value, unsigned long long seq) {
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Scalars travel between GPUs as two self-validating 8-byte words per (slot, source rank): {low half | seq32 << 32} and
+// {high half | seq32 << 32}.  An aligned 8-byte store is delivered whole, so a word whose upper half equals the expected
+// sequence number carries valid data and no fence is needed on the value path (the scheme of NCCL's low-latency protocol).
+// Producer: first warp of the CTA that finished last; lane q serves rank q.  Ordering of the HALO planes other CTAs
+// stored into the peers is given by the system-scope fence every CTA executes before it takes its ticket: those stores
+// are performed before the ticket is visible, hence before this function is even entered.
+__device__ __forceinline__ void publish_partial_warp(unsigned long long* const* peer_ll, int world, int rank, int slot,
+                                                     double value, unsigned long long seq) {
     const int lane = threadIdx.x & 31;
-    const int off = slot * kMaxRanks + rank;
     if (lane < world) {
-        peer_gather[lane][off] = value;
-        __threadfence_system();
-        st_release_sys(peer_flags[lane] + off, seq);
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(value);
+        const unsigned long long tag = (seq & 0xffffffffull) << 32;
+        unsigned long long* dst = peer_ll[lane] + (size_t)(slot * kMaxRanks + rank) * 2;
+        st_relaxed_sys(dst, (bits & 0xffffffffull) | tag);
+        st_relaxed_sys(dst + 1, (bits >> 32) | tag);
     }
 }
-// Consumer side: returns once every rank's flag of `slot` has reached `seq`.  Lane q of the first warp polls rank q's
-// flag with relaxed loads (all flags in parallel); one system-scope fence afterwards gives the acquire ordering; the CTA
-// then synchronises.  Flags live in LOCAL memory (peers store into it), so polling costs only L2 hits.
-__device__ __forceinline__ void wait_partials(const unsigned long long* flags, int world, int slot, unsigned long long seq) {
+// Consumer: waits until every rank's pair of `slot` carries `seq`, then returns the rank-ordered sum (same bits on every
+// rank).  Lane q of the first warp polls rank q's pair in LOCAL memory; the fence afterwards orders this CTA's later reads
+// of peer-written halo planes behind the observation.
+__device__ __forceinline__ double peer_wait_sum(const unsigned long long* ll, int world, int slot, unsigned long long seq) {
+    __shared__ double peer_vals[kMaxRanks];
     if (linear_thread_id() < 32) {
         const int lane = linear_thread_id();
         if (lane < world) {
-            const unsigned long long* f = flags + slot * kMaxRanks + lane;
-            while (ld_relaxed_sys(f) < seq) __nanosleep(32);
+            const unsigned long long* src = ll + (size_t)(slot * kMaxRanks + lane) * 2;
+            const unsigned long long tag = seq & 0xffffffffull;
+            unsigned long long w0, w1;
+            do {
+                w0 = ld_relaxed_sys(src);
+                w1 = ld_relaxed_sys(src + 1);
+            } while ((w0 >> 32) != tag || (w1 >> 32) != tag);
+            peer_vals[lane] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
         }
         __syncwarp();
         __threadfence_system();
     }
     __syncthreads();
+    double s = peer_vals[0];
+    for (int q = 1; q < world; ++q) s = add_rn(s, peer_vals[q]);
+    __syncthreads();  // peer_vals may be reused by a later call
+    return s;
 }
 
 // Sum of a reduction slot over ranks, in rank order (what every consumer kernel does in its prologue).

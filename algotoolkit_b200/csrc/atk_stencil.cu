@@ -177,9 +177,8 @@ struct FusedArgs {
     // peer-memory mode (Context::p2p): no NCCL inside the iteration
     int p2p;
     int rank;
-    const unsigned long long* flags;             // local sequence flags
-    double* const* peer_gather;                  // every rank's reduction slots, mapped here
-    unsigned long long* const* peer_flags;
+    const unsigned long long* ll;                // local packed value/sequence words
+    unsigned long long* const* peer_ll;          // every rank's packed words, mapped here
     const double* my_p_lo[2];                    // local p halo planes, indexed by ping-pong parity
     const double* my_p_hi[2];
     double* nb_lo_p_hi[2];                       // lower neighbour's p_hi halo planes (null on rank 0)
@@ -377,11 +376,10 @@ __global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_smem_kernel(StencilG
         p_halo_hi = a.my_p_hi[cnt & 1];
         nb_lo = a.nb_lo_p_hi[(cnt + 1) & 1];
         nb_hi = a.nb_hi_p_lo[(cnt + 1) & 1];
-        // every rank's r.r partial of the previous KB must have landed (this is also what orders the halo planes)
-        if (!first) wait_partials(a.flags, a.world, kSlotRR, st->epoch + (unsigned long long)cnt);
     }
     if (!first) {
-        rs_new = slot_sum(a.slot_rr, a.world);
+        // peer mode: every rank's r.r partial of the previous KB must have landed (this is also what orders the halo planes)
+        rs_new = a.p2p ? peer_wait_sum(a.ll, a.world, kSlotRR, st->epoch + (unsigned long long)cnt) : slot_sum(a.slot_rr, a.world);
         beta = __ddiv_rn(rs_new, st->rs_old);
         alpha = st->alpha;
     }
@@ -540,8 +538,7 @@ __global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_smem_kernel(StencilG
         __threadfence();
         const double total = partials_sum<TX * TY>(partials, partial_base + nb);
         if (a.p2p && linear_thread_id() < 32)
-            publish_partial_warp(a.peer_gather, a.peer_flags, a.world, a.rank, kSlotPAp, total,
-                                 st->epoch + (unsigned long long)cnt + 1ull);
+            publish_partial_warp(a.peer_ll, a.world, a.rank, kSlotPAp, total, st->epoch + (unsigned long long)cnt + 1ull);
         if (linear_thread_id() == 0) {
             if (!a.p2p) *dot_out = total;
             if (!first) {  // the p update of the previous iteration is now complete (:79-80)
@@ -801,9 +798,8 @@ struct Stencil7 : public Operator {
             // halo planes were written by the neighbours' previous KB (r) and KA (p); one launch over all planes
             fa.p2p = 1;
             fa.rank = c->rank;
-            fa.flags = c->d_flags;
-            fa.peer_gather = c->d_peer_gather;
-            fa.peer_flags = c->d_peer_flags;
+            fa.ll = c->d_ll;
+            fa.peer_ll = c->d_peer_ll;
             fa.r_halo_lo = frecv;
             fa.r_halo_hi = frecv + 2 * plane;
             fa.my_p_lo[0] = frecv + plane;
