@@ -717,6 +717,15 @@ struct Stencil7 : public Operator {
         else cudaFree(frecv);
     }
 
+    // Planes per z-chunk: the configured length on large grids; on small ones shorter chunks, so that there are about as
+    // many CTAs as four per SM - but never below 8 planes, the pipeline fill costs 3.
+    int chunk_planes(int configured, int planes, int tiles_xy) const {
+        const int want_ctas = ctx->sm_count * 4;
+        int kcc = std::min(configured, planes);
+        while (kcc > 8 && (int64_t)tiles_xy * ((planes + kcc - 1) / kcc) < want_ctas) kcc = (kcc + 1) / 2;
+        return std::max(1, kcc);
+    }
+
     bool fused_cg_capable() const override { return true; }
     bool peer_mode = false;  // set by the CG driver for the duration of a solve (all ranks agree)
 
@@ -750,7 +759,7 @@ struct Stencil7 : public Operator {
         const int planes = k_hi - k_lo;
         *blocks_out = 0;
         if (planes <= 0) return;
-        const int kcc = std::min(fkc, planes);
+        const int kcc = chunk_planes(fkc, planes, ((g.nx + 2 * TX - 1) / (2 * TX)) * ((g.ny + TY - 1) / TY));
         dim3 grid((g.nx + 2 * TX - 1) / (2 * TX), (g.ny + TY - 1) / TY, (planes + kcc - 1) / kcc);
         dim3 block(TX, TY, 1);
         const int nblocks = (int)(grid.x * grid.y * grid.z);
@@ -846,7 +855,7 @@ struct Stencil7 : public Operator {
         const int planes = k_hi - k_lo;
         *blocks_out = 0;
         if (planes <= 0) return;
-        const int kcc = std::min(kc, planes);
+        const int kcc = chunk_planes(kc, planes, ((g.nx + 2 * TX - 1) / (2 * TX)) * ((g.ny + TY - 1) / TY));
         dim3 grid((g.nx + 2 * TX - 1) / (2 * TX), (g.ny + TY - 1) / TY, (planes + kcc - 1) / kcc);
         dim3 block(TX, TY, 1);
         const int nblocks = (int)(grid.x * grid.y * grid.z);
