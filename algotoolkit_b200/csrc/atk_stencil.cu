@@ -665,6 +665,161 @@ __global__ void __launch_bounds__(TX* TY) stencil7_smem_kernel(StencilGeom g, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------- plain apply, TMA bulk copies
+// Same ring of shared-memory plane tiles as stencil7_smem_kernel, but filled by the TMA unit: one elected thread arms an
+// mbarrier with the byte count of a plane tile and issues one cp.async.bulk (global -> shared, completion on the mbarrier)
+// per tile ROW (2TX+4 doubles incl. the left/right halo columns, clipped at the domain edge); all threads wait on the
+// mbarrier's phase.  No thread spends issue slots or registers on address generation for loads.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ATK_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra ATK_DONE_%=;\n"
+        "bra ATK_WAIT_%=;\n"
+        "ATK_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int TX, int TY, bool DOT>
+__global__ void __launch_bounds__(TX* TY) stencil7_tma_kernel(StencilGeom g, const double* __restrict__ x, double* __restrict__ y,
+                                                               const double* __restrict__ halo_lo,
+                                                               const double* __restrict__ halo_hi, int k_lo, int k_hi, int kc,
+                                                               double* partials, int partial_base, unsigned* ticket,
+                                                               double* dot_out, int dot_final, const int* skip_flag) {
+    constexpr int DEPTH = 4;
+    constexpr int W = 2 * TX + 4;
+    extern __shared__ __align__(128) double smem_dyn[];
+    double(*xt)[TY + 2][W] = reinterpret_cast<double(*)[TY + 2][W]>(smem_dyn);
+    __shared__ __align__(8) unsigned long long full[DEPTH];
+    if (skip_flag && *skip_flag) return;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i_lo = blockIdx.x * 2 * TX;
+    const int j_lo = blockIdx.y * TY;
+    const int i0 = i_lo + 2 * tx;
+    const int j = j_lo + ty;
+    const int kb = k_lo + blockIdx.z * kc;
+    const int ke = min(kb + kc, k_hi);
+    const bool active = (i0 < g.nx) && (j < g.ny);
+    const int64_t sxy = (int64_t)g.nx * g.ny;
+    const int64_t row = (int64_t)j * g.nx + i0;
+    const bool leader = (tx == 0 && ty == 0);
+    double dacc = 0.0;
+    if (leader) {
+#pragma unroll
+        for (int s = 0; s < DEPTH; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // tile geometry shared by every plane: columns [c_lo, c_hi) of the grid land at tile columns c_lo - (i_lo - 2) ...
+    const int c_lo = max(i_lo - 2, 0), c_hi = min(i_lo + 2 * TX + 2, g.nx);
+    const int jr_lo = max(j_lo - 1, 0), jr_hi = min(j_lo + TY + 1, g.ny);  // grid rows [jr_lo, jr_hi)
+    const unsigned row_bytes = (unsigned)(c_hi - c_lo) * 8u;
+    auto stage_of = [&](int k) -> int { return ((k % DEPTH) + DEPTH) % DEPTH; };
+    auto plane_exists = [&](int k) -> bool { const int kg = g.k_off + k; return kg >= 0 && kg < g.nz; };
+    auto issue_plane = [&](int k) {  // leader only
+        if (!plane_exists(k)) return;
+        const int s = stage_of(k);
+        const double* src = (k < 0 ? halo_lo : (k >= g.nz_loc ? halo_hi : x + (int64_t)k * sxy));
+        mbar_expect_tx(&full[s], row_bytes * (unsigned)(jr_hi - jr_lo));
+        for (int jr = jr_lo; jr < jr_hi; ++jr)
+            tma_bulk_g2s(&xt[s][jr - (j_lo - 1)][c_lo - (i_lo - 2)], src + (int64_t)jr * g.nx + c_lo, row_bytes, &full[s]);
+    };
+    unsigned phase_bits = 0;  // bit s = parity to wait for on stage s
+    auto wait_plane = [&](int k) {
+        if (!plane_exists(k)) return;
+        const int s = stage_of(k);
+        mbar_wait(&full[s], (phase_bits >> s) & 1u);
+        phase_bits ^= 1u << s;
+    };
+    auto centre = [&](int s) -> double2 { return *reinterpret_cast<const double2*>(&xt[s][ty + 1][2 * tx + 2]); };
+    if (kb < ke) {
+        const bool j_shell = (j == 0 || j == g.ny - 1);
+        const bool a_shell_i = (i0 == 0 || i0 == g.nx - 1);
+        const bool b_shell_i = (i0 + 1 == g.nx - 1);
+        const double2 zero2 = make_double2(0.0, 0.0);
+        if (leader) {
+            issue_plane(kb - 1);
+            issue_plane(kb);
+            issue_plane(kb + 1);
+            issue_plane(kb + 2);
+        }
+        wait_plane(kb - 1);
+        wait_plane(kb);
+        double2 vA = zero2, vB = zero2, vC = zero2;
+        if (active) {
+            if (plane_exists(kb - 1)) vA = centre(stage_of(kb - 1));
+            vB = centre(stage_of(kb));
+        }
+        for (int k = kb; k < ke; ++k) {
+            const int kg = g.k_off + k;
+            const int64_t idx = (int64_t)k * sxy + row;
+            wait_plane(k + 1);
+            __syncthreads();  // everyone is done reading plane k-1's stage: it may be refilled
+            if (leader) issue_plane(k + 3);
+            if (active) {
+                const int s = stage_of(k);
+                if (kg + 1 < g.nz) vC = centre(stage_of(k + 1));
+                double2 out;
+                if (j_shell || kg == 0 || kg == g.nz - 1) {
+                    out.x = shell_row(vB.x);
+                    out.y = shell_row(vB.y);
+                } else {
+                    const double2 jm = *reinterpret_cast<const double2*>(&xt[s][ty][2 * tx + 2]);
+                    const double2 jp = *reinterpret_cast<const double2*>(&xt[s][ty + 2][2 * tx + 2]);
+                    out.x = a_shell_i ? shell_row(vB.x) : tap7(g, vA.x, jm.x, xt[s][ty + 1][2 * tx + 1], vB.x, vB.y, jp.x, vC.x);
+                    out.y = b_shell_i ? shell_row(vB.y) : tap7(g, vA.y, jm.y, vB.x, vB.y, xt[s][ty + 1][2 * tx + 4], jp.y, vC.y);
+                }
+                *reinterpret_cast<double2*>(y + idx) = out;
+                if constexpr (DOT) {
+                    dacc = add_rn(dacc, mul_rn(vB.x, out.x));
+                    dacc = add_rn(dacc, mul_rn(vB.y, out.y));
+                }
+                vA = vB;
+                vB = vC;
+            }
+        }
+        // planes k+1.. that were requested beyond the chunk must have landed before the CTA may exit
+        wait_plane(ke + 1);
+        wait_plane(ke + 2);
+    }
+    if constexpr (DOT) {
+        const double bs = block_sum<TX * TY>(dacc);
+        __shared__ bool is_last;
+        const unsigned nb = total_blocks();
+        if (linear_thread_id() == 0) {
+            partials[partial_base + linear_block_id()] = bs;
+            is_last = false;
+            if (dot_final) {
+                __threadfence();
+                const unsigned t = atomicInc(ticket, nb - 1);
+                is_last = (t == nb - 1);
+            }
+        }
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            const double total = partials_sum<TX * TY>(partials, partial_base + nb);
+            if (linear_thread_id() == 0) *dot_out = total;
+        }
+    }
+}
+
 // packs the boundary planes of r and of the current p (selected on the device by the ping-pong parity) for the
 // halo exchange: send = [r_first | p_first | r_last | p_last]
 __global__ void __launch_bounds__(256) pack_halo_kernel(const CgFusedState* st, const double* __restrict__ r, const double* P0,
@@ -703,6 +858,7 @@ struct Stencil7 : public Operator {
     int fkc = 64;
     int ftile = 4;
     bool fsmem = true;
+    bool use_tma = false;  // plain apply through TMA bulk copies (experiment switch ATK_STENCIL_TMA)
 
     bool arena_exported = false;
 
@@ -862,6 +1018,21 @@ struct Stencil7 : public Operator {
         ATK_REQUIRE(partial_base + nblocks <= kMaxPartials, ATK_ERR_INVALID_ARGUMENT, "stencil grid exceeds the partial-sum scratch");
         const bool vec = (g.nx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) &&
                          ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
+        if (vec && fsmem && use_tma) {
+            constexpr size_t smem = (size_t)4 * (TY + 2) * (2 * TX + 4) * sizeof(double);
+            if (dot)
+                stencil7_tma_kernel<TX, TY, true><<<grid, block, smem, c->stream>>>(g, x, y, halo_lo, halo_hi, k_lo, k_hi, kcc,
+                                                                                    c->d_partials, partial_base, c->d_tickets + 2,
+                                                                                    dot_out, dot_final ? 1 : 0, skip_flag);
+            else
+                stencil7_tma_kernel<TX, TY, false><<<grid, block, smem, c->stream>>>(g, x, y, halo_lo, halo_hi, k_lo, k_hi, kcc,
+                                                                                     c->d_partials, partial_base, c->d_tickets + 2,
+                                                                                     dot_out, dot_final ? 1 : 0, skip_flag);
+            ATK_CUDA_CHECK(cudaGetLastError());
+            count_launch(c);
+            *blocks_out = nblocks;
+            return;
+        }
         if (vec && fsmem) {
             constexpr size_t smem = (size_t)4 * (TY + 2) * (2 * TX + 4) * sizeof(double);
             if (dot)
@@ -1034,6 +1205,7 @@ Operator* make_stencil7(Context* ctx, int nx, int ny, int nz, double cx, double 
     if (const char* e = std::getenv("ATK_FUSED_KC")) S->fkc = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("ATK_FUSED_TILE")) S->ftile = std::atoi(e);
     if (const char* e = std::getenv("ATK_FUSED_SMEM")) S->fsmem = std::atoi(e) != 0;
+    if (const char* e = std::getenv("ATK_STENCIL_TMA")) S->use_tma = std::atoi(e) != 0;
     try {
         if (ctx->world > 1) {
             ATK_CUDA_CHECK(cudaMalloc(&S->halo_lo, sizeof(double) * (size_t)plane));
