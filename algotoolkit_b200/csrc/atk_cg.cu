@@ -46,6 +46,7 @@ __global__ void cg_begin_kernel(CgState* st, const double* slot_rr, const double
     st->ka_count = 0;
     st->first = 1;
     st->epoch = epoch;
+    st->peer_timeout = 0;
     const int zero = (sqrt(bb) < 1e-12) ? 1 : 0;
     st->zero_rhs = zero;
     st->done = zero;
@@ -205,10 +206,11 @@ __global__ void __launch_bounds__(kReduceBlock) cg_fused_update_r_kernel(int64_t
                                                                          const double* __restrict__ Ap, double* partials,
                                                                          unsigned* ticket, double* rr_out, double* pAp_trace,
                                                                          PeerKb pk) {
-    if (st->done) return;
+    if (st->done || st->peer_timeout) return;
     // peer mode: wait until every rank's p.Ap partial of this iteration has been stored into our packed words
-    const double pAp = pk.on ? peer_wait_sum(pk.ll, world, kSlotPAp, st->epoch + (unsigned long long)st->ka_count)
+    const double pAp = pk.on ? peer_wait_sum(pk.ll, world, kSlotPAp, st->epoch + (unsigned long long)st->ka_count, &st->peer_timeout)
                              : slot_sum(slot_pAp, world);
+    if (pk.on && *reinterpret_cast<volatile int*>(&st->peer_timeout)) return;
     if (fabs(pAp) < 1e-12) {  // :53-57
         if (threadIdx.x == 0 && blockIdx.x == 0) {
             st->last_pAp = pAp;
@@ -277,9 +279,12 @@ __global__ void __launch_bounds__(kReduceBlock) cg_fused_flush_kernel(int64_t n,
                                                                       int world, const double* __restrict__ r, double* x,
                                                                       const double* P0, const double* P1, double* p_user,
                                                                       unsigned* ticket, double* rs_trace, PeerKb pk) {
-    if (st->first) return;  // no KA ran: nothing pending, p_user untouched
+    if (st->first || st->peer_timeout) return;  // no KA ran: nothing pending, p_user untouched
     double rs_peer = 0.0;
-    if (pk.on && !st->done) rs_peer = peer_wait_sum(pk.ll, world, kSlotRR, st->epoch + (unsigned long long)st->ka_count);
+    if (pk.on && !st->done) {
+        rs_peer = peer_wait_sum(pk.ll, world, kSlotRR, st->epoch + (unsigned long long)st->ka_count, &st->peer_timeout);
+        if (*reinterpret_cast<volatile int*>(&st->peer_timeout)) return;
+    }
     const double* pc = (st->ka_count & 1) ? P1 : P0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -456,6 +461,8 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
             ctx->launches = l0;  // capture did not launch anything
         }
 
+        // completion tickets wrap back to zero by themselves; clear them anyway in case an earlier solve was aborted
+        ATK_CUDA_CHECK(cudaMemsetAsync(ctx->d_tickets, 0, sizeof(unsigned) * kNumTickets, st));
         ATK_CUDA_CHECK(cudaEventRecord(ctx->ev_t0, st));
         // rs_old = r.r ; ||b||   (:37-38)
         launch_dot(ctx, n, r, r, kSlotRR);
@@ -521,6 +528,8 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
         for (auto e : kev) cudaEventDestroy(e);
         kev.clear();
         op->set_peer_mode(false);
+        ATK_REQUIRE(!hs.peer_timeout, ATK_ERR_RUNTIME,
+                    "peer-memory CG: a wait for another rank's partial sum timed out (rank crashed or out of step)");
         info->iterations = hs.it;
         info->stopped_on_pAp = hs.stopped_on_pAp;
         info->zero_rhs = hs.zero_rhs;

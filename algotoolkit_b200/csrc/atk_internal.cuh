@@ -143,6 +143,7 @@ struct CgFusedState {
     int first;        // 1 until the first KA of this solve has run: p is taken as is, no pending x update
     int trace_cap;
     unsigned long long epoch;  // peer-signalling sequence base of this solve: flags carry epoch + ka_count
+    int peer_timeout;          // set when a wait on another rank's partial gave up (a rank died / fell out of step)
 };
 
 // ------------------------------------------------------------------------------------------ operators
@@ -328,7 +329,17 @@ __device__ __forceinline__ void publish_partial_warp(unsigned long long* const* 
 // Consumer: waits until every rank's pair of `slot` carries `seq`, then returns the rank-ordered sum (same bits on every
 // rank).  Lane q of the first warp polls rank q's pair in LOCAL memory; the fence afterwards orders this CTA's later reads
 // of peer-written halo planes behind the observation.
-__device__ __forceinline__ double peer_wait_sum(const unsigned long long* ll, int world, int slot, unsigned long long seq) {
+//
+// A wait that lasts longer than kPeerWaitNs (a rank crashed or the ranks fell out of step) gives up instead of hanging the
+// GPU: it raises *timeout_flag, every later kernel of the solve turns into a no-op and the host reports ATK_ERR_RUNTIME.
+constexpr unsigned long long kPeerWaitNs = 10ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ double peer_wait_sum(const unsigned long long* ll, int world, int slot, unsigned long long seq,
+                                                int* timeout_flag) {
     __shared__ double peer_vals[kMaxRanks];
     if (linear_thread_id() < 32) {
         const int lane = linear_thread_id();
@@ -336,10 +347,21 @@ __device__ __forceinline__ double peer_wait_sum(const unsigned long long* ll, in
             const unsigned long long* src = ll + (size_t)(slot * kMaxRanks + lane) * 2;
             const unsigned long long tag = seq & 0xffffffffull;
             unsigned long long w0, w1;
-            do {
+            unsigned spins = 0;
+            unsigned long long t0 = 0;
+            for (;;) {
                 w0 = ld_relaxed_sys(src);
                 w1 = ld_relaxed_sys(src + 1);
-            } while ((w0 >> 32) != tag || (w1 >> 32) != tag);
+                if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
+                if ((++spins & 0xfffu) == 0) {  // look at the clock only now and then
+                    const unsigned long long now = global_timer_ns();
+                    if (t0 == 0) t0 = now;
+                    if (now - t0 > kPeerWaitNs || *reinterpret_cast<volatile int*>(timeout_flag)) {
+                        *timeout_flag = 1;
+                        break;
+                    }
+                }
+            }
             peer_vals[lane] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
         }
         __syncwarp();

@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_smem_kernel(StencilG
     double(*pt)[TY + 2][W] = reinterpret_cast<double(*)[TY + 2][W]>(smem_dyn + (size_t)DEPTH * (TY + 2) * W);
 
     CgFusedState* st = a.st;
-    if (st->done) return;
+    if (st->done || st->peer_timeout) return;
     const int first = st->first;
     const int cnt = st->ka_count;
     const double* __restrict__ ps = (cnt & 1) ? a.P1 : a.P0;
@@ -379,7 +379,9 @@ __global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_smem_kernel(StencilG
     }
     if (!first) {
         // peer mode: every rank's r.r partial of the previous KB must have landed (this is also what orders the halo planes)
-        rs_new = a.p2p ? peer_wait_sum(a.ll, a.world, kSlotRR, st->epoch + (unsigned long long)cnt) : slot_sum(a.slot_rr, a.world);
+        rs_new = a.p2p ? peer_wait_sum(a.ll, a.world, kSlotRR, st->epoch + (unsigned long long)cnt, &st->peer_timeout)
+                       : slot_sum(a.slot_rr, a.world);
+        if (a.p2p && *reinterpret_cast<volatile int*>(&st->peer_timeout)) return;  // CTA-uniform: read after the wait's barrier
         beta = __ddiv_rn(rs_new, st->rs_old);
         alpha = st->alpha;
     }
