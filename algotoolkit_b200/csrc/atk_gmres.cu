@@ -198,6 +198,7 @@ struct MgsArgs {
     int64_t chunk;       // rows per CTA (multiple of 2)
     int sequential;
     double skip_below;   // V[j+1] is left untouched when ||w|| < skip_below (the reference breaks before assigning it)
+    int* stop;           // optional {stopped, step}: set by the step whose norm ends the cycle; later steps return at once
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
@@ -239,6 +240,9 @@ template <int BLOCK, bool REG>
 __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
     extern __shared__ __align__(16) double wsm[];  // REG: products [chunk] (sequential mode only); else w [chunk] (+ products)
     __shared__ double bcast;
+    // Written only by the last instruction of an earlier step (every CTA of that step has passed its grid barriers by
+    // then), so all CTAs of this launch read the same value.
+    if (a.stop && *reinterpret_cast<volatile int*>(a.stop)) return;
     const int64_t c0 = (int64_t)blockIdx.x * a.chunk;
     const int64_t len = max((int64_t)0, min(a.chunk, a.n - c0));
     unsigned target = 0;
@@ -306,7 +310,10 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
                 }
             } else {
                 const double nrm = sqrt(h);                                // (:79)
-                if (blockIdx.x == 0 && threadIdx.x == 0) a.h_out[a.j] = nrm;
+                if (blockIdx.x == 0 && threadIdx.x == 0) {
+                    a.h_out[a.j] = nrm;
+                    if (a.stop && (nrm == 0.0 || nrm < a.skip_below)) { a.stop[1] = a.j; a.stop[0] = 1; }
+                }
                 if (nrm != 0.0 && !(nrm < a.skip_below)) {
 #pragma unroll
                     for (int q = 0; q < kMgsRegRows; ++q) {
@@ -339,7 +346,10 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
                 __syncthreads();
             } else {
                 const double nrm = sqrt(h);                                                                       // (:79)
-                if (blockIdx.x == 0 && threadIdx.x == 0) a.h_out[a.j] = nrm;
+                if (blockIdx.x == 0 && threadIdx.x == 0) {
+                    a.h_out[a.j] = nrm;
+                    if (a.stop && (nrm == 0.0 || nrm < a.skip_below)) { a.stop[1] = a.j; a.stop[0] = 1; }
+                }
                 if (nrm != 0.0 && !(nrm < a.skip_below))
                     for (int64_t e = threadIdx.x; e < len; e += BLOCK) a.vnext[c0 + e] = __ddiv_rn(wsm[e], nrm);  // (:86)
             }
@@ -401,9 +411,9 @@ struct PersistentMgs {
     void reset_barriers(cudaStream_t st) { ATK_CUDA_CHECK(cudaMemsetAsync(d_bar, 0, sizeof(unsigned) * (size_t)n_bars, st)); }
     // projections of w against columns [0, ncols) of V, then the norm and V_next = w / norm; h_out[0..ncols] on the device
     void launch(Context* ctx, int64_t n, int ncols, int step, const double* V, int64_t ldv, const double* w, double* vnext,
-                double* h_out, double skip_below) {
+                double* h_out, double skip_below, int* stop = nullptr) {
         MgsArgs ma{n, ncols, V, ldv, w, vnext, h_out, d_part, d_bar + step, chunk, ctx->reduction == ATK_REDUCE_SEQUENTIAL ? 1 : 0,
-                   skip_below};
+                   skip_below, stop};
         void* kargs[] = {&ma};
         ATK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(block), kargs, smem, ctx->stream));
         count_launch(ctx);
@@ -480,42 +490,25 @@ void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t
         }
         struct PinFree { double*& p; ~PinFree() { if (p) cudaFreeHost(p); } } pin_free{h_cg};
 
-        // ---- persistent MGS step: usable when every CTA's slice of w fits in shared memory (single-GPU contexts)
-        bool persistent = false;
-        int mgs_grid = 1, mgs_block = 512;
-        MgsKernel mgs_kernel = nullptr;
-        int64_t mgs_chunk = 0;
-        size_t mgs_smem = 0;
-        unsigned* d_bar = nullptr;
-        double* d_mgs_part = nullptr;
-        if (ortho == ATK_GMRES_MGS && ctx->world == 1 && n > 0 && !std::getenv("ATK_GMRES_NO_PERSISTENT")) {
-            const bool seq = ctx->reduction == ATK_REDUCE_SEQUENTIAL;
-            int64_t chunk = seq ? n : std::max<int64_t>(2048, (n + ctx->sm_count - 1) / ctx->sm_count);
-            chunk = (chunk + 1) & ~(int64_t)1;
-            // 8 rows per thread: small systems run on a few warps and pay almost nothing per barrier
-            const int64_t rows = std::min(chunk, n);
-            mgs_block = rows <= 64 * 8 ? 64 : rows <= 128 * 8 ? 128 : rows <= 256 * 8 ? 256 : 512;
-            const bool reg = rows <= (int64_t)mgs_block * kMgsRegRows;
-            const size_t smem = sizeof(double) * (size_t)chunk * (reg ? (seq ? 1 : 0) : (seq ? 2 : 1));
-            mgs_kernel = mgs_kernel_for(mgs_block, reg);
-            int max_smem = 0;
-            ATK_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-            if (smem + 1024 <= (size_t)max_smem) {
-                ATK_CUDA_CHECK(cudaFuncSetAttribute(mgs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                int per_sm = 0;
-                ATK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mgs_kernel, mgs_block, smem));
-                const int g = (int)((n + chunk - 1) / chunk);
-                if (per_sm >= 1 && g <= per_sm * ctx->sm_count) {
-                    persistent = true;
-                    mgs_grid = g;
-                    mgs_chunk = chunk;
-                    mgs_smem = smem;
-                    ATK_CUDA_CHECK(cudaMalloc(&d_bar, sizeof(unsigned) * (size_t)(K + 1)));
-                    ATK_CUDA_CHECK(cudaMalloc(&d_mgs_part, sizeof(double) * 2 * (size_t)g));
-                }
-            }
+        // ---- persistent MGS step: usable when every CTA's slice of w fits on chip (single-GPU contexts).  The whole
+        // restart cycle is then queued without a host round trip: step j writes column j of H to d_hcols, the step whose
+        // norm ends the cycle raises d_stop and the remaining launches return at once; the host reads everything back
+        // once per cycle and runs the Givens recurrences over the columns in order - the same arithmetic, later.
+        PersistentMgs pm;
+        if (ortho == ATK_GMRES_MGS) pm.setup(ctx, n, K);
+        const bool persistent = pm.usable;
+        double *d_hcols = nullptr, *h_hcols = nullptr;
+        int *d_stop = nullptr, *h_stop = nullptr;
+        struct DeferFree {
+            double*& a; double*& b; int*& c; int*& d;
+            ~DeferFree() { cudaFree(a); cudaFree(c); if (b) cudaFreeHost(b); if (d) cudaFreeHost(d); }
+        } defer_free{d_hcols, h_hcols, d_stop, h_stop};
+        if (persistent) {
+            ATK_CUDA_CHECK(cudaMalloc(&d_hcols, sizeof(double) * (size_t)K * (size_t)ld));
+            ATK_CUDA_CHECK(cudaMallocHost(&h_hcols, sizeof(double) * (size_t)K * (size_t)ld));
+            ATK_CUDA_CHECK(cudaMalloc(&d_stop, sizeof(int) * 2));
+            ATK_CUDA_CHECK(cudaMallocHost(&h_stop, sizeof(int) * 2));
         }
-        struct BarFree { unsigned*& b; double*& p; ~BarFree() { cudaFree(b); cudaFree(p); } } bar_free{d_bar, d_mgs_part};
 
         std::vector<double> H((size_t)ld * ld, 0.0);  // :55 - allocated once, never cleared
         std::vector<double> cs(K, 1.0), sn(K, 0.0), rho(K, 0.0), e1(ld, 0.0), y(ld, 0.0);
@@ -542,73 +535,17 @@ void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t
             for (int iter = 0; iter < max_iter && !finished; ++iter) {
                 ATK_REQUIRE(beta != 0.0, ATK_ERR_RUNTIME, "Division by zero.");  // V[0] = r / beta (:63)
                 launch_div(ctx, n, r, beta, V);
-                if (persistent) ATK_CUDA_CHECK(cudaMemsetAsync(d_bar, 0, sizeof(unsigned) * (size_t)(K + 1), st));
                 int kry = K;
-                for (int j = 0; j < K; ++j) {
-                    const double* vj = V + (size_t)j * nn;
-                    op->apply(vj, w, -1, nullptr);  // :70
-                    if (persistent) {
-                        MgsArgs ma{n, j, V, (int64_t)nn, w, V + (size_t)(j + 1) * nn, d_h, d_mgs_part, d_bar + j, mgs_chunk,
-                                   ctx->reduction == ATK_REDUCE_SEQUENTIAL ? 1 : 0, tol};
-                        void* kargs[] = {&ma};
-                        ATK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)mgs_kernel, dim3(mgs_grid), dim3(mgs_block), kargs, mgs_smem,
-                                                                   st));
-                        count_launch(ctx);
-                    } else if (ortho == ATK_GMRES_MGS) {
-                        for (int i = 0; i < j; ++i) {  // :73-77
-                            const double* vi = V + (size_t)i * nn;
-                            launch_dot(ctx, n, vi, w, kSlotH);
-                            mgs_axmy_kernel<<<grid, 256, 0, st>>>(n, vi, w, ctx->slot(kSlotH), ctx->world, d_h + i);
-                            count_launch(ctx);
-                        }
-                    } else if (j > 0) {
-                        // ---- batched MGS: pass 1 (c = V[0:j]^T w, g = V[0:j+1]^T v_j), triangular solve, pass 2
-                        const int ncw = j, ncg = j + 1, len = 2 * ncg;
-                        multi_dot2_kernel<<<bd_blocks, kBdBlock, 0, st>>>(n, ncw, ncg, V, (int64_t)nn, w, vj, d_part);
-                        multi_dot2_final_kernel<<<len, 256, 0, st>>>(ncw, ncg, bd_blocks, d_part, d_cg + (size_t)ctx->rank * len);
-                        count_launch(ctx, 2);
-                        allgather_doubles(ctx, d_cg, (size_t)len, st);
-                        ATK_CUDA_CHECK(cudaMemcpyAsync(h_cg, d_cg, sizeof(double) * (size_t)len * ctx->world, cudaMemcpyDeviceToHost, st));
-                        ATK_CUDA_CHECK(cudaStreamSynchronize(st));
-                        auto Gm = [&](int a, int b) -> double& { return G[(size_t)a + (size_t)b * ld]; };
-                        for (int i = 0; i < ncg; ++i) {  // rank-ordered sums: identical on every rank
-                            double c = 0.0, g = 0.0;
-                            for (int q = 0; q < ctx->world; ++q) {
-                                c = c + h_cg[(size_t)q * len + i];
-                                g = g + h_cg[(size_t)q * len + ncg + i];
-                            }
-                            hvec[(size_t)i] = c;  // c_i for i < j (entry j unused)
-                            Gm(j, i) = g;         // G(j,i) = v_j . v_i
-                            Gm(i, j) = g;
-                        }
-                        for (int i = 0; i < j; ++i) {  // (I + strict_lower(G)) h = c, forward substitution
-                            double hi = hvec[(size_t)i];
-                            for (int m = 0; m < i; ++m) hi = hi - Gm(i, m) * hvec[(size_t)m];
-                            hvec[(size_t)i] = hi;
-                        }
-                        ATK_CUDA_CHECK(cudaMemcpyAsync(d_h, hvec.data(), sizeof(double) * (size_t)j, cudaMemcpyHostToDevice, st));
-                        multi_axmy_norm_kernel<<<ctx->reduce_grid(), kReduceBlock, sizeof(double) * (size_t)j, st>>>(
-                            n, j, V, (int64_t)nn, d_h, w, ctx->d_partials, ctx->d_tickets + 6, ctx->slot(kSlotNorm) + ctx->rank);
-                        count_launch(ctx);
-                        allgather_slot(ctx, kSlotNorm, st);
-                    }
-                    if (!persistent) {
-                        if (!(batched && j > 0)) launch_dot(ctx, n, w, w, kSlotNorm);  // :79 (the batched pass 2 already summed w.w)
-                        normalize_kernel<<<grid, 256, 0, st>>>(n, w, V + (size_t)(j + 1) * nn, ctx->slot(kSlotNorm), ctx->world,
-                                                               d_h + j, tol);  // :86 (skipped when the norm is 0 or below tol)
-                        count_launch(ctx);
-                    }
-                    ATK_CUDA_CHECK(cudaGetLastError());
-                    ATK_CUDA_CHECK(cudaMemcpyAsync(h_col, d_h, sizeof(double) * (size_t)(j + 1), cudaMemcpyDeviceToHost, st));
-                    ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+                // Givens recurrences for column j of H (entries 0..j-1 = projections, entry j = ||w||); false = the cycle ends
+                auto absorb_column = [&](int j, const double* col) -> bool {
                     info->arnoldi_steps++;
-                    for (int i = 0; i < j; ++i) Hm(i, j) = h_col[i];  // :75
-                    const double w_norm = h_col[j];
+                    for (int i = 0; i < j; ++i) Hm(i, j) = col[i];  // :75
+                    const double w_norm = col[j];
                     Hm(j + 1, j) = w_norm;  // :80
                     if (w_norm < tol) {     // :81-85
                         kry = j;
                         notify(ATK_GMRES_KRYLOV_UPDATE, (double)kry);
-                        break;
+                        return false;
                     }
                     ATK_REQUIRE(w_norm != 0.0, ATK_ERR_RUNTIME, "Division by zero.");  // VectorObj.hpp:76 via :86
                     for (int i = 0; i < j; ++i) {  // :89-91 / :134-137
@@ -623,6 +560,73 @@ void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t
                         const double tmp = e1[j];
                         e1[j] = cs[j] * tmp + sn[j] * e1[j + 1];
                         e1[j + 1] = -sn[j] * tmp + cs[j] * e1[j + 1];
+                    }
+                    return true;
+                };
+                if (persistent) {
+                    pm.reset_barriers(st);
+                    ATK_CUDA_CHECK(cudaMemsetAsync(d_stop, 0, sizeof(int) * 2, st));
+                    for (int j = 0; j < K; ++j) {
+                        op->apply(V + (size_t)j * nn, w, -1, d_stop);  // :70
+                        pm.launch(ctx, n, j, j, V, (int64_t)nn, w, V + (size_t)(j + 1) * nn, d_hcols + (size_t)j * ld, tol, d_stop);
+                    }
+                    ATK_CUDA_CHECK(cudaGetLastError());
+                    ATK_CUDA_CHECK(cudaMemcpyAsync(h_stop, d_stop, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+                    ATK_CUDA_CHECK(cudaMemcpyAsync(h_hcols, d_hcols, sizeof(double) * (size_t)K * (size_t)ld, cudaMemcpyDeviceToHost, st));
+                    ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+                    const int steps = h_stop[0] ? h_stop[1] + 1 : K;
+                    for (int j = 0; j < steps; ++j)
+                        if (!absorb_column(j, h_hcols + (size_t)j * ld)) break;
+                } else {
+                    for (int j = 0; j < K; ++j) {
+                        const double* vj = V + (size_t)j * nn;
+                        op->apply(vj, w, -1, nullptr);  // :70
+                        if (ortho == ATK_GMRES_MGS) {
+                            for (int i = 0; i < j; ++i) {  // :73-77
+                                const double* vi = V + (size_t)i * nn;
+                                launch_dot(ctx, n, vi, w, kSlotH);
+                                mgs_axmy_kernel<<<grid, 256, 0, st>>>(n, vi, w, ctx->slot(kSlotH), ctx->world, d_h + i);
+                                count_launch(ctx);
+                            }
+                        } else if (j > 0) {
+                            // ---- batched MGS: pass 1 (c = V[0:j]^T w, g = V[0:j+1]^T v_j), triangular solve, pass 2
+                            const int ncw = j, ncg = j + 1, len = 2 * ncg;
+                            multi_dot2_kernel<<<bd_blocks, kBdBlock, 0, st>>>(n, ncw, ncg, V, (int64_t)nn, w, vj, d_part);
+                            multi_dot2_final_kernel<<<len, 256, 0, st>>>(ncw, ncg, bd_blocks, d_part, d_cg + (size_t)ctx->rank * len);
+                            count_launch(ctx, 2);
+                            allgather_doubles(ctx, d_cg, (size_t)len, st);
+                            ATK_CUDA_CHECK(cudaMemcpyAsync(h_cg, d_cg, sizeof(double) * (size_t)len * ctx->world, cudaMemcpyDeviceToHost, st));
+                            ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+                            auto Gm = [&](int a, int b) -> double& { return G[(size_t)a + (size_t)b * ld]; };
+                            for (int i = 0; i < ncg; ++i) {  // rank-ordered sums: identical on every rank
+                                double c = 0.0, g = 0.0;
+                                for (int q = 0; q < ctx->world; ++q) {
+                                    c = c + h_cg[(size_t)q * len + i];
+                                    g = g + h_cg[(size_t)q * len + ncg + i];
+                                }
+                                hvec[(size_t)i] = c;  // c_i for i < j (entry j unused)
+                                Gm(j, i) = g;         // G(j,i) = v_j . v_i
+                                Gm(i, j) = g;
+                            }
+                            for (int i = 0; i < j; ++i) {  // (I + strict_lower(G)) h = c, forward substitution
+                                double hi = hvec[(size_t)i];
+                                for (int m = 0; m < i; ++m) hi = hi - Gm(i, m) * hvec[(size_t)m];
+                                hvec[(size_t)i] = hi;
+                            }
+                            ATK_CUDA_CHECK(cudaMemcpyAsync(d_h, hvec.data(), sizeof(double) * (size_t)j, cudaMemcpyHostToDevice, st));
+                            multi_axmy_norm_kernel<<<ctx->reduce_grid(), kReduceBlock, sizeof(double) * (size_t)j, st>>>(
+                                n, j, V, (int64_t)nn, d_h, w, ctx->d_partials, ctx->d_tickets + 6, ctx->slot(kSlotNorm) + ctx->rank);
+                            count_launch(ctx);
+                            allgather_slot(ctx, kSlotNorm, st);
+                        }
+                        if (!(batched && j > 0)) launch_dot(ctx, n, w, w, kSlotNorm);  // :79 (the batched pass 2 already summed w.w)
+                        normalize_kernel<<<grid, 256, 0, st>>>(n, w, V + (size_t)(j + 1) * nn, ctx->slot(kSlotNorm), ctx->world, d_h + j,
+                                                               tol);  // :86 (skipped when the norm is 0 or below tol)
+                        count_launch(ctx);
+                        ATK_CUDA_CHECK(cudaGetLastError());
+                        ATK_CUDA_CHECK(cudaMemcpyAsync(h_col, d_h, sizeof(double) * (size_t)(j + 1), cudaMemcpyDeviceToHost, st));
+                        ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+                        if (!absorb_column(j, h_col)) break;
                     }
                 }
                 // updateSolution (:153-171)
