@@ -109,12 +109,13 @@ PYBIND11_MODULE(fastsolver, m) {
         .def("__mul__", [](const Csc& A, const Vec& x) { return A * x; }, py::is_operator())
         .def("__call__", [](const Csc& A, int i, int j) { return A(i, j); }, py::arg("i"), py::arg("j"));
 
-    m.def("read_matrix_market", [](const std::string& filename, py::object matrix) {
+    m.def("read_matrix_market", [](const std::string& filename, py::object matrix, bool expand_symmetric) {
         py::scoped_ostream_redirect out(std::cout, py::module_::import("sys").attr("stdout"));
-        if (py::isinstance<Dense>(matrix)) utils::readMatrixMarket<double, Dense>(filename, matrix.cast<Dense&>());
-        else if (py::isinstance<Csc>(matrix)) utils::readMatrixMarket<double, Csc>(filename, matrix.cast<Csc&>());
+        if (py::isinstance<Dense>(matrix)) utils::readMatrixMarket<double, Dense>(filename, matrix.cast<Dense&>(), expand_symmetric);
+        else if (py::isinstance<Csc>(matrix)) utils::readMatrixMarket<double, Csc>(filename, matrix.cast<Csc&>(), expand_symmetric);
         else throw fastsolverError("Unsupported matrix type");
-    }, "Read matrix from Matrix Market format file", py::arg("filename"), py::arg("matrix"));
+    }, "Read matrix from Matrix Market format file (expand_symmetric=True mirrors the stored triangle of a symmetric file)",
+          py::arg("filename"), py::arg("matrix"), py::arg("expand_symmetric") = false);
 
     py::class_<Cg>(m, "ConjugateGrad")
         .def(py::init<const Csc&, const Vec&, int, double>(), py::arg("A"), py::arg("b"), py::arg("max_iter"), py::arg("tol"))

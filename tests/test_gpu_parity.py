@@ -568,3 +568,31 @@ def test_arnoldi(ctx, port):
     op2 = ctx.operator_from_csc(4, 4, A2.col_ptr, A2.row_idx, A2.vals)
     g2, o2 = capi.arnoldi_host(ctx, op2, [1.0, 0, 0, 0], 3, 1e-8), port.arnoldi(A2, [1.0, 0, 0, 0], 3, 1e-8)
     assert g2["breakdown"] == o2["breakdown"] == 1 and np.array_equal(g2["Q"], o2["Q"]) and np.array_equal(g2["H"], o2["H"])
+
+
+# ------------------------------------------------------------------------------------------------ 8(f) rank 3
+@pytest.mark.parametrize("name,iters", [("bcsstk01", 60), ("bcsstk08", 150)])
+def test_cg_on_symmetric_expanded_matrix_market(ctx, port, name, iters):
+    """Opt-in symmetric expansion -> the SPD matrix the file describes -> device SELL -> CG; the reference-ordered
+    reductions reproduce the oracle's CG on the same CSC arrays bit for bit."""
+    from algotoolkit_b200.mmio import read_matrix_market_csc
+    from oracle.pyoracle import CscMatrix
+
+    d = read_matrix_market_csc(mm_path(name), expand_symmetric=True)
+    n = d["n_rows"]
+    A = CscMatrix(n, n, d["col_ptr"], d["row_idx"], d["vals"])
+    x_ext = port.u01_array(777, n)
+    b = port.spmv(A, x_ext)
+    op = ctx.operator_from_csc(n, n, d["col_ptr"], d["row_idx"], d["vals"])
+    assert digest(op.apply_numpy(x_ext)) == digest(b)
+    ora = port.cg(A, b, iters)
+    ctx.set_reduction(capi.REDUCE_SEQUENTIAL)
+    try:
+        res = ctx.cg_solve_host(op, b, iters)
+    finally:
+        ctx.set_reduction(capi.REDUCE_TREE)
+    assert res["iters"] == ora["iters"]
+    assert digest(res["x"]) == digest(ora["x"]) and digest(res["r"]) == digest(ora["r"])
+    tree = ctx.cg_solve_host(op, b, 10)  # a few iterations: rounding-order noise has not been amplified yet
+    ora10 = port.cg(A, b, 10)
+    assert tree["iters"] == ora10["iters"] and relerr(tree["x"], ora10["x"]) < 1e-8
