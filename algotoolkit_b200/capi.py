@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -17,6 +18,8 @@ ATK_OK, ATK_ERR_INVALID_ARGUMENT, ATK_ERR_RUNTIME, ATK_ERR_OUT_OF_RANGE, ATK_ERR
 REDUCE_TREE, REDUCE_SEQUENTIAL = 0, 1
 FORMAT_SELL, FORMAT_CSR_VECTOR = 0, 1
 GMRES_MGS, GMRES_MGS_BATCHED = 0, 1
+(GMRES_INITIAL_RESIDUAL, GMRES_INITIAL_GOOD, GMRES_KRYLOV_UPDATE, GMRES_RESTART_RESIDUAL, GMRES_CONVERGED,
+ GMRES_MAX_ITER) = range(6)  # atk_gmres_event
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -77,7 +80,8 @@ EXPORTS = [
     "atk_operator_destroy",
     "atk_operator_shape", "atk_operator_row_range", "atk_operator_export_csr", "atk_operator_apply", "atk_cg_solve",
     "atk_cg_solve_host", "atk_gmres_solve", "atk_gmres_solve_host", "atk_gd_solve", "atk_gd_solve_host", "atk_arnoldi",
-    "atk_arnoldi_host",
+    "atk_arnoldi_host", "atk_ilu_compute", "atk_ilu_solve", "atk_ilu_solve_host", "atk_ilu_export",
+    "atk_preconditioner_destroy", "atk_gmres_solve_precond", "atk_gmres_solve_precond_host",
 ]
 
 _lib = None
@@ -143,6 +147,14 @@ def load():
     sig["atk_gd_solve_host"] = sig["atk_gd_solve"]
     sig["atk_arnoldi"] = [_vp, _vp, _vp, i64, C.c_int, _dp, C.c_double, _ip]
     sig["atk_arnoldi_host"] = sig["atk_arnoldi"]
+    sig["atk_ilu_compute"] = [_vp, i64, i64, i64, _vp, _vp, _vp, C.POINTER(_vp)]
+    sig["atk_ilu_solve"] = [_vp, _vp, i64, _vp, _vp]
+    sig["atk_ilu_solve_host"] = [_vp, _vp, i64, _vp, _vp]
+    sig["atk_ilu_export"] = [_vp, _vp, _vp]
+    sig["atk_preconditioner_destroy"] = [_vp]
+    sig["atk_gmres_solve_precond"] = [_vp, _vp, _vp, _vp, _vp, i64, C.c_int, C.c_int, C.c_double, C.c_int, GMRES_CALLBACK, _vp,
+                                      C.POINTER(GmresInfo)]
+    sig["atk_gmres_solve_precond_host"] = sig["atk_gmres_solve_precond"]
     for name, args in sig.items():
         fn = getattr(L, name)
         fn.argtypes = args
@@ -181,6 +193,7 @@ class DeviceVector:
         p = _vp()
         _check(ctx.L.atk_malloc(ctx.h, max(self.n, 1) * 8, C.byref(p)))
         self.ptr = p
+        ctx._adopt(self)
 
     @classmethod
     def from_numpy(cls, ctx, a):
@@ -210,7 +223,8 @@ class DeviceVector:
 
     def free(self):
         if self.ptr:
-            self.ctx.L.atk_free(self.ctx.h, self.ptr)
+            if self.ctx.h:  # a destroyed context has already released its children
+                self.ctx.L.atk_free(self.ctx.h, self.ptr)
             self.ptr = None
 
     def __del__(self):
@@ -223,6 +237,7 @@ class DeviceVector:
 class Operator:
     def __init__(self, ctx, handle):
         self.ctx, self.h = ctx, handle
+        ctx._adopt(self)
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         _check(ctx.L.atk_operator_shape(handle, C.byref(a), C.byref(b), C.byref(c)))
         self.n_rows_local, self.n_cols, self.nnz = a.value, b.value, c.value
@@ -251,7 +266,8 @@ class Operator:
 
     def destroy(self):
         if self.h:
-            self.ctx.L.atk_operator_destroy(self.h)
+            if self.ctx.h:
+                self.ctx.L.atk_operator_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -271,6 +287,11 @@ class Context:
             buf = C.create_string_buffer(nccl_uid, len(nccl_uid))
             _check(self.L.atk_context_create_distributed(device, rank, world, buf, len(nccl_uid), C.byref(h)))
         self.h, self.rank, self.world, self.device = h, rank, world, device
+        self._children = weakref.WeakSet()  # vectors, operators, preconditioners: released before the context goes
+
+    def _adopt(self, child):
+        self._children.add(child)
+        return child
 
     @staticmethod
     def nccl_unique_id() -> bytes:
@@ -293,6 +314,8 @@ class Context:
 
     def destroy(self):
         if self.h:
+            for child in list(self._children):  # objects still referenced elsewhere (e.g. by a traceback) die here, safely
+                (child.free if isinstance(child, DeviceVector) else child.destroy)()
             self.L.atk_context_destroy(self.h)
             self.h = None
 
@@ -413,8 +436,18 @@ class Context:
         out.update(x=x, r=r, p=p)
         return out
 
+    def ilu_compute(self, n_rows, n_cols, col_ptr, row_idx, vals) -> "IluPreconditioner":
+        """ILUPreconditioner::compute on finished CSC arrays (ValueError: not square, RuntimeError: singular)."""
+        col_ptr = np.ascontiguousarray(col_ptr, np.int32)
+        row_idx = np.ascontiguousarray(row_idx, np.int32)
+        vals = np.ascontiguousarray(vals, np.float64)
+        h = _vp()
+        _check(self.L.atk_ilu_compute(self.h, n_rows, n_cols, vals.size, _np_ptr(col_ptr), _np_ptr(row_idx), _np_ptr(vals),
+                                      C.byref(h)))
+        return IluPreconditioner(self, h, n_rows)
+
     def gmres_solve_host(self, op: Operator, b, x0, max_iter: int, krylov_dim: int, tol: float, ortho=GMRES_MGS,
-                         on_event=None):
+                         on_event=None, precond: "IluPreconditioner | None" = None):
         b = np.ascontiguousarray(b, np.float64)
         x = np.ascontiguousarray(x0, np.float64).copy()
         info = GmresInfo()
@@ -429,8 +462,9 @@ class Context:
                 on_event(ev, val)
 
         cb = GMRES_CALLBACK(_cb)
-        rc = self.L.atk_gmres_solve_host(self.h, op.h, _np_ptr(b), _np_ptr(x), x.size, max_iter, krylov_dim, tol, ortho,
-                                         cb, None, C.byref(info))
+        rc = self.L.atk_gmres_solve_precond_host(self.h, op.h, precond.h if precond is not None else None, _np_ptr(b),
+                                                 _np_ptr(x), x.size, max_iter, krylov_dim, tol, ortho, cb, None,
+                                                 C.byref(info))
         err = None
         if rc == ATK_ERR_RUNTIME:
             err = self.L.atk_last_error().decode()
@@ -439,6 +473,38 @@ class Context:
         return dict(x=x, rc=rc, error=err, resid=trace[: min(info.trace_count, cap)].copy(), status=info.status,
                     restarts=info.restarts, arnoldi_steps=info.arnoldi_steps, device_ms=info.device_ms,
                     kernel_launches=info.kernel_launches, events=events)
+
+
+class IluPreconditioner:
+    """Device-resident factors of ILUPreconditioner::compute (reference src/LinearAlgebra/Preconditioner/ILU.hpp)."""
+
+    def __init__(self, ctx, handle, n):
+        self.ctx, self.h, self.n = ctx, handle, n
+        ctx._adopt(self)
+
+    def solve_host(self, b):
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.zeros_like(b)
+        _check(self.ctx.L.atk_ilu_solve_host(self.ctx.h, self.h, b.size, _np_ptr(b), _np_ptr(x)))
+        return x
+
+    def factors(self):
+        """(L, U) as dense arrays indexed [row, col], as getLFactor()/getUFactor() hold them."""
+        Lf, Uf = np.zeros((self.n, self.n)), np.zeros((self.n, self.n))  # column-major on the C side
+        _check(self.ctx.L.atk_ilu_export(self.h, _np_ptr(Lf), _np_ptr(Uf)))
+        return Lf.T.copy(), Uf.T.copy()
+
+    def destroy(self):
+        if self.h:
+            if self.ctx.h:
+                self.ctx.L.atk_preconditioner_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
 
 
 def gd_solve_host(ctx: Context, op: Operator, b, x0, max_iter: int, tol: float):

@@ -13,6 +13,10 @@ void nccl_unique_id(void* buf, size_t cap, size_t* bytes);
 void context_destroy(atk_context_s* h);
 }  // namespace atk
 
+struct atk_preconditioner {
+    atk::Preconditioner* pc = nullptr;
+};
+
 namespace {
 thread_local std::string g_last_error;
 
@@ -44,6 +48,12 @@ atk::Context* C(atk_context_t h) {
 atk::Operator* O(atk_operator_t h) {
     ATK_REQUIRE(h != nullptr && h->op != nullptr, ATK_ERR_INVALID_ARGUMENT, "null operator");
     return h->op;
+}
+atk::Preconditioner* P(atk_preconditioner_t h, atk::Context* c, bool nullable) {
+    if (!h && nullable) return nullptr;
+    ATK_REQUIRE(h != nullptr && h->pc != nullptr, ATK_ERR_INVALID_ARGUMENT, "ILU factorization not computed");  // ILU.hpp:85-87
+    ATK_REQUIRE(h->pc->ctx == c, ATK_ERR_INVALID_ARGUMENT, "preconditioner belongs to another context");
+    return h->pc;
 }
 }  // namespace
 
@@ -347,22 +357,96 @@ int atk_cg_solve_host(atk_context_t ctx, atk_operator_t op, const double* b, dou
 }
 
 // ------------------------------------------------------------------------------------------------ GMRES
-int atk_gmres_solve(atk_context_t ctx, atk_operator_t op, const double* b, double* x, int64_t n_x, int max_iter,
-                    int krylov_dim, double tol, atk_gmres_ortho ortho, atk_gmres_callback cb, void* user,
-                    atk_gmres_info* info) {
+// ------------------------------------------------------------------------------------------------ ILU preconditioner
+int atk_ilu_compute(atk_context_t ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* col_ptr,
+                    const int32_t* row_idx, const double* vals, atk_preconditioner_t* out) {
+    return guarded([&] {
+        atk::Context* c = C(ctx);
+        ATK_REQUIRE(out, ATK_ERR_INVALID_ARGUMENT, "null pointer");
+        *out = nullptr;
+        atk::Preconditioner* pc = atk::make_ilu(c, n_rows, n_cols, nnz, col_ptr, row_idx, vals);
+        *out = new atk_preconditioner{pc};
+    });
+}
+int atk_ilu_solve(atk_context_t ctx, atk_preconditioner_t pc, int64_t n, const double* b, double* x) {
+    return guarded([&] {
+        atk::Context* c = C(ctx);
+        atk::Preconditioner* m = P(pc, c, false);
+        ATK_REQUIRE(n == m->n, ATK_ERR_INVALID_ARGUMENT, "Vector size does not match matrix size");  // ILU.hpp:88-90
+        ATK_REQUIRE((b && x) || n == 0, ATK_ERR_INVALID_ARGUMENT, "null pointer");
+        m->solve(b, x, nullptr);
+    });
+}
+int atk_ilu_solve_host(atk_context_t ctx, atk_preconditioner_t pc, int64_t n, const double* b, double* x) {
+    return guarded([&] {
+        atk::Context* c = C(ctx);
+        atk::Preconditioner* m = P(pc, c, false);
+        ATK_REQUIRE(n == m->n, ATK_ERR_INVALID_ARGUMENT, "Vector size does not match matrix size");
+        ATK_REQUIRE((b && x) || n == 0, ATK_ERR_INVALID_ARGUMENT, "null pointer");
+        const size_t bytes = sizeof(double) * (size_t)n;
+        double *db = nullptr, *dx = nullptr;
+        try {
+            ATK_CUDA_CHECK(cudaMalloc(&db, bytes ? bytes : 8));
+            ATK_CUDA_CHECK(cudaMalloc(&dx, bytes ? bytes : 8));
+            ATK_CUDA_CHECK(cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, c->stream));
+            m->solve(db, dx, nullptr);
+            ATK_CUDA_CHECK(cudaMemcpyAsync(x, dx, bytes, cudaMemcpyDeviceToHost, c->stream));
+            ATK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        } catch (...) {
+            cudaFree(db);
+            cudaFree(dx);
+            throw;
+        }
+        cudaFree(db);
+        cudaFree(dx);
+    });
+}
+int atk_ilu_export(atk_preconditioner_t pc, double* L, double* U) {
+    return guarded([&] {
+        ATK_REQUIRE(pc != nullptr && pc->pc != nullptr, ATK_ERR_INVALID_ARGUMENT, "ILU factorization not computed");
+        ATK_CUDA_CHECK(cudaSetDevice(pc->pc->ctx->device));
+        pc->pc->export_factors(L, U);
+    });
+}
+int atk_preconditioner_destroy(atk_preconditioner_t pc) {
+    return guarded([&] {
+        if (!pc) return;
+        if (pc->pc) {
+            cudaSetDevice(pc->pc->ctx->device);
+            cudaStreamSynchronize(pc->pc->ctx->stream);
+            delete pc->pc;
+        }
+        delete pc;
+    });
+}
+
+int atk_gmres_solve_precond(atk_context_t ctx, atk_operator_t op, atk_preconditioner_t pc, const double* b, double* x,
+                            int64_t n_x, int max_iter, int krylov_dim, double tol, atk_gmres_ortho ortho,
+                            atk_gmres_callback cb, void* user, atk_gmres_info* info) {
     return guarded([&] {
         atk::Context* c = C(ctx);
         atk::Operator* o = O(op);
         ATK_REQUIRE(o->ctx == c, ATK_ERR_INVALID_ARGUMENT, "operator belongs to another context");
-        atk::gmres_solve(c, o, b, x, n_x, max_iter, krylov_dim, tol, ortho, cb, user, info);
+        atk::gmres_solve(c, o, P(pc, c, true), b, x, n_x, max_iter, krylov_dim, tol, ortho, cb, user, info);
     });
+}
+int atk_gmres_solve(atk_context_t ctx, atk_operator_t op, const double* b, double* x, int64_t n_x, int max_iter,
+                    int krylov_dim, double tol, atk_gmres_ortho ortho, atk_gmres_callback cb, void* user,
+                    atk_gmres_info* info) {
+    return atk_gmres_solve_precond(ctx, op, nullptr, b, x, n_x, max_iter, krylov_dim, tol, ortho, cb, user, info);
 }
 int atk_gmres_solve_host(atk_context_t ctx, atk_operator_t op, const double* b, double* x, int64_t n_x, int max_iter,
                          int krylov_dim, double tol, atk_gmres_ortho ortho, atk_gmres_callback cb, void* user,
                          atk_gmres_info* info) {
+    return atk_gmres_solve_precond_host(ctx, op, nullptr, b, x, n_x, max_iter, krylov_dim, tol, ortho, cb, user, info);
+}
+int atk_gmres_solve_precond_host(atk_context_t ctx, atk_operator_t op, atk_preconditioner_t pc, const double* b, double* x,
+                                 int64_t n_x, int max_iter, int krylov_dim, double tol, atk_gmres_ortho ortho,
+                                 atk_gmres_callback cb, void* user, atk_gmres_info* info) {
     return guarded([&] {
         atk::Context* c = C(ctx);
         atk::Operator* o = O(op);
+        atk::Preconditioner* m = P(pc, c, true);
         ATK_REQUIRE(o->ctx == c, ATK_ERR_INVALID_ARGUMENT, "operator belongs to another context");
         ATK_REQUIRE(b && x && info, ATK_ERR_INVALID_ARGUMENT, "null argument");
         // the size checks of GMRES.hpp:28-37 come before any work
@@ -377,7 +461,7 @@ int atk_gmres_solve_host(atk_context_t ctx, atk_operator_t op, const double* b, 
             int rc = ATK_OK;
             std::string msg;
             try {
-                atk::gmres_solve(c, o, db, dx, n_x, max_iter, krylov_dim, tol, ortho, cb, user, info);
+                atk::gmres_solve(c, o, m, db, dx, n_x, max_iter, krylov_dim, tol, ortho, cb, user, info);
             } catch (const atk::Error& e) {
                 // a runtime_error mid-solve leaves x at its last value in the reference too: copy it back, then rethrow
                 if (e.code != ATK_ERR_RUNTIME) throw;

@@ -437,8 +437,8 @@ struct Givens {
 
 }  // namespace
 
-void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t n_x, int max_iter, int krylov_dim,
-                 double tol, atk_gmres_ortho ortho, atk_gmres_callback cb, void* user, atk_gmres_info* info) {
+void gmres_solve(Context* ctx, Operator* op, Preconditioner* pc, const double* b, double* x, int64_t n_x, int max_iter,
+                 int krylov_dim, double tol, atk_gmres_ortho ortho, atk_gmres_callback cb, void* user, atk_gmres_info* info) {
     ATK_REQUIRE(op && b && x && info, ATK_ERR_INVALID_ARGUMENT, "null argument to gmres_solve");
     const int64_t n = op->n_rows_local;
     const int64_t n_global = op->n_cols;
@@ -446,6 +446,8 @@ void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t
     ATK_REQUIRE(n_x == n, ATK_ERR_INVALID_ARGUMENT, "Initial guess vector must match system size");
     ATK_REQUIRE(krylov_dim > 0 && krylov_dim <= n_global, ATK_ERR_INVALID_ARGUMENT, "Invalid Krylov subspace dimension");
     ATK_REQUIRE(ortho == ATK_GMRES_MGS || ortho == ATK_GMRES_MGS_BATCHED, ATK_ERR_INVALID_ARGUMENT, "unknown orthogonalisation mode");
+    ATK_REQUIRE(!pc || (pc->ctx == ctx && pc->n == n && ctx->world == 1), ATK_ERR_INVALID_ARGUMENT,
+                "Vector size does not match matrix size");  // ILU.hpp:88-90
     const int K = krylov_dim;
     const int64_t ld = K + 1;
     cudaStream_t st = ctx->stream;
@@ -517,7 +519,12 @@ void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t
         ATK_CUDA_CHECK(cudaEventRecord(ctx->ev_t0, st));
         auto residual = [&]() -> double {  // r = b - A*x ; ||r||   (:42,47 / :99,104)
             op->apply(x, t, -1, nullptr);
-            launch_sub(ctx, n, b, t, r);
+            if (pc) {  // r = M^-1 (b - A x)   (:43-45 / :100-102)
+                launch_sub(ctx, n, b, t, w);
+                pc->solve(w, r, nullptr);
+            } else {
+                launch_sub(ctx, n, b, t, r);
+            }
             launch_dot(ctx, n, r, r, kSlotNorm);
             return std::sqrt(read_slot(ctx, kSlotNorm));
         };
@@ -567,7 +574,12 @@ void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t
                     pm.reset_barriers(st);
                     ATK_CUDA_CHECK(cudaMemsetAsync(d_stop, 0, sizeof(int) * 2, st));
                     for (int j = 0; j < K; ++j) {
-                        op->apply(V + (size_t)j * nn, w, -1, d_stop);  // :70
+                        if (pc) {  // w = M^-1 (A v_j)   (:67-68)
+                            op->apply(V + (size_t)j * nn, t, -1, d_stop);
+                            pc->solve(t, w, d_stop);
+                        } else {
+                            op->apply(V + (size_t)j * nn, w, -1, d_stop);  // :70
+                        }
                         pm.launch(ctx, n, j, j, V, (int64_t)nn, w, V + (size_t)(j + 1) * nn, d_hcols + (size_t)j * ld, tol, d_stop);
                     }
                     ATK_CUDA_CHECK(cudaGetLastError());
@@ -580,7 +592,12 @@ void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t
                 } else {
                     for (int j = 0; j < K; ++j) {
                         const double* vj = V + (size_t)j * nn;
-                        op->apply(vj, w, -1, nullptr);  // :70
+                        if (pc) {  // w = M^-1 (A v_j)   (:67-68)
+                            op->apply(vj, t, -1, nullptr);
+                            pc->solve(t, w, nullptr);
+                        } else {
+                            op->apply(vj, w, -1, nullptr);  // :70
+                        }
                         if (ortho == ATK_GMRES_MGS) {
                             for (int i = 0; i < j; ++i) {  // :73-77
                                 const double* vi = V + (size_t)i * nn;

@@ -7,6 +7,7 @@
 //   atk_stencil.cu   matrix-free 7-point Poisson operator (+ fused p.Ap), device-side assembly
 //   atk_cg.cu        ConjugateGrad::solve device loop
 //   atk_gmres.cu     GMRES::solve device loop
+//   atk_ilu.cu       ILUPreconditioner (dense-in-disguise elimination + triangular sweeps) for GMRES::enablePreconditioner
 //   atk_api.cu       extern "C" wrappers (exceptions -> status codes)
 #pragma once
 
@@ -202,8 +203,18 @@ void launch_axmy(Context* ctx, int64_t n, const double* x, const double* y, doub
 void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r, double* p, int max_iter, atk_cg_info* info);
 void gd_solve(Context* ctx, Operator* op, const double* b, double* x, int max_iter, double tol, atk_gd_info* info);
 void arnoldi(Context* ctx, Operator* op, double* Q, int64_t ldq, int m, double* H, double tol, int* breakdown);
-void gmres_solve(Context* ctx, Operator* op, const double* b, double* x, int64_t n_x, int max_iter, int krylov_dim,
-                 double tol, atk_gmres_ortho ortho, atk_gmres_callback cb, void* user, atk_gmres_info* info);
+// Left preconditioner handle: x = M^-1 b on ctx->stream (a set skip_flag turns the launch into a no-op).
+struct Preconditioner {
+    Context* ctx = nullptr;
+    int64_t n = 0;
+    virtual ~Preconditioner() {}
+    virtual void solve(const double* b, double* x, const int* skip_flag) = 0;
+    virtual void export_factors(double* L, double* U) = 0;  // dense n x n column-major host arrays (either may be null)
+};
+Preconditioner* make_ilu(Context* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* col_ptr, const int32_t* row_idx,
+                         const double* vals);
+void gmres_solve(Context* ctx, Operator* op, Preconditioner* pc, const double* b, double* x, int64_t n_x, int max_iter,
+                 int krylov_dim, double tol, atk_gmres_ortho ortho, atk_gmres_callback cb, void* user, atk_gmres_info* info);
 
 // ------------------------------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

@@ -139,7 +139,7 @@ PYBIND11_MODULE(fastsolver, m) {
 
     py::class_<Gm>(m, "GMRES")
         .def(py::init<>())
-        .def("enablePreconditioner", &Gm::enablePreconditioner, "Enable preconditioning for GMRES (not available in the CUDA build).")
+        .def("enablePreconditioner", &Gm::enablePreconditioner, "Enable preconditioning for GMRES.")
         .def("solve", [](Gm& g, const Csc& A, const Vec& b, Vec& x, int maxIter, int KrylovDim, double tol) {
             py::scoped_ostream_redirect out(std::cout, py::module_::import("sys").attr("stdout"));
             g.solve(A, b, x, maxIter, KrylovDim, tol);

@@ -74,6 +74,7 @@ int atk_context_create(int device, atk_context_t* out);
 int atk_nccl_unique_id(void* buf, size_t capacity, size_t* bytes);
 int atk_context_create_distributed(int device, int rank, int world, const void* nccl_uid, size_t uid_bytes,
                                    atk_context_t* out);
+/* Destroy the operators and preconditioners created on a context before the context itself. */
 int atk_context_destroy(atk_context_t ctx);
 int atk_context_rank(atk_context_t ctx, int* rank, int* world);
 int atk_context_set_reduction(atk_context_t ctx, atk_reduction mode);
@@ -250,6 +251,35 @@ int atk_arnoldi(atk_context_t ctx, atk_operator_t op, double* Q, int64_t ldq, in
                 int* breakdown_at);
 int atk_arnoldi_host(atk_context_t ctx, atk_operator_t op, double* Q, int64_t ldq, int m, double* H, double tol,
                      int* breakdown_at);
+
+/* ------------------------------------------------------------------------------------------------ "next" row
+ * the enablePreconditioner() branch of GMRES::solve.
+ *
+ * ILUPreconditioner (src/LinearAlgebra/Preconditioner/ILU.hpp).  atk_ilu_compute = compute() (:21-81) on finished CSC
+ * arrays (host pointers): the reference's full elimination without pivoting with its 1e-12 drop rules, carried out on
+ * the device on a dense n x n array - the factors are bit-identical to getLFactor()/getUFactor().  Errors:
+ * ATK_ERR_INVALID_ARGUMENT "Matrix must be square for ILU factorization" (:24-26), ATK_ERR_RUNTIME "Matrix is
+ * numerically singular" (:38-40).  Single-GPU contexts, n <= 14000.
+ * atk_ilu_solve = solve() (:84-112): x = U^-1 L^-1 b.  The forward sweep always adds in the reference's order; the
+ * backward sweep does so under ATK_REDUCE_SEQUENTIAL (bit-exact) and accumulates column by column under
+ * ATK_REDUCE_TREE (same result up to rounding, far less serial).  n must equal the factor size
+ * (ATK_ERR_INVALID_ARGUMENT "Vector size does not match matrix size", :88-90).
+ * atk_ilu_export: L and U as dense n x n column-major host arrays (either may be NULL). */
+typedef struct atk_preconditioner* atk_preconditioner_t;
+int atk_ilu_compute(atk_context_t ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* col_ptr,
+                    const int32_t* row_idx, const double* vals, atk_preconditioner_t* out);
+int atk_ilu_solve(atk_context_t ctx, atk_preconditioner_t pc, int64_t n, const double* b, double* x);      /* device */
+int atk_ilu_solve_host(atk_context_t ctx, atk_preconditioner_t pc, int64_t n, const double* b, double* x); /* host */
+int atk_ilu_export(atk_preconditioner_t pc, double* L, double* U);
+int atk_preconditioner_destroy(atk_preconditioner_t pc);
+/* GMRES::solve with usePreconditioner (GMRES.hpp:39-45,67-68,100-102): r = M^-1 (b - A x), w = M^-1 (A v_j); everything
+ * else as atk_gmres_solve.  pc == NULL is the unpreconditioned solve. */
+int atk_gmres_solve_precond(atk_context_t ctx, atk_operator_t op, atk_preconditioner_t pc, const double* b, double* x,
+                            int64_t n_x, int max_iter, int krylov_dim, double tol, atk_gmres_ortho ortho,
+                            atk_gmres_callback cb, void* user, atk_gmres_info* info);
+int atk_gmres_solve_precond_host(atk_context_t ctx, atk_operator_t op, atk_preconditioner_t pc, const double* b, double* x,
+                                 int64_t n_x, int max_iter, int krylov_dim, double tol, atk_gmres_ortho ortho,
+                                 atk_gmres_callback cb, void* user, atk_gmres_info* info);
 
 #ifdef __cplusplus
 }

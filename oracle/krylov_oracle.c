@@ -323,9 +323,74 @@ int orc_cg_solve(int n, const int* col_ptr, const int* row_idx, const double* va
 
 /* ------------------------------------------------------------------ GMRES */
 /* GMRES.hpp:27-171 (usePreconditioner == false) */
-int orc_gmres_solve(int n, const int* col_ptr, const int* row_idx, const double* vals, const double* b, double* x,
-                    int n_x, int max_iter, int krylov_dim, double tol, double* resid, int resid_cap, int* n_resid,
-                    int* status, int* last_kry_update) {
+/* ---- ILUPreconditioner (src/LinearAlgebra/Preconditioner/ILU.hpp) ----
+ * compute() (:21-81) is a full elimination without pivoting carried out through SparseMatrixCSC lookups, so a dense
+ * n x n array (column-major, absent entry == 0.0) restates it exactly:
+ *   step j: |A(j,j)| < 1e-12 -> "numerically singular" (:38-40); for i > j: factor = A(i,j)/A(j,j); only when
+ *   |factor| > 1e-12 (:50) is A(i,j) overwritten by the multiplier (:51) and row i updated, and only entries whose
+ *   new value exceeds 1e-12 in magnitude are written (:55-57) - a smaller update leaves the OLD value in place.
+ * Entries become L (i > j) or U (i <= j) only when |value| > 1e-12 (:67-76); L has a unit diagonal (:65). */
+#define ORC_ILU_EPS 1e-12
+int orc_ilu_compute(int n, const int* col_ptr, const int* row_idx, const double* vals, double* LU) {
+    const size_t N = (size_t)n;
+    memset(LU, 0, sizeof(double) * N * N);
+    for (int c = 0; c < n; ++c)
+        for (int k = col_ptr[c]; k < col_ptr[c + 1]; ++k) LU[(size_t)row_idx[k] + (size_t)c * N] = vals[k];
+#define A_(i, j) LU[(size_t)(i) + (size_t)(j) * N]
+    for (int j = 0; j < n; ++j) {
+        const double pivot = A_(j, j);
+        if (fabs(pivot) < ORC_ILU_EPS) return 2;
+        for (int i = j + 1; i < n; ++i) {
+            const double factor = A_(i, j) / pivot;
+            if (fabs(factor) > ORC_ILU_EPS) {
+                A_(i, j) = factor;
+                for (int k = j + 1; k < n; ++k) {
+                    const double prod = factor * A_(j, k);
+                    const double update = A_(i, k) - prod;
+                    if (fabs(update) > ORC_ILU_EPS) A_(i, k) = update;
+                }
+            }
+        }
+    }
+#undef A_
+    return 0;
+}
+
+/* solve() (:84-112): y_i = b_i - sum_{j<i} L(i,j) y_j ; x_i = (y_i - sum_{j>i} U(i,j) x_j) / U(i,i), every sum from 0.0
+ * in ascending j with one rounding per product and per add, over ALL j (zeros included), as the reference loops. */
+void orc_ilu_solve(int n, const double* LU, const double* b, double* x) {
+    const size_t N = (size_t)n;
+    double* y = (double*)malloc(sizeof(double) * (N ? N : 1));
+#define M_(i, j) (fabs(LU[(size_t)(i) + (size_t)(j) * N]) > ORC_ILU_EPS ? LU[(size_t)(i) + (size_t)(j) * N] : 0.0)
+    for (int i = 0; i < n; ++i) {
+        double sum = 0.0;
+        for (int j = 0; j < i; ++j) { const double prod = M_(i, j) * y[j]; sum = sum + prod; }
+        y[i] = b[i] - sum;
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        double sum = 0.0;
+        for (int j = i + 1; j < n; ++j) { const double prod = M_(i, j) * x[j]; sum = sum + prod; }
+        x[i] = (y[i] - sum) / M_(i, i);
+    }
+#undef M_
+    free(y);
+}
+
+/* dense n x n exports of the two factors as the reference's getLFactor()/getUFactor() hold them */
+void orc_ilu_factors(int n, const double* LU, double* L, double* U) {
+    const size_t N = (size_t)n;
+    for (size_t j = 0; j < N; ++j)
+        for (size_t i = 0; i < N; ++i) {
+            const double v = LU[i + j * N];
+            const double m = fabs(v) > ORC_ILU_EPS ? v : 0.0;
+            L[i + j * N] = i == j ? 1.0 : (i > j ? m : 0.0);
+            U[i + j * N] = i <= j ? m : 0.0;
+        }
+}
+
+static int gmres_impl(int n, const int* col_ptr, const int* row_idx, const double* vals, const double* LU, const double* b,
+                      double* x, int n_x, int max_iter, int krylov_dim, double tol, double* resid, int resid_cap,
+                      int* n_resid, int* status, int* last_kry_update) {
     const int K = krylov_dim;
     *n_resid = 0;
     *status = 0;
@@ -340,6 +405,7 @@ int orc_gmres_solve(int n, const int* col_ptr, const int* row_idx, const double*
     /* :42 r = b - A*x */
     orc_spmv_csc(n, n, col_ptr, row_idx, vals, x, t);
     orc_vec_sub(n, b, t, r);
+    if (LU) { orc_ilu_solve(n, LU, r, t); memcpy(r, t, sizeof(double) * N); }   /* :43-45 r = M^-1 (b - A x) */
     double beta = orc_nrm2(n, r);      /* :47 */
     if (*n_resid < resid_cap) resid[(*n_resid)++] = beta;
     if (beta < tol) {                  /* :49-52 */
@@ -361,7 +427,11 @@ int orc_gmres_solve(int n, const int* col_ptr, const int* row_idx, const double*
         if (orc_vec_div(n, r, beta, V) != 0) { rc = 2; goto done; } /* :63 */
         int kry = K;
         for (int j = 0; j < K; ++j) {                              /* :65 */
-            orc_spmv_csc(n, n, col_ptr, row_idx, vals, V + N * (size_t)j, w);   /* :70 */
+            if (LU) {                                                  /* :67-68 w = M^-1 (A v_j) */
+                orc_spmv_csc(n, n, col_ptr, row_idx, vals, V + N * (size_t)j, t);
+                orc_ilu_solve(n, LU, t, w);
+            } else
+                orc_spmv_csc(n, n, col_ptr, row_idx, vals, V + N * (size_t)j, w);   /* :70 */
             for (int i = 0; i < j; ++i) {                          /* :73  NOTE i<j */
                 const double* vi = V + N * (size_t)i;
                 const double h = orc_dot(n, vi, w);                /* :74 */
@@ -410,6 +480,7 @@ int orc_gmres_solve(int n, const int* col_ptr, const int* row_idx, const double*
         }
         orc_spmv_csc(n, n, col_ptr, row_idx, vals, x, t);          /* :99 */
         orc_vec_sub(n, b, t, r);
+        if (LU) { orc_ilu_solve(n, LU, r, t); memcpy(r, t, sizeof(double) * N); }   /* :100-102 */
         beta = orc_nrm2(n, r);                                     /* :104 */
         if (*n_resid < resid_cap) resid[(*n_resid)++] = beta;
         if (beta < tol) { *status = 1; goto done; }                /* :107-110 */
@@ -420,6 +491,29 @@ int orc_gmres_solve(int n, const int* col_ptr, const int* row_idx, const double*
 done:
     free(V); free(H); free(cs); free(sn); free(rho); free(e1); free(y);
     free(r); free(w); free(t);
+    return rc;
+}
+
+int orc_gmres_solve(int n, const int* col_ptr, const int* row_idx, const double* vals, const double* b, double* x,
+                    int n_x, int max_iter, int krylov_dim, double tol, double* resid, int resid_cap, int* n_resid,
+                    int* status, int* last_kry_update) {
+    return gmres_impl(n, col_ptr, row_idx, vals, NULL, b, x, n_x, max_iter, krylov_dim, tol, resid, resid_cap, n_resid, status,
+                      last_kry_update);
+}
+
+int orc_gmres_solve_precond(int n, const int* col_ptr, const int* row_idx, const double* vals, const double* b, double* x,
+                            int n_x, int max_iter, int krylov_dim, double tol, double* resid, int resid_cap, int* n_resid,
+                            int* status, int* last_kry_update) {
+    *n_resid = 0;
+    *status = 0;
+    if (n_x != n) return 1;                       /* argument checks come before compute() (:28-41) */
+    if (krylov_dim <= 0 || krylov_dim > n) return 1;
+    double* LU = (double*)malloc(sizeof(double) * (size_t)n * (size_t)n);
+    int rc = orc_ilu_compute(n, col_ptr, row_idx, vals, LU);
+    if (rc == 0)
+        rc = gmres_impl(n, col_ptr, row_idx, vals, LU, b, x, n_x, max_iter, krylov_dim, tol, resid, resid_cap, n_resid, status,
+                        last_kry_update);
+    free(LU);
     return rc;
 }
 

@@ -96,6 +96,17 @@ int orc_gmres_solve(int n, const int* col_ptr, const int* row_idx, const double*
                     int n_x, int max_iter, int krylov_dim, double tol, double* resid, int resid_cap, int* n_resid,
                     int* status, int* last_kry_update);
 
+/* ---- "next" row: the enablePreconditioner() branch ----
+ * ILUPreconditioner::compute / solve / getLFactor / getUFactor (src/LinearAlgebra/Preconditioner/ILU.hpp:21-115) on a
+ * dense column-major n x n array, and GMRES::solve with usePreconditioner (GMRES.hpp:39-45,67-68,100-102).
+ * orc_ilu_compute returns 0 ok, 2 "Matrix is numerically singular". */
+int orc_ilu_compute(int n, const int* col_ptr, const int* row_idx, const double* vals, double* LU);
+void orc_ilu_solve(int n, const double* LU, const double* b, double* x);
+void orc_ilu_factors(int n, const double* LU, double* L, double* U);
+int orc_gmres_solve_precond(int n, const int* col_ptr, const int* row_idx, const double* vals, const double* b, double* x,
+                            int n_x, int max_iter, int krylov_dim, double tol, double* resid, int resid_cap, int* n_resid,
+                            int* status, int* last_kry_update);
+
 /* ---- "next" rows: compositions of the same kernels ---- */
 /* GradientDescent::solve (src/LinearAlgebra/Solver/IterSolver.hpp:23-44): steepest descent with the residual-norm loop
  * condition and the change-norm early exit.  x in/out; iters = iterations whose update was applied. */

@@ -104,6 +104,10 @@ class Port:
         L.orc_gmres_solve.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, _dp,
                                       C.c_int, _ip, _ip, _ip]
         L.orc_gd_solve.argtypes = [C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_int, C.c_double, _ip, _dp, _dp]
+        L.orc_ilu_compute.argtypes = [C.c_int, _ip, _ip, _dp, _dp]
+        L.orc_ilu_solve.argtypes = [C.c_int, _dp, _dp, _dp]
+        L.orc_ilu_factors.argtypes = [C.c_int, _dp, _dp, _dp]
+        L.orc_gmres_solve_precond.argtypes = L.orc_gmres_solve.argtypes
         L.orc_arnoldi.argtypes = [C.c_int, _ip, _ip, _dp, _dp, C.c_int, _dp, C.c_double, _ip]
 
     # -- vectors
@@ -263,6 +267,43 @@ class Port:
             raise ValueError("invalid argument")
         return dict(x=x, resid=resid[: nres.value].copy(), status=status.value, rc=rc, kry_update=kry.value)
 
+    # -- ILU preconditioner (dense restatement) and the preconditioned GMRES branch
+    def ilu_compute(self, A):
+        """Eliminated matrix as an (n, n) array indexed [row, col]; RuntimeError when the reference would throw."""
+        n = A.n_rows
+        if A.n_rows != A.n_cols:
+            raise ValueError("Matrix must be square for ILU factorization")
+        LU = np.zeros((n, n))  # column-major for the C side: LU[c] is column c
+        rc = self.L.orc_ilu_compute(n, _i(A.col_ptr), _i(A.row_idx), _d(A.vals), _d(LU))
+        if rc == 2:
+            raise RuntimeError("Matrix is numerically singular")
+        return LU.T.copy()
+
+    def ilu_solve(self, LU, b):
+        LUc = np.ascontiguousarray(np.asarray(LU, np.float64).T)
+        b = _f64(b)
+        x = np.zeros_like(b)
+        self.L.orc_ilu_solve(b.size, _d(LUc), _d(b), _d(x))
+        return x
+
+    def ilu_factors(self, LU):
+        LUc = np.ascontiguousarray(np.asarray(LU, np.float64).T)
+        n = LUc.shape[0]
+        Lf, Uf = np.zeros((n, n)), np.zeros((n, n))
+        self.L.orc_ilu_factors(n, _d(LUc), _d(Lf), _d(Uf))
+        return Lf.T.copy(), Uf.T.copy()
+
+    def gmres_precond(self, A, b, x0, max_iter, krylov_dim, tol):
+        b, x = _f64(b), _f64(x0).copy()
+        cap = max_iter + 2
+        resid = np.zeros(cap)
+        nres, status, kry = C.c_int(0), C.c_int(0), C.c_int(0)
+        rc = self.L.orc_gmres_solve_precond(A.n_rows, _i(A.col_ptr), _i(A.row_idx), _d(A.vals), _d(b), _d(x), x.size,
+                                            max_iter, krylov_dim, tol, _d(resid), cap, C.byref(nres), C.byref(status),
+                                            C.byref(kry))
+        if rc == 1:
+            raise ValueError("invalid argument")
+        return dict(x=x, resid=resid[: nres.value].copy(), status=status.value, rc=rc, kry_update=kry.value)
 
     def gd(self, A, b, x0, max_iter, tol):
         b, x = _f64(b), _f64(x0).copy()
@@ -435,6 +476,50 @@ class Ref:
         if rc == 1:
             raise ValueError("invalid argument")
         return dict(x=x, rc=rc, log=text, resid=parse_gmres_log(text)[0], status=parse_gmres_log(text)[1])
+
+    def gmres_precond(self, M, b, x0, max_iter, krylov_dim, tol, precision=17):
+        b, x = _f64(b), _f64(x0).copy()
+        cap = 1 << 20
+        log = C.create_string_buffer(cap)
+        self.L.ref_gmres_solve_precond.argtypes = [C.c_void_p, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                                   C.c_char_p, C.c_int]
+        rc = self.L.ref_gmres_solve_precond(M.h, _d(b), _d(x), x.size, max_iter, krylov_dim, tol, precision, log, cap)
+        text = log.value.decode()
+        if rc == 1:
+            raise ValueError("invalid argument")
+        return dict(x=x, rc=rc, log=text, resid=parse_gmres_log(text)[0], status=parse_gmres_log(text)[1])
+
+    def ilu(self, M):
+        """ILUPreconditioner<double>::compute on M; returns dict(L=, U= as dense [row, col] arrays, solve=callable)."""
+        L = self.L
+        L.ref_ilu_compute.restype = C.c_void_p
+        L.ref_ilu_compute.argtypes = [C.c_void_p, _ip]
+        L.ref_ilu_factor.restype = C.c_void_p
+        L.ref_ilu_factor.argtypes = [C.c_void_p, C.c_int]
+        L.ref_ilu_solve.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+        L.ref_ilu_free.argtypes = [C.c_void_p]
+        rc = C.c_int(0)
+        h = L.ref_ilu_compute(M.h, C.byref(rc))
+        if rc.value == 1:
+            raise ValueError("Matrix must be square for ILU factorization")
+        if rc.value == 2:
+            raise RuntimeError("Matrix is numerically singular")
+        out = {}
+        for which, key in ((0, "L"), (1, "U")):
+            F = Ref.Mat(self, L.ref_ilu_factor(h, which))
+            out[key] = F.export().to_scipy().toarray()
+
+        def solve(b, _h=h):
+            b = _f64(b)
+            x = np.zeros_like(b)
+            r = L.ref_ilu_solve(_h, b.size, _d(b), _d(x))
+            if r == 1:
+                raise ValueError("Vector size does not match matrix size")
+            return x
+
+        out["solve"] = solve
+        out["free"] = lambda _h=h: L.ref_ilu_free(_h)
+        return out
 
     def gd(self, M, b, x0, max_iter, tol):
         b, x = _f64(b), _f64(x0).copy()

@@ -20,6 +20,7 @@
 //   src/utils.hpp:30-71                 readMatrixMarket
 //   src/LinearAlgebra/Solver/IterSolver.hpp:23-44      GradientDescent   ("next" row)
 //   src/LinearAlgebra/Krylov/KrylovSubspace.hpp:11-38  Krylov::Arnoldi   ("next" row)
+//   src/LinearAlgebra/Preconditioner/ILU.hpp:21-115    ILUPreconditioner + GMRES::enablePreconditioner ("next" row)
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -294,6 +295,68 @@ int ref_gmres_solve(void* h, const double* b, double* x_inout, int n_x, int max_
 }
 
 // ---------------------------------------------------------------- GradientDescent / Krylov::Arnoldi ("next" rows)
+// ---------------------------------------------------------------- ILU preconditioner ("next" row)
+// compute() on the sparse instantiation; rc 0 ok, 1 invalid_argument (non-square), 2 runtime_error (singular).
+void* ref_ilu_compute(void* h, int* rc) {
+    auto* ilu = new ILUPreconditioner<double, Csc>();
+    *rc = 0;
+    try {
+        ilu->compute(*static_cast<Csc*>(h));
+    } catch (const std::invalid_argument&) {
+        *rc = 1;
+    } catch (const std::out_of_range&) {
+        *rc = 3;
+    } catch (const std::runtime_error&) {
+        *rc = 2;
+    }
+    if (*rc) {
+        delete ilu;
+        return nullptr;
+    }
+    return ilu;
+}
+void ref_ilu_free(void* p) { delete static_cast<ILUPreconditioner<double, Csc>*>(p); }
+// which = 0: copy of getLFactor(), 1: copy of getUFactor(); free with ref_mat_free
+void* ref_ilu_factor(void* p, int which) {
+    auto* ilu = static_cast<ILUPreconditioner<double, Csc>*>(p);
+    return new Csc(which == 0 ? ilu->getLFactor() : ilu->getUFactor());
+}
+int ref_ilu_solve(void* p, int n, const double* b, double* x) {
+    auto* ilu = static_cast<ILUPreconditioner<double, Csc>*>(p);
+    try {
+        copy_out(ilu->solve(make_vec(b, n)), x);
+    } catch (const std::invalid_argument&) {
+        return 1;
+    } catch (const std::runtime_error&) {
+        return 2;
+    }
+    return 0;
+}
+// GMRES<double, SparseMatrixCSC, VectorObj> with enablePreconditioner() (GMRES.hpp:23-25,39-45,67-68,100-102)
+int ref_gmres_solve_precond(void* h, const double* b, double* x_inout, int n_x, int max_iter, int krylov_dim, double tol,
+                            int log_precision, char* log, int log_cap) {
+    Csc& A = *static_cast<Csc*>(h);
+    const int n = A.getRows();
+    Vec bb = make_vec(b, n);
+    Vec x = make_vec(x_inout, n_x);
+    int rc = 0;
+    CoutCapture cap(log_precision);
+    try {
+        GMRES<double, Csc, Vec> g;
+        g.enablePreconditioner();
+        g.solve(A, bb, x, max_iter, krylov_dim, tol);
+    } catch (const std::invalid_argument&) {
+        rc = 1;
+    } catch (const std::out_of_range&) {
+        rc = 3;
+    } catch (const std::runtime_error&) {
+        rc = 2;
+    }
+    copy_log(cap.os.str(), log, log_cap);
+    if (rc == 0 || rc == 2) copy_out(x, x_inout);
+    return rc;
+}
+
 int ref_gd_solve(void* h, const double* b, double* x_inout, int max_iter, double tol) {
     Csc& A = *static_cast<Csc*>(h);
     Vec bb = make_vec(b, A.getRows());
