@@ -99,38 +99,100 @@ __global__ void __launch_bounds__(1024) ilu_solve_kernel(int n, const double* __
     __shared__ double bc[2];
     const int T = blockDim.x, t = threadIdx.x;
     const int64_t N = n;
-    for (int i = t; i < n; i += T) acc[i] = 0.0;
+    for (int i = t; i < n; i += T) {
+        acc[i] = 0.0;
+        yv[i] = b[i];  // keeps the global loads off the dependent chain of the sweep
+    }
     __syncthreads();
     // ---- forward: y_i = b_i - sum_{j<i} L(i,j) y_j                                                  (ILU.hpp:94-100)
-    for (int j = 0; j < n; ++j) {
+    // The factor entries of column j+1 are requested while column j is being applied (kPre rows per thread in
+    // registers, i.e. every row for n <= kPre*T), so the per-column cost is one barrier plus the shared-memory update.
+    constexpr int kPre = 4;
+    double cur[kPre], nxt[kPre];
+    auto first_below = [&](int j) {  // first row owned by this thread strictly below j
+        int i0 = (j + 1) - ((j + 1) % T) + t;
+        return i0 < j + 1 ? i0 + T : i0;
+    };
+    {
+        const int i0 = first_below(0);
+#pragma unroll
+        for (int q = 0; q < kPre; ++q) cur[q] = (n > 0 && i0 + q * T < n) ? M[i0 + q * T] : 0.0;
+    }
+    // one column; `c` holds this column's entries, `nx` receives the next column's (two-step unrolling below swaps the
+    // roles, so no register copy waits on the loads)
+    auto forward_step = [&](int j, double (&c)[kPre], double (&nx)[kPre]) {
         if (t == j % T) {  // this thread added the last term of row j itself in the previous step
-            const double y = sub_rn(b[j], acc[j]);
+            const double y = sub_rn(yv[j], acc[j]);
             bc[j & 1] = y;
             yv[j] = y;
         }
-        int i0 = (j + 1) - ((j + 1) % T) + t;  // first owned row below j
-        if (i0 < j + 1) i0 += T;
-        const double m0 = i0 < n ? M[i0 + j * N] : 0.0;  // requested before the barrier
+        if (j + 1 < n) {
+            const int i1 = first_below(j + 1);
+#pragma unroll
+            for (int q = 0; q < kPre; ++q) nx[q] = i1 + q * T < n ? M[i1 + q * T + (j + 1) * N] : 0.0;
+        }
         __syncthreads();
         const double yj = bc[j & 1];
-        if (i0 < n) acc[i0] = add_rn(acc[i0], mul_rn(m0, yj));
-        for (int i = i0 + T; i < n; i += T) acc[i] = add_rn(acc[i], mul_rn(M[i + j * N], yj));
+        const int i0 = first_below(j);
+#pragma unroll
+        for (int q = 0; q < kPre; ++q) {
+            const int i = i0 + q * T;
+            if (i < n) acc[i] = add_rn(acc[i], mul_rn(c[q], yj));
+        }
+        for (int i = i0 + kPre * T; i < n; i += T) acc[i] = add_rn(acc[i], mul_rn(M[i + j * N], yj));
+    };
+    {
+        int j = 0;
+        for (; j + 1 < n; j += 2) {
+            forward_step(j, cur, nxt);
+            forward_step(j + 1, nxt, cur);
+        }
+        if (j < n) forward_step(j, cur, nxt);
     }
     __syncthreads();
     // ---- backward: x_i = (y_i - sum_{j>i} U(i,j) x_j) / U(i,i)                                      (ILU.hpp:103-109)
     if (!exact_order) {
         for (int i = t; i < n; i += T) acc[i] = 0.0;
         __syncthreads();
-        for (int j = n - 1; j >= 0; --j) {
+        double dg[kPre];  // diagonal of U for the first kPre owned rows (the rest are read when needed)
+#pragma unroll
+        for (int q = 0; q < kPre; ++q) {
+            cur[q] = (n > 0 && t + q * T < n - 1) ? M[t + q * T + (N - 1) * N] : 0.0;
+            dg[q] = t + q * T < n ? M[(t + q * T) * (N + 1)] : 1.0;
+        }
+        auto backward_step = [&](int j, double (&c)[kPre], double (&nx)[kPre]) {
             if (t == j % T) {
-                const double xj = __ddiv_rn(sub_rn(yv[j], acc[j]), M[j + j * N]);
+                const int q = j / T;
+                double d = dg[0];
+                if (q >= kPre) {
+                    d = M[j + j * N];
+                } else {
+#pragma unroll
+                    for (int k = 1; k < kPre; ++k) d = q == k ? dg[k] : d;
+                }
+                const double xj = __ddiv_rn(sub_rn(yv[j], acc[j]), d);
                 bc[j & 1] = xj;
                 yv[j] = xj;
             }
+            if (j > 0) {
+#pragma unroll
+                for (int q = 0; q < kPre; ++q) nx[q] = t + q * T < j - 1 ? M[t + q * T + (j - 1) * N] : 0.0;
+            }
             __syncthreads();
             const double xj = bc[j & 1];
-            for (int i = t; i < j; i += T) acc[i] = add_rn(acc[i], mul_rn(M[i + j * N], xj));
+#pragma unroll
+            for (int q = 0; q < kPre; ++q) {
+                const int i = t + q * T;
+                if (i < j) acc[i] = add_rn(acc[i], mul_rn(c[q], xj));
+            }
+            for (int i = t + kPre * T; i < j; i += T) acc[i] = add_rn(acc[i], mul_rn(M[i + j * N], xj));
+        };
+        int j = n - 1;
+        for (; j >= 1; j -= 2) {
+            backward_step(j, cur, nxt);
+            backward_step(j - 1, nxt, cur);
         }
+        if (j == 0) backward_step(0, cur, nxt);
     } else {
         for (int i = n - 1; i >= 0; --i) {
             const double* row = Mt + (int64_t)i * N;  // row i of U, contiguous
