@@ -345,6 +345,13 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
 }
+// same, destination given as a shared-space byte address (saves the generic->shared conversion per copy)
+__device__ __forceinline__ void cp_async16_s(unsigned sa, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8_s(unsigned sa, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
@@ -566,8 +573,12 @@ __global__ void __launch_bounds__(TX* TY) stencil7_smem_kernel(StencilGeom g, co
                                                                 double* dot_out, int dot_final, const int* skip_flag) {
     constexpr int DEPTH = 4;
     constexpr int W = 2 * TX + 4;
+    constexpr int STAGE = (TY + 2) * W;  // doubles per ring stage
+    constexpr int NT = TX * TY;
+    constexpr int CPR = W / 2;               // 16-byte chunks per tile row: [left halo pair | TX centre pairs | right halo pair]
+    constexpr int NCH = (TY + 2) * CPR;      // chunks per plane tile
+    constexpr int Q = (NCH + NT - 1) / NT;   // chunks per thread
     extern __shared__ __align__(16) double smem_dyn[];
-    double(*xt)[TY + 2][W] = reinterpret_cast<double(*)[TY + 2][W]>(smem_dyn);
     if (skip_flag && *skip_flag) return;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int i_lo = blockIdx.x * 2 * TX;
@@ -578,70 +589,99 @@ __global__ void __launch_bounds__(TX* TY) stencil7_smem_kernel(StencilGeom g, co
     const int ke = min(kb + kc, k_hi);
     const bool active = (i0 < g.nx) && (j < g.ny);
     const int64_t sxy = (int64_t)g.nx * g.ny;
-    const int64_t row = (int64_t)j * g.nx + i0;
-    const bool do_jlo = active && ty == 0 && j_lo > 0;
-    const bool do_jhi = active && ty == TY - 1 && (j + 1 < g.ny);
-    const bool do_ilo = active && tx == 0 && i_lo > 0;
-    const bool do_ihi = active && tx == TX - 1 && (i_lo + 2 * TX < g.nx);
     double dacc = 0.0;
-    auto stage_of = [&](int k) -> int { return ((k % DEPTH) + DEPTH) % DEPTH; };
-    auto issue_plane = [&](int k) {
-        const int kg = g.k_off + k;
-        if (kg >= 0 && kg < g.nz && active) {
-            const int s = stage_of(k);
-            const double* xp = (k < 0 ? halo_lo : (k >= g.nz_loc ? halo_hi : x + (int64_t)k * sxy)) + row;
-            cp_async16(&xt[s][ty + 1][2 * tx + 2], xp);
-            if (do_jlo) cp_async16(&xt[s][0][2 * tx + 2], xp - g.nx);
-            if (do_jhi) cp_async16(&xt[s][TY + 1][2 * tx + 2], xp + g.nx);
-            if (do_ilo) cp_async8(&xt[s][ty + 1][1], xp - 1);
-            if (do_ihi) cp_async8(&xt[s][ty + 1][2 * TX + 2], xp + 2);
-        }
-        cp_async_commit();
-    };
-    auto centre = [&](int s) -> double2 { return *reinterpret_cast<const double2*>(&xt[s][ty + 1][2 * tx + 2]); };
     if (kb < ke) {
-        const bool j_shell = (j == 0 || j == g.ny - 1);
-        const bool a_shell_i = (i0 == 0 || i0 == g.nx - 1);
-        const bool b_shell_i = (i0 + 1 == g.nx - 1);
-        const double2 zero2 = make_double2(0.0, 0.0);
-        issue_plane(kb - 1);
-        issue_plane(kb);
-        issue_plane(kb + 1);
-        issue_plane(kb + 2);
+        // Planes kb-1 .. ke are read; those outside the global grid do not exist.  Plane k lives in ring stage
+        // (k - kb + 1) mod DEPTH.  The steady-state loop is kept lean - this kernel was issue-bound (ncu: 76 % issue-active,
+        // shared-memory pipe 70 %, ~160 instructions per plane and thread): the tile is copied as a flat list of 16-byte
+        // chunks, Q per thread with addresses fixed before the loop (the halo columns come as the aligned pair that holds
+        // them - same 32-byte sector), and the k-1 / k / k+1 registers rotate by renaming (three planes per trip).
+        const int k_first = max(kb - 1, -g.k_off);
+        const int k_last = min(ke, g.nz - 1 - g.k_off);
+        const unsigned s0 = (unsigned)__cvta_generic_to_shared(smem_dyn);
+        unsigned c_sm[Q];    // shared-memory byte address of the chunk in stage 0
+        int64_t c_off[Q];    // element offset of the chunk inside a plane
+        bool c_ok[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int e = (ty * TX + tx) + q * NT;
+            const int jj = e / CPR, c = e - jj * CPR;
+            const int gj = j_lo - 1 + jj, gi = i_lo - 2 + 2 * c;
+            const bool corner = (jj == 0 || jj == TY + 1) && (c == 0 || c == CPR - 1);
+            c_ok[q] = e < NCH && !corner && gj >= 0 && gj < g.ny && gi >= 0 && gi < g.nx;
+            c_sm[q] = s0 + 8u * (unsigned)(jj * W + 2 * c);
+            c_off[q] = (int64_t)gj * g.nx + gi;
+        }
+        auto plane_of = [&](int k) -> const double* { return k < 0 ? halo_lo : (k >= g.nz_loc ? halo_hi : x + (int64_t)k * sxy); };
+        auto issue_plane = [&](int k, const double* plane) {
+            if (k >= k_first && k <= k_last) {
+                const unsigned so = (unsigned)((k - kb + 1) & (DEPTH - 1)) * (unsigned)(STAGE * 8);
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+                    if (c_ok[q]) cp_async16_s(c_sm[q] + so, plane + c_off[q]);
+            }
+            cp_async_commit();
+        };
+        const double* tile = smem_dyn + (ty + 1) * W + 2 * tx + 2;  // this thread's centre slot in stage 0
+        auto ld2 = [](const double* q) -> double2 { return *reinterpret_cast<const double2*>(q); };
+        const bool shA = (j == 0 || j == g.ny - 1) || (i0 == 0 || i0 == g.nx - 1);
+        const bool shB = (j == 0 || j == g.ny - 1) || (i0 + 1 == g.nx - 1);
+        issue_plane(kb - 1, plane_of(kb - 1));
+        issue_plane(kb, plane_of(kb));
+        issue_plane(kb + 1, plane_of(kb + 1));
+        const double* plane = plane_of(kb + 2);
+        issue_plane(kb + 2, plane);
         cp_async_wait<2>();
         __syncthreads();
-        double2 vA = zero2, vB = zero2, vC = zero2;
+        double2 v0 = make_double2(0.0, 0.0), v1 = v0, v2 = v0;
         if (active) {
-            if (g.k_off + kb - 1 >= 0) vA = centre(stage_of(kb - 1));
-            vB = centre(stage_of(kb));
+            if (kb - 1 >= k_first) v0 = ld2(tile);  // stage 0
+            v1 = ld2(tile + STAGE);                 // stage 1
         }
-        for (int k = kb; k < ke; ++k) {
-            const int kg = g.k_off + k;
-            const int64_t idx = (int64_t)k * sxy + row;
+        double* yp = y + (int64_t)kb * sxy + (int64_t)j * g.nx + i0;
+        unsigned m = 1;  // ring position of plane k
+        int k = kb;
+        // one plane: vA = k-1, vB = k (both in registers), vC receives k+1
+        auto step = [&](const double2& vA, const double2& vB, double2& vC) {
             cp_async_wait<1>();
             __syncthreads();
-            issue_plane(k + 3);
+            plane = (k + 3 == g.nz_loc) ? halo_hi : plane + sxy;
+            issue_plane(k + 3, plane);
             if (active) {
-                const int s = stage_of(k);
-                if (kg + 1 < g.nz) vC = centre(stage_of(k + 1));
+                const double* st = tile + (m & (DEPTH - 1)) * STAGE;
+                // plane k+1 may not exist (last global plane): its stage then holds stale data, and every row of this
+                // plane takes the identity branch below
+                vC = ld2(tile + ((m + 1) & (DEPTH - 1)) * STAGE);
+                const double2 jm = ld2(st - W);
+                const double2 jp = ld2(st + W);
+                const double im = st[-1], ip = st[2];
                 double2 out;
-                if (j_shell || kg == 0 || kg == g.nz - 1) {
-                    out.x = shell_row(vB.x);
-                    out.y = shell_row(vB.y);
-                } else {
-                    const double2 jm = *reinterpret_cast<const double2*>(&xt[s][ty][2 * tx + 2]);
-                    const double2 jp = *reinterpret_cast<const double2*>(&xt[s][ty + 2][2 * tx + 2]);
-                    out.x = a_shell_i ? shell_row(vB.x) : tap7(g, vA.x, jm.x, xt[s][ty + 1][2 * tx + 1], vB.x, vB.y, jp.x, vC.x);
-                    out.y = b_shell_i ? shell_row(vB.y) : tap7(g, vA.y, jm.y, vB.x, vB.y, xt[s][ty + 1][2 * tx + 4], jp.y, vC.y);
+                out.x = tap7(g, vA.x, jm.x, im, vB.x, vB.y, jp.x, vC.x);
+                out.y = tap7(g, vA.y, jm.y, vB.x, vB.y, ip, jp.y, vC.y);
+                const int kg = g.k_off + k;
+                const bool ksh = (kg == 0) || (kg == g.nz - 1);
+                if (shA || shB || ksh) {  // Dirichlet shell: identity rows (the taps computed above are discarded)
+                    if (shA || ksh) out.x = shell_row(vB.x);
+                    if (shB || ksh) out.y = shell_row(vB.y);
                 }
-                *reinterpret_cast<double2*>(y + idx) = out;
+                *reinterpret_cast<double2*>(yp) = out;
                 if constexpr (DOT) {
                     dacc = add_rn(dacc, mul_rn(vB.x, out.x));
                     dacc = add_rn(dacc, mul_rn(vB.y, out.y));
                 }
-                vA = vB;
-                vB = vC;
             }
+            ++k;
+            ++m;
+            yp += sxy;
+        };
+        while (k + 3 <= ke) {
+            step(v0, v1, v2);
+            step(v1, v2, v0);
+            step(v2, v0, v1);
+        }
+        if (k < ke) {
+            step(v0, v1, v2);
+            if (k < ke) step(v1, v2, v0);
         }
         cp_async_wait<0>();
     }

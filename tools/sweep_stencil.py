@@ -10,6 +10,9 @@ from algotoolkit_b200 import capi, synthetic
 
 g = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+tiles = [int(t) for t in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1, 2, 3]
+kcs = [int(t) for t in sys.argv[4].split(",")] if len(sys.argv) > 4 else [4, 8, 16, 32, 64]
+os.environ["ATK_CG_FUSED"] = "0"  # the three-kernel CG: K1 is the plain apply (+ p.Ap)
 ctx = capi.Context(0)
 cx, cy, cz = synthetic.poisson_coeffs(g, g, g)
 n = g ** 3
@@ -17,8 +20,8 @@ b = synthetic.poisson_rhs_r(g, g, g)
 db = ctx.vector(b)
 dx, dr, dp = ctx.empty(n), ctx.empty(n), ctx.empty(n)
 print(f"grid {g}^3 rows {n}  iters {iters}")
-for tile in (0, 1, 2, 3):
-    for kc in (4, 8, 16, 32, 64):
+for tile in tiles:
+    for kc in kcs:
         os.environ["ATK_STENCIL_TILE"] = str(tile)
         os.environ["ATK_STENCIL_KC"] = str(kc)
         op = ctx.operator_stencil7(g, g, g, cx, cy, cz)
