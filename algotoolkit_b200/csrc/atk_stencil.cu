@@ -337,6 +337,14 @@ __global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_kernel(StencilGeom g
 //   jj = 0 and TY+1 the halo rows (copied by the first / last thread row, halo columns by the first / last thread).
 // p_new at a neighbour is re-formed from the two raw values (one multiply-add), exactly as the reference forms it.
 // One __syncthreads per plane.
+// LDGSTS moves a 32-byte global sector into shared memory in one piece only when the destination has the same offset
+// inside its 32-byte segment as the source has inside its sector; otherwise each 16-byte half is fetched from L2 by a
+// request of its own (measured on the plain apply at 512^3: L2->SM traffic 3.42 GB instead of 1.87 GB, 0.400 ms instead
+// of 0.347 ms).  Tile rows keep their centre columns at tile column 2 (16 bytes into the row, row pitch a multiple of
+// 32 bytes) while the grid columns they hold start on a sector boundary, so the ring of tiles starts 16 bytes past a
+// 128-byte aligned base.  (The fused kernel had this alignment by accident of its static shared-memory size.)
+constexpr int kRingShift = 2;  // doubles
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
@@ -362,7 +370,8 @@ __global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_smem_kernel(StencilG
                                                                          double* dot_out, int is_final) {
     constexpr int DEPTH = 4;       // ring stages: planes k-1 .. k+2 resident / in flight while plane k is computed
     constexpr int W = 2 * TX + 4;  // tile width in doubles
-    extern __shared__ __align__(16) double smem_dyn[];
+    extern __shared__ __align__(128) double smem_raw[];
+    double* smem_dyn = smem_raw + kRingShift;
     double(*rt)[TY + 2][W] = reinterpret_cast<double(*)[TY + 2][W]>(smem_dyn);
     double(*pt)[TY + 2][W] = reinterpret_cast<double(*)[TY + 2][W]>(smem_dyn + (size_t)DEPTH * (TY + 2) * W);
 
@@ -578,7 +587,8 @@ __global__ void __launch_bounds__(TX* TY) stencil7_smem_kernel(StencilGeom g, co
     constexpr int CPR = W / 2;               // 16-byte chunks per tile row: [left halo pair | TX centre pairs | right halo pair]
     constexpr int NCH = (TY + 2) * CPR;      // chunks per plane tile
     constexpr int Q = (NCH + NT - 1) / NT;   // chunks per thread
-    extern __shared__ __align__(16) double smem_dyn[];
+    extern __shared__ __align__(128) double smem_raw[];
+    double* smem_dyn = smem_raw + kRingShift;  // see kRingShift: tile chunks must sit in shared memory as they sit in their sector
     if (skip_flag && *skip_flag) return;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int i_lo = blockIdx.x * 2 * TX;
@@ -746,8 +756,8 @@ __global__ void __launch_bounds__(TX* TY) stencil7_tma_kernel(StencilGeom g, con
                                                                double* dot_out, int dot_final, const int* skip_flag) {
     constexpr int DEPTH = 4;
     constexpr int W = 2 * TX + 4;
-    extern __shared__ __align__(128) double smem_dyn[];
-    double(*xt)[TY + 2][W] = reinterpret_cast<double(*)[TY + 2][W]>(smem_dyn);
+    extern __shared__ __align__(128) double smem_raw[];
+    double(*xt)[TY + 2][W] = reinterpret_cast<double(*)[TY + 2][W]>(smem_raw + kRingShift);
     __shared__ __align__(8) unsigned long long full[DEPTH];
     if (skip_flag && *skip_flag) return;
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -878,7 +888,7 @@ __global__ void __launch_bounds__(256) pack_halo_kernel(const CgFusedState* st, 
 }
 
 template <int TX, int TY>
-constexpr size_t fused_smem_bytes() { return (size_t)2 * 4 * (TY + 2) * (2 * TX + 4) * sizeof(double); }
+constexpr size_t fused_smem_bytes() { return (size_t)2 * 4 * (TY + 2) * (2 * TX + 4) * sizeof(double) + kRingShift * sizeof(double); }
 template <int TX, int TY>
 void allow_fused_smem() {
     ATK_CUDA_CHECK(cudaFuncSetAttribute(stencil7_cg_fused_smem_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -901,6 +911,7 @@ struct Stencil7 : public Operator {
     int ftile = 4;
     bool fsmem = true;
     bool use_tma = false;  // plain apply through TMA bulk copies (experiment switch ATK_STENCIL_TMA)
+    bool force_dot = false;  // experiment switch ATK_STENCIL_FORCE_DOT: plain apply runs the x.y-accumulating variant
 
     bool arena_exported = false;
 
@@ -1061,7 +1072,7 @@ struct Stencil7 : public Operator {
         const bool vec = (g.nx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) &&
                          ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
         if (vec && fsmem && use_tma) {
-            constexpr size_t smem = (size_t)4 * (TY + 2) * (2 * TX + 4) * sizeof(double);
+            constexpr size_t smem = (size_t)4 * (TY + 2) * (2 * TX + 4) * sizeof(double) + kRingShift * sizeof(double);
             if (dot)
                 stencil7_tma_kernel<TX, TY, true><<<grid, block, smem, c->stream>>>(g, x, y, halo_lo, halo_hi, k_lo, k_hi, kcc,
                                                                                     c->d_partials, partial_base, c->d_tickets + 2,
@@ -1076,7 +1087,7 @@ struct Stencil7 : public Operator {
             return;
         }
         if (vec && fsmem) {
-            constexpr size_t smem = (size_t)4 * (TY + 2) * (2 * TX + 4) * sizeof(double);
+            constexpr size_t smem = (size_t)4 * (TY + 2) * (2 * TX + 4) * sizeof(double) + kRingShift * sizeof(double);
             if (dot)
                 stencil7_smem_kernel<TX, TY, true><<<grid, block, smem, c->stream>>>(g, x, y, halo_lo, halo_hi, k_lo, k_hi, kcc,
                                                                                      c->d_partials, partial_base, c->d_tickets + 2,
@@ -1120,6 +1131,8 @@ struct Stencil7 : public Operator {
         double* dot_out = dot ? c->slot(dot_slot) + c->rank : nullptr;
         int nb = 0;
         if (c->world == 1) {
+            if (force_dot && !dot) launch_tile(x, y, 0, g.nz_loc, true, 0, true, c->slot(kSlotGeneric), skip_flag, &nb);
+            else
             launch_tile(x, y, 0, g.nz_loc, dot, 0, true, dot_out, skip_flag, &nb);
         } else {
             // halo exchange on the communication stream, overlapped with the planes that do not need it
@@ -1248,6 +1261,7 @@ Operator* make_stencil7(Context* ctx, int nx, int ny, int nz, double cx, double 
     if (const char* e = std::getenv("ATK_FUSED_TILE")) S->ftile = std::atoi(e);
     if (const char* e = std::getenv("ATK_FUSED_SMEM")) S->fsmem = std::atoi(e) != 0;
     if (const char* e = std::getenv("ATK_STENCIL_TMA")) S->use_tma = std::atoi(e) != 0;
+    if (const char* e = std::getenv("ATK_STENCIL_FORCE_DOT")) S->force_dot = std::atoi(e) != 0;
     try {
         if (ctx->world > 1) {
             ATK_CUDA_CHECK(cudaMalloc(&S->halo_lo, sizeof(double) * (size_t)plane));
