@@ -911,7 +911,6 @@ struct Stencil7 : public Operator {
     int ftile = 4;
     bool fsmem = true;
     bool use_tma = false;  // plain apply through TMA bulk copies (experiment switch ATK_STENCIL_TMA)
-    bool force_dot = false;  // experiment switch ATK_STENCIL_FORCE_DOT: plain apply runs the x.y-accumulating variant
 
     bool arena_exported = false;
 
@@ -1131,8 +1130,6 @@ struct Stencil7 : public Operator {
         double* dot_out = dot ? c->slot(dot_slot) + c->rank : nullptr;
         int nb = 0;
         if (c->world == 1) {
-            if (force_dot && !dot) launch_tile(x, y, 0, g.nz_loc, true, 0, true, c->slot(kSlotGeneric), skip_flag, &nb);
-            else
             launch_tile(x, y, 0, g.nz_loc, dot, 0, true, dot_out, skip_flag, &nb);
         } else {
             // halo exchange on the communication stream, overlapped with the planes that do not need it
@@ -1261,7 +1258,6 @@ Operator* make_stencil7(Context* ctx, int nx, int ny, int nz, double cx, double 
     if (const char* e = std::getenv("ATK_FUSED_TILE")) S->ftile = std::atoi(e);
     if (const char* e = std::getenv("ATK_FUSED_SMEM")) S->fsmem = std::atoi(e) != 0;
     if (const char* e = std::getenv("ATK_STENCIL_TMA")) S->use_tma = std::atoi(e) != 0;
-    if (const char* e = std::getenv("ATK_STENCIL_FORCE_DOT")) S->force_dot = std::atoi(e) != 0;
     try {
         if (ctx->world > 1) {
             ATK_CUDA_CHECK(cudaMalloc(&S->halo_lo, sizeof(double) * (size_t)plane));

@@ -1,5 +1,7 @@
+"""Plain 7-point apply at 512^3: K1 inside the three-kernel CG (CUDA events) vs back-to-back launches (wall clock),
+LDGSTS ring vs TMA ring.  python tools/ab_plain_apply.py"""
 import os, sys, time
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from algotoolkit_b200 import capi, synthetic
 os.environ["ATK_CG_FUSED"] = "0"
@@ -25,8 +27,7 @@ for rep in range(3):
     print(f"rep {rep}: K1 (apply + dot, events) {k[0]:.4f} ms   plain apply (20 back-to-back, wall) {t*1e3:.4f} ms", flush=True)
 
 
-for fd, tma in (("0", "0"), ("1", "0"), ("0", "1"), ("0", "0"), ("1", "0"), ("0", "1")):
-    os.environ["ATK_STENCIL_FORCE_DOT"] = fd
+for tma in ("0", "1", "0", "1"):
     os.environ["ATK_STENCIL_TMA"] = tma
     op2 = ctx.operator_stencil7(g, g, g, cx, cy, cz)
     y2 = ctx.empty(n)
@@ -36,6 +37,6 @@ for fd, tma in (("0", "0"), ("1", "0"), ("0", "1"), ("0", "0"), ("1", "0"), ("0"
     for _ in range(20): op2.apply(db, y2)
     ctx.synchronize()
     t = (time.perf_counter() - t0) / 20
-    print(f"force_dot={fd} tma={tma}: plain apply {t*1e3:.4f} ms  ({16 * n / t / 1e9:.0f} GB/s)", flush=True)
+    print(f"tma={tma}: plain apply {t*1e3:.4f} ms  ({16 * n / t / 1e9:.0f} GB/s)", flush=True)
     op2.destroy()
     y2.free()
