@@ -1157,8 +1157,11 @@ struct Stencil7 : public Operator {
 // the grid are dropped), A(r, r+d) = coef[d].  Taps are added from 0.0 in ascending column order (dk, dj, di
 // ascending), which is the order the assembled CSC matvec uses, so the result is bit-identical to the SELL operator
 // built by atk_operator_stencil27_assembled.  Zero coefficients are skipped (they are never stored by addValue).
-// One thread per two adjacent x points; neighbours come through L1/L2.  In GMRES(300) this kernel is < 1 % of a
-// restart cycle (the projection loop is the cost), so it is kept simple.
+// Two kernels: stencil27_smem_kernel (nx even, 16-byte aligned vectors) streams x through the same cp.async ring of
+// shared-memory plane tiles as the 7-point kernels and keeps the 3x3x4 neighbourhood of its two points in registers,
+// loading only the 12 values of the incoming plane per step; rows, columns and planes outside the grid are zeros in
+// the tiles, and a product with such a zero leaves the running sum unchanged, exactly as dropping the tap does.
+// stencil27_kernel (neighbours through L1/L2, explicit tests) is the general fallback.
 struct Coef27 {
     double v[27];
 };
@@ -1194,6 +1197,133 @@ __global__ void __launch_bounds__(256) stencil27_kernel(StencilGeom g, Coef27 cf
     }
 }
 
+template <int TX, int TY>
+__global__ void __launch_bounds__(TX* TY) stencil27_smem_kernel(StencilGeom g, Coef27 cf, const double* __restrict__ x,
+                                                                 double* __restrict__ y, const double* __restrict__ halo_lo,
+                                                                 const double* __restrict__ halo_hi, int k_lo, int k_hi, int kc) {
+    constexpr int DEPTH = 4;
+    constexpr int W = 2 * TX + 4;
+    constexpr int STAGE = (TY + 2) * W;
+    constexpr int NT = TX * TY;
+    constexpr int CPR = W / 2;
+    constexpr int NCH = (TY + 2) * CPR;
+    constexpr int Q = (NCH + NT - 1) / NT;
+    extern __shared__ __align__(128) double smem_raw[];
+    double* ring = smem_raw + kRingShift;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * TX + tx;
+    const int i_lo = blockIdx.x * 2 * TX;
+    const int j_lo = blockIdx.y * TY;
+    const int i0 = i_lo + 2 * tx;
+    const int j = j_lo + ty;
+    const int kb = k_lo + blockIdx.z * kc;
+    const int ke = min(kb + kc, k_hi);
+    if (kb >= ke) return;
+    const bool active = (i0 < g.nx) && (j < g.ny);
+    const int64_t sxy = (int64_t)g.nx * g.ny;
+    // everything that is never a copy destination (rows / columns outside the grid) stays zero for the whole kernel
+    for (int e = tid; e < DEPTH * STAGE; e += NT) ring[e] = 0.0;
+    __syncthreads();
+    const int k_first = max(kb - 1, -g.k_off);             // planes kb-1 .. ke are read; these two bound the existing ones
+    const int k_last = min(ke, g.nz - 1 - g.k_off);
+    const unsigned s0 = (unsigned)__cvta_generic_to_shared(ring);
+    unsigned c_sm[Q];
+    int64_t c_off[Q];
+    bool c_ok[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int e = tid + q * NT;
+        const int jj = e / CPR, c = e - jj * CPR;
+        const int gj = j_lo - 1 + jj, gi = i_lo - 2 + 2 * c;
+        c_ok[q] = e < NCH && gj >= 0 && gj < g.ny && gi >= 0 && gi < g.nx;  // corners included: the 27 taps reach them
+        c_sm[q] = 8u * (unsigned)(jj * W + 2 * c);
+        c_off[q] = (int64_t)gj * g.nx + gi;
+    }
+    auto plane_of = [&](int k) -> const double* { return k < 0 ? halo_lo : (k >= g.nz_loc ? halo_hi : x + (int64_t)k * sxy); };
+    // plane k -> ring stage (k - kb + 1) mod DEPTH; a plane outside the global grid is written as zeros
+    auto issue_plane = [&](int k, const double* plane) {
+        if (k >= kb - 1 && k <= ke) {
+            const unsigned so = (unsigned)((k - kb + 1) & (DEPTH - 1)) * (unsigned)(STAGE * 8);
+            if (k >= k_first && k <= k_last) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+                    if (c_ok[q]) cp_async16_s(s0 + c_sm[q] + so, plane + c_off[q]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+                    if (c_ok[q]) *reinterpret_cast<double2*>(reinterpret_cast<char*>(ring) + c_sm[q] + so) = make_double2(0.0, 0.0);
+            }
+        }
+        cp_async_commit();
+    };
+    // the 3 x 4 values of one plane this thread needs: tile rows ty .. ty+2, tile columns 2tx+1 .. 2tx+4
+    struct Nb {
+        double v[3][4];
+    };
+    const double* corner = ring + ty * W + 2 * tx + 1;
+    auto load_nb = [&](Nb& n, unsigned m) {
+        const double* st = corner + (m & (DEPTH - 1)) * STAGE;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            n.v[r][0] = st[r * W];
+            const double2 mid = *reinterpret_cast<const double2*>(st + r * W + 1);
+            n.v[r][1] = mid.x;
+            n.v[r][2] = mid.y;
+            n.v[r][3] = st[r * W + 3];
+        }
+    };
+    auto taps = [&](const Nb& n, int dk, double& acc0, double& acc1) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const double c = cf.v[dk * 9 + r * 3 + d];
+                if (c != 0.0) {  // uniform: zero coefficients are not stored by the assembled form
+                    acc0 = add_rn(acc0, mul_rn(c, n.v[r][d]));
+                    acc1 = add_rn(acc1, mul_rn(c, n.v[r][d + 1]));
+                }
+            }
+    };
+    issue_plane(kb - 1, plane_of(kb - 1));
+    issue_plane(kb, plane_of(kb));
+    issue_plane(kb + 1, plane_of(kb + 1));
+    const double* plane = plane_of(kb + 2);
+    issue_plane(kb + 2, plane);
+    cp_async_wait<2>();
+    __syncthreads();
+    Nb n0, n1, n2;
+    load_nb(n0, 0);
+    load_nb(n1, 1);
+    double* yp = y + (int64_t)kb * sxy + (int64_t)j * g.nx + i0;
+    unsigned m = 1;  // ring position of plane k
+    int k = kb;
+    auto step = [&](const Nb& A, const Nb& B, Nb& C) {
+        cp_async_wait<1>();
+        __syncthreads();
+        plane = (k + 3 == g.nz_loc) ? halo_hi : plane + sxy;
+        issue_plane(k + 3, plane);
+        load_nb(C, m + 1);
+        double acc0 = 0.0, acc1 = 0.0;
+        taps(A, 0, acc0, acc1);
+        taps(B, 1, acc0, acc1);
+        taps(C, 2, acc0, acc1);
+        if (active) *reinterpret_cast<double2*>(yp) = make_double2(acc0, acc1);
+        ++k;
+        ++m;
+        yp += sxy;
+    };
+    while (k + 3 <= ke) {
+        step(n0, n1, n2);
+        step(n1, n2, n0);
+        step(n2, n0, n1);
+    }
+    if (k < ke) {
+        step(n0, n1, n2);
+        if (k < ke) step(n1, n2, n0);
+    }
+    cp_async_wait<0>();
+}
+
 struct Stencil27 : public Operator {
     StencilGeom g;
     Coef27 cf;
@@ -1203,11 +1333,24 @@ struct Stencil27 : public Operator {
         cudaFree(halo_lo);
         cudaFree(halo_hi);
     }
+    int kc27 = 64;  // planes per chunk of the shared-memory kernel (ATK_STENCIL27_KC)
     void launch(const double* x, double* y, int k_lo, int k_hi) {
         if (k_hi <= k_lo) return;
-        dim3 block(32, 8, 1);
-        dim3 grid((g.nx + 31) / 32, (g.ny + 7) / 8, std::min(k_hi - k_lo, 64));
-        stencil27_kernel<<<grid, block, 0, ctx->stream>>>(g, cf, x, y, halo_lo, halo_hi, k_lo, k_hi);
+        const bool vec = (g.nx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(y) & 15u) == 0) && !std::getenv("ATK_STENCIL27_SIMPLE");
+        if (vec) {
+            constexpr int TX = 32, TY = 4;
+            const int tiles = ((g.nx + 2 * TX - 1) / (2 * TX)) * ((g.ny + TY - 1) / TY);
+            int kcc = std::min(kc27, k_hi - k_lo);  // enough CTAs for a few waves, but never chunks shorter than 8 planes
+            while (kcc > 8 && (int64_t)tiles * ((k_hi - k_lo + kcc - 1) / kcc) < (int64_t)ctx->sm_count * 8) kcc = (kcc + 1) / 2;
+            dim3 grid((g.nx + 2 * TX - 1) / (2 * TX), (g.ny + TY - 1) / TY, (k_hi - k_lo + kcc - 1) / kcc);
+            constexpr size_t smem = (size_t)4 * (TY + 2) * (2 * TX + 4) * sizeof(double) + kRingShift * sizeof(double);
+            stencil27_smem_kernel<TX, TY><<<grid, dim3(TX, TY, 1), smem, ctx->stream>>>(g, cf, x, y, halo_lo, halo_hi, k_lo, k_hi, kcc);
+        } else {
+            dim3 block(32, 8, 1);
+            dim3 grid((g.nx + 31) / 32, (g.ny + 7) / 8, std::min(k_hi - k_lo, 64));
+            stencil27_kernel<<<grid, block, 0, ctx->stream>>>(g, cf, x, y, halo_lo, halo_hi, k_lo, k_hi);
+        }
         ATK_CUDA_CHECK(cudaGetLastError());
         count_launch(ctx);
     }
@@ -1294,6 +1437,7 @@ Operator* make_stencil27(Context* ctx, int nx, int ny, int nz, const double* coe
     slab_partition(nz, ctx->rank, ctx->world, &k_begin, &k_end);
     S->g = StencilGeom{nx, ny, nz, k_begin, k_end - k_begin, 0.0, 0.0, 0.0, 0.0};
     for (int t = 0; t < 27; ++t) S->cf.v[t] = coef[t];
+    if (const char* e = std::getenv("ATK_STENCIL27_KC")) S->kc27 = std::max(1, std::atoi(e));
     const int64_t plane = (int64_t)nx * ny;
     S->n_rows_local = plane * (k_end - k_begin);
     S->n_cols = plane * nz;

@@ -181,7 +181,8 @@ def test_op27_assembled_bit_exact(ctx, port, golden):
     assert np.array_equal(op.apply_numpy(x), port.spmv(A, x))
 
 
-@pytest.mark.parametrize("dims", [(8, 8, 8), (7, 9, 5), (1, 3, 4), (33, 6, 2)])
+@pytest.mark.parametrize("dims", [(8, 8, 8), (7, 9, 5), (1, 3, 4), (33, 6, 2), (64, 12, 9), (66, 5, 70), (130, 7, 3), (2, 2, 2),
+                                  (4, 1, 1), (96, 40, 33)])
 def test_op27_matrix_free_bit_exact(ctx, port, dims):
     from algotoolkit_b200 import synthetic
 
