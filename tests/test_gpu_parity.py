@@ -597,3 +597,26 @@ def test_cg_on_symmetric_expanded_matrix_market(ctx, port, name, iters):
     tree = ctx.cg_solve_host(op, b, 10)  # a few iterations: rounding-order noise has not been amplified yet
     ora10 = port.cg(A, b, 10)
     assert tree["iters"] == ora10["iters"] and relerr(tree["x"], ora10["x"]) < 1e-8
+
+
+# ------------------------------------------------------------------------------------------------ alternative kernels
+@pytest.mark.parametrize("env", [{"ATK_STENCIL_TMA": "1"}, {"ATK_FUSED_SMEM": "0"}, {"ATK_STENCIL27_SIMPLE": "1"},
+                                 {"ATK_STENCIL_TILE": "0", "ATK_STENCIL_KC": "16"}, {"ATK_STENCIL27_KC": "8"}])
+def test_alternative_stencil_kernels_stay_bit_exact(ctx, port, env, monkeypatch):
+    """The selectable kernel variants (TMA ring, L1-served fallbacks, other tile / chunk shapes) against the oracle."""
+    from algotoolkit_b200 import synthetic
+
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    nx, ny, nz = 66, 13, 21
+    cx, cy, cz, _ = port.poisson_coeffs(nx, ny, nz)
+    x = np.random.default_rng(3).standard_normal(nx * ny * nz)
+    op = ctx.operator_stencil7(nx, ny, nz, cx, cy, cz)
+    assert np.array_equal(op.apply_numpy(x), port.poisson_apply(nx, ny, nz, cx, cy, cz, x))
+    b = port.poisson_rhs(nx, ny, nz, rhs_kind=1, seed=12345)
+    res = ctx.cg_solve_host(op, b, 40)
+    ora = port.cg(None, b, 40, stencil=(nx, ny, nz, cx, cy, cz))
+    assert res["iters"] == ora["iters"] and relerr(res["x"], ora["x"]) < REL
+    A27 = port.op27_csc(nx, ny, nz)
+    op27 = ctx.operator_stencil27(nx, ny, nz, synthetic.stencil27_coefficients())
+    assert np.array_equal(op27.apply_numpy(x), port.spmv(A27, x))
