@@ -620,3 +620,43 @@ def test_alternative_stencil_kernels_stay_bit_exact(ctx, port, env, monkeypatch)
     A27 = port.op27_csc(nx, ny, nz)
     op27 = ctx.operator_stencil27(nx, ny, nz, synthetic.stencil27_coefficients())
     assert np.array_equal(op27.apply_numpy(x), port.spmv(A27, x))
+
+
+# ------------------------------------------------------------------------------------------------ config 3 at full size
+@pytest.mark.parametrize("n", [128, 256])
+def test_poisson_cg_to_exit_full_size_vs_reference(ctx, n):
+    """BASELINE config 3: CG to the |pAp| < 1e-12 exit against fixtures computed by the unmodified reference at the same
+    size (tests/golden/make_golden_large.py): iteration count within +-2, solution within 1e-10 (norm and 512 sampled
+    entries); at 128^3 the reference-ordered mode must reproduce the reference's x bit for bit."""
+    import json
+    import os
+
+    from algotoolkit_b200 import synthetic
+    from tests.conftest import GOLDEN
+
+    path = os.path.join(GOLDEN, "golden_large.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/golden_large.json not generated")
+    with open(path) as f:
+        gl = json.load(f)
+    if str(n) not in gl:
+        pytest.skip(f"no {n}^3 fixture")
+    g = gl[str(n)]
+    cx, cy, cz = synthetic.poisson_coeffs(n, n, n)
+    b = synthetic.poisson_rhs_r(n, n, n)
+    assert abs(np.linalg.norm(b) - g["b_norm"]) <= 1e-13 * g["b_norm"]
+    op = ctx.operator_stencil7(n, n, n, cx, cy, cz)
+    res = ctx.cg_solve_host(op, b, 100000)
+    assert res["stopped_on_pAp"] and abs(res["iters"] - g["iterations"]) <= 2
+    x = res["x"]
+    idx = np.array(g["sample_index"])
+    want = np.array(g["sample_x"])
+    assert abs(np.linalg.norm(x) - g["x_norm"]) <= REL * g["x_norm"]
+    assert np.linalg.norm(x[idx] - want) <= REL * np.linalg.norm(want)
+    if n <= 128:
+        ctx.set_reduction(capi.REDUCE_SEQUENTIAL)
+        try:
+            seq = ctx.cg_solve_host(op, b, 100000)
+        finally:
+            ctx.set_reduction(capi.REDUCE_TREE)
+        assert seq["iters"] == g["iterations"] and digest(seq["x"]) == g["x_sha256"]
