@@ -244,3 +244,30 @@ def test_next_rows_gd_and_arnoldi_vs_reference(port, ref):
     a2, r2 = port.arnoldi(A2, [1.0, 0, 0, 0], 3, 1e-8), ref.arnoldi(ref.mat_from_csc(A2), [1.0, 0, 0, 0], 3, 1e-8)
     assert a2["breakdown"] == 1 and r2["log"] == "Breakdown: Norm below tolerance at iteration 1\n"
     assert np.array_equal(a2["Q"], r2["Q"]) and np.array_equal(a2["H"], r2["H"])
+
+
+def test_port_matches_full_size_reference_fixture_128(port):
+    """Config 3 at 128^3: the fixture was produced by the unmodified reference (make_golden_large.py); the C port must
+    reproduce its iteration count and solution bit for bit (18 s of one core)."""
+    import hashlib
+    import json
+    import os
+
+    from tests.conftest import GOLDEN
+
+    path = os.path.join(GOLDEN, "golden_large.json")
+    if not os.path.exists(path):
+        pytest.skip("golden_large.json not generated")
+    g = json.load(open(path))["128"]
+    n = 128
+    cx, cy, cz, _ = port.poisson_coeffs(n, n, n)
+    b = port.poisson_rhs(n, n, n, rhs_kind=1, seed=12345)
+    res = port.cg(None, b, 100000, stencil=(n, n, n, cx, cy, cz))
+    assert res["iters"] == g["iterations"]
+    assert hashlib.sha256(np.ascontiguousarray(res["x"]).tobytes()).hexdigest() == g["x_sha256"]
+    gm = json.load(open(path))["gmres_op27_32_K60"]
+    A = port.op27_csc(32, 32, 32)
+    bb = port.spmv(A, port.u01_array(777, A.n_cols))
+    gp = port.gmres(A, bb, np.zeros(A.n_rows), gm["max_iter"], gm["K"], 1e-6)
+    assert list(gp["resid"]) == gm["resid"]
+    assert hashlib.sha256(np.ascontiguousarray(gp["x"]).tobytes()).hexdigest() == gm["x_sha256"]
