@@ -17,13 +17,13 @@
 //   compute: step j is two launches - the multipliers of column j (one thread per row), then the rank-1 update of the
 //            trailing block (one thread per entry, warps along a column so the loads coalesce).  Every entry does the
 //            reference's two roundings (product, then difference): the factors are bit-identical.
-//   solve:   one launch, one CTA, both sweeps.  Forward substitution runs column by column: when y_j is final every row
-//            below adds L(i,j)*y_j to its running sum - ascending j, i.e. the reference's order, so the forward sweep is
-//            always bit-exact.  The backward sweep has two forms: with ATK_REDUCE_TREE the same column wavefront
+//   solve:   one launch, one CTA, both sweeps, in blocks of 32 columns.  Forward substitution: when the y_j of a block are
+//            final every row below adds L(i,j)*y_j to its running sum, j ascending - the reference's order, so the
+//            forward sweep is always bit-exact.  The backward sweep has two forms: with ATK_REDUCE_TREE the same column wavefront
 //            (x_j final -> rows above add U(i,j)*x_j), which accumulates in DESCENDING j and therefore differs from the
 //            reference by rounding only; with ATK_REDUCE_SEQUENTIAL each row's products are formed in parallel and one
 //            thread adds them in ascending j, the reference's chain - bit-exact, and inherently serial (n^2/2 dependent
-//            adds).  Running sums and y live in shared memory: n <= 14000.
+//            adds).  Running sums and y live in shared memory: n <= 13500.
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -88,111 +88,110 @@ __global__ void ilu_mask_kernel(int64_t n, const double* __restrict__ A, double*
     Mt[k + i * n] = m;
 }
 
-// x = U^-1 L^-1 b.  One CTA; thread t owns rows t, t+T, ...
+// x = U^-1 L^-1 b.  One CTA; thread t owns rows t, t+T, ...; the sweeps go in blocks of 32 columns.
+//
+// Forward, block [jb, jb+32): warp 0 solves the 32 x 32 diagonal block (staged in shared memory) as a wavefront inside the
+// warp - lane l owns row jb+l, y_j is broadcast by shuffle as soon as lane j-jb has subtracted its last term - then, after
+// ONE block-wide barrier, every row below adds its 32 products L(i,j)*y_j, j ascending.  Each row's running sum therefore
+// still receives its terms in ascending j from 0.0: the reference's order (ILU.hpp:94-100), bit-exact, with n/32 barriers
+// instead of n.  The backward sweep mirrors it in tree mode (terms arrive in descending j: rounding-level difference to
+// the reference); in reference-ordered mode each row's products are formed in parallel and ONE thread adds them in
+// ascending j (ILU.hpp:103-109) - bit-exact, inherently serial.
+constexpr int kIluB = 32;
+
 __global__ void __launch_bounds__(1024) ilu_solve_kernel(int n, const double* __restrict__ M, const double* __restrict__ Mt,
                                                          const double* __restrict__ b, double* __restrict__ x, int exact_order,
                                                          const int* __restrict__ skip_flag) {
     if (skip_flag && *skip_flag) return;
     extern __shared__ __align__(16) double ilu_sm[];
-    double* acc = ilu_sm;      // running sums (forward, then backward)
-    double* yv = ilu_sm + n;   // y, overwritten by x entry by entry during the backward sweep
-    __shared__ double bc[2];
+    double* acc = ilu_sm;     // running sums (forward, then backward)
+    double* yv = ilu_sm + n;  // b, then y, then x - entry by entry
+    __shared__ double diag[kIluB][kIluB + 1];  // diagonal block of the current step, [row][col]
     const int T = blockDim.x, t = threadIdx.x;
+    const int lane = t & 31;
     const int64_t N = n;
     for (int i = t; i < n; i += T) {
         acc[i] = 0.0;
-        yv[i] = b[i];  // keeps the global loads off the dependent chain of the sweep
+        yv[i] = b[i];
     }
-    __syncthreads();
-    // ---- forward: y_i = b_i - sum_{j<i} L(i,j) y_j                                                  (ILU.hpp:94-100)
-    // The factor entries of column j+1 are requested while column j is being applied (kPre rows per thread in
-    // registers, i.e. every row for n <= kPre*T), so the per-column cost is one barrier plus the shared-memory update.
-    constexpr int kPre = 4;
-    double cur[kPre], nxt[kPre];
-    auto first_below = [&](int j) {  // first row owned by this thread strictly below j
-        int i0 = (j + 1) - ((j + 1) % T) + t;
-        return i0 < j + 1 ? i0 + T : i0;
-    };
-    {
-        const int i0 = first_below(0);
-#pragma unroll
-        for (int q = 0; q < kPre; ++q) cur[q] = (n > 0 && i0 + q * T < n) ? M[i0 + q * T] : 0.0;
-    }
-    // one column; `c` holds this column's entries, `nx` receives the next column's (two-step unrolling below swaps the
-    // roles, so no register copy waits on the loads)
-    auto forward_step = [&](int j, double (&c)[kPre], double (&nx)[kPre]) {
-        if (t == j % T) {  // this thread added the last term of row j itself in the previous step
-            const double y = sub_rn(yv[j], acc[j]);
-            bc[j & 1] = y;
-            yv[j] = y;
+    // diagonal block of [jb, jb+32) -> shared memory (entries outside the matrix are never read)
+    auto load_diag = [&](int jb) {
+        for (int e = t; e < kIluB * kIluB; e += T) {
+            const int r = e & (kIluB - 1), c = e >> 5;  // consecutive threads walk down a column: coalesced
+            if (jb + r < n && jb + c < n) diag[r][c] = M[(jb + r) + (jb + c) * N];
         }
-        if (j + 1 < n) {
-            const int i1 = first_below(j + 1);
+    };
+    // rows [lo, hi) add the products of columns [jb, jb+w) in the order given by `descending`
+    auto update_rows = [&](int lo, int hi, int jb, int w, bool descending) {
+        int i0 = lo - (lo % T) + t;
+        if (i0 < lo) i0 += T;
+        for (int i = i0; i < hi; i += T) {
+            double a = acc[i];
+#pragma unroll 1
+            for (int c0 = 0; c0 < w; c0 += 16) {
+                double m[16];
 #pragma unroll
-            for (int q = 0; q < kPre; ++q) nx[q] = i1 + q * T < n ? M[i1 + q * T + (j + 1) * N] : 0.0;
+                for (int q = 0; q < 16; ++q) {
+                    const int s = descending ? w - 1 - (c0 + q) : c0 + q;
+                    m[q] = (c0 + q < w) ? M[i + (jb + s) * N] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int s = descending ? w - 1 - (c0 + q) : c0 + q;
+                    if (c0 + q < w) a = add_rn(a, mul_rn(m[q], yv[jb + s]));
+                }
+            }
+            acc[i] = a;
+        }
+    };
+    load_diag(0);
+    __syncthreads();
+    // ---- forward: y_i = b_i - sum_{j<i} L(i,j) y_j
+    for (int jb = 0; jb < n; jb += kIluB) {
+        const int w = min(kIluB, n - jb);
+        if (t < 32) {
+            const int i = jb + lane;
+            double a = lane < w ? acc[i] : 0.0;
+            const double bi = lane < w ? yv[i] : 0.0;
+            double y = 0.0;
+            for (int s = 0; s < w; ++s) {
+                if (lane == s) y = sub_rn(bi, a);
+                const double ys = __shfl_sync(0xffffffffu, y, s);
+                if (lane > s && lane < w) a = add_rn(a, mul_rn(diag[lane][s], ys));
+            }
+            if (lane < w) yv[i] = y;
         }
         __syncthreads();
-        const double yj = bc[j & 1];
-        const int i0 = first_below(j);
-#pragma unroll
-        for (int q = 0; q < kPre; ++q) {
-            const int i = i0 + q * T;
-            if (i < n) acc[i] = add_rn(acc[i], mul_rn(c[q], yj));
-        }
-        for (int i = i0 + kPre * T; i < n; i += T) acc[i] = add_rn(acc[i], mul_rn(M[i + j * N], yj));
-    };
-    {
-        int j = 0;
-        for (; j + 1 < n; j += 2) {
-            forward_step(j, cur, nxt);
-            forward_step(j + 1, nxt, cur);
-        }
-        if (j < n) forward_step(j, cur, nxt);
+        update_rows(jb + w, n, jb, w, false);
+        if (jb + kIluB < n) load_diag(jb + kIluB);  // warp 0 has left the old block (barrier above)
+        __syncthreads();
     }
-    __syncthreads();
-    // ---- backward: x_i = (y_i - sum_{j>i} U(i,j) x_j) / U(i,i)                                      (ILU.hpp:103-109)
+    // ---- backward: x_i = (y_i - sum_{j>i} U(i,j) x_j) / U(i,i)
     if (!exact_order) {
         for (int i = t; i < n; i += T) acc[i] = 0.0;
+        const int last = ((n - 1) / kIluB) * kIluB;
+        if (n > 0) load_diag(last);
         __syncthreads();
-        double dg[kPre];  // diagonal of U for the first kPre owned rows (the rest are read when needed)
-#pragma unroll
-        for (int q = 0; q < kPre; ++q) {
-            cur[q] = (n > 0 && t + q * T < n - 1) ? M[t + q * T + (N - 1) * N] : 0.0;
-            dg[q] = t + q * T < n ? M[(t + q * T) * (N + 1)] : 1.0;
-        }
-        auto backward_step = [&](int j, double (&c)[kPre], double (&nx)[kPre]) {
-            if (t == j % T) {
-                const int q = j / T;
-                double d = dg[0];
-                if (q >= kPre) {
-                    d = M[j + j * N];
-                } else {
-#pragma unroll
-                    for (int k = 1; k < kPre; ++k) d = q == k ? dg[k] : d;
+        for (int jb = last; jb >= 0; jb -= kIluB) {
+            const int w = min(kIluB, n - jb);
+            if (t < 32) {
+                const int i = jb + lane;
+                double a = lane < w ? acc[i] : 0.0;
+                const double yi = lane < w ? yv[i] : 0.0;
+                const double d = lane < w ? diag[lane][lane] : 1.0;
+                double xv = 0.0;
+                for (int s = w - 1; s >= 0; --s) {
+                    if (lane == s) xv = __ddiv_rn(sub_rn(yi, a), d);
+                    const double xs = __shfl_sync(0xffffffffu, xv, s);
+                    if (lane < s) a = add_rn(a, mul_rn(diag[lane][s], xs));
                 }
-                const double xj = __ddiv_rn(sub_rn(yv[j], acc[j]), d);
-                bc[j & 1] = xj;
-                yv[j] = xj;
-            }
-            if (j > 0) {
-#pragma unroll
-                for (int q = 0; q < kPre; ++q) nx[q] = t + q * T < j - 1 ? M[t + q * T + (j - 1) * N] : 0.0;
+                if (lane < w) yv[i] = xv;
             }
             __syncthreads();
-            const double xj = bc[j & 1];
-#pragma unroll
-            for (int q = 0; q < kPre; ++q) {
-                const int i = t + q * T;
-                if (i < j) acc[i] = add_rn(acc[i], mul_rn(c[q], xj));
-            }
-            for (int i = t + kPre * T; i < j; i += T) acc[i] = add_rn(acc[i], mul_rn(M[i + j * N], xj));
-        };
-        int j = n - 1;
-        for (; j >= 1; j -= 2) {
-            backward_step(j, cur, nxt);
-            backward_step(j - 1, nxt, cur);
+            update_rows(0, jb, jb, w, true);
+            if (jb > 0) load_diag(jb - kIluB);
+            __syncthreads();
         }
-        if (j == 0) backward_step(0, cur, nxt);
     } else {
         for (int i = n - 1; i >= 0; --i) {
             const double* row = Mt + (int64_t)i * N;  // row i of U, contiguous
@@ -250,8 +249,8 @@ Preconditioner* make_ilu(Context* ctx, int64_t n_rows, int64_t n_cols, int64_t n
     ATK_REQUIRE(n_rows >= 0 && nnz >= 0 && (n_rows == 0 || (col_ptr && (nnz == 0 || (row_idx && vals)))), ATK_ERR_INVALID_ARGUMENT,
                 "bad CSC arrays");
     const int64_t n = n_rows;
-    ATK_REQUIRE(n <= 14000, ATK_ERR_INVALID_ARGUMENT,
-                "ILU factorization: the reference's elimination is dense (n x n); this build keeps n <= 14000");
+    ATK_REQUIRE(n <= 13500, ATK_ERR_INVALID_ARGUMENT,
+                "ILU factorization: the reference's elimination is dense (n x n); this build keeps n <= 13500");
     cudaStream_t st = ctx->stream;
     auto pc = new IluPreconditioner();
     pc->ctx = ctx;

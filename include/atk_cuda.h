@@ -259,7 +259,7 @@ int atk_arnoldi_host(atk_context_t ctx, atk_operator_t op, double* Q, int64_t ld
  * arrays (host pointers): the reference's full elimination without pivoting with its 1e-12 drop rules, carried out on
  * the device on a dense n x n array - the factors are bit-identical to getLFactor()/getUFactor().  Errors:
  * ATK_ERR_INVALID_ARGUMENT "Matrix must be square for ILU factorization" (:24-26), ATK_ERR_RUNTIME "Matrix is
- * numerically singular" (:38-40).  Single-GPU contexts, n <= 14000.
+ * numerically singular" (:38-40).  Single-GPU contexts, n <= 13500.
  * atk_ilu_solve = solve() (:84-112): x = U^-1 L^-1 b.  The forward sweep always adds in the reference's order; the
  * backward sweep does so under ATK_REDUCE_SEQUENTIAL (bit-exact) and accumulates column by column under
  * ATK_REDUCE_TREE (same result up to rounding, far less serial).  n must equal the factor size

@@ -211,3 +211,31 @@ def test_fastsolver_gmres_enable_preconditioner(gilu, port, capsys):
     assert digest(x.to_numpy()) == e["gmres_x_sha256"]
     out = capsys.readouterr().out
     assert out.count("KrylovUpdate : 1") == 3 and "Reached maximum iterations without convergence." in out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 64, 65, 97, 1056, 1100])
+def test_device_ilu_sweep_block_boundaries(ctx, port, n):
+    """Sizes around the 32-column blocks of the sweeps and the 1024-thread row ownership, dense factors."""
+    from algotoolkit_b200 import capi
+
+    rng = np.random.default_rng(n)
+    dens = 1.0 if n <= 100 else 0.01
+    D = np.where(rng.random((n, n)) < dens, rng.standard_normal((n, n)), 0.0)
+    D[np.arange(n), np.arange(n)] = np.abs(D).sum(1) + 1.0
+    c, r = np.nonzero(D.T)
+    A = port.csc_from_triplets(n, n, r, c, D[r, c])
+    pc = ctx.ilu_compute(n, n, A.col_ptr, A.row_idx, A.vals)
+    LU = port.ilu_compute(A)
+    Lw, Uw = port.ilu_factors(LU)
+    Lf, Uf = pc.factors()
+    assert np.array_equal(Lf, Lw) and np.array_equal(Uf, Uw)
+    b = rng.standard_normal(n)
+    want = port.ilu_solve(LU, b)
+    assert relerr(pc.solve_host(b), want) < REL
+    ctx.set_reduction(capi.REDUCE_SEQUENTIAL)
+    try:
+        assert np.array_equal(pc.solve_host(b), want)
+    finally:
+        ctx.set_reduction(capi.REDUCE_TREE)
+    pc.destroy()
