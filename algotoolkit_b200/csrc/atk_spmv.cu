@@ -11,7 +11,8 @@
 // Why SELL and one thread per row: the reference matvec (:131-152) adds val*x[col] into y[row] for col ascending,
 // starting from 0.0, so the bit pattern of y[row] is fixed by a strictly sequential sum over the row.  A thread
 // that walks its own row in order reproduces it exactly, and the column-major slice makes those walks coalesced.
-// The CSR-vector kernel (several lanes per row + shuffle tree) is kept as the throughput alternative for long,
+// In the CSR format short rows go through the CSR-stream kernel (bit-exact, see there); the CSR-vector kernel (several
+// lanes per row + shuffle tree) is kept as the throughput alternative for long,
 // irregular rows; it is deterministic but sums in a different order.
 //
 // Algorithmic traffic per SpMV: 12*nnz + 4*(n+1) + 8*m + 8*n bytes.
@@ -338,6 +339,128 @@ __global__ void __launch_bounds__(kReduceBlock) csr_vector_spmv_kernel(int n_row
     }
 }
 
+// CSR-stream (the CSR-format kernel for short rows): a CTA takes a run of consecutive rows holding at most kStreamCap
+// entries, streams their values / column indices in with fully coalesced loads (8 entries in flight per thread), gathers
+// x, and leaves the rounded products in shared memory; then one thread per row adds its row's products from 0.0 in
+// ascending column order.  Per row that is exactly the CSC matvec's sequence of operations (an exact-zero x entry adds
+// +0.0, which leaves any running sum unchanged, as skipping it does): bit-identical to the SELL kernel and the reference,
+// unlike the lane-tree of CSR-vector, with no padding and no format conversion beyond CSR.
+// blk_row[b] = first row whose first entry is at or after b*T, T = kStreamCap - (longest row), so that block b's entries
+// [row_ptr[blk_row[b]], row_ptr[blk_row[b+1]]) always fit.
+constexpr int kStreamCap = 4096;   // products per CTA (32 KB of shared memory)
+constexpr int kStreamBlock = 256;
+
+__global__ void csr_stream_blocks_kernel(int n_rows, int n_blocks, int target, const int* __restrict__ row_ptr, int* __restrict__ blk_row) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > n_blocks) return;
+    if (b == n_blocks) {
+        blk_row[b] = n_rows;
+        return;
+    }
+    const int64_t want = (int64_t)b * target;
+    int lo = 0, hi = n_rows;  // first row r in [0, n_rows] with row_ptr[r] >= want
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (row_ptr[mid] >= want) hi = mid;
+        else lo = mid + 1;
+    }
+    blk_row[b] = lo;
+}
+__global__ void max_row_len_kernel(int n_rows, const int* __restrict__ row_ptr, int* __restrict__ out) {
+    int m = 0;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) m = max(m, row_ptr[r + 1] - row_ptr[r]);
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
+template <bool DOT>
+__global__ void __launch_bounds__(kStreamBlock) csr_stream_spmv_kernel(int n_blocks, const int* __restrict__ blk_row,
+                                                                       const int* __restrict__ row_ptr,
+                                                                       const int* __restrict__ csr_col,
+                                                                       const double* __restrict__ csr_val,
+                                                                       const double* __restrict__ x, double* __restrict__ y,
+                                                                       double* partials, unsigned* ticket, double* dot_out,
+                                                                       const int* skip_flag) {
+    if (skip_flag && *skip_flag) return;
+    extern __shared__ __align__(16) double prod[];
+    double dacc = 0.0;
+    constexpr int U = 8;
+    // block metadata one trip ahead, so that the chain blk_row -> row_ptr -> entries is not paid serially per block
+    int b = blockIdx.x;
+    int r0 = 0, r1 = 0, e0 = 0, e1 = 0;
+    if (b < n_blocks) {
+        r0 = blk_row[b];
+        r1 = blk_row[b + 1];
+        e0 = row_ptr[r0];
+        e1 = row_ptr[r1];
+    }
+    while (b < n_blocks) {
+        const int bn = b + gridDim.x;
+        int nr0 = 0, nr1 = 0;
+        if (bn < n_blocks) {
+            nr0 = blk_row[bn];
+            nr1 = blk_row[bn + 1];
+        }
+        // this thread's first row of the summation phase: its bounds are requested before the entries are
+        int r = r0 + threadIdx.x;
+        int k0 = 0, k1 = 0;
+        if (r < r1) {
+            k0 = row_ptr[r];
+            k1 = row_ptr[r + 1];
+        }
+        for (int e = e0 + threadIdx.x; e < e1; e += kStreamBlock * U) {
+            int c[U];
+            double v[U], xv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = e + u * kStreamBlock;
+                c[u] = q < e1 ? __ldg(csr_col + q) : -1;
+                v[u] = q < e1 ? __ldg(csr_val + q) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) xv[u] = x[c[u] < 0 ? 0 : c[u]];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = e + u * kStreamBlock;
+                if (q < e1) prod[q - e0] = xv[u] != 0.0 ? mul_rn(v[u], xv[u]) : 0.0;
+            }
+        }
+        int ne0 = 0, ne1 = 0;
+        if (bn < n_blocks) {
+            ne0 = row_ptr[nr0];
+            ne1 = row_ptr[nr1];
+        }
+        __syncthreads();
+        while (r < r1) {
+            const int rn = r + kStreamBlock;
+            int nk0 = 0, nk1 = 0;
+            if (rn < r1) {  // bounds of the next row before this row's dependent chain of adds
+                nk0 = row_ptr[rn];
+                nk1 = row_ptr[rn + 1];
+            }
+            double acc = 0.0;
+            for (int k = k0 - e0; k < k1 - e0; ++k) acc = add_rn(acc, prod[k]);
+            y[r] = acc;
+            if constexpr (DOT) dacc = add_rn(dacc, mul_rn(x[r], acc));
+            r = rn;
+            k0 = nk0;
+            k1 = nk1;
+        }
+        __syncthreads();  // prod[] free again
+        b = bn;
+        r0 = nr0;
+        r1 = nr1;
+        e0 = ne0;
+        e1 = ne1;
+    }
+    if constexpr (DOT) {
+        double total;
+        if (grid_sum_last_block<kStreamBlock>(dacc, partials, ticket, &total)) {
+            if (linear_thread_id() == 0) *dot_out = total;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ the operator
 struct AssembledMatrix : public Operator {
     int n_rows = 0;
@@ -354,10 +477,13 @@ struct AssembledMatrix : public Operator {
     double* sell_val = nullptr;
     int64_t sell_elems = 0;
     int lanes = 8;
+    // CSR-stream (CSR format, short rows)
+    int* blk_row = nullptr;  // [stream_blocks + 1]
+    int stream_blocks = 0;   // 0: rows too long for the stream kernel -> CSR-vector
 
     ~AssembledMatrix() override {
         cudaFree(row_ptr); cudaFree(csr_col); cudaFree(csr_val);
-        cudaFree(wscan); cudaFree(perm); cudaFree(sell_col); cudaFree(sell_val);
+        cudaFree(wscan); cudaFree(perm); cudaFree(sell_col); cudaFree(sell_val); cudaFree(blk_row);
     }
     bool has_csr() const override { return true; }
     void export_csr(int* h_row_ptr, int* h_col, double* h_val) const override {
@@ -380,6 +506,17 @@ struct AssembledMatrix : public Operator {
             else
                 sell_spmv_kernel<false><<<g, kReduceBlock, 0, c->stream>>>(n_rows, n_slices, wscan, sell_col, sell_val, perm,
                                                                            x, y, nullptr, nullptr, nullptr, skip_flag);
+        } else if (stream_blocks > 0) {
+            const int g = std::min(stream_blocks, c->sm_count * 32);
+            constexpr size_t smem = sizeof(double) * kStreamCap;
+            if (dot_slot >= 0)
+                csr_stream_spmv_kernel<true><<<g, kStreamBlock, smem, c->stream>>>(stream_blocks, blk_row, row_ptr, csr_col, csr_val,
+                                                                                 x, y, c->d_partials, c->d_tickets + 1, dot_out,
+                                                                                 skip_flag);
+            else
+                csr_stream_spmv_kernel<false><<<g, kStreamBlock, smem, c->stream>>>(stream_blocks, blk_row, row_ptr, csr_col,
+                                                                                  csr_val, x, y, nullptr, nullptr, nullptr,
+                                                                                  skip_flag);
         } else {
             const int g = (int)std::max<int64_t>(1, std::min<int64_t>(grid, ((int64_t)n_rows * lanes + kReduceBlock - 1) / kReduceBlock));
 #define ATK_CSRV(L)                                                                                                      \
@@ -474,6 +611,27 @@ static Operator* build_from_device_csc(Context* ctx, int n_rows, int n_cols, int
         int lanes = 2;
         while (lanes < 32 && lanes < mean) lanes <<= 1;
         A->lanes = lanes;
+        // CSR format: rows short enough (longest row <= half the product buffer, mean <= 64) go through the stream kernel
+        if (format != ATK_FORMAT_SELL && n_rows > 0 && nnz > 0 && !std::getenv("ATK_CSR_NO_STREAM")) {
+            int* d_max = dalloc<int>(1);
+            int h_max = 0;
+            ATK_CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof(int), st));
+            max_row_len_kernel<<<grid_for(n_rows, 256, cap), 256, 0, st>>>(n_rows, A->row_ptr, d_max);
+            ATK_CUDA_CHECK(cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+            ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+            cudaFree(d_max);
+            count_launch(ctx);
+            if (h_max <= kStreamCap / 2 && mean <= 64.0) {
+                const int target = kStreamCap - h_max;
+                const int nb = (int)((nnz + target - 1) / target);
+                A->blk_row = dalloc<int>((size_t)nb + 1);
+                csr_stream_blocks_kernel<<<(nb + 1 + 255) / 256, 256, 0, st>>>(n_rows, nb, target, A->row_ptr, A->blk_row);
+                count_launch(ctx);
+                ATK_CUDA_CHECK(cudaGetLastError());
+                ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+                A->stream_blocks = nb;
+            }
+        }
 
         // ---- CSR -> SELL-32-sigma
         if (format == ATK_FORMAT_SELL) {

@@ -366,7 +366,7 @@ def secondary_measurements(ctx, capi, synthetic, stencil_op, g, peak):
                                         "frac_of_measured_peak": 16.0 * n / t / 1e9 / peak}
     ga = 256
     cx, cy, cz = synthetic.poisson_coeffs(ga, ga, ga)
-    for name, fmt in (("spmv_sell32_assembled", capi.FORMAT_SELL), ("spmv_csr_vector_assembled", capi.FORMAT_CSR_VECTOR)):
+    for name, fmt in (("spmv_sell32_assembled", capi.FORMAT_SELL), ("spmv_csr_stream_assembled", capi.FORMAT_CSR_VECTOR)):
         t0 = time.perf_counter()
         op = ctx.operator_poisson_assembled(ga, ga, ga, cx, cy, cz, fmt)
         ctx.synchronize()

@@ -697,3 +697,43 @@ def test_gmres_op27_larger_systems_vs_reference(ctx, port, key):
         finally:
             ctx.set_reduction(capi.REDUCE_TREE)
         assert digest(seq["x"]) == g["x_sha256"] and list(seq["resid"]) == g["resid"]
+
+
+# ------------------------------------------------------------------------------------------------ CSR format kernels
+def test_csr_stream_is_bit_exact_and_vector_kernel_still_covered(ctx, port, monkeypatch):
+    """CSR format: short rows -> CSR-stream (per-row ascending sums: bit-identical to the CSC matvec, empty rows, rows
+    straddling the block boundaries, exact-zero x entries); long rows or ATK_CSR_NO_STREAM=1 -> CSR-vector (lane tree)."""
+    rng = np.random.default_rng(17)
+    n_rows, n_cols = 5000, 4100
+    lens = rng.integers(0, 40, n_rows)
+    lens[100:400] = 0  # a run of empty rows inside a block
+    lens[-50:] = 0     # trailing empty rows
+    rows = np.repeat(np.arange(n_rows), lens)
+    cols = np.concatenate([np.sort(rng.choice(n_cols, k, replace=False)) for k in lens]) if lens.sum() else np.zeros(0, int)
+    vals = rng.standard_normal(rows.size)
+    A = port.csc_from_triplets(n_rows, n_cols, rows, cols, vals)
+    x = rng.standard_normal(n_cols)
+    x[::7] = 0.0
+    want = port.spmv(A, x)
+    op = ctx.operator_from_csc(n_rows, n_cols, A.col_ptr, A.row_idx, A.vals, capi.FORMAT_CSR_VECTOR)
+    assert np.array_equal(op.apply_numpy(x), want)
+    monkeypatch.setenv("ATK_CSR_NO_STREAM", "1")
+    opv = ctx.operator_from_csc(n_rows, n_cols, A.col_ptr, A.row_idx, A.vals, capi.FORMAT_CSR_VECTOR)
+    assert relerr(opv.apply_numpy(x), want) < 1e-14
+    monkeypatch.delenv("ATK_CSR_NO_STREAM")
+    # one row longer than half the product buffer: the operator falls back to CSR-vector by itself
+    n2 = 3000
+    rows2 = np.concatenate([np.zeros(n2, int), np.arange(1, 50)])
+    cols2 = np.concatenate([np.arange(n2), rng.integers(0, n2, 49)])
+    A2 = port.csc_from_triplets(50, n2, rows2, cols2, rng.standard_normal(rows2.size))
+    x2 = rng.standard_normal(n2)
+    op2 = ctx.operator_from_csc(50, n2, A2.col_ptr, A2.row_idx, A2.vals, capi.FORMAT_CSR_VECTOR)
+    assert relerr(op2.apply_numpy(x2), port.spmv(A2, x2)) < 1e-13
+    # CG through the CSR format on the assembled Poisson matrix: same iterations and solution as the oracle
+    n = 16
+    cx, cy, cz, _ = port.poisson_coeffs(n, n, n)
+    b = port.poisson_rhs(n, n, n, rhs_kind=1, seed=12345)
+    opp = ctx.operator_poisson_assembled(n, n, n, cx, cy, cz, capi.FORMAT_CSR_VECTOR)
+    res = ctx.cg_solve_host(opp, b, 100000)
+    ora = port.cg(None, b, 100000, stencil=(n, n, n, cx, cy, cz))
+    assert res["iters"] == ora["iters"] and relerr(res["x"], ora["x"]) < REL

@@ -40,7 +40,7 @@ t1 = time.perf_counter()
 ops["sell"] = ctx.operator_poisson_assembled(g, g, g, cx, cy, cz, capi.FORMAT_SELL)
 ctx.synchronize()
 t2 = time.perf_counter()
-ops["csr_vector"] = ctx.operator_poisson_assembled(g, g, g, cx, cy, cz, capi.FORMAT_CSR_VECTOR)
+ops["csr_stream"] = ctx.operator_poisson_assembled(g, g, g, cx, cy, cz, capi.FORMAT_CSR_VECTOR)
 ctx.synchronize()
 t3 = time.perf_counter()
 nnz = ops["sell"].nnz
