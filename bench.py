@@ -310,6 +310,29 @@ def run_ours(args):
     # ---- secondary measurements of the same hot path (N=1 only; a few seconds): SpMV GB/s and GMRES restarts/s
     if world == 1 and not args.no_extra:
         line["extra"] = secondary_measurements(ctx, capi, synthetic, op, g, peak)
+    elif not args.no_extra:
+        # N > 1: the distributed matrix-free SpMV alone (z-slabs, halo planes exchanged over NCCL on the communication
+        # stream while the interior planes run); every rank takes part, time = max over ranks, bytes = whole grid
+        xs = ctx.vector(np.random.default_rng(rank).standard_normal(op.n_rows_local))
+        ys = ctx.empty(op.n_rows_local)
+        for _ in range(3):
+            op.apply(xs, ys)
+        ctx.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        reps = 20
+        for _ in range(reps):
+            op.apply(xs, ys)
+        ctx.synchronize()
+        tt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        xs.free()
+        ys.free()
+        tsec = float(tt.item())
+        line["extra"] = {"spmv_stencil7_matrix_free": {
+            "grid": g, "n_gpus": world, "ms": tsec * 1e3, "algorithmic_bytes": 16.0 * N, "GBs": 16.0 * N / tsec / 1e9,
+            "GBs_per_gpu": 16.0 * N / tsec / 1e9 / world, "frac_of_measured_peak_per_gpu": 16.0 * N / tsec / 1e9 / world / peak,
+            "note": "aggregate over ranks; includes the halo exchange of every apply"}}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the unmodified reference on a bounded sample
     if world == 1 and not args.no_cpu_baseline:
