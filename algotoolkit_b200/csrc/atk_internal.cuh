@@ -128,6 +128,10 @@ double read_slot(Context* ctx, int slot);
 void ipc_share(Context* ctx, void* local, std::vector<void*>& peers, const std::vector<int>& want);
 // Collective all-gather of `bytes` host bytes per rank (setup-time helper, goes through NCCL).
 void allgather_host_bytes(Context* ctx, const void* send, void* recv, size_t bytes);
+// Neighbour exchange with independent counts (row-block partitioned assembled operators): send `to_prev` / `to_next`
+// to ranks rank-1 / rank+1 and receive `from_prev` / `from_next` from them; a count of 0 skips that transfer.
+void exchange_ranges(Context* ctx, const double* to_prev, size_t n_to_prev, const double* to_next, size_t n_to_next,
+                     double* from_prev, size_t n_from_prev, double* from_next, size_t n_from_next, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------ fused CG state
 // Device-resident scalars of the fused two-kernel CG iteration (atk_cg.cu drives it, the operator supplies KA).
@@ -286,6 +290,31 @@ __device__ __forceinline__ bool grid_sum_last_block(double v, double* partials, 
     if (!is_last) return false;
     __threadfence();
     *total = partials_sum<BLOCK>(partials, nb);
+    return true;
+}
+
+// The same for a sum spread over several launches on one stream: every launch leaves its blocks' sums at
+// partials[partial_base + block]; only the launch marked final takes tickets, and its last block adds ALL partials
+// [0, partial_base + blocks of this launch) in index order (the earlier launches have completed: stream order).
+template <int BLOCK>
+__device__ __forceinline__ bool grid_sum_last_block_chained(double v, double* partials, int partial_base, int is_final,
+                                                            unsigned* ticket, double* total) {
+    __shared__ bool is_last_c;
+    const double bs = block_sum<BLOCK>(v);
+    const unsigned nb = total_blocks();
+    if (linear_thread_id() == 0) {
+        partials[partial_base + linear_block_id()] = bs;
+        is_last_c = false;
+        if (is_final) {
+            __threadfence();
+            const unsigned t = atomicInc(ticket, nb - 1);
+            is_last_c = (t == nb - 1);
+        }
+    }
+    __syncthreads();
+    if (!is_last_c) return false;
+    __threadfence();
+    *total = partials_sum<BLOCK>(partials, partial_base + nb);
     return true;
 }
 

@@ -217,20 +217,30 @@ __global__ void sell_fill_kernel(int n_rows, const int* __restrict__ row_ptr, co
 // SELL: one warp per slice (persistent, grid-stride over slices), one thread per row.
 // acc starts at 0.0 and takes val*x[col] in ascending column order; a column whose x is exactly 0 is skipped,
 // as the reference does (SparseObj.hpp:141).
-template <bool DOT>
+// Row-block partitioned operator (distributed context): column c of the local matrix lives in one of three arrays -
+// [0, h_lo) the tail of the previous rank's block (received), [h_lo, h_lo + n_mid) this rank's x, the rest the head of
+// the next rank's block (received).
+struct DistX {
+    const double* lo;
+    const double* hi;
+    int h_lo;
+    int n_mid;
+};
+template <bool DOT, bool DIST>
 __global__ void __launch_bounds__(kReduceBlock) sell_spmv_kernel(int n_rows, int n_slices, const int* __restrict__ wscan,
                                                                  const int* __restrict__ sell_col,
                                                                  const double* __restrict__ sell_val,
                                                                  const int* __restrict__ perm, const double* __restrict__ x,
                                                                  double* __restrict__ y, double* partials, unsigned* ticket,
-                                                                 double* dot_out, const int* skip_flag) {
+                                                                 double* dot_out, const int* skip_flag, DistX dx, int s_begin,
+                                                                 int s_end, int partial_base, int is_final) {
     if (skip_flag && *skip_flag) return;
     const int lane = threadIdx.x & 31;
     const int warp0 = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
     double dacc = 0.0;
     constexpr int U = 8;  // entries of a row handled per batch: all 2U matrix loads are issued together, then all U gathers
-    for (int s = warp0; s < n_slices; s += nwarps) {
+    for (int s = s_begin + warp0; s < s_end; s += nwarps) {
         const int w0 = wscan[s], w = wscan[s + 1] - w0;
         const int64_t off = (int64_t)w0 * kSliceRows + lane;
         double acc = 0.0;
@@ -244,7 +254,15 @@ __global__ void __launch_bounds__(kReduceBlock) sell_spmv_kernel(int n_rows, int
                 v[u] = in ? __ldg(sell_val + off + (int64_t)(kb + u) * kSliceRows) : 0.0;
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) xv[u] = x[c[u] < 0 ? 0 : c[u]];  // unconditional (padding reads x[0], then ignored)
+            for (int u = 0; u < U; ++u) {  // unconditional (padding reads the first local entry, then ignored)
+                if constexpr (DIST) {
+                    const int cc = c[u] < 0 ? dx.h_lo : c[u];
+                    const double* base = cc < dx.h_lo ? dx.lo : (cc < dx.h_lo + dx.n_mid ? x - dx.h_lo : dx.hi - dx.h_lo - dx.n_mid);
+                    xv[u] = base[cc];
+                } else {
+                    xv[u] = x[c[u] < 0 ? 0 : c[u]];
+                }
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 // ascending column order; padding and exact-zero x entries contribute nothing (SparseObj.hpp:141)
@@ -261,7 +279,7 @@ __global__ void __launch_bounds__(kReduceBlock) sell_spmv_kernel(int n_rows, int
     }
     if constexpr (DOT) {
         double total;
-        if (grid_sum_last_block<kReduceBlock>(dacc, partials, ticket, &total)) {
+        if (grid_sum_last_block_chained<kReduceBlock>(dacc, partials, partial_base, is_final, ticket, &total)) {
             if (linear_thread_id() == 0) *dot_out = total;
         }
     }
@@ -480,10 +498,19 @@ struct AssembledMatrix : public Operator {
     // CSR-stream (CSR format, short rows)
     int* blk_row = nullptr;  // [stream_blocks + 1]
     int stream_blocks = 0;   // 0: rows too long for the stream kernel -> CSR-vector
+    // row-block partition on a distributed context (SELL only): local columns = [h_lo received | n_rows own | h_hi received]
+    bool dist = false;
+    int h_lo = 0, h_hi = 0;            // entries needed from the previous / next rank
+    int send_prev = 0, send_next = 0;  // entries the previous / next rank needs from this one
+    double* halo_lo = nullptr;
+    double* halo_hi = nullptr;
+    int col_shift = 0;                 // local column + col_shift = global column
+    int s_int_begin = 0, s_int_end = 0;  // slices whose rows touch no received entry: they run while the exchange is in flight
 
     ~AssembledMatrix() override {
         cudaFree(row_ptr); cudaFree(csr_col); cudaFree(csr_val);
         cudaFree(wscan); cudaFree(perm); cudaFree(sell_col); cudaFree(sell_val); cudaFree(blk_row);
+        cudaFree(halo_lo); cudaFree(halo_hi);
     }
     bool has_csr() const override { return true; }
     void export_csr(int* h_row_ptr, int* h_col, double* h_val) const override {
@@ -491,6 +518,8 @@ struct AssembledMatrix : public Operator {
         if (nnz > 0) {
             ATK_CUDA_CHECK(cudaMemcpy(h_col, csr_col, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost));
             ATK_CUDA_CHECK(cudaMemcpy(h_val, csr_val, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost));
+            if (col_shift != 0)
+                for (int64_t k = 0; k < nnz; ++k) h_col[k] += col_shift;  // back to global column indices
         }
     }
 
@@ -499,13 +528,45 @@ struct AssembledMatrix : public Operator {
         double* dot_out = dot_slot >= 0 ? c->slot(dot_slot) + c->rank : nullptr;
         const int grid = c->sm_count * 8;
         if (format == ATK_FORMAT_SELL) {
-            const int g = (int)std::max<int64_t>(1, std::min<int64_t>(grid, ((int64_t)n_slices * 32 + kReduceBlock - 1) / kReduceBlock));
-            if (dot_slot >= 0)
-                sell_spmv_kernel<true><<<g, kReduceBlock, 0, c->stream>>>(n_rows, n_slices, wscan, sell_col, sell_val, perm, x,
-                                                                          y, c->d_partials, c->d_tickets + 1, dot_out, skip_flag);
-            else
-                sell_spmv_kernel<false><<<g, kReduceBlock, 0, c->stream>>>(n_rows, n_slices, wscan, sell_col, sell_val, perm,
-                                                                           x, y, nullptr, nullptr, nullptr, skip_flag);
+            const DistX dx{halo_lo, halo_hi, h_lo, n_rows};
+            const bool dot = dot_slot >= 0;
+            int pbase = 0;
+            // (measured at 2 GPUs, 256^3: the persistent grid of the interior piece fills every SM, so the one-CTA transfer
+            // kernel mostly runs after it - 0.173 ms per apply against 0.176 ms without the split; shrinking the grid to
+            // leave room, or launching the piece as short CTAs, made the piece itself slower: 0.201 / 0.185 ms)
+            auto piece = [&](int sb, int se, bool final_piece, bool beside_exchange = false) {
+                if (se <= sb) return;
+                (void)beside_exchange;
+                const int cap_g = grid;
+                const int g = (int)std::max<int64_t>(1, std::min<int64_t>(cap_g, ((int64_t)(se - sb) * 32 + kReduceBlock - 1) / kReduceBlock));
+#define ATK_SELL(D, X)                                                                                                            \
+    sell_spmv_kernel<D, X><<<g, kReduceBlock, 0, c->stream>>>(n_rows, n_slices, wscan, sell_col, sell_val, perm, x, y,           \
+                                                              D ? c->d_partials : nullptr, D ? c->d_tickets + 1 : nullptr,      \
+                                                              D ? dot_out : nullptr, skip_flag, dx, sb, se, pbase, final_piece ? 1 : 0)
+                if (dist) { if (dot) ATK_SELL(true, true); else ATK_SELL(false, true); }
+                else      { if (dot) ATK_SELL(true, false); else ATK_SELL(false, false); }
+#undef ATK_SELL
+                pbase += g;
+                count_launch(c);
+            };
+            if (!dist) {
+                piece(0, n_slices, true);
+            } else {
+                // neighbour entries on the communication stream while the slices that need none of them run
+                ATK_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+                ATK_CUDA_CHECK(cudaStreamWaitEvent(c->comm_stream, c->ev_fork, 0));
+                exchange_ranges(c, x, (size_t)send_prev, x + (n_rows - send_next), (size_t)send_next, halo_lo, (size_t)h_lo, halo_hi,
+                                (size_t)h_hi, c->comm_stream);
+                ATK_CUDA_CHECK(cudaEventRecord(c->ev_join, c->comm_stream));
+                const bool has_lo = s_int_begin > 0, has_hi = s_int_end < n_slices;
+                piece(s_int_begin, s_int_end, !has_lo && !has_hi, true);
+                ATK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+                piece(0, s_int_begin, !has_hi);
+                piece(s_int_end, n_slices, true);
+            }
+            ATK_CUDA_CHECK(cudaGetLastError());
+            if (dot) allgather_slot(c, dot_slot, c->stream);
+            return;
         } else if (stream_blocks > 0) {
             const int g = std::min(stream_blocks, c->sm_count * 32);
             constexpr size_t smem = sizeof(double) * kStreamCap;
@@ -556,11 +617,53 @@ inline int grid_for(int64_t work, int block, int cap) {
 }  // namespace
 
 // Takes DEVICE CSC arrays and builds the operator.  The CSC arrays are not retained.
+// ---- row-block slicing of a global CSR (distributed contexts)
+__global__ void slice_row_ptr_kernel(int n_loc, int r0, const int* __restrict__ g_row_ptr, int* __restrict__ row_ptr) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n_loc) row_ptr[i] = g_row_ptr[r0 + i] - g_row_ptr[r0];
+}
+__global__ void col_range_kernel(int64_t nnz, const int* __restrict__ col, int* __restrict__ min_max) {
+    int lo = 0x7fffffff, hi = -1;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) {
+        const int c = col[k];
+        lo = min(lo, c);
+        hi = max(hi, c);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(min_max, lo);
+        atomicMax(min_max + 1, hi);
+    }
+}
+// rows [0, out[0]) may read entries received from the previous rank, rows [out[1], n) entries from the next one
+// (columns are ascending inside a row, so its first / last entry decide); out starts as {0, n_rows}
+__global__ void halo_rows_kernel(int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col, int h_lo, int n_mid,
+                                 int* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int b = row_ptr[r], e = row_ptr[r + 1];
+    if (e <= b) return;
+    if (col[b] < h_lo) atomicMax(out, r + 1);
+    if (col[e - 1] >= h_lo + n_mid) atomicMin(out + 1, r);
+}
+__global__ void shift_cols_kernel(int64_t nnz, int shift, int* __restrict__ col) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) col[k] -= shift;
+}
+
+// row_lo / row_hi: the row block of this rank on a distributed context (row_hi < 0: balanced blocks of rows)
 static Operator* build_from_device_csc(Context* ctx, int n_rows, int n_cols, int64_t nnz, const int* d_col_ptr,
-                                       const int* d_row_idx, const double* d_vals, atk_format format) {
+                                       const int* d_row_idx, const double* d_vals, atk_format format, int row_lo = 0,
+                                       int row_hi = -1) {
     ATK_REQUIRE(nnz >= 0 && nnz < (int64_t)0x7fffffff, ATK_ERR_INVALID_ARGUMENT, "nnz must be below 2^31");
-    ATK_REQUIRE(ctx->world == 1, ATK_ERR_INVALID_ARGUMENT,
-                "assembled operators are single-GPU in this version (use the stencil operators on a distributed context)");
+    const bool dist = ctx->world > 1;
+    if (dist) {
+        ATK_REQUIRE(format == ATK_FORMAT_SELL, ATK_ERR_INVALID_ARGUMENT, "distributed assembled operators use the SELL format");
+        ATK_REQUIRE(n_rows == n_cols, ATK_ERR_INVALID_ARGUMENT, "distributed assembled operators must be square");
+        if (row_hi < 0) slab_partition(n_rows, ctx->rank, ctx->world, &row_lo, &row_hi);
+    }
     auto* A = new AssembledMatrix();
     try {
         A->ctx = ctx;
@@ -605,6 +708,85 @@ static Operator* build_from_device_csc(Context* ctx, int n_rows, int n_cols, int
         ATK_CUDA_CHECK(cudaGetLastError());
         ATK_CUDA_CHECK(cudaStreamSynchronize(st));
         cudaFree(fill); cudaFree(col_of_pos); cudaFree(pos_of_slot); cudaFree(bad);
+
+        // ---- distributed context: keep rows [row_lo, row_hi) and renumber the columns they reach
+        if (dist) {
+            const int n_loc = row_hi - row_lo;
+            int e0 = 0, e1 = 0;
+            ATK_CUDA_CHECK(cudaMemcpy(&e0, A->row_ptr + row_lo, sizeof(int), cudaMemcpyDeviceToHost));
+            ATK_CUDA_CHECK(cudaMemcpy(&e1, A->row_ptr + row_hi, sizeof(int), cudaMemcpyDeviceToHost));
+            const int64_t nnz_loc = (int64_t)e1 - e0;
+            int* rp = dalloc<int>((size_t)n_loc + 1);
+            int* cl = dalloc<int>((size_t)nnz_loc);
+            double* vl = dalloc<double>((size_t)nnz_loc);
+            int* d_mm = dalloc<int>(2);
+            const int init_mm[2] = {0x7fffffff, -1};
+            int h_mm[2] = {0, -1};
+            try {
+                slice_row_ptr_kernel<<<(n_loc + 1 + 255) / 256, 256, 0, st>>>(n_loc, row_lo, A->row_ptr, rp);
+                if (nnz_loc > 0) {
+                    ATK_CUDA_CHECK(cudaMemcpyAsync(cl, A->csr_col + e0, sizeof(int) * (size_t)nnz_loc, cudaMemcpyDeviceToDevice, st));
+                    ATK_CUDA_CHECK(cudaMemcpyAsync(vl, A->csr_val + e0, sizeof(double) * (size_t)nnz_loc, cudaMemcpyDeviceToDevice, st));
+                }
+                ATK_CUDA_CHECK(cudaMemcpyAsync(d_mm, init_mm, sizeof(init_mm), cudaMemcpyHostToDevice, st));
+                if (nnz_loc > 0) col_range_kernel<<<grid_for(nnz_loc, 256, cap), 256, 0, st>>>(nnz_loc, cl, d_mm);
+                ATK_CUDA_CHECK(cudaMemcpyAsync(h_mm, d_mm, sizeof(h_mm), cudaMemcpyDeviceToHost, st));
+                ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+                count_launch(ctx, 2);
+            } catch (...) {
+                cudaFree(rp); cudaFree(cl); cudaFree(vl); cudaFree(d_mm);
+                throw;
+            }
+            cudaFree(d_mm);
+            cudaFree(A->row_ptr); cudaFree(A->csr_col); cudaFree(A->csr_val);
+            A->row_ptr = rp;
+            A->csr_col = cl;
+            A->csr_val = vl;
+            A->dist = true;
+            A->h_lo = nnz_loc > 0 ? std::max(0, row_lo - h_mm[0]) : 0;
+            A->h_hi = nnz_loc > 0 ? std::max(0, h_mm[1] - (row_hi - 1)) : 0;
+            // every rank learns what its neighbours need, and checks that nobody reaches past an adjacent block
+            struct Need { int h_lo, h_hi, n_loc, pad; } mine{A->h_lo, A->h_hi, n_loc, 0};
+            std::vector<Need> all((size_t)ctx->world);
+            allgather_host_bytes(ctx, &mine, all.data(), sizeof(Need));
+            for (int q = 0; q < ctx->world; ++q) {
+                const bool ok = (q == 0 ? all[q].h_lo == 0 : all[q].h_lo <= all[q - 1].n_loc) &&
+                                (q == ctx->world - 1 ? all[q].h_hi == 0 : all[q].h_hi <= all[q + 1].n_loc);
+                ATK_REQUIRE(ok, ATK_ERR_INVALID_ARGUMENT,
+                            "distributed assembled operator: a row block reaches columns beyond the adjacent rank's block");
+            }
+            A->send_prev = ctx->rank > 0 ? all[(size_t)ctx->rank - 1].h_hi : 0;
+            A->send_next = ctx->rank + 1 < ctx->world ? all[(size_t)ctx->rank + 1].h_lo : 0;
+            A->halo_lo = dalloc<double>((size_t)A->h_lo);
+            A->halo_hi = dalloc<double>((size_t)A->h_hi);
+            A->col_shift = row_lo - A->h_lo;
+            if (nnz_loc > 0 && A->col_shift != 0) {
+                shift_cols_kernel<<<grid_for(nnz_loc, 256, cap), 256, 0, st>>>(nnz_loc, A->col_shift, A->csr_col);
+                count_launch(ctx);
+            }
+            if (n_loc > 0) {
+                int* d_hr = dalloc<int>(2);
+                const int init_hr[2] = {0, n_loc};
+                int h_hr[2] = {0, n_loc};
+                ATK_CUDA_CHECK(cudaMemcpyAsync(d_hr, init_hr, sizeof(init_hr), cudaMemcpyHostToDevice, st));
+                halo_rows_kernel<<<(n_loc + 255) / 256, 256, 0, st>>>(n_loc, A->row_ptr, A->csr_col, A->h_lo, n_loc, d_hr);
+                ATK_CUDA_CHECK(cudaMemcpyAsync(h_hr, d_hr, sizeof(h_hr), cudaMemcpyDeviceToHost, st));
+                ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+                cudaFree(d_hr);
+                count_launch(ctx);
+                const int sa = (h_hr[0] + kSliceRows - 1) / kSliceRows, sb = h_hr[1] / kSliceRows;
+                if (sa < sb) {
+                    A->s_int_begin = sa;
+                    A->s_int_end = sb;
+                }
+            }
+            n_rows = n_loc;
+            nnz = nnz_loc;
+            A->n_rows = n_loc;
+            A->n_rows_local = n_loc;
+            A->row_begin = row_lo;
+            A->nnz = nnz_loc;
+        }
 
         // lanes per row for the CSR-vector kernel: next power of two >= mean row length, in [2,32]
         const double mean = n_rows > 0 ? (double)nnz / n_rows : 0.0;
@@ -652,6 +834,7 @@ static Operator* build_from_device_csc(Context* ctx, int n_rows, int n_cols, int
             // padding above 25 %: sort rows by length inside windows of 1024 rows
             if (nnz > 0 && (double)tw * kSliceRows > 1.25 * (double)nnz && n_rows > kSliceRows) {
                 A->perm = dalloc<int>((size_t)n_rows);
+                A->s_int_begin = A->s_int_end = 0;  // permuted rows: slices no longer map to contiguous row ranges
                 sigma_rank_kernel<<<(n_rows + kSigma - 1) / kSigma, kSigma, 0, st>>>(n_rows, A->row_ptr, A->perm);
                 count_launch(ctx);
                 ATK_CUDA_CHECK(cudaMemsetAsync(A->wscan, 0, sizeof(int) * ((size_t)n_slices + 1), st));
@@ -758,8 +941,21 @@ __global__ void op27_csc_kernel(int nx, int ny, int nz, Coef27 coef, int* __rest
 }
 }  // namespace
 
+// grid operators on a distributed context own whole z-planes, like the matrix-free stencils (same vector partition)
+static int slab_rows_lo(Context* ctx, int nx, int ny, int nz) {
+    int k0 = 0, k1 = 0;
+    ATK_REQUIRE(nz >= ctx->world, ATK_ERR_INVALID_ARGUMENT, "fewer z-planes than ranks");
+    slab_partition(nz, ctx->rank, ctx->world, &k0, &k1);
+    return k0 * nx * ny;
+}
+static int slab_rows_hi(Context* ctx, int nx, int ny, int nz) {
+    int k0 = 0, k1 = 0;
+    slab_partition(nz, ctx->rank, ctx->world, &k0, &k1);
+    return ctx->world > 1 ? k1 * nx * ny : -1;
+}
 template <typename CountK, typename FillK>
-static Operator* assemble_on_device(Context* ctx, int64_t n, atk_format format, CountK count, FillK fill) {
+static Operator* assemble_on_device(Context* ctx, int64_t n, atk_format format, CountK count, FillK fill, int row_lo = 0,
+                                    int row_hi = -1) {
     ATK_REQUIRE(n > 0 && n < (int64_t)0x7fffffff, ATK_ERR_INVALID_ARGUMENT, "grid too large for int32 indices");
     int* d_cp = dalloc<int>((size_t)n + 1);
     int* d_ri = nullptr;
@@ -778,7 +974,7 @@ static Operator* assemble_on_device(Context* ctx, int64_t n, atk_format format, 
         fill(d_cp, d_ri, d_v);
         count_launch(ctx);
         ATK_CUDA_CHECK(cudaGetLastError());
-        op = build_from_device_csc(ctx, (int)n, (int)n, nnz, d_cp, d_ri, d_v, format);
+        op = build_from_device_csc(ctx, (int)n, (int)n, nnz, d_cp, d_ri, d_v, format, row_lo, row_hi);
     } catch (...) {
         cudaFree(d_cp); cudaFree(d_ri); cudaFree(d_v);
         throw;
@@ -796,7 +992,8 @@ Operator* make_poisson_assembled(Context* ctx, int nx, int ny, int nz, double cx
     return assemble_on_device(
         ctx, n, format,
         [&](int* cp) { poisson_csc_kernel<false><<<grid, 256, 0, st>>>(nx, ny, nz, cx, cy, cz, cc, cp, nullptr, nullptr); },
-        [&](int* cp, int* ri, double* v) { poisson_csc_kernel<true><<<grid, 256, 0, st>>>(nx, ny, nz, cx, cy, cz, cc, cp, ri, v); });
+        [&](int* cp, int* ri, double* v) { poisson_csc_kernel<true><<<grid, 256, 0, st>>>(nx, ny, nz, cx, cy, cz, cc, cp, ri, v); },
+        slab_rows_lo(ctx, nx, ny, nz), slab_rows_hi(ctx, nx, ny, nz));
 }
 
 Operator* make_stencil27_assembled(Context* ctx, int nx, int ny, int nz, const double* coef, atk_format format) {
@@ -808,7 +1005,8 @@ Operator* make_stencil27_assembled(Context* ctx, int nx, int ny, int nz, const d
     cudaStream_t st = ctx->stream;
     return assemble_on_device(
         ctx, n, format, [&](int* cp) { op27_csc_kernel<false><<<grid, 256, 0, st>>>(nx, ny, nz, cf, cp, nullptr, nullptr); },
-        [&](int* cp, int* ri, double* v) { op27_csc_kernel<true><<<grid, 256, 0, st>>>(nx, ny, nz, cf, cp, ri, v); });
+        [&](int* cp, int* ri, double* v) { op27_csc_kernel<true><<<grid, 256, 0, st>>>(nx, ny, nz, cf, cp, ri, v); },
+        slab_rows_lo(ctx, nx, ny, nz), slab_rows_hi(ctx, nx, ny, nz));
 }
 
 }  // namespace atk

@@ -333,6 +333,33 @@ def run_ours(args):
             "grid": g, "n_gpus": world, "ms": tsec * 1e3, "algorithmic_bytes": 16.0 * N, "GBs": 16.0 * N / tsec / 1e9,
             "GBs_per_gpu": 16.0 * N / tsec / 1e9 / world, "frac_of_measured_peak_per_gpu": 16.0 * N / tsec / 1e9 / world / peak,
             "note": "aggregate over ranks; includes the halo exchange of every apply"}}
+        # the assembled 256^3 Poisson matrix in SELL-32, partitioned by row blocks (z-slabs), neighbour ranges over NCCL
+        ga = 256
+        ca = synthetic.poisson_coeffs(ga, ga, ga)
+        opa = ctx.operator_poisson_assembled(ga, ga, ga, ca[0], ca[1], ca[2], capi.FORMAT_SELL)
+        nnz_loc = torch.tensor([float(opa.nnz)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(nnz_loc)
+        xs = ctx.vector(np.random.default_rng(rank).standard_normal(opa.n_rows_local))
+        ys = ctx.empty(opa.n_rows_local)
+        for _ in range(3):
+            opa.apply(xs, ys)
+        ctx.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            opa.apply(xs, ys)
+        ctx.synchronize()
+        tt = torch.tensor([(time.perf_counter() - t0) / reps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ta = float(tt.item())
+        alg = 12.0 * float(nnz_loc.item()) + 4.0 * (ga ** 3 + world) + 16.0 * ga ** 3
+        line["extra"]["spmv_sell32_assembled"] = {
+            "grid": ga, "n_gpus": world, "nnz": int(nnz_loc.item()), "ms": ta * 1e3, "algorithmic_bytes": alg, "GBs": alg / ta / 1e9,
+            "GBs_per_gpu": alg / ta / 1e9 / world, "frac_of_measured_peak_per_gpu": alg / ta / 1e9 / world / peak,
+            "note": "row blocks = z-slabs; aggregate over ranks; includes the neighbour exchange of every apply"}
+        xs.free()
+        ys.free()
+        opa.destroy()
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the unmodified reference on a bounded sample
     if world == 1 and not args.no_cpu_baseline:
