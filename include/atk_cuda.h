@@ -109,7 +109,8 @@ int atk_vec_axmy(atk_context_t ctx, int64_t n, const double* x, const double* y,
 /* ------------------------------------------------------------------------------------------------ operators */
 /* SparseMatrixCSC<double> (src/Obj/SparseObj.hpp:22-39): takes the finished CSC arrays (values, row_indices,
  * col_ptr after finalize(), :76-100) and converts them ON THE DEVICE to CSR (stable in column order) and then to
- * the requested format.  `on_device` != 0 means the three arrays are already device pointers.  * On a distributed context (SELL format, square matrices): every rank passes the WHOLE matrix and keeps a balanced block
+ * the requested format.  `on_device` != 0 means the three arrays are already device pointers.
+ * On a distributed context (SELL format, square matrices): every rank passes the WHOLE matrix and keeps a balanced block
  * of rows (atk_operator_row_range tells which; the grid operators below keep whole z-planes); a row block may reach
  * columns of the two adjacent blocks only (ATK_ERR_INVALID_ARGUMENT otherwise); vectors are the local row blocks. */
 int atk_operator_from_csc(atk_context_t ctx, int n_rows, int n_cols, int64_t nnz, const int* col_ptr,
