@@ -309,7 +309,10 @@ def run_ours(args):
 
     # ---- secondary measurements of the same hot path (N=1 only; a few seconds): SpMV GB/s and GMRES restarts/s
     if world == 1 and not args.no_extra:
-        line["extra"] = secondary_measurements(ctx, capi, synthetic, op, g, peak)
+        try:
+            line["extra"] = secondary_measurements(ctx, capi, synthetic, op, g, peak)
+        except Exception as e:  # the headline above must survive a failure of the side measurements
+            line["extra_error"] = f"{type(e).__name__}: {e}"
     elif not args.no_extra:
         # N > 1: the distributed matrix-free SpMV alone (z-slabs, halo planes exchanged over NCCL on the communication
         # stream while the interior planes run); every rank takes part, time = max over ranks, bytes = whole grid
