@@ -328,6 +328,8 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
     const char* env_fused = std::getenv("ATK_CG_FUSED");
     const bool fused = op->fused_cg_capable() && ctx->reduction == ATK_REDUCE_TREE && !(env_fused && env_fused[0] == '0');
     info->fused = fused ? 1 : 0;
+    // small single-GPU systems: the whole loop as one cooperative launch with the vectors in registers
+    const bool onchip = fused && ctx->world == 1 && !info->time_kernels && max_iter > 0 && op->cg_onchip_blocks() > 0;
     // peer-memory mode: every rank must agree (it changes who waits for whom)
     bool peer = false;
     if (fused && ctx->world > 1) {
@@ -444,7 +446,7 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
         // ---- capture one iteration, replay it
         int launches_per_iter = 0;
         const bool use_graph = !info->time_kernels;
-        if (max_iter > 0 && use_graph) {
+        if (max_iter > 0 && use_graph && !onchip) {
             const int64_t l0 = ctx->launches;
             ATK_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             try {
@@ -474,8 +476,9 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
         // ---- run: iterations are enqueued in batches; the exit flag is read back after every batch and examined
         // two batches later (a blocking wait on that batch's event, so every rank of a distributed run takes the
         // same decision after the same batch and enqueues the same number of collectives).
+        if (onchip) op->cg_onchip(d_state, x, r, p, p_alt, max_iter, d_ptrace, d_rtrace);
         constexpr int kBatch = 16, kLag = 2;
-        const int n_batches = (max_iter + kBatch - 1) / kBatch;
+        const int n_batches = onchip ? 0 : (max_iter + kBatch - 1) / kBatch;
         if (n_batches <= kHostFlags) h_done = ctx->h_flags;
         else ATK_CUDA_CHECK(cudaMallocHost(&h_done, sizeof(int) * (size_t)n_batches));
         poll_events.resize(std::max(n_batches, 1), nullptr);
@@ -499,7 +502,7 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
             ATK_CUDA_CHECK(cudaEventCreateWithFlags(&poll_events[bt], cudaEventDisableTiming));
             ATK_CUDA_CHECK(cudaEventRecord(poll_events[bt], st));
         }
-        if (fused) {  // KF: pending x / p updates of the last iteration, or p copied back after an exit
+        if (fused && !onchip) {  // KF: pending x / p updates of the last iteration, or p copied back after an exit
             cg_fused_flush_kernel<<<ctx->reduce_grid(), kReduceBlock, 0, st>>>(n, d_state, ctx->slot(kSlotRR), ctx->world, r, x, p,
                                                                                p_alt, p, ctx->d_tickets + 4, d_rtrace, pk);
             count_launch(ctx);

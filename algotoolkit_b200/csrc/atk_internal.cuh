@@ -172,6 +172,13 @@ struct Operator {
         throw Error(ATK_ERR_INVALID_ARGUMENT, "operator has no fused CG step");
     }
     // peer-memory mode of the fused step (distributed stencil operators on NVLink-connected GPUs)
+    // Whole CG loop in ONE cooperative launch with x, r, p in registers (small single-GPU systems; see atk_stencil.cu).
+    // cg_onchip_blocks: CTAs the launch would use, or 0 when this operator / size is not eligible.
+    virtual int cg_onchip_blocks() const { return 0; }
+    virtual void cg_onchip(CgFusedState*, double* /*x*/, double* /*r*/, double* /*p*/, double* /*p_alt*/, int /*max_iter*/,
+                           double* /*pAp_trace*/, double* /*rs_trace*/) {
+        throw Error(ATK_ERR_INVALID_ARGUMENT, "operator has no on-chip CG loop");
+    }
     virtual bool peer_capable() const { return false; }
     virtual void set_peer_mode(bool) {}
     virtual void peer_r_targets(double** lo, double** hi, int64_t* plane_elems) const { *lo = *hi = nullptr; *plane_elems = 0; }
@@ -316,6 +323,22 @@ __device__ __forceinline__ bool grid_sum_last_block_chained(double v, double* pa
     __threadfence();
     *total = partials_sum<BLOCK>(partials, partial_base + nb);
     return true;
+}
+
+// Software grid barrier for cooperative launches (all CTAs co-resident): `counter` starts at 0 at launch, every CTA keeps
+// its own running `target`.
+__device__ __forceinline__ void coop_grid_barrier(unsigned* counter, unsigned& target) {
+    __syncthreads();
+    if (gridDim.x > 1) {
+        if (threadIdx.x == 0) {
+            target += gridDim.x;
+            __threadfence();
+            atomicAdd(counter, 1u);
+            while (*reinterpret_cast<volatile unsigned*>(counter) < target) {}
+            __threadfence();
+        }
+        __syncthreads();
+    }
 }
 
 // Election without a sum: true in the block that finishes last.

@@ -887,6 +887,135 @@ __global__ void __launch_bounds__(256) pack_halo_kernel(const CgFusedState* st, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------- on-chip CG loop
+// Small systems (up to ~1 M rows on one GPU) are bound by launch and reduction latency, not by HBM: two graph nodes per
+// iteration cost 17-18 us at 32^3 - 64^3.  Here the WHOLE loop of ConjugateGradient.hpp:49-83 is one cooperative launch:
+// every thread keeps its rows of x, r and p in registers for the entire solve, p is mirrored in a ping-pong pair of global
+// buffers (L2-resident at these sizes) for the six neighbours, and the two dot products are grid-wide sums - per-CTA
+// partial, software grid barrier, every CTA adds all partials in the same fixed order, so every thread derives identical
+// alpha, beta and exit decisions.  Three grid barriers per iteration (p.Ap, r.r, visibility of the new p).
+// Per-element arithmetic and its order are the reference's (same tap order, two roundings per multiply-add).
+struct OnchipArgs {
+    StencilGeom g;
+    CgFusedState* st;
+    double* x;
+    double* r;
+    double* p;       // user p: the buffer that holds p on entry and on exit
+    double* p_alt;   // second buffer of the ping-pong pair
+    double* part_a;  // [gridDim.x] partials of p.Ap
+    double* part_b;  // [gridDim.x] partials of r.r
+    unsigned* bar;   // zero at launch
+    int max_iter;
+    double* pAp_trace;
+    double* rs_trace;
+    int64_t n;
+};
+constexpr int kOnchipBlock = 256;
+constexpr int kOnchipRows = 8;
+
+__global__ void __launch_bounds__(kOnchipBlock) cg_onchip_kernel(OnchipArgs a) {
+    CgFusedState* st = a.st;
+    if (st->done) return;  // zero right-hand side: decided by the begin kernel, same for every CTA
+    const StencilGeom g = a.g;
+    const int64_t sxy = (int64_t)g.nx * g.ny;
+    const int64_t c0 = (int64_t)blockIdx.x * kOnchipBlock * kOnchipRows;
+    const unsigned G = gridDim.x;
+    unsigned target = 0;
+    double xr[kOnchipRows], rr[kOnchipRows], pr[kOnchipRows], ap[kOnchipRows];
+    bool in[kOnchipRows], shell[kOnchipRows];
+#pragma unroll
+    for (int q = 0; q < kOnchipRows; ++q) {
+        const int64_t e = c0 + (int64_t)q * kOnchipBlock + threadIdx.x;
+        in[q] = e < a.n;
+        xr[q] = in[q] ? a.x[e] : 0.0;
+        rr[q] = in[q] ? a.r[e] : 0.0;
+        pr[q] = in[q] ? a.p[e] : 0.0;
+        const int64_t ee = in[q] ? e : 0;
+        const int k = (int)(ee / sxy);
+        const int rem = (int)(ee - (int64_t)k * sxy);
+        const int j = rem / g.nx, i = rem - j * g.nx;
+        shell[q] = i == 0 || i == g.nx - 1 || j == 0 || j == g.ny - 1 || k == 0 || k == g.nz - 1;
+    }
+    double* pcur = a.p;
+    double* pnext = a.p_alt;
+    double rs_old = st->rs_old;
+    int it = 0;
+    bool stopped = false;
+    double last_pAp = 0.0;
+    while (it < a.max_iter) {
+        // Ap = A p   (:50): own value from the register, the six neighbours from the mirror (written before the last barrier)
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < kOnchipRows; ++q) {
+            const int64_t e = c0 + (int64_t)q * kOnchipBlock + threadIdx.x;
+            double v = 0.0;
+            if (in[q]) {
+                if (shell[q]) {
+                    v = shell_row(pr[q]);
+                } else {
+                    v = tap7(g, __ldcg(pcur + e - sxy), __ldcg(pcur + e - g.nx), __ldcg(pcur + e - 1), pr[q], __ldcg(pcur + e + 1),
+                             __ldcg(pcur + e + g.nx), __ldcg(pcur + e + sxy));
+                }
+            }
+            ap[q] = v;
+            acc = add_rn(acc, mul_rn(pr[q], v));
+        }
+        const double bs = block_sum<kOnchipBlock>(acc);
+        if (threadIdx.x == 0) __stcg(a.part_a + blockIdx.x, bs);
+        coop_grid_barrier(a.bar, target);
+        const double pAp = partials_sum<kOnchipBlock>(a.part_a, G);  // :51
+        last_pAp = pAp;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && a.pAp_trace && it < st->trace_cap) a.pAp_trace[it] = pAp;
+        if (fabs(pAp) < 1e-12) {  // :53-57 - x, r, p stay as they are
+            stopped = true;
+            break;
+        }
+        const double alpha = __ddiv_rn(rs_old, pAp);  // :58
+        double acc2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < kOnchipRows; ++q) {
+            xr[q] = add_rn(xr[q], mul_rn(pr[q], alpha));  // :60
+            rr[q] = sub_rn(rr[q], mul_rn(ap[q], alpha));  // :61
+            acc2 = add_rn(acc2, mul_rn(rr[q], rr[q]));
+        }
+        const double bs2 = block_sum<kOnchipBlock>(acc2);
+        if (threadIdx.x == 0) __stcg(a.part_b + blockIdx.x, bs2);
+        coop_grid_barrier(a.bar, target);
+        const double rs_new = partials_sum<kOnchipBlock>(a.part_b, G);  // :63
+        const double beta = __ddiv_rn(rs_new, rs_old);
+#pragma unroll
+        for (int q = 0; q < kOnchipRows; ++q) {
+            const int64_t e = c0 + (int64_t)q * kOnchipBlock + threadIdx.x;
+            pr[q] = add_rn(rr[q], mul_rn(pr[q], beta));  // :79
+            if (in[q]) __stcg(pnext + e, pr[q]);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0 && a.rs_trace && it < st->trace_cap) a.rs_trace[it] = rs_new;
+        rs_old = rs_new;  // :80
+        ++it;
+        coop_grid_barrier(a.bar, target);  // the new p is visible to every CTA
+        double* tmp = pcur;
+        pcur = pnext;
+        pnext = tmp;
+    }
+#pragma unroll
+    for (int q = 0; q < kOnchipRows; ++q) {
+        const int64_t e = c0 + (int64_t)q * kOnchipBlock + threadIdx.x;
+        if (in[q]) {
+            a.x[e] = xr[q];
+            a.r[e] = rr[q];
+            if (pcur != a.p) a.p[e] = pr[q];  // leave p where the caller expects it
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->it = it;
+        st->rs_old = rs_old;
+        st->last_pAp = last_pAp;
+        st->stopped_on_pAp = stopped ? 1 : 0;
+        st->first = 0;
+        st->done = stopped ? 1 : 0;
+    }
+}
+
 template <int TX, int TY>
 constexpr size_t fused_smem_bytes() { return (size_t)2 * 4 * (TY + 2) * (2 * TX + 4) * sizeof(double) + kRingShift * sizeof(double); }
 template <int TX, int TY>
@@ -915,6 +1044,7 @@ struct Stencil7 : public Operator {
     bool arena_exported = false;
 
     ~Stencil7() override {
+        cudaFree(oc_part);
         cudaFree(halo_lo);
         cudaFree(halo_hi);
         cudaFree(fsend);
@@ -935,6 +1065,37 @@ struct Stencil7 : public Operator {
     }
 
     bool fused_cg_capable() const override { return true; }
+    // ---- on-chip CG loop (single GPU, every CTA co-resident)
+    double* oc_part = nullptr;  // [2 * oc_blocks] partial sums, then the barrier counter
+    int oc_blocks = -1;         // -1: not evaluated yet, 0: not eligible
+    int cg_onchip_blocks() const override {
+        auto* self = const_cast<Stencil7*>(this);
+        if (self->oc_blocks >= 0) return self->oc_blocks;
+        self->oc_blocks = 0;
+        const char* env = std::getenv("ATK_CG_ONCHIP");
+        if (ctx->world != 1 || (env && env[0] == '0')) return 0;
+        const int64_t rows_per_cta = (int64_t)kOnchipBlock * kOnchipRows;
+        const int64_t blocks = (n_rows_local + rows_per_cta - 1) / rows_per_cta;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_onchip_kernel, kOnchipBlock, 0) != cudaSuccess) return 0;
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        if (!coop || blocks < 1 || blocks > (int64_t)per_sm * ctx->sm_count) return 0;
+        if (cudaMalloc(&self->oc_part, sizeof(double) * (2 * (size_t)blocks + 2)) != cudaSuccess) return 0;
+        self->oc_blocks = (int)blocks;
+        return self->oc_blocks;
+    }
+    void cg_onchip(CgFusedState* st, double* x, double* r, double* p, double* p_alt, int max_iter, double* pAp_trace,
+                   double* rs_trace) override {
+        ATK_REQUIRE(oc_blocks > 0, ATK_ERR_INVALID_ARGUMENT, "on-chip CG not available for this operator");
+        unsigned* bar = reinterpret_cast<unsigned*>(oc_part + 2 * (size_t)oc_blocks);
+        ATK_CUDA_CHECK(cudaMemsetAsync(bar, 0, sizeof(unsigned), ctx->stream));
+        OnchipArgs oa{g, st, x, r, p, p_alt, oc_part, oc_part + oc_blocks, bar, max_iter, pAp_trace, rs_trace, n_rows_local};
+        void* kargs[] = {&oa};
+        ATK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)cg_onchip_kernel, dim3((unsigned)oc_blocks), dim3(kOnchipBlock), kargs, 0,
+                                                   ctx->stream));
+        count_launch(ctx);
+    }
     bool peer_mode = false;  // set by the CG driver for the duration of a solve (all ranks agree)
 
     // peer mode helpers for the CG driver
