@@ -204,6 +204,14 @@ def test_op27_matrix_free_bit_exact(ctx, port, dims):
 
 
 # ------------------------------------------------------------------------------------------------ ConjugateGrad
+@pytest.fixture(params=["onchip", "graph"])
+def cg_loop(request, monkeypatch):
+    """Small grids can run the CG loop two ways: one cooperative launch with the vectors on chip (default), or the fused
+    two-kernel iteration replayed from a CUDA graph (what large grids use).  Tests taking this fixture cover both."""
+    monkeypatch.setenv("ATK_CG_ONCHIP", "1" if request.param == "onchip" else "0")
+    return request.param
+
+
 def test_cg_kats(ctx, port, golden):
     k = golden["kat"]["cg_tridiag3"]  # tests/ConjugateGradient_test.cpp:67-76
     A = port.csc_from_triplets(3, 3, k["rows"], k["cols"], k["vals"])
@@ -229,7 +237,7 @@ def test_cg_kats(ctx, port, golden):
 
 
 @pytest.mark.parametrize("n", [8, 16, 32])
-def test_poisson_readme_case(ctx, port, golden, n):
+def test_poisson_readme_case(ctx, port, golden, n, cg_loop):
     """README / code/PDE.ipynb: RHS is an eigenvector of the discrete operator -> exactly 1 CG iteration."""
     g = golden["poisson_readme"][str(n)]
     b = port.poisson_rhs(n, n, n, rhs_kind=0)
@@ -248,7 +256,7 @@ def test_poisson_readme_case(ctx, port, golden, n):
 
 
 @pytest.mark.parametrize("n,kind", [(12, "stencil"), (32, "stencil"), (32, "sell"), (32, "csrv"), (64, "stencil")])
-def test_poisson_cg_to_exit(ctx, port, golden, n, kind):
+def test_poisson_cg_to_exit(ctx, port, golden, n, kind, cg_loop):
     """RHS-R run until |p.Ap| < 1e-12 fires: iteration count +-2, x / r within 1e-10 relative of the reference."""
     g = golden["poisson_rhsr"][str(n)]
     b = port.poisson_rhs(n, n, n, rhs_kind=1, seed=12345)
@@ -274,7 +282,7 @@ def test_poisson_cg_to_exit(ctx, port, golden, n, kind):
 
 
 @pytest.mark.parametrize("dims", [(13, 11, 9), (6, 30, 7), (34, 5, 12)])
-def test_poisson_cg_ragged_grids(ctx, port, dims):
+def test_poisson_cg_ragged_grids(ctx, port, dims, cg_loop):
     """Odd / non-tile-multiple grids: the fused step falls back to its L1 variant for odd nx, partial tiles everywhere."""
     nx, ny, nz = dims
     cx, cy, cz, _ = port.poisson_coeffs(nx, ny, nz, 1.0, 2.0, 0.5)
@@ -300,7 +308,7 @@ def test_cg_sequential_mode_is_bit_exact(ctx, port, golden):
         ctx.set_reduction(capi.REDUCE_TREE)
 
 
-def test_cg_fixed_work_and_continuation(ctx, port, golden):
+def test_cg_fixed_work_and_continuation(ctx, port, golden, cg_loop):
     """maxIter iterations exactly (no tolerance test in the reference); a second solve continues from x, r, p."""
     n = 32
     b = port.poisson_rhs(n, n, n, rhs_kind=1, seed=12345)
@@ -316,7 +324,7 @@ def test_cg_fixed_work_and_continuation(ctx, port, golden):
     assert relerr(bb["x"], ora2["x"]) < REL and relerr(bb["x"], r50["x"]) < REL
 
 
-def test_cg_resident_device_api(ctx, port):
+def test_cg_resident_device_api(ctx, port, cg_loop):
     n = 16
     b = port.poisson_rhs(n, n, n, rhs_kind=1, seed=12345)
     cx, cy, cz, _ = port.poisson_coeffs(n, n, n)
