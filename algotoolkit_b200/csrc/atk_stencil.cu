@@ -893,7 +893,9 @@ __global__ void __launch_bounds__(256) pack_halo_kernel(const CgFusedState* st, 
 // every thread keeps its rows of x, r and p in registers for the entire solve, p is mirrored in a ping-pong pair of global
 // buffers (L2-resident at these sizes) for the six neighbours, and the two dot products are grid-wide sums - per-CTA
 // partial, software grid barrier, every CTA adds all partials in the same fixed order, so every thread derives identical
-// alpha, beta and exit decisions.  Three grid barriers per iteration (p.Ap, r.r, visibility of the new p).
+// alpha, beta and exit decisions.  Two grid barriers per iteration (p.Ap, r.r).  (Publishing the partials as tagged words
+// that every CTA polls - the peer-memory protocol - was tried instead of barrier + read: faster with 2 CTAs, 1.5-2x slower
+// from 64 CTAs up, the polls being quadratic in the CTA count.)
 // Per-element arithmetic and its order are the reference's (same tap order, two roundings per multiply-add).
 struct OnchipArgs {
     StencilGeom g;
@@ -936,25 +938,37 @@ __global__ void __launch_bounds__(kOnchipBlock) cg_onchip_kernel(OnchipArgs a) {
         const int j = rem / g.nx, i = rem - j * g.nx;
         shell[q] = i == 0 || i == g.nx - 1 || j == 0 || j == g.ny - 1 || k == 0 || k == g.nz - 1;
     }
-    double* pcur = a.p;
-    double* pnext = a.p_alt;
+    // Mirrors for the neighbours: r in the caller's r array, p in a ping-pong pair.  Iteration i forms p_i = r_i + beta_i *
+    // p_(i-1) for its own rows AND, from the mirrors of r_i and p_(i-1), for the six neighbours of each row (one
+    // multiply-add each, the very expression the owner evaluates), so the new p needs no barrier of its own: what it is
+    // built from was complete before the r.r barrier of the previous iteration.  Two grid barriers per iteration.
+    double* pm_prev = a.p;     // holds p_(i-1) of every row (iteration 0: the incoming p itself)
+    double* pm_cur = a.p_alt;  // receives this iteration's own p_i
     double rs_old = st->rs_old;
+    double beta = 0.0;
     int it = 0;
     bool stopped = false;
     double last_pAp = 0.0;
     while (it < a.max_iter) {
-        // Ap = A p   (:50): own value from the register, the six neighbours from the mirror (written before the last barrier)
+        const bool first = it == 0;
         double acc = 0.0;
 #pragma unroll
         for (int q = 0; q < kOnchipRows; ++q) {
             const int64_t e = c0 + (int64_t)q * kOnchipBlock + threadIdx.x;
+            if (!first) {  // p = r + p*beta of the previous iteration (:79)
+                pr[q] = add_rn(rr[q], mul_rn(pr[q], beta));
+                if (in[q]) __stcg(pm_cur + e, pr[q]);
+            }
             double v = 0.0;
             if (in[q]) {
                 if (shell[q]) {
                     v = shell_row(pr[q]);
                 } else {
-                    v = tap7(g, __ldcg(pcur + e - sxy), __ldcg(pcur + e - g.nx), __ldcg(pcur + e - 1), pr[q], __ldcg(pcur + e + 1),
-                             __ldcg(pcur + e + g.nx), __ldcg(pcur + e + sxy));
+                    auto nb = [&](int64_t o) -> double {
+                        const double pv = __ldcg(pm_prev + e + o);
+                        return first ? pv : add_rn(__ldcg(a.r + e + o), mul_rn(pv, beta));
+                    };
+                    v = tap7(g, nb(-sxy), nb(-(int64_t)g.nx), nb(-1), pr[q], nb(1), nb(g.nx), nb(sxy));  // Ap = A p (:50)
                 }
             }
             ap[q] = v;
@@ -966,7 +980,12 @@ __global__ void __launch_bounds__(kOnchipBlock) cg_onchip_kernel(OnchipArgs a) {
         const double pAp = partials_sum<kOnchipBlock>(a.part_a, G);  // :51
         last_pAp = pAp;
         if (blockIdx.x == 0 && threadIdx.x == 0 && a.pAp_trace && it < st->trace_cap) a.pAp_trace[it] = pAp;
-        if (fabs(pAp) < 1e-12) {  // :53-57 - x, r, p stay as they are
+        if (!first) {  // the mirror written above is complete: it is the "previous p" of the next iteration
+            double* tmp = pm_prev;
+            pm_prev = pm_cur;
+            pm_cur = tmp;
+        }
+        if (fabs(pAp) < 1e-12) {  // :53-57 - x and r stay as they are; p keeps the value formed for this iteration
             stopped = true;
             break;
         }
@@ -974,36 +993,30 @@ __global__ void __launch_bounds__(kOnchipBlock) cg_onchip_kernel(OnchipArgs a) {
         double acc2 = 0.0;
 #pragma unroll
         for (int q = 0; q < kOnchipRows; ++q) {
+            const int64_t e = c0 + (int64_t)q * kOnchipBlock + threadIdx.x;
             xr[q] = add_rn(xr[q], mul_rn(pr[q], alpha));  // :60
             rr[q] = sub_rn(rr[q], mul_rn(ap[q], alpha));  // :61
+            if (in[q]) __stcg(a.r + e, rr[q]);
             acc2 = add_rn(acc2, mul_rn(rr[q], rr[q]));
         }
         const double bs2 = block_sum<kOnchipBlock>(acc2);
         if (threadIdx.x == 0) __stcg(a.part_b + blockIdx.x, bs2);
         coop_grid_barrier(a.bar, target);
         const double rs_new = partials_sum<kOnchipBlock>(a.part_b, G);  // :63
-        const double beta = __ddiv_rn(rs_new, rs_old);
-#pragma unroll
-        for (int q = 0; q < kOnchipRows; ++q) {
-            const int64_t e = c0 + (int64_t)q * kOnchipBlock + threadIdx.x;
-            pr[q] = add_rn(rr[q], mul_rn(pr[q], beta));  // :79
-            if (in[q]) __stcg(pnext + e, pr[q]);
-        }
+        beta = __ddiv_rn(rs_new, rs_old);
         if (blockIdx.x == 0 && threadIdx.x == 0 && a.rs_trace && it < st->trace_cap) a.rs_trace[it] = rs_new;
         rs_old = rs_new;  // :80
         ++it;
-        coop_grid_barrier(a.bar, target);  // the new p is visible to every CTA
-        double* tmp = pcur;
-        pcur = pnext;
-        pnext = tmp;
     }
 #pragma unroll
     for (int q = 0; q < kOnchipRows; ++q) {
         const int64_t e = c0 + (int64_t)q * kOnchipBlock + threadIdx.x;
         if (in[q]) {
+            // a completed iteration still owes its p update (:79); after a |pAp| stop p is already what it must be
+            if (!stopped && it > 0) pr[q] = add_rn(rr[q], mul_rn(pr[q], beta));
             a.x[e] = xr[q];
             a.r[e] = rr[q];
-            if (pcur != a.p) a.p[e] = pr[q];  // leave p where the caller expects it
+            a.p[e] = pr[q];
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1015,7 +1028,6 @@ __global__ void __launch_bounds__(kOnchipBlock) cg_onchip_kernel(OnchipArgs a) {
         st->done = stopped ? 1 : 0;
     }
 }
-
 template <int TX, int TY>
 constexpr size_t fused_smem_bytes() { return (size_t)2 * 4 * (TY + 2) * (2 * TX + 4) * sizeof(double) + kRingShift * sizeof(double); }
 template <int TX, int TY>
