@@ -893,7 +893,7 @@ __device__ __forceinline__ bool on_shell(int i, int j, int k, int nx, int ny, in
 }
 template <bool FILL>
 __global__ void poisson_csc_kernel(int nx, int ny, int nz, double cx, double cy, double cz, double cc, int* __restrict__ col_ptr,
-                                   int* __restrict__ row_idx, double* __restrict__ vals) {
+                                   int* __restrict__ row_idx, double* __restrict__ vals, int64_t r_lo, int64_t r_hi) {
     const int64_t n = (int64_t)nx * ny * nz;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
@@ -901,6 +901,7 @@ __global__ void poisson_csc_kernel(int nx, int ny, int nz, double cx, double cy,
     const int64_t sxy = (int64_t)nx * ny;
     int p = FILL ? col_ptr[c] : 0;
     auto emit = [&](int64_t row, double v) {
+        if (row < r_lo || row >= r_hi) return;  // a distributed context assembles only the rows it owns
         if (FILL) { row_idx[p] = (int)row; vals[p] = v; }
         ++p;
     };
@@ -917,7 +918,7 @@ __global__ void poisson_csc_kernel(int nx, int ny, int nz, double cx, double cy,
 struct Coef27 { double v[27]; };
 template <bool FILL>
 __global__ void op27_csc_kernel(int nx, int ny, int nz, Coef27 coef, int* __restrict__ col_ptr, int* __restrict__ row_idx,
-                                double* __restrict__ vals) {
+                                double* __restrict__ vals, int64_t r_lo, int64_t r_hi) {
     const int64_t n = (int64_t)nx * ny * nz;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
@@ -931,8 +932,10 @@ __global__ void op27_csc_kernel(int nx, int ny, int nz, Coef27 coef, int* __rest
                 if (ir < 0 || ir >= nx || jr < 0 || jr >= ny || kr < 0 || kr >= nz) continue;
                 const double v = coef.v[(dk + 1) * 9 + (dj + 1) * 3 + (di + 1)];
                 if (v == 0.0) continue;  // addValue never stores an explicit zero (SparseObj.hpp:71-73)
+                const int64_t row = ir + (int64_t)jr * nx + (int64_t)kr * sxy;
+                if (row < r_lo || row >= r_hi) continue;  // a distributed context assembles only the rows it owns
                 if (FILL) {
-                    row_idx[p] = (int)(ir + (int64_t)jr * nx + (int64_t)kr * sxy);
+                    row_idx[p] = (int)row;
                     vals[p] = v;
                 }
                 ++p;
@@ -989,11 +992,15 @@ Operator* make_poisson_assembled(Context* ctx, int nx, int ny, int nz, double cx
     const double cc = -2.0 * (cx + cy + cz);  // Poisson.hpp:57
     const unsigned grid = (unsigned)((n + 255) / 256);
     cudaStream_t st = ctx->stream;
+    const int row_lo = slab_rows_lo(ctx, nx, ny, nz), row_hi = slab_rows_hi(ctx, nx, ny, nz);
+    const int64_t r_lo = row_hi < 0 ? 0 : row_lo, r_hi = row_hi < 0 ? n : row_hi;
     return assemble_on_device(
         ctx, n, format,
-        [&](int* cp) { poisson_csc_kernel<false><<<grid, 256, 0, st>>>(nx, ny, nz, cx, cy, cz, cc, cp, nullptr, nullptr); },
-        [&](int* cp, int* ri, double* v) { poisson_csc_kernel<true><<<grid, 256, 0, st>>>(nx, ny, nz, cx, cy, cz, cc, cp, ri, v); },
-        slab_rows_lo(ctx, nx, ny, nz), slab_rows_hi(ctx, nx, ny, nz));
+        [&](int* cp) { poisson_csc_kernel<false><<<grid, 256, 0, st>>>(nx, ny, nz, cx, cy, cz, cc, cp, nullptr, nullptr, r_lo, r_hi); },
+        [&](int* cp, int* ri, double* v) {
+            poisson_csc_kernel<true><<<grid, 256, 0, st>>>(nx, ny, nz, cx, cy, cz, cc, cp, ri, v, r_lo, r_hi);
+        },
+        row_lo, row_hi);
 }
 
 Operator* make_stencil27_assembled(Context* ctx, int nx, int ny, int nz, const double* coef, atk_format format) {
@@ -1003,10 +1010,13 @@ Operator* make_stencil27_assembled(Context* ctx, int nx, int ny, int nz, const d
     for (int t = 0; t < 27; ++t) cf.v[t] = coef[t];
     const unsigned grid = (unsigned)((n + 255) / 256);
     cudaStream_t st = ctx->stream;
+    const int row_lo = slab_rows_lo(ctx, nx, ny, nz), row_hi = slab_rows_hi(ctx, nx, ny, nz);
+    const int64_t r_lo = row_hi < 0 ? 0 : row_lo, r_hi = row_hi < 0 ? n : row_hi;
     return assemble_on_device(
-        ctx, n, format, [&](int* cp) { op27_csc_kernel<false><<<grid, 256, 0, st>>>(nx, ny, nz, cf, cp, nullptr, nullptr); },
-        [&](int* cp, int* ri, double* v) { op27_csc_kernel<true><<<grid, 256, 0, st>>>(nx, ny, nz, cf, cp, ri, v); },
-        slab_rows_lo(ctx, nx, ny, nz), slab_rows_hi(ctx, nx, ny, nz));
+        ctx, n, format,
+        [&](int* cp) { op27_csc_kernel<false><<<grid, 256, 0, st>>>(nx, ny, nz, cf, cp, nullptr, nullptr, r_lo, r_hi); },
+        [&](int* cp, int* ri, double* v) { op27_csc_kernel<true><<<grid, 256, 0, st>>>(nx, ny, nz, cf, cp, ri, v, r_lo, r_hi); },
+        row_lo, row_hi);
 }
 
 }  // namespace atk
