@@ -93,3 +93,32 @@ def test_fastsolver_module_builds_and_imports():
     assert v[1] == 2.5 and v.size() == 4
     with pytest.raises(IndexError):
         v[4]
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """The drop-in boundary is a C ABI: include/atk_cuda.h must compile as C99 (no C++ in the signatures) and a C
+    program must link against libatk_cuda.so and get a clean status without a device (no compute)."""
+    import subprocess
+
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "atk_cuda.h"\n'
+        "int main(void) {\n"
+        "    atk_context_t ctx = 0;\n"
+        "    int k0 = -1, k1 = -1;\n"
+        "    if (atk_abi_version() != ATK_ABI_VERSION) return 2;\n"
+        "    if (atk_slab_partition(10, 1, 3, &k0, &k1) != ATK_OK || k0 >= k1) return 3;\n"
+        "    int rc = atk_context_create(0, &ctx);\n"
+        '    printf("%d %s\\n", rc, rc == ATK_OK ? "device" : atk_last_error());\n'
+        "    if (rc == ATK_OK) atk_context_destroy(ctx);\n"
+        "    return 0;\n}\n")
+    exe = tmp_path / "abi.bin"
+    lib_dir = os.path.join(ROOT, "algotoolkit_b200")
+    cmd = ["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o",
+           str(exe), "-L", lib_dir, "-latk_cuda", "-Wl,-rpath," + lib_dir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    status = int(r.stdout.split()[0])
+    assert status in (0, 4), r.stdout  # ATK_OK on a GPU box, ATK_ERR_CUDA without a device - never a crash, never a CPU path
