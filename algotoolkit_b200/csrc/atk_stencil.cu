@@ -1370,7 +1370,9 @@ __global__ void __launch_bounds__(256) stencil27_kernel(StencilGeom g, Coef27 cf
     }
 }
 
-template <int TX, int TY>
+// DENSE: all 27 coefficients are non-zero (the config-5 operator), so the per-tap zero tests are compiled out - the kernel
+// is issue-bound (ncu: 79 % issue-active, FP64 pipe 50 %).
+template <int TX, int TY, bool DENSE>
 __global__ void __launch_bounds__(TX* TY) stencil27_smem_kernel(StencilGeom g, Coef27 cf, const double* __restrict__ x,
                                                                  double* __restrict__ y, const double* __restrict__ halo_lo,
                                                                  const double* __restrict__ halo_hi, int k_lo, int k_hi, int kc) {
@@ -1451,7 +1453,7 @@ __global__ void __launch_bounds__(TX* TY) stencil27_smem_kernel(StencilGeom g, C
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 const double c = cf.v[dk * 9 + r * 3 + d];
-                if (c != 0.0) {  // uniform: zero coefficients are not stored by the assembled form
+                if (DENSE || c != 0.0) {  // uniform: zero coefficients are not stored by the assembled form
                     acc0 = add_rn(acc0, mul_rn(c, n.v[r][d]));
                     acc1 = add_rn(acc1, mul_rn(c, n.v[r][d + 1]));
                 }
@@ -1518,7 +1520,14 @@ struct Stencil27 : public Operator {
             while (kcc > 8 && (int64_t)tiles * ((k_hi - k_lo + kcc - 1) / kcc) < (int64_t)ctx->sm_count * 8) kcc = (kcc + 1) / 2;
             dim3 grid((g.nx + 2 * TX - 1) / (2 * TX), (g.ny + TY - 1) / TY, (k_hi - k_lo + kcc - 1) / kcc);
             constexpr size_t smem = (size_t)4 * (TY + 2) * (2 * TX + 4) * sizeof(double) + kRingShift * sizeof(double);
-            stencil27_smem_kernel<TX, TY><<<grid, dim3(TX, TY, 1), smem, ctx->stream>>>(g, cf, x, y, halo_lo, halo_hi, k_lo, k_hi, kcc);
+            bool dense = true;
+            for (int t = 0; t < 27; ++t) dense = dense && cf.v[t] != 0.0;
+            if (dense)
+                stencil27_smem_kernel<TX, TY, true><<<grid, dim3(TX, TY, 1), smem, ctx->stream>>>(g, cf, x, y, halo_lo, halo_hi, k_lo,
+                                                                                                  k_hi, kcc);
+            else
+                stencil27_smem_kernel<TX, TY, false><<<grid, dim3(TX, TY, 1), smem, ctx->stream>>>(g, cf, x, y, halo_lo, halo_hi, k_lo,
+                                                                                                   k_hi, kcc);
         } else {
             dim3 block(32, 8, 1);
             dim3 grid((g.nx + 31) / 32, (g.ny + 7) / 8, std::min(k_hi - k_lo, 64));
