@@ -15,6 +15,8 @@ iterations/s is a like-for-like unit.  The 512^3 total is fixed for every N ("st
   e2e     the same solve through the reference-facing C-ABI call with HOST buffers (atk_cg_solve_host): pinned b is
           uploaded, K iterations run, x is downloaded; wall clock around the call, max over ranks.
   roofline  per-kernel CUDA-event times from a second run of the same loop launched kernel by kernel.
+  extra   side measurements of the same hot path: at N = 1 SpMV GB/s (matrix-free stencil, SELL-32, CSR-stream) and
+          GMRES(300) on bcsstk08; at N > 1 the distributed SpMV alone (matrix-free and assembled SELL-32), aggregate.
 
 --impl reference times the reference's own CPU implementation (oracle/_ref, the unmodified headers; or the C port
 when that library is absent) on a bounded sample of the same workload and prints the same JSON line.
