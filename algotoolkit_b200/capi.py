@@ -53,7 +53,8 @@ def _raise(code, msg):
 class CgInfo(C.Structure):
     _fields_ = [("iterations", C.c_int), ("stopped_on_pAp", C.c_int), ("zero_rhs", C.c_int), ("last_pAp", C.c_double),
                 ("rs", C.c_double), ("device_ms", C.c_float), ("kernel_launches", C.c_int), ("pAp_trace", _dp),
-                ("rs_trace", _dp), ("trace_capacity", C.c_int), ("time_kernels", C.c_int), ("kernel_ms", C.c_float * 3), ("fused", C.c_int), ("peer", C.c_int)]
+                ("rs_trace", _dp), ("trace_capacity", C.c_int), ("time_kernels", C.c_int), ("kernel_ms", C.c_float * 3), ("fused", C.c_int), ("peer", C.c_int),
+                ("persistent", C.c_int), ("h2d_ms", C.c_float), ("solve_ms", C.c_float), ("d2h_ms", C.c_float)]
 
 
 class GmresInfo(C.Structure):
@@ -74,7 +75,7 @@ EXPORTS = [
     "atk_abi_version", "atk_last_error", "atk_device_count", "atk_context_create", "atk_nccl_unique_id",
     "atk_context_create_distributed", "atk_context_destroy", "atk_context_rank", "atk_context_set_reduction",
     "atk_context_synchronize", "atk_context_launch_count", "atk_malloc", "atk_free", "atk_memcpy_h2d", "atk_memcpy_d2h",
-    "atk_memcpy_d2d", "atk_memset_zero", "atk_host_alloc", "atk_host_free", "atk_dot", "atk_nrm2", "atk_vec_scale",
+    "atk_memcpy_d2d", "atk_memset_zero", "atk_host_alloc", "atk_host_free", "atk_host_numa_node", "atk_dot", "atk_nrm2", "atk_vec_scale",
     "atk_vec_div", "atk_vec_add", "atk_vec_sub", "atk_vec_axpy", "atk_vec_axmy", "atk_operator_from_csc",
     "atk_operator_stencil7", "atk_operator_poisson_assembled", "atk_operator_stencil27", "atk_operator_stencil27_assembled", "atk_slab_partition",
     "atk_operator_destroy",
@@ -116,6 +117,7 @@ def load():
         "atk_memset_zero": [_vp, _vp, C.c_size_t],
         "atk_host_alloc": [C.c_size_t, C.POINTER(_vp)],
         "atk_host_free": [_vp],
+        "atk_host_numa_node": [_vp, _ip, _ip],
         "atk_dot": [_vp, i64, _vp, _vp, _dp],
         "atk_nrm2": [_vp, i64, _vp, _dp],
         "atk_vec_scale": [_vp, i64, _vp, C.c_double, _vp],
@@ -531,4 +533,5 @@ def arnoldi_host(ctx: Context, op: Operator, q0, m: int, tol: float):
 def _cg_result(info, tp, tr):
     return dict(iters=info.iterations, stopped_on_pAp=bool(info.stopped_on_pAp), zero_rhs=bool(info.zero_rhs),
                 last_pAp=info.last_pAp, rs=info.rs, device_ms=info.device_ms, kernel_launches=info.kernel_launches,
-                pAp_trace=tp, rs_trace=tr, kernel_ms=list(info.kernel_ms), fused=bool(info.fused), peer=bool(info.peer))
+                pAp_trace=tp, rs_trace=tr, kernel_ms=list(info.kernel_ms), fused=bool(info.fused), peer=bool(info.peer),
+                persistent=bool(info.persistent), h2d_ms=info.h2d_ms, solve_ms=info.solve_ms, d2h_ms=info.d2h_ms)

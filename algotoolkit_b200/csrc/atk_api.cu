@@ -173,11 +173,14 @@ int atk_memset_zero(atk_context_t ctx, void* dptr, size_t bytes) {
 int atk_host_alloc(size_t bytes, void** hptr) {
     return guarded([&] {
         ATK_REQUIRE(hptr, ATK_ERR_INVALID_ARGUMENT, "null pointer");
-        ATK_CUDA_CHECK(cudaMallocHost(hptr, bytes ? bytes : 8));
+        *hptr = atk::host_alloc_pinned(bytes ? bytes : 8);
     });
 }
 int atk_host_free(void* hptr) {
-    return guarded([&] { ATK_CUDA_CHECK(cudaFreeHost(hptr)); });
+    return guarded([&] { atk::host_free_pinned(hptr); });
+}
+int atk_host_numa_node(const void* hptr, int* buffer_node, int* device_node) {
+    return guarded([&] { atk::host_numa_query(hptr, buffer_node, device_node); });
 }
 
 // ------------------------------------------------------------------------------------------------ vectors
@@ -333,6 +336,7 @@ int atk_cg_solve_host(atk_context_t ctx, atk_operator_t op, const double* b, dou
         auto release = [&] { for (auto* q : d) if (q) c->ws_release(q); };
         try {
             for (auto& q : d) q = static_cast<double*>(c->ws_alloc(bytes ? bytes : 8));
+            ATK_CUDA_CHECK(cudaEventRecord(c->ev_h0, c->stream));
             ATK_CUDA_CHECK(cudaMemcpyAsync(d[0], b, bytes, cudaMemcpyHostToDevice, c->stream));
             if (fresh) {  // what the ctor leaves: x = 0, r = b - A*0 = b, p = r  (ConjugateGradient.hpp:26-30)
                 ATK_CUDA_CHECK(cudaMemsetAsync(d[1], 0, bytes, c->stream));
@@ -343,11 +347,18 @@ int atk_cg_solve_host(atk_context_t ctx, atk_operator_t op, const double* b, dou
                 ATK_CUDA_CHECK(cudaMemcpyAsync(d[2], r, bytes, cudaMemcpyHostToDevice, c->stream));
                 ATK_CUDA_CHECK(cudaMemcpyAsync(d[3], p, bytes, cudaMemcpyHostToDevice, c->stream));
             }
+            ATK_CUDA_CHECK(cudaEventRecord(c->ev_h1, c->stream));
             atk::cg_solve(c, o, d[0], d[1], d[2], d[3], max_iter, info);
+            ATK_CUDA_CHECK(cudaEventRecord(c->ev_h2, c->stream));
             ATK_CUDA_CHECK(cudaMemcpyAsync(x, d[1], bytes, cudaMemcpyDeviceToHost, c->stream));
             if (r) ATK_CUDA_CHECK(cudaMemcpyAsync(r, d[2], bytes, cudaMemcpyDeviceToHost, c->stream));
             if (p) ATK_CUDA_CHECK(cudaMemcpyAsync(p, d[3], bytes, cudaMemcpyDeviceToHost, c->stream));
+            ATK_CUDA_CHECK(cudaEventRecord(c->ev_h3, c->stream));
             ATK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            // where the call's time went: copies up, device loop with its setup, copies down
+            ATK_CUDA_CHECK(cudaEventElapsedTime(&info->h2d_ms, c->ev_h0, c->ev_h1));
+            ATK_CUDA_CHECK(cudaEventElapsedTime(&info->solve_ms, c->ev_h1, c->ev_h2));
+            ATK_CUDA_CHECK(cudaEventElapsedTime(&info->d2h_ms, c->ev_h2, c->ev_h3));
         } catch (...) {
             release();
             throw;

@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(kReduceBlock) cg_fused_update_r_kernel(int64_t
     if (pk.on) __threadfence_system();  // each thread orders its peer stores before its CTA's ticket
     double total;
     if (grid_sum_last_block<kReduceBlock>(acc, partials, ticket, &total)) {
+        if (pk.on) __threadfence_system();  // system-scope release by the publishing threads (see KA)
         if (pk.on && threadIdx.x < 32)
             publish_partial_warp(pk.peer_ll, world, pk.rank, kSlotRR, total, st->epoch + (unsigned long long)st->ka_count);
         if (threadIdx.x == 0) {
@@ -330,21 +331,27 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
     info->fused = fused ? 1 : 0;
     // small single-GPU systems: the whole loop as one cooperative launch with the vectors in registers
     const bool onchip = fused && ctx->world == 1 && !info->time_kernels && max_iter > 0 && op->cg_onchip_blocks() > 0;
-    // peer-memory mode: every rank must agree (it changes who waits for whom)
+    // peer-memory mode and the persistent one-launch loop: every rank must agree (they change who waits for whom)
     bool peer = false;
+    const bool all_aligned = (n % 2 == 0) && aligned16(x) && aligned16(r) && aligned16(p) && aligned16(b);
+    const char* env_persistent = std::getenv("ATK_CG_PERSISTENT");
+    bool persistent = fused && !onchip && max_iter > 0 && all_aligned && !(env_persistent && env_persistent[0] == '0') &&
+                      op->cg_persistent_blocks() > 0;
     if (fused && ctx->world > 1) {
         const char* force_nccl = std::getenv("ATK_CG_FORCE_NCCL");
-        int mine = op->peer_capable() && (n % 2 == 0) && aligned16(x) && aligned16(r) && aligned16(p) &&
-                           !(force_nccl && force_nccl[0] == '1')
-                       ? 1
-                       : 0;
+        const int peer_ok = op->peer_capable() && (n % 2 == 0) && aligned16(x) && aligned16(r) && aligned16(p) &&
+                            !(force_nccl && force_nccl[0] == '1');
+        int mine = (peer_ok ? 1 : 0) | (peer_ok && persistent ? 2 : 0);
         std::vector<int> all((size_t)ctx->world);
         allgather_host_bytes(ctx, &mine, all.data(), sizeof(int));
-        peer = true;
-        for (int v : all) peer = peer && v;
+        int agreed = 3;
+        for (int v : all) agreed &= v;
+        peer = (agreed & 1) != 0;
+        persistent = (agreed & 2) != 0;
     }
     op->set_peer_mode(peer);
     info->peer = peer ? 1 : 0;
+    info->persistent = persistent ? 1 : 0;
     PeerKb pk;
     if (peer) {
         pk.on = 1;
@@ -446,7 +453,7 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
         // ---- capture one iteration, replay it
         int launches_per_iter = 0;
         const bool use_graph = !info->time_kernels;
-        if (max_iter > 0 && use_graph && !onchip) {
+        if (max_iter > 0 && use_graph && !onchip && !persistent) {
             const int64_t l0 = ctx->launches;
             ATK_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             try {
@@ -465,20 +472,35 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
 
         // completion tickets wrap back to zero by themselves; clear them anyway in case an earlier solve was aborted
         ATK_CUDA_CHECK(cudaMemsetAsync(ctx->d_tickets, 0, sizeof(unsigned) * kNumTickets, st));
+        // persistent mode: phase stamps for the per-phase times (time_kernels) - [cap] stamps + their count
+        unsigned long long* d_stamps = nullptr;
+        int stamp_cap = 0;
+        if (persistent && info->time_kernels) {
+            stamp_cap = 2 * std::min(max_iter, 1 << 15) + 1;
+            d_stamps = static_cast<unsigned long long*>(ctx->ws_alloc(sizeof(unsigned long long) * ((size_t)stamp_cap + 1)));
+            ATK_CUDA_CHECK(cudaMemsetAsync(d_stamps, 0, sizeof(unsigned long long) * ((size_t)stamp_cap + 1), st));
+        }
+        struct StampFree { Context* c; unsigned long long*& p; ~StampFree() { if (p) c->ws_release(p); } } stamp_free{ctx, d_stamps};
         ATK_CUDA_CHECK(cudaEventRecord(ctx->ev_t0, st));
+        if (persistent) {
+            // the start-up sums, the initial halo planes, every iteration and the final pending updates: one launch
+            op->cg_persistent(d_state, b, x, r, Ap, p, p_alt, max_iter, d_ptrace, d_rtrace, trace_cap, ctx->epoch, d_stamps, stamp_cap);
+            ctx->epoch += 2ull * (unsigned long long)max_iter + 8ull;  // same advance on every rank
+        } else {
         // rs_old = r.r ; ||b||   (:37-38)
         launch_dot(ctx, n, r, r, kSlotRR);
         launch_dot(ctx, n, b, b, kSlotBnorm);
         cg_begin_kernel<<<1, 32, 0, st>>>(d_state, ctx->slot(kSlotRR), ctx->slot(kSlotBnorm), ctx->world, ctx->epoch);
         count_launch(ctx);
         if (peer) op->initial_halo_exchange(r, p);  // boundary planes of the incoming r and p, once, through NCCL
+        }
 
         // ---- run: iterations are enqueued in batches; the exit flag is read back after every batch and examined
         // two batches later (a blocking wait on that batch's event, so every rank of a distributed run takes the
         // same decision after the same batch and enqueues the same number of collectives).
         if (onchip) op->cg_onchip(d_state, x, r, p, p_alt, max_iter, d_ptrace, d_rtrace);
         constexpr int kBatch = 16, kLag = 2;
-        const int n_batches = onchip ? 0 : (max_iter + kBatch - 1) / kBatch;
+        const int n_batches = (onchip || persistent) ? 0 : (max_iter + kBatch - 1) / kBatch;
         if (n_batches <= kHostFlags) h_done = ctx->h_flags;
         else ATK_CUDA_CHECK(cudaMallocHost(&h_done, sizeof(int) * (size_t)n_batches));
         poll_events.resize(std::max(n_batches, 1), nullptr);
@@ -502,12 +524,12 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
             ATK_CUDA_CHECK(cudaEventCreateWithFlags(&poll_events[bt], cudaEventDisableTiming));
             ATK_CUDA_CHECK(cudaEventRecord(poll_events[bt], st));
         }
-        if (fused && !onchip) {  // KF: pending x / p updates of the last iteration, or p copied back after an exit
+        if (fused && !onchip && !persistent) {  // KF: pending x / p updates of the last iteration, or p copied back after an exit
             cg_fused_flush_kernel<<<ctx->reduce_grid(), kReduceBlock, 0, st>>>(n, d_state, ctx->slot(kSlotRR), ctx->world, r, x, p,
                                                                                p_alt, p, ctx->d_tickets + 4, d_rtrace, pk);
             count_launch(ctx);
         }
-        if (peer) ctx->epoch += (unsigned long long)std::max(max_iter, 0) + 4ull;  // same advance on every rank
+        if (peer && !persistent) ctx->epoch += (unsigned long long)std::max(max_iter, 0) + 4ull;  // same advance on every rank
         ATK_CUDA_CHECK(cudaEventRecord(ctx->ev_t1, st));
 
         CgState hs{};
@@ -518,10 +540,19 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
             if (info->rs_trace)
                 ATK_CUDA_CHECK(cudaMemcpyAsync(info->rs_trace, d_rtrace, sizeof(double) * trace_cap, cudaMemcpyDeviceToHost, st));
         }
+        std::vector<unsigned long long> h_stamps;
+        if (d_stamps) {
+            h_stamps.resize((size_t)stamp_cap + 1);
+            ATK_CUDA_CHECK(cudaMemcpyAsync(h_stamps.data(), d_stamps, sizeof(unsigned long long) * h_stamps.size(), cudaMemcpyDeviceToHost, st));
+        }
         ATK_CUDA_CHECK(cudaStreamSynchronize(st));
         float ms = 0.f;
         ATK_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
         info->kernel_ms[0] = info->kernel_ms[1] = info->kernel_ms[2] = 0.f;
+        if (!h_stamps.empty()) {  // [0] end of start-up, [1+2i] after p.Ap of iteration i, [2+2i] after its r.r
+            const int cnt = (int)h_stamps[(size_t)stamp_cap];
+            for (int q = 0; q + 1 < cnt; ++q) info->kernel_ms[q & 1] += (float)((double)(h_stamps[(size_t)q + 1] - h_stamps[(size_t)q]) * 1e-6);
+        }
         for (size_t q = 0; q + 3 < kev.size(); q += 4)
             for (int c = 0; c < 3; ++c) {
                 float t = 0.f;

@@ -6,7 +6,11 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <sys/mman.h>
+#include <sys/syscall.h>
 #include <unistd.h>
+
+#include <cctype>
 
 #include <algorithm>
 #include <cstdlib>
@@ -120,6 +124,18 @@ void allgather_host_bytes(Context* ctx, const void* send, void* recv, size_t byt
         std::memcpy(recv, send, bytes);
         return;
     }
+    if (bytes <= kSetupBytes && ctx->d_setup) {  // the context's own staging buffers: no cudaMalloc / cudaFree per call
+        std::memcpy(ctx->h_setup + bytes * (size_t)ctx->rank, send, bytes);
+        char* d = ctx->d_setup;
+        ATK_CUDA_CHECK(cudaMemcpyAsync(d + bytes * (size_t)ctx->rank, ctx->h_setup + bytes * (size_t)ctx->rank, bytes,
+                                       cudaMemcpyHostToDevice, ctx->stream));
+        nccl_check(g_nccl.AllGather(d + bytes * (size_t)ctx->rank, d, bytes, ncclChar, (ncclComm_t)ctx->nccl_comm, ctx->stream),
+                   "ncclAllGather(setup)");
+        ATK_CUDA_CHECK(cudaMemcpyAsync(ctx->h_setup, d, bytes * (size_t)ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
+        ATK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        std::memcpy(recv, ctx->h_setup, bytes * (size_t)ctx->world);
+        return;
+    }
     char* d = nullptr;
     ATK_CUDA_CHECK(cudaMalloc(&d, bytes * (size_t)ctx->world));
     try {
@@ -151,6 +167,24 @@ void ipc_share(Context* ctx, void* local, std::vector<void*>& peers, const std::
         peers[(size_t)q] = p;
         ctx->ipc_opened.push_back(p);
     }
+}
+
+void* Context::arena_take(size_t bytes) {
+    for (auto& a : arena_pool)
+        if (!a.busy && a.bytes == bytes) {
+            a.busy = true;
+            ATK_CUDA_CHECK(cudaMemsetAsync(a.ptr, 0, bytes, stream));
+            return a.ptr;
+        }
+    void* p = nullptr;
+    ATK_CUDA_CHECK(cudaMalloc(&p, bytes));
+    ATK_CUDA_CHECK(cudaMemset(p, 0, bytes));
+    arena_pool.push_back(Arena{p, bytes, true});
+    return p;
+}
+void Context::arena_give(void* ptr) {
+    for (auto& a : arena_pool)
+        if (a.ptr == ptr) a.busy = false;
 }
 
 void Context::ipc_close(void* mapped) {
@@ -215,6 +249,86 @@ double read_slot(Context* ctx, int slot) {
     return s;
 }
 
+// ------------------------------------------------------------------------------------------ pinned host memory
+// One process per GPU: each rank's staging buffers should live on the socket its GPU hangs off, otherwise the uploads of
+// the far ranks all squeeze through the inter-socket link (measured in round 1: 12-14 ms per call at 4 and 8 ranks that
+// were neither loop nor PCIe time).  libnuma is not assumed: mbind / get_mempolicy / move_pages are raw syscalls.
+namespace {
+std::mutex g_pin_mutex;
+struct PinRec { void* p; size_t bytes; };
+std::vector<PinRec> g_pinned;  // buffers that came from mmap + cudaHostRegister
+
+int device_numa_node() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) != cudaSuccess) return -1;
+    for (char* q = bus; *q; ++q) *q = (char)std::tolower((unsigned char)*q);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+    FILE* f = std::fopen(path.c_str(), "r");
+    if (!f) return -1;
+    int node = -1;
+    if (std::fscanf(f, "%d", &node) != 1) node = -1;
+    std::fclose(f);
+    return node;
+}
+}  // namespace
+
+void* host_alloc_pinned(size_t bytes) {
+    const char* env = std::getenv("ATK_NUMA_PIN");
+    const int node = (env && env[0] == '0') ? -1 : device_numa_node();
+    if (node >= 0 && node < 1024) {
+        const size_t page = 2u << 20;  // round to 2 MiB so that transparent huge pages can back the buffer
+        const size_t len = (bytes + page - 1) / page * page;
+        void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p != MAP_FAILED) {
+            unsigned long mask[16] = {0};
+            mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+            // MPOL_PREFERRED = 1: fall back to other nodes rather than fail when the node is full
+            (void)syscall(SYS_mbind, p, len, 1 /*MPOL_PREFERRED*/, mask, sizeof(mask) * 8, 0u);
+            if (cudaHostRegister(p, len, cudaHostRegisterPortable) == cudaSuccess) {
+                std::lock_guard<std::mutex> lk(g_pin_mutex);
+                g_pinned.push_back(PinRec{p, len});
+                return p;
+            }
+            cudaGetLastError();
+            munmap(p, len);
+        }
+    }
+    void* p = nullptr;
+    ATK_CUDA_CHECK(cudaMallocHost(&p, bytes));
+    return p;
+}
+
+void host_free_pinned(void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mutex);
+        for (size_t i = 0; i < g_pinned.size(); ++i)
+            if (g_pinned[i].p == p) {
+                const size_t len = g_pinned[i].bytes;
+                g_pinned.erase(g_pinned.begin() + (long)i);
+                cudaHostUnregister(p);
+                munmap(p, len);
+                return;
+            }
+    }
+    ATK_CUDA_CHECK(cudaFreeHost(p));
+}
+
+void host_numa_query(const void* p, int* buffer_node, int* device_node) {
+    if (device_node) *device_node = device_numa_node();
+    if (buffer_node) {
+        *buffer_node = -1;
+        if (p) {
+            int node = -1;
+            // get_mempolicy(MPOL_F_NODE | MPOL_F_ADDR): the node the page at `p` is allocated on
+            if (syscall(SYS_get_mempolicy, &node, nullptr, 0ul, const_cast<void*>(p), 3ul /*MPOL_F_NODE|MPOL_F_ADDR*/) == 0)
+                *buffer_node = node;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ workspace cache
 void* Context::ws_alloc(size_t bytes) {
     if (bytes == 0) bytes = 8;
@@ -277,6 +391,12 @@ static void init_context(Context& c, int device) {
     ATK_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
     ATK_CUDA_CHECK(cudaEventCreate(&c.ev_t0));
     ATK_CUDA_CHECK(cudaEventCreate(&c.ev_t1));
+    ATK_CUDA_CHECK(cudaEventCreate(&c.ev_h0));
+    ATK_CUDA_CHECK(cudaEventCreate(&c.ev_h1));
+    ATK_CUDA_CHECK(cudaEventCreate(&c.ev_h2));
+    ATK_CUDA_CHECK(cudaEventCreate(&c.ev_h3));
+    ATK_CUDA_CHECK(cudaMalloc(&c.d_setup, kSetupBytes * kMaxRanks));
+    ATK_CUDA_CHECK(cudaMallocHost(&c.h_setup, kSetupBytes * kMaxRanks));
     ATK_CUDA_CHECK(cudaMalloc(&c.d_partials, sizeof(double) * kMaxPartials));
     ATK_CUDA_CHECK(cudaMalloc(&c.d_tickets, sizeof(unsigned) * kNumTickets));
     // reduction slots followed by their sequence flags: one allocation, so that one IPC handle shares both
@@ -345,7 +465,8 @@ void context_destroy(atk_context_s* h) {
     for (auto& b : c.ws_blocks) cudaFree(b.ptr);
     c.ws_blocks.clear();
     for (void* p : c.ipc_opened) cudaIpcCloseMemHandle(p);
-    for (void* p : c.ipc_exported) cudaFree(p);  // exported halo arenas: kept alive until now for the peers' sake
+    for (void* p : c.ipc_exported) cudaFree(p);  // exported allocations: kept alive until now for the peers' sake
+    for (auto& a : c.arena_pool) cudaFree(a.ptr);
     cudaFree(c.d_peer_gather);
     cudaFree(c.d_peer_flags);
     cudaFree(c.d_peer_ll);
@@ -359,6 +480,12 @@ void context_destroy(atk_context_s* h) {
     cudaEventDestroy(c.ev_join);
     cudaEventDestroy(c.ev_t0);
     cudaEventDestroy(c.ev_t1);
+    cudaEventDestroy(c.ev_h0);
+    cudaEventDestroy(c.ev_h1);
+    cudaEventDestroy(c.ev_h2);
+    cudaEventDestroy(c.ev_h3);
+    cudaFree(c.d_setup);
+    cudaFreeHost(c.h_setup);
     cudaStreamDestroy(c.stream);
     cudaStreamDestroy(c.comm_stream);
     delete h;

@@ -395,7 +395,12 @@ struct PersistentMgs {
         int max_smem = 0;
         ATK_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
         if (sm + 1024 > (size_t)max_smem) return;
-        ATK_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        // per function and process-wide: always the device maximum, so that a later, smaller solve cannot lower the limit
+        // under a live, larger one (two GMRES objects of different sizes)
+        cudaFuncAttributes fa;
+        ATK_CUDA_CHECK(cudaFuncGetAttributes(&fa, kernel));
+        ATK_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            max_smem - (int)fa.sharedSizeBytes));
         int per_sm = 0;
         ATK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, sm));
         const int g = (int)((n + c - 1) / c);

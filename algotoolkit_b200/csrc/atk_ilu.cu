@@ -308,7 +308,16 @@ Preconditioner* make_ilu(Context* ctx, int64_t n_rows, int64_t n_cols, int64_t n
         ATK_REQUIRE(singular == 0, ATK_ERR_RUNTIME, "Matrix is numerically singular");  // :38-40
         pc->block = (int)std::min<int64_t>(1024, std::max<int64_t>(32, (n + 31) / 32 * 32));
         pc->smem = sizeof(double) * 2 * (size_t)std::max<int64_t>(n, 1);
-        ATK_CUDA_CHECK(cudaFuncSetAttribute(ilu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc->smem));
+        // The attribute is per FUNCTION and process-wide, not per preconditioner: raise it to the device's opt-in maximum
+        // once, so that building a small factorisation later can never lower the limit under a live, larger one.
+        int max_optin = 0;
+        ATK_CUDA_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+        cudaFuncAttributes fa;
+        ATK_CUDA_CHECK(cudaFuncGetAttributes(&fa, ilu_solve_kernel));
+        ATK_REQUIRE(pc->smem + fa.sharedSizeBytes <= (size_t)max_optin, ATK_ERR_INVALID_ARGUMENT,
+                    "ILU preconditioner: system too large for the single-CTA triangular sweeps");
+        ATK_CUDA_CHECK(cudaFuncSetAttribute(ilu_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            max_optin - (int)fa.sharedSizeBytes));
     } catch (...) {
         cudaStreamSynchronize(st);
         cleanup();

@@ -51,6 +51,7 @@ constexpr int kMaxPartials = 1 << 16;  // per-block partial sums a single kernel
 constexpr int kNumSlots = 8;           // independent reduction result slots
 constexpr int kNumTickets = 16;
 constexpr int kHostFlags = 1 << 16;
+constexpr size_t kSetupBytes = 256;    // largest per-rank record of a setup-time host all-gather
 
 // Reduction slots: slot s lives at gather[s*kMaxRanks + q], q = rank.  Each rank writes its
 // own entry; on a distributed context an in-place all-gather fills the others; consumers add
@@ -64,6 +65,9 @@ struct Context {
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t comm_stream = nullptr;  // halo exchange
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr, ev_h2 = nullptr, ev_h3 = nullptr;  // phases of the *_host entry points
+    char* d_setup = nullptr;             // [kSetupBytes * kMaxRanks] staging of allgather_host_bytes (no cudaMalloc per call)
+    char* h_setup = nullptr;             // pinned mirror
     atk_reduction reduction = ATK_REDUCE_TREE;
     double* d_partials = nullptr;  // [kMaxPartials]
     unsigned* d_tickets = nullptr; // [kNumTickets], self-resetting (atomicInc wrap)
@@ -85,6 +89,12 @@ struct Context {
     unsigned long long** d_peer_ll = nullptr;    // device array [world]
     std::vector<void*> ipc_opened;               // mappings to close at destruction
     std::vector<void*> ipc_exported;             // allocations other ranks may still have mapped: freed with the context
+    // Exported halo arenas are recycled, not freed, when their operator dies (a peer may still have them mapped): creating
+    // and destroying operators in a loop then costs one arena per distinct size, not one per operator.
+    struct Arena { void* ptr; size_t bytes; bool busy; };
+    std::vector<Arena> arena_pool;
+    void* arena_take(size_t bytes);              // a free pooled arena of exactly `bytes`, else a new zeroed allocation
+    void arena_give(void* ptr);                  // back to the pool
     void ipc_close(void* mapped);                // close one mapping early (operator destruction)
     unsigned long long epoch = 1;                // sequence-number base, advanced identically on all ranks
 
@@ -126,6 +136,10 @@ double read_slot(Context* ctx, int slot);
 // Collective: every rank passes a device allocation of its own (same size everywhere); on return peers[q] is rank q's
 // allocation mapped into this process (peers[rank] = local).  Only ranks listed in `want` are mapped (empty = all).
 void ipc_share(Context* ctx, void* local, std::vector<void*>& peers, const std::vector<int>& want);
+// Pinned host memory on the NUMA node of the current CUDA device (atk_context.cu).
+void* host_alloc_pinned(size_t bytes);
+void host_free_pinned(void* p);
+void host_numa_query(const void* p, int* buffer_node, int* device_node);
 // Collective all-gather of `bytes` host bytes per rank (setup-time helper, goes through NCCL).
 void allgather_host_bytes(Context* ctx, const void* send, void* recv, size_t bytes);
 // Neighbour exchange with independent counts (row-block partitioned assembled operators): send `to_prev` / `to_next`
@@ -178,6 +192,14 @@ struct Operator {
     virtual void cg_onchip(CgFusedState*, double* /*x*/, double* /*r*/, double* /*p*/, double* /*p_alt*/, int /*max_iter*/,
                            double* /*pAp_trace*/, double* /*rs_trace*/) {
         throw Error(ATK_ERR_INVALID_ARGUMENT, "operator has no on-chip CG loop");
+    }
+    // Whole CG loop as ONE cooperative launch per rank at any size (phases separated by grid + cross-GPU reductions
+    // instead of kernel boundaries; see atk_stencil.cu).  cg_persistent_blocks: CTAs of the launch, 0 when not eligible.
+    virtual int cg_persistent_blocks() const { return 0; }
+    virtual void cg_persistent(CgFusedState*, const double* /*b*/, double* /*x*/, double* /*r*/, double* /*Ap*/, double* /*P0*/,
+                               double* /*P1*/, int /*max_iter*/, double* /*pAp_trace*/, double* /*rs_trace*/, int /*trace_cap*/,
+                               unsigned long long /*epoch*/, unsigned long long* /*stamps*/, int /*stamp_cap*/) {
+        throw Error(ATK_ERR_INVALID_ARGUMENT, "operator has no persistent CG loop");
     }
     virtual bool peer_capable() const { return false; }
     virtual void set_peer_mode(bool) {}

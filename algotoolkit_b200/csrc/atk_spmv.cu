@@ -96,8 +96,22 @@ __global__ void count_rows_kernel(int64_t nnz, const int* __restrict__ row_idx, 
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += stride) {
         const int r = row_idx[p];
-        if (r < 0 || r >= n_rows) { *bad = 1; continue; }
+        if (r < 0 || r >= n_rows) { atomicOr(bad, 1); continue; }
         atomicAdd(row_cnt + r, 1);
+    }
+}
+
+// col_ptr must be a valid CSC column pointer array before anything scatters through it: first entry 0, non-decreasing,
+// last entry nnz (bad |= 2 otherwise)
+__global__ void check_col_ptr_kernel(int n_cols, int64_t nnz, const int* __restrict__ col_ptr, int* __restrict__ bad) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c <= n_cols; c += stride) {
+        const int v = col_ptr[c];
+        bool ok = v >= 0 && (int64_t)v <= nnz;
+        if (c == 0) ok = ok && v == 0;
+        if (c == n_cols) ok = ok && (int64_t)v == nnz;
+        if (c < n_cols) ok = ok && col_ptr[c + 1] >= v;
+        if (!ok) atomicOr(bad, 2);
     }
 }
 
@@ -662,7 +676,11 @@ static Operator* build_from_device_csc(Context* ctx, int n_rows, int n_cols, int
     if (dist) {
         ATK_REQUIRE(format == ATK_FORMAT_SELL, ATK_ERR_INVALID_ARGUMENT, "distributed assembled operators use the SELL format");
         ATK_REQUIRE(n_rows == n_cols, ATK_ERR_INVALID_ARGUMENT, "distributed assembled operators must be square");
+        // every rank must own at least one row: a rank without rows would launch nothing and leave a stale partial in the
+        // reduction slot that the all-gather then feeds into p.Ap on every rank
+        ATK_REQUIRE(n_rows >= ctx->world, ATK_ERR_INVALID_ARGUMENT, "distributed assembled operator: fewer rows than ranks");
         if (row_hi < 0) slab_partition(n_rows, ctx->rank, ctx->world, &row_lo, &row_hi);
+        ATK_REQUIRE(row_hi > row_lo, ATK_ERR_INVALID_ARGUMENT, "distributed assembled operator: empty row block");
     }
     auto* A = new AssembledMatrix();
     try {
@@ -686,6 +704,8 @@ static Operator* build_from_device_csc(Context* ctx, int n_rows, int n_cols, int
         ATK_CUDA_CHECK(cudaMemsetAsync(A->row_ptr, 0, sizeof(int) * ((size_t)n_rows + 1), st));
         ATK_CUDA_CHECK(cudaMemsetAsync(fill, 0, sizeof(int) * ((size_t)n_rows + 1), st));
         ATK_CUDA_CHECK(cudaMemsetAsync(bad, 0, sizeof(int), st));
+        check_col_ptr_kernel<<<grid_for((int64_t)n_cols + 1, 256, cap), 256, 0, st>>>(n_cols, nnz, d_col_ptr, bad);
+        count_launch(ctx);
         if (nnz > 0) {
             count_rows_kernel<<<grid_for(nnz, 256, cap), 256, 0, st>>>(nnz, d_row_idx, A->row_ptr, n_rows, bad);
             count_launch(ctx);
@@ -695,6 +715,8 @@ static Operator* build_from_device_csc(Context* ctx, int n_rows, int n_cols, int
         ATK_CUDA_CHECK(cudaStreamSynchronize(st));
         if (h_bad) {
             cudaFree(fill); cudaFree(col_of_pos); cudaFree(pos_of_slot); cudaFree(bad);
+            if (h_bad & 2)
+                throw Error(ATK_ERR_INVALID_ARGUMENT, "col_ptr is not a CSC column pointer array (first 0, non-decreasing, last nnz)");
             throw Error(ATK_ERR_OUT_OF_RANGE, "Index out of range");
         }
         exclusive_scan_i32(ctx, A->row_ptr, A->row_ptr, (int64_t)n_rows + 1);

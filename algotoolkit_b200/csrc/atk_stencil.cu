@@ -555,6 +555,9 @@ __global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_smem_kernel(StencilG
     if (is_last) {
         __threadfence();
         const double total = partials_sum<TX * TY>(partials, partial_base + nb);
+        // system-scope release by the publishing threads themselves: the halo planes other CTAs stored (each behind its
+        // own system fence and the gpu-scope ticket) are then formally ordered before the words the remote readers poll
+        if (a.p2p) __threadfence_system();
         if (a.p2p && linear_thread_id() < 32)
             publish_partial_warp(a.peer_ll, a.world, a.rank, kSlotPAp, total, st->epoch + (unsigned long long)cnt + 1ull);
         if (linear_thread_id() == 0) {
@@ -1028,6 +1031,427 @@ __global__ void __launch_bounds__(kOnchipBlock) cg_onchip_kernel(OnchipArgs a) {
         st->done = stopped ? 1 : 0;
     }
 }
+// ---------------------------------------------------------------------------------------------- persistent CG loop
+// The whole of ConjugateGradient.hpp:36-84 as ONE cooperative launch per rank (any grid size, one GPU or a z-slab of a
+// distributed run in peer-memory mode).  Per iteration the kernel runs the two passes of the fused formulation above -
+// phase A = KA (p update, deferred x update, operator apply, p.Ap), phase B = KB (r update, r.r) - but without kernel
+// boundaries, last-CTA elections or NCCL calls: a reduction is
+//     per-CTA partial -> arrive counter -> CTA 0 adds the partials in CTA order -> stores the rank's sum into EVERY rank's
+//     packed {value half | sequence} words (one lane per peer, NVLink stores; the local rank included) ->
+//     every CTA of every rank polls its LOCAL words and adds the rank sums in rank order.
+// That single wait is both the grid barrier and the cross-GPU all-reduce, and it orders the halo planes the neighbours
+// stored during the phase (every CTA's thread 0 issues a system-scope fence between its CTA's stores and its arrival).
+// Work is split statically: item = (xy tile, z chunk), item i belongs to CTA i mod gridDim.x in every iteration, so x is
+// only ever touched by one thread; everything another CTA (or GPU) may have written since the previous phase is read
+// through L2 (cp.async.cg / ld.global.cg) - L1 is not coherent inside one launch.
+// The r.r / b.b start-up sums, the initial halo planes and the final pending x / p updates (KF) are part of the launch.
+struct PersistArgs {
+    StencilGeom g;
+    CgFusedState* st;
+    const double* b;
+    double* x;
+    double* r;
+    double* Ap;
+    double* P0;  // the caller's p: holds p on entry and on exit
+    double* P1;
+    int max_iter;
+    double* pAp_trace;
+    double* rs_trace;
+    int trace_cap;
+    int tiles_x, tiles_y, kc, n_chunks, n_items;
+    double* partials;             // [gridDim.x]
+    unsigned long long* arrive;   // zero at launch
+    unsigned long long* ll;       // local packed words
+    unsigned long long* const* peer_ll;  // every rank's packed words as mapped here (null when world == 1)
+    int world, rank;
+    unsigned long long epoch;
+    const double* r_halo_lo;
+    const double* r_halo_hi;
+    const double* my_p_lo[2];
+    const double* my_p_hi[2];
+    double* nb_lo_r_hi;
+    double* nb_hi_r_lo;
+    double* nb_lo_p_hi[2];
+    double* nb_hi_p_lo[2];
+    unsigned long long* stamps;   // optional globaltimer stamps: [0] after the start-up sums, then one per reduction
+    int stamp_cap;
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ double2 ldcg2(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
+
+template <int TX, int TY>
+__global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a) {
+    constexpr int DEPTH = 4;
+    constexpr int W = 2 * TX + 4;
+    constexpr int STAGE = (TY + 2) * W;
+    constexpr int NT = TX * TY;
+    constexpr int CPR = W / 2;
+    constexpr int NCH = (TY + 2) * CPR;
+    constexpr int Q = (NCH + NT - 1) / NT;
+    extern __shared__ __align__(128) double smem_raw[];
+    double* ring_r = smem_raw + kRingShift;  // see kRingShift
+    double* ring_p = ring_r + DEPTH * STAGE;
+    __shared__ double rank_vals[kMaxRanks];
+    __shared__ int s_abort;
+
+    const StencilGeom g = a.g;
+    CgFusedState* st = a.st;
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+    const unsigned G = gridDim.x, bid = blockIdx.x;
+    const int64_t sxy = (int64_t)g.nx * g.ny;
+    const int64_t n2 = (sxy * g.nz_loc) >> 1;  // nx is even: the slab is a whole number of double2
+    const int64_t plane2 = sxy >> 1;
+    const bool dist = a.world > 1;
+    unsigned long long phase = 0;
+    int n_stamps = 0;
+    bool aborted = false;
+    if (tid == 0) s_abort = 0;
+
+    auto stamp = [&]() {
+        if (a.stamps && bid == 0 && tid == 0 && n_stamps < a.stamp_cap) a.stamps[n_stamps] = global_timer_ns();
+        ++n_stamps;
+    };
+    // grid-wide and cross-GPU sum of one value per thread; every thread of every rank returns the same bits
+    auto reduce = [&](double v) -> double {
+        const double bs = block_sum<NT>(v);
+        ++phase;
+        const int slot = (int)(phase & 1ull);
+        const unsigned long long seq = a.epoch + phase;
+        if (tid == 0) {
+            __stcg(a.partials + bid, bs);
+            if (dist) __threadfence_system();  // this CTA's halo stores (all threads: ordered by the barrier in block_sum) first
+            else __threadfence();
+            atomicAdd(a.arrive, 1ull);
+        }
+        if (bid == 0) {
+            if (tid == 0) {
+                const unsigned long long want = phase * (unsigned long long)G;
+                unsigned spins = 0;
+                unsigned long long t0 = 0;
+                while (ld_volatile_u64(a.arrive) < want) {
+                    if ((++spins & 0xfffu) == 0) {
+                        const unsigned long long now = global_timer_ns();
+                        if (t0 == 0) t0 = now;
+                        if (now - t0 > kPeerWaitNs || *reinterpret_cast<volatile int*>(&st->peer_timeout)) {
+                            st->peer_timeout = 1;
+                            break;
+                        }
+                    }
+                }
+                __threadfence();
+            }
+            __syncthreads();
+            const double total = partials_sum<NT>(a.partials, G);
+            if (tid < 32 && tid < a.world) {
+                if (dist) __threadfence_system();
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(total);
+                const unsigned long long tag = (seq & 0xffffffffull) << 32;
+                unsigned long long* dst = (tid == a.rank ? a.ll : a.peer_ll[tid]) + (size_t)(slot * kMaxRanks + a.rank) * 2;
+                st_relaxed_sys(dst, (bits & 0xffffffffull) | tag);
+                st_relaxed_sys(dst + 1, (bits >> 32) | tag);
+            }
+        }
+        // every CTA: wait for all ranks' words of this phase (local memory), lane q polls rank q
+        if (tid < 32) {
+            if (tid < a.world) {
+                const unsigned long long* src = a.ll + (size_t)(slot * kMaxRanks + tid) * 2;
+                const unsigned long long tag = seq & 0xffffffffull;
+                unsigned long long w0, w1;
+                unsigned spins = 0;
+                unsigned long long t0 = 0;
+                bool ok = true;
+                for (;;) {
+                    w0 = ld_relaxed_sys(src);
+                    w1 = ld_relaxed_sys(src + 1);
+                    if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
+                    if ((++spins & 0xfffu) == 0) {
+                        const unsigned long long now = global_timer_ns();
+                        if (t0 == 0) t0 = now;
+                        if (now - t0 > kPeerWaitNs || *reinterpret_cast<volatile int*>(&st->peer_timeout)) {
+                            st->peer_timeout = 1;
+                            ok = false;
+                            break;
+                        }
+                    }
+                }
+                if (ok) {  // the words can only change again after this CTA has arrived at the next reduction
+                    w0 = ld_acquire_sys(src);
+                    w1 = ld_acquire_sys(src + 1);
+                } else {
+                    s_abort = 1;
+                }
+                rank_vals[tid] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+            }
+        }
+        __syncthreads();
+        double s = rank_vals[0];
+        for (int q = 1; q < a.world; ++q) s = add_rn(s, rank_vals[q]);
+        aborted = s_abort != 0;
+        __syncthreads();  // rank_vals is rewritten by the next reduction
+        return s;
+    };
+
+    // ---- start-up: rs_old = r.r, ||b||^2 (:37-38); the boundary planes of r and p go to the neighbours' halo planes
+    const int64_t t_lin = (int64_t)bid * NT + tid;
+    const int64_t stride = (int64_t)G * NT;
+    double rr0 = 0.0, bb0 = 0.0;
+    {
+        double r1 = 0.0, b1 = 0.0;
+        for (int64_t i = t_lin; i < n2; i += stride) {
+            const double2 rv = ldcg2(a.r + 2 * i), bv = ldcg2(a.b + 2 * i);
+            rr0 = add_rn(rr0, mul_rn(rv.x, rv.x));
+            r1 = add_rn(r1, mul_rn(rv.y, rv.y));
+            bb0 = add_rn(bb0, mul_rn(bv.x, bv.x));
+            b1 = add_rn(b1, mul_rn(bv.y, bv.y));
+            if (dist) {
+                if (i < plane2) {
+                    if (a.nb_lo_r_hi) reinterpret_cast<double2*>(a.nb_lo_r_hi)[i] = rv;
+                    if (a.nb_lo_p_hi[0]) reinterpret_cast<double2*>(a.nb_lo_p_hi[0])[i] = ldcg2(a.P0 + 2 * i);
+                }
+                if (i >= n2 - plane2) {
+                    const int64_t h = i - (n2 - plane2);
+                    if (a.nb_hi_r_lo) reinterpret_cast<double2*>(a.nb_hi_r_lo)[h] = rv;
+                    if (a.nb_hi_p_lo[0]) reinterpret_cast<double2*>(a.nb_hi_p_lo[0])[h] = ldcg2(a.P0 + 2 * i);
+                }
+            }
+        }
+        rr0 = add_rn(rr0, r1);
+        bb0 = add_rn(bb0, b1);
+    }
+    double rs_old = reduce(rr0);
+    const double bb = reduce(bb0);
+    stamp();
+    const bool zero_rhs = sqrt(bb) < 1e-12;  // :38-42
+    double alpha = 0.0, beta = 0.0, last_pAp = 0.0;
+    int it = 0;
+    bool stopped = false;
+    const int n_tiles = a.tiles_x * a.tiles_y;
+    const unsigned s_r = (unsigned)__cvta_generic_to_shared(ring_r);
+    const unsigned s_p = (unsigned)__cvta_generic_to_shared(ring_p);
+
+    if (!zero_rhs && !aborted) {
+        for (; it < a.max_iter; ++it) {
+            const bool first = it == 0;
+            const double* __restrict__ ps = (it & 1) ? a.P1 : a.P0;
+            double* __restrict__ pd = (it & 1) ? a.P0 : a.P1;
+            const double* p_halo_lo = a.my_p_lo[it & 1];
+            const double* p_halo_hi = a.my_p_hi[it & 1];
+            double* nb_lo = a.nb_lo_p_hi[(it + 1) & 1];
+            double* nb_hi = a.nb_hi_p_lo[(it + 1) & 1];
+            auto pnew = [&](double rv, double pv) -> double { return first ? pv : add_rn(rv, mul_rn(pv, beta)); };
+            auto pnew2 = [&](double2 rv, double2 pv) -> double2 { return make_double2(pnew(rv.x, pv.x), pnew(rv.y, pv.y)); };
+            double dacc = 0.0;
+            // ================================================================ phase A (KA)
+            for (int item = (int)bid; item < a.n_items; item += (int)G) {
+                const int crank = item / n_tiles, tile = item - crank * n_tiles;
+                const int chunk = a.n_chunks - 1 - crank;  // upper chunks first: their neighbour stores are then acknowledged early
+                const int tyi = tile / a.tiles_x, txi = tile - tyi * a.tiles_x;
+                const int i_lo = txi * 2 * TX, j_lo = tyi * TY;
+                const int i0 = i_lo + 2 * tx, j = j_lo + ty;
+                const int kb = chunk * a.kc, ke = min(kb + a.kc, g.nz_loc);
+                const bool active = (i0 < g.nx) && (j < g.ny);
+                const int64_t row = (int64_t)j * g.nx + i0;
+                const int k_first = max(kb - 1, -g.k_off);
+                const int k_last = min(ke, g.nz - 1 - g.k_off);
+                unsigned c_sm[Q];
+                int c_off[Q];
+                bool c_ok[Q];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const int e = tid + q * NT;
+                    const int jj = e / CPR, c = e - jj * CPR;
+                    const int gj = j_lo - 1 + jj, gi = i_lo - 2 + 2 * c;
+                    const bool corner = (jj == 0 || jj == TY + 1) && (c == 0 || c == CPR - 1);
+                    c_ok[q] = e < NCH && !corner && gj >= 0 && gj < g.ny && gi >= 0 && gi < g.nx;
+                    c_sm[q] = 8u * (unsigned)(jj * W + 2 * c);
+                    c_off[q] = gj * g.nx + gi;
+                }
+                auto issue_plane = [&](int k) {
+                    if (k >= k_first && k <= k_last) {
+                        const unsigned so = (unsigned)((k - kb + 1) & (DEPTH - 1)) * (unsigned)(STAGE * 8);
+                        const double* rp = k < 0 ? a.r_halo_lo : (k >= g.nz_loc ? a.r_halo_hi : a.r + (int64_t)k * sxy);
+                        const double* pp = k < 0 ? p_halo_lo : (k >= g.nz_loc ? p_halo_hi : ps + (int64_t)k * sxy);
+#pragma unroll
+                        for (int q = 0; q < Q; ++q)
+                            if (c_ok[q]) {
+                                cp_async16_s(s_r + so + c_sm[q], rp + c_off[q]);
+                                cp_async16_s(s_p + so + c_sm[q], pp + c_off[q]);
+                            }
+                    }
+                    cp_async_commit();
+                };
+                const int centre = (ty + 1) * W + 2 * tx + 2;  // this thread's pair inside a stage
+                auto ld2s = [](const double* q) -> double2 { return *reinterpret_cast<const double2*>(q); };
+                const bool j_shell = (j == 0 || j == g.ny - 1);
+                const bool a_shell_i = (i0 == 0 || i0 == g.nx - 1);
+                const bool b_shell_i = (i0 + 1 == g.nx - 1);
+                const double2 zero2 = make_double2(0.0, 0.0);
+                issue_plane(kb - 1);
+                issue_plane(kb);
+                issue_plane(kb + 1);
+                issue_plane(kb + 2);
+                double2 xv = zero2;
+                if (active && !first) xv = ldcg2(a.x + (int64_t)kb * sxy + row);
+                cp_async_wait<2>();
+                __syncthreads();
+                double2 pnA = zero2, pnB = zero2, pnC = zero2, poB = zero2;
+                if (active) {
+                    if (g.k_off + kb - 1 >= 0) pnA = pnew2(ld2s(ring_r + centre), ld2s(ring_p + centre));  // stage 0 = plane kb-1
+                    poB = ld2s(ring_p + STAGE + centre);                                                     // stage 1 = plane kb
+                    pnB = pnew2(ld2s(ring_r + STAGE + centre), poB);
+                }
+                for (int k = kb; k < ke; ++k) {
+                    const int kg = g.k_off + k;
+                    const int64_t idx = (int64_t)k * sxy + row;
+                    cp_async_wait<1>();
+                    __syncthreads();
+                    issue_plane(k + 3);
+                    double2 xn = zero2;
+                    if (active && !first && k + 1 < ke) xn = ldcg2(a.x + idx + sxy);
+                    if (active) {
+                        const int so = ((k - kb + 1) & (DEPTH - 1)) * STAGE, sn = ((k - kb + 2) & (DEPTH - 1)) * STAGE;
+                        const double* rs = ring_r + so + centre;
+                        const double* pss = ring_p + so + centre;
+                        double2 poC = zero2;
+                        if (kg + 1 < g.nz) {
+                            poC = ld2s(ring_p + sn + centre);
+                            pnC = pnew2(ld2s(ring_r + sn + centre), poC);
+                        }
+                        double2 out;
+                        if (j_shell || kg == 0 || kg == g.nz - 1) {
+                            out.x = shell_row(pnB.x);
+                            out.y = shell_row(pnB.y);
+                        } else {
+                            const double2 jm = pnew2(ld2s(rs - W), ld2s(pss - W));
+                            const double2 jp = pnew2(ld2s(rs + W), ld2s(pss + W));
+                            if (a_shell_i) {
+                                out.x = shell_row(pnB.x);
+                            } else {
+                                const double left = pnew(rs[-1], pss[-1]);
+                                out.x = tap7(g, pnA.x, jm.x, left, pnB.x, pnB.y, jp.x, pnC.x);
+                            }
+                            if (b_shell_i) {
+                                out.y = shell_row(pnB.y);
+                            } else {
+                                const double right = pnew(rs[2], pss[2]);
+                                out.y = tap7(g, pnA.y, jm.y, pnB.x, pnB.y, right, jp.y, pnC.y);
+                            }
+                        }
+                        *reinterpret_cast<double2*>(a.Ap + idx) = out;
+                        *reinterpret_cast<double2*>(pd + idx) = pnB;
+                        if (dist) {  // boundary planes of p_new go straight into the neighbours' halo planes over NVLink
+                            if (k == 0 && nb_lo) *reinterpret_cast<double2*>(nb_lo + row) = pnB;
+                            if (k == g.nz_loc - 1 && nb_hi) *reinterpret_cast<double2*>(nb_hi + row) = pnB;
+                        }
+                        dacc = add_rn(dacc, mul_rn(pnB.x, out.x));
+                        dacc = add_rn(dacc, mul_rn(pnB.y, out.y));
+                        if (!first) {
+                            xv.x = add_rn(xv.x, mul_rn(poB.x, alpha));  // x = x + p*alpha of the previous iteration (:60)
+                            xv.y = add_rn(xv.y, mul_rn(poB.y, alpha));
+                            *reinterpret_cast<double2*>(a.x + idx) = xv;
+                        }
+                        pnA = pnB;
+                        pnB = pnC;
+                        poB = poC;
+                    }
+                    xv = xn;
+                }
+                cp_async_wait<0>();
+                __syncthreads();  // the ring is free for the next item
+            }
+            const double pAp = reduce(dacc);  // :51
+            stamp();
+            if (aborted) break;
+            last_pAp = pAp;
+            if (bid == 0 && tid == 0 && a.pAp_trace && it < a.trace_cap) a.pAp_trace[it] = pAp;
+            if (fabs(pAp) < 1e-12) {  // :53-57
+                stopped = true;
+                break;
+            }
+            alpha = __ddiv_rn(rs_old, pAp);  // :58
+            // ================================================================ phase B (KB): r = r - Ap*alpha ; r.r
+            double acc0 = 0.0, acc1 = 0.0;
+            {
+                // distributed: start with the last plane, then the first, so that the stores into the neighbours' halo
+                // planes have long been acknowledged when the fence before the arrival is reached
+                const int64_t off = dist ? n2 - plane2 : 0;
+                auto one = [&](int64_t i, const double2 rv0, const double2 av) {
+                    int64_t e = i + off;
+                    if (e >= n2) e -= n2;
+                    double2 rv = rv0;
+                    rv.x = sub_rn(rv.x, mul_rn(av.x, alpha));
+                    rv.y = sub_rn(rv.y, mul_rn(av.y, alpha));
+                    *reinterpret_cast<double2*>(a.r + 2 * e) = rv;
+                    if (dist) {
+                        if (e < plane2 && a.nb_lo_r_hi) reinterpret_cast<double2*>(a.nb_lo_r_hi)[e] = rv;
+                        if (e >= n2 - plane2 && a.nb_hi_r_lo) reinterpret_cast<double2*>(a.nb_hi_r_lo)[e - (n2 - plane2)] = rv;
+                    }
+                    acc0 = add_rn(acc0, mul_rn(rv.x, rv.x));
+                    acc1 = add_rn(acc1, mul_rn(rv.y, rv.y));
+                };
+                auto at = [&](int64_t i) -> int64_t {
+                    int64_t e = i + off;
+                    if (e >= n2) e -= n2;
+                    return 2 * e;
+                };
+                int64_t i = t_lin;
+                for (; i + 3 * stride < n2; i += 4 * stride) {
+                    const double2 r0 = ldcg2(a.r + at(i)), a0 = ldcg2(a.Ap + at(i));
+                    const double2 r1 = ldcg2(a.r + at(i + stride)), a1 = ldcg2(a.Ap + at(i + stride));
+                    const double2 r2 = ldcg2(a.r + at(i + 2 * stride)), a2 = ldcg2(a.Ap + at(i + 2 * stride));
+                    const double2 r3 = ldcg2(a.r + at(i + 3 * stride)), a3 = ldcg2(a.Ap + at(i + 3 * stride));
+                    one(i, r0, a0);
+                    one(i + stride, r1, a1);
+                    one(i + 2 * stride, r2, a2);
+                    one(i + 3 * stride, r3, a3);
+                }
+                for (; i < n2; i += stride) one(i, ldcg2(a.r + at(i)), ldcg2(a.Ap + at(i)));
+            }
+            const double rs_new = reduce(add_rn(acc0, acc1));  // :63
+            stamp();
+            if (aborted) break;
+            beta = __ddiv_rn(rs_new, rs_old);
+            if (bid == 0 && tid == 0 && a.rs_trace && it < a.trace_cap) a.rs_trace[it] = rs_new;
+            rs_old = rs_new;  // :80
+        }
+    }
+    // ---- KF: bring the caller's x and p to the reference's state
+    if (!aborted && (it > 0 || stopped)) {
+        const int ka = stopped ? it + 1 : it;  // KA passes executed: the current direction lives in P[ka & 1]
+        const double* pc = (ka & 1) ? a.P1 : a.P0;
+        if (stopped) {  // x and r are complete; p keeps the value formed for this iteration
+            if (pc != a.P0)
+                for (int64_t i = t_lin; i < n2; i += stride) *reinterpret_cast<double2*>(a.P0 + 2 * i) = ldcg2(pc + 2 * i);
+        } else {  // the last iteration still owes x = x + p*alpha (:60) and p = r + p*beta (:79)
+            for (int64_t i = t_lin; i < n2; i += stride) {
+                const double2 pv = ldcg2(pc + 2 * i), rv = ldcg2(a.r + 2 * i);
+                double2 xv = ldcg2(a.x + 2 * i);
+                xv.x = add_rn(xv.x, mul_rn(pv.x, alpha));
+                xv.y = add_rn(xv.y, mul_rn(pv.y, alpha));
+                *reinterpret_cast<double2*>(a.x + 2 * i) = xv;
+                *reinterpret_cast<double2*>(a.P0 + 2 * i) = make_double2(add_rn(rv.x, mul_rn(pv.x, beta)), add_rn(rv.y, mul_rn(pv.y, beta)));
+            }
+        }
+    }
+    if (bid == 0 && tid == 0) {
+        st->it = it;
+        st->rs_old = rs_old;
+        st->b_norm2 = bb;
+        st->alpha = alpha;
+        st->last_pAp = last_pAp;
+        st->stopped_on_pAp = stopped ? 1 : 0;
+        st->zero_rhs = zero_rhs ? 1 : 0;
+        st->done = (stopped || zero_rhs) ? 1 : 0;
+        st->first = 0;
+        st->ka_count = stopped ? it + 1 : it;
+        st->epoch = a.epoch;
+        if (a.stamps && a.stamp_cap > 0) a.stamps[a.stamp_cap] = (unsigned long long)min(n_stamps, a.stamp_cap);
+    }
+}
+
 template <int TX, int TY>
 constexpr size_t fused_smem_bytes() { return (size_t)2 * 4 * (TY + 2) * (2 * TX + 4) * sizeof(double) + kRingShift * sizeof(double); }
 template <int TX, int TY>
@@ -1057,13 +1481,14 @@ struct Stencil7 : public Operator {
 
     ~Stencil7() override {
         cudaFree(oc_part);
+        cudaFree(ps_part);
         cudaFree(halo_lo);
         cudaFree(halo_hi);
         cudaFree(fsend);
         // the neighbours may still have this rank's halo arena mapped: unmap theirs now, free ours with the context
         ctx->ipc_close(nb_lo_arena);
         ctx->ipc_close(nb_hi_arena);
-        if (arena_exported) ctx->ipc_exported.push_back(frecv);
+        if (arena_exported) ctx->arena_give(frecv);  // recycled by the next operator of the same plane size
         else cudaFree(frecv);
     }
 
@@ -1107,6 +1532,107 @@ struct Stencil7 : public Operator {
         ATK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)cg_onchip_kernel, dim3((unsigned)oc_blocks), dim3(kOnchipBlock), kargs, 0,
                                                    ctx->stream));
         count_launch(ctx);
+    }
+    // ---- persistent CG loop (one cooperative launch per solve; single GPU, or a z-slab in peer-memory mode)
+    double* ps_part = nullptr;  // [ps_grid] per-CTA partials, then the 64-bit arrival counter
+    int ps_grid = -1;           // -1: not evaluated yet, 0: not eligible
+    int ps_kc = 0, ps_chunks = 0;
+    int cg_persistent_blocks() const override {
+        auto* self = const_cast<Stencil7*>(this);
+        if (self->ps_grid >= 0) return self->ps_grid;
+        self->ps_grid = 0;
+        if ((g.nx & 1) || !fsmem || n_rows_local <= 0 || g.nz_loc < 1) return 0;
+        if (ctx->world > 1 && !(ctx->p2p && frecv)) return 0;
+        constexpr int TX = 32, TY = 4;
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        if (!coop) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_kernel<TX, TY>, TX * TY, fused_smem_bytes<TX, TY>()) !=
+                cudaSuccess || per_sm < 1)
+            return 0;
+        const int64_t g_max = (int64_t)per_sm * ctx->sm_count;
+        const int64_t tiles = (int64_t)((g.nx + 2 * TX - 1) / (2 * TX)) * ((g.ny + TY - 1) / TY);
+        // z-chunk length: the one that minimises the planes the busiest CTA has to stream (every chunk re-reads its two
+        // neighbour planes), among chunkings that give every SM something to do
+        int min_chunks = 1;
+        if (const char* e = std::getenv("ATK_PERSIST_SPLIT")) min_chunks = std::max(1, std::atoi(e));
+        int64_t best = -1;
+        int best_chunks = 1;
+        for (int chunks = min_chunks; chunks <= std::max(min_chunks, g.nz_loc); ++chunks) {
+            const int kcc = (g.nz_loc + chunks - 1) / chunks;
+            if (kcc < 8 && chunks > min_chunks) break;
+            if ((g.nz_loc + kcc - 1) / kcc != chunks) continue;
+            const int64_t items = tiles * chunks;
+            if (items > 0x3fffffff) break;
+            const int64_t gu = std::min(g_max, items);
+            const int64_t load = ((items + gu - 1) / gu) * (kcc + 2);
+            if (best < 0 || load < best) {
+                best = load;
+                best_chunks = chunks;
+            }
+        }
+        if (const char* e = std::getenv("ATK_PERSIST_KC")) {
+            const int kcc = std::max(1, std::min(std::atoi(e), g.nz_loc));
+            best_chunks = (g.nz_loc + kcc - 1) / kcc;
+        }
+        self->ps_chunks = best_chunks;
+        self->ps_kc = (g.nz_loc + best_chunks - 1) / best_chunks;
+        self->ps_chunks = (g.nz_loc + self->ps_kc - 1) / self->ps_kc;
+        const int64_t items = tiles * self->ps_chunks;
+        const int grid = (int)std::min(g_max, items);
+        if (cudaMalloc(&self->ps_part, sizeof(double) * ((size_t)grid + 2)) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        self->ps_grid = grid;
+        return grid;
+    }
+    void cg_persistent(CgFusedState* st, const double* b, double* x, double* r, double* Ap, double* P0, double* P1, int max_iter,
+                       double* pAp_trace, double* rs_trace, int trace_cap, unsigned long long epoch, unsigned long long* stamps,
+                       int stamp_cap) override {
+        ATK_REQUIRE(ps_grid > 0, ATK_ERR_INVALID_ARGUMENT, "persistent CG loop not available for this operator");
+        constexpr int TX = 32, TY = 4;
+        Context* c = ctx;
+        const size_t plane = (size_t)g.nx * g.ny;
+        PersistArgs pa{};
+        pa.g = g;
+        pa.st = st;
+        pa.b = b; pa.x = x; pa.r = r; pa.Ap = Ap; pa.P0 = P0; pa.P1 = P1;
+        pa.max_iter = max_iter;
+        pa.pAp_trace = pAp_trace; pa.rs_trace = rs_trace; pa.trace_cap = trace_cap;
+        pa.tiles_x = (g.nx + 2 * TX - 1) / (2 * TX);
+        pa.tiles_y = (g.ny + TY - 1) / TY;
+        pa.kc = ps_kc;
+        pa.n_chunks = ps_chunks;
+        pa.n_items = pa.tiles_x * pa.tiles_y * ps_chunks;
+        pa.partials = ps_part;
+        pa.arrive = reinterpret_cast<unsigned long long*>(ps_part + ps_grid);
+        pa.ll = c->d_ll;
+        pa.peer_ll = c->d_peer_ll;
+        pa.world = c->world;
+        pa.rank = c->rank;
+        pa.epoch = epoch;
+        if (c->world > 1) {
+            pa.r_halo_lo = frecv;
+            pa.r_halo_hi = frecv + 2 * plane;
+            pa.my_p_lo[0] = frecv + plane;
+            pa.my_p_hi[0] = frecv + 3 * plane;
+            pa.my_p_lo[1] = frecv + 4 * plane;
+            pa.my_p_hi[1] = frecv + 5 * plane;
+            pa.nb_lo_r_hi = nb_lo_arena ? nb_lo_arena + 2 * plane : nullptr;
+            pa.nb_hi_r_lo = nb_hi_arena ? nb_hi_arena : nullptr;
+            pa.nb_lo_p_hi[0] = nb_lo_arena ? nb_lo_arena + 3 * plane : nullptr;
+            pa.nb_lo_p_hi[1] = nb_lo_arena ? nb_lo_arena + 5 * plane : nullptr;
+            pa.nb_hi_p_lo[0] = nb_hi_arena ? nb_hi_arena + plane : nullptr;
+            pa.nb_hi_p_lo[1] = nb_hi_arena ? nb_hi_arena + 4 * plane : nullptr;
+        }
+        pa.stamps = stamps;
+        pa.stamp_cap = stamp_cap;
+        ATK_CUDA_CHECK(cudaMemsetAsync(pa.arrive, 0, sizeof(unsigned long long), c->stream));
+        void* kargs[] = {&pa};
+        ATK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)cg_persistent_kernel<TX, TY>, dim3((unsigned)ps_grid), dim3(TX, TY, 1), kargs,
+                                                   fused_smem_bytes<TX, TY>(), c->stream));
+        count_launch(c);
     }
     bool peer_mode = false;  // set by the CG driver for the duration of a solve (all ranks agree)
 
@@ -1590,15 +2116,20 @@ Operator* make_stencil7(Context* ctx, int nx, int ny, int nz, double cx, double 
             ATK_CUDA_CHECK(cudaMemset(S->halo_lo, 0, sizeof(double) * (size_t)plane));
             ATK_CUDA_CHECK(cudaMemset(S->halo_hi, 0, sizeof(double) * (size_t)plane));
             ATK_CUDA_CHECK(cudaMalloc(&S->fsend, sizeof(double) * 4 * (size_t)plane));
-            ATK_CUDA_CHECK(cudaMalloc(&S->frecv, sizeof(double) * 6 * (size_t)plane));
-            ATK_CUDA_CHECK(cudaMemset(S->frecv, 0, sizeof(double) * 6 * (size_t)plane));
+            if (ctx->p2p) {
+                S->frecv = static_cast<double*>(ctx->arena_take(sizeof(double) * 6 * (size_t)plane));
+                S->arena_exported = true;
+                ATK_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            } else {
+                ATK_CUDA_CHECK(cudaMalloc(&S->frecv, sizeof(double) * 6 * (size_t)plane));
+                ATK_CUDA_CHECK(cudaMemset(S->frecv, 0, sizeof(double) * 6 * (size_t)plane));
+            }
             if (ctx->p2p) {  // collective: map the z-neighbours' halo arenas
                 std::vector<void*> peers;
                 std::vector<int> want;
                 if (ctx->rank > 0) want.push_back(ctx->rank - 1);
                 if (ctx->rank + 1 < ctx->world) want.push_back(ctx->rank + 1);
                 ipc_share(ctx, S->frecv, peers, want);
-                S->arena_exported = true;
                 if (ctx->rank > 0) S->nb_lo_arena = static_cast<double*>(peers[(size_t)ctx->rank - 1]);
                 if (ctx->rank + 1 < ctx->world) S->nb_hi_arena = static_cast<double*>(peers[(size_t)ctx->rank + 1]);
             }

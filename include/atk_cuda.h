@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define ATK_ABI_VERSION 1
+#define ATK_ABI_VERSION 2
 
 typedef enum atk_status {
     ATK_OK = 0,
@@ -89,8 +89,13 @@ int atk_memcpy_h2d(atk_context_t ctx, void* dst_device, const void* src_host, si
 int atk_memcpy_d2h(atk_context_t ctx, void* dst_host, const void* src_device, size_t bytes);
 int atk_memcpy_d2d(atk_context_t ctx, void* dst_device, const void* src_device, size_t bytes);
 int atk_memset_zero(atk_context_t ctx, void* dptr, size_t bytes);
-int atk_host_alloc(size_t bytes, void** hptr); /* pinned */
+/* Pinned host memory for the `_host` entry points.  The pages are placed on the NUMA node the CURRENT CUDA device hangs
+ * off (mmap + mbind + cudaHostRegister; plain cudaMallocHost when the node is unknown), so that with one process per GPU
+ * the 8 concurrent uploads of a box do not all cross the socket interconnect. */
+int atk_host_alloc(size_t bytes, void** hptr);
 int atk_host_free(void* hptr);
+/* Diagnostics: NUMA node the first page of `hptr` lives on and the node of the current CUDA device (-1 = unknown). */
+int atk_host_numa_node(const void* hptr, int* buffer_node, int* device_node);
 
 /* ------------------------------------------------------------------------------------------------ VectorObj ops
  * Replaces src/Obj/VectorObj.hpp for T=double.  n is the LOCAL length; on a distributed context dot/nrm2 return
@@ -171,6 +176,15 @@ typedef struct atk_cg_info {
      * direct stores into the neighbouring GPUs' memory (CUDA IPC over NVLink) and sequence flags, no NCCL call inside
      * the loop.  0: NCCL send/recv + all-gather (also selectable with ATK_COMM=nccl). */
     int peer;
+    /* out: 1 when the whole loop ran as ONE persistent cooperative launch per rank (matrix-free operator, tree reductions,
+     * 16-byte aligned vectors; single GPU or peer-memory mode): phases A (= KA) and B (= KB) are separated by grid-wide /
+     * cross-GPU reductions inside the kernel instead of kernel boundaries.  With time_kernels set, kernel_ms[0] / [1] are
+     * then the summed phase A / phase B times (their reductions included) from in-kernel %globaltimer stamps.
+     * ATK_CG_PERSISTENT=0 selects the CUDA-graph loop of two kernels per iteration instead. */
+    int persistent;
+    /* out (atk_cg_solve_host only): wall-clock milliseconds of the phases of the call - host->device copies (b and the
+     * state), device loop incl. its setup, device->host copies - measured with CUDA events on the context's stream */
+    float h2d_ms, solve_ms, d2h_ms;
 } atk_cg_info;
 
 /* ConjugateGrad::solve (src/LinearAlgebra/Krylov/ConjugateGradient.hpp:36-84).  The solver state x, r, p lives in

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/atk_cuda.h but not exported"
     assert sorted(capi.EXPORTS) == declared
-    assert lib.atk_abi_version() == 1
+    assert lib.atk_abi_version() == 2
     out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert " T atk_cg_solve" in out and " T atk_gmres_solve" in out
 

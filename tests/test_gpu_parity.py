@@ -101,6 +101,13 @@ def test_csc_out_of_range_row(ctx):
         ctx.operator_from_csc(2, 2, np.array([0, 1, 2], np.int32), np.array([0, 5], np.int32), np.array([1.0, 2.0]))
 
 
+@pytest.mark.parametrize("col_ptr", [[1, 1, 2], [0, 2, 1], [0, 1, 3], [0, 1, 1], [0, -1, 2]])
+def test_csc_malformed_col_ptr_is_rejected_before_any_scatter(ctx, col_ptr):
+    """first entry 0, non-decreasing, last entry nnz - anything else must not reach the scatter kernels"""
+    with pytest.raises(ValueError):
+        ctx.operator_from_csc(2, 2, np.array(col_ptr, np.int32), np.array([0, 1], np.int32), np.array([1.0, 2.0]))
+
+
 @pytest.mark.parametrize("name", ["bcsstk01", "bcsstk08"])
 def test_spmv_matrix_market_bit_exact(ctx, port, golden, name):
     A = port.read_matrix_market(mm_path(name))
@@ -204,11 +211,14 @@ def test_op27_matrix_free_bit_exact(ctx, port, dims):
 
 
 # ------------------------------------------------------------------------------------------------ ConjugateGrad
-@pytest.fixture(params=["onchip", "graph"])
+@pytest.fixture(params=["onchip", "persistent", "graph"])
 def cg_loop(request, monkeypatch):
-    """Small grids can run the CG loop two ways: one cooperative launch with the vectors on chip (default), or the fused
-    two-kernel iteration replayed from a CUDA graph (what large grids use).  Tests taking this fixture cover both."""
+    """The CG loop of the matrix-free operator runs three ways: one cooperative launch with the vectors on chip (small
+    grids, default there), one persistent cooperative launch that streams the vectors (what large grids and the z-slabs
+    of a distributed run use), or the fused two-kernel iteration replayed from a CUDA graph (fallback).  Tests taking
+    this fixture cover all three."""
     monkeypatch.setenv("ATK_CG_ONCHIP", "1" if request.param == "onchip" else "0")
+    monkeypatch.setenv("ATK_CG_PERSISTENT", "0" if request.param == "graph" else "1")
     return request.param
 
 
@@ -322,6 +332,46 @@ def test_cg_fixed_work_and_continuation(ctx, port, golden, cg_loop):
     ora = port.cg(None, b, 20, stencil=(n, n, n, cx, cy, cz))
     ora2 = port.cg(None, b, 30, state=(ora["x"], ora["r"], ora["p"]), stencil=(n, n, n, cx, cy, cz))
     assert relerr(bb["x"], ora2["x"]) < REL and relerr(bb["x"], r50["x"]) < REL
+
+
+@pytest.mark.parametrize("dims,split", [((96, 70, 40), None), ((64, 8, 130), None), ((130, 36, 24), "3"), ((32, 4, 9), None)])
+def test_cg_persistent_loop(ctx, port, dims, split, monkeypatch):
+    """The one-launch persistent loop on grids with partial tiles, several z-chunks per tile and more items than CTAs:
+    it must be the path taken (info.persistent), agree with the oracle per iteration (traces), honour the exit, the
+    zero right-hand side and the continuation semantics, and report phase times."""
+    monkeypatch.setenv("ATK_CG_ONCHIP", "0")
+    monkeypatch.setenv("ATK_CG_PERSISTENT", "1")
+    if split:
+        monkeypatch.setenv("ATK_PERSIST_SPLIT", split)
+    nx, ny, nz = dims
+    cx, cy, cz, _ = port.poisson_coeffs(nx, ny, nz, 1.0, 2.0, 0.5)
+    b = port.poisson_rhs(nx, ny, nz, 1.0, 2.0, 0.5, rhs_kind=1, seed=99)
+    op = ctx.operator_stencil7(nx, ny, nz, cx, cy, cz)
+    ora = port.cg(None, b, 37, stencil=(nx, ny, nz, cx, cy, cz), trace=True)
+    res = ctx.cg_solve_host(op, b, 37, trace=True)
+    assert res["persistent"] and res["fused"] and res["iters"] == ora["iters"] == 37 and res["kernel_launches"] == 1
+    assert relerr(res["x"], ora["x"]) < REL and relerr(res["r"], ora["r"]) < 1e-8 and relerr(res["p"], ora["p"]) < 1e-8
+    assert np.allclose(res["pAp_trace"], ora["pAp_trace"], rtol=1e-9) and np.allclose(res["rs_trace"], ora["rs_trace"], rtol=1e-9)
+    # continuation: 15 + 22 iterations == 37 iterations
+    a = ctx.cg_solve_host(op, b, 15)
+    c = ctx.cg_solve_host(op, b, 22, state=(a["x"], a["r"], a["p"]))
+    assert c["persistent"] and relerr(c["x"], ora["x"]) < REL and relerr(c["p"], ora["p"]) < 1e-8
+    # run to the |pAp| < 1e-12 exit
+    full = ctx.cg_solve_host(op, b, 100000)
+    ofull = port.cg(None, b, 100000, stencil=(nx, ny, nz, cx, cy, cz))
+    assert full["stopped_on_pAp"] and abs(full["iters"] - ofull["iters"]) <= 2 and relerr(full["x"], ofull["x"]) < REL
+    # zero right-hand side: immediate return, x untouched (ConjugateGradient.hpp:38-42)
+    z = ctx.cg_solve_host(op, np.zeros_like(b), 10)
+    assert z["zero_rhs"] and z["iters"] == 0 and not z["x"].any()
+    # phase stamps (time_kernels): both phases must have been timed
+    db = ctx.vector(b)
+    x, r, p = ctx.vector(np.zeros_like(b)), ctx.vector(b), ctx.vector(b)
+    t = ctx.cg_solve(op, db, x, r, p, 12, time_kernels=True)
+    assert t["persistent"] and t["kernel_ms"][0] > 0 and t["kernel_ms"][1] > 0
+    assert t["kernel_ms"][0] + t["kernel_ms"][1] <= t["device_ms"] * 1.05
+    o12 = port.cg(None, b, 12, stencil=(nx, ny, nz, cx, cy, cz))
+    assert relerr(x.numpy(), o12["x"]) < REL
+    op.destroy()
 
 
 def test_cg_resident_device_api(ctx, port, cg_loop):

@@ -188,6 +188,35 @@ def test_device_ilu_larger_dense_system(ctx, port):
 
 
 @pytest.mark.gpu
+def test_two_live_preconditioners_of_different_sizes(ctx):
+    """The dynamic shared-memory limit of the sweep kernel is per function, not per preconditioner: a small factorisation
+    built AFTER a large one (n = 3400 needs 54 KB, above the 48 KB default) must not break solves with the large one."""
+    rng = np.random.default_rng(5)
+
+    def tridiag(n):
+        rows = np.concatenate([np.arange(n), np.arange(1, n), np.arange(n - 1)])
+        cols = np.concatenate([np.arange(n), np.arange(n - 1), np.arange(1, n)])
+        vals = np.concatenate([np.full(n, 4.0), np.full(n - 1, -1.0), np.full(n - 1, -1.0)])
+        order = np.lexsort((rows, cols))
+        cp = np.zeros(n + 1, np.int32)
+        np.add.at(cp, cols + 1, 1)
+        return np.cumsum(cp).astype(np.int32), rows[order].astype(np.int32), vals[order]
+
+    big_n, small_n = 3400, 40
+    big = ctx.ilu_compute(big_n, big_n, *tridiag(big_n))
+    small = ctx.ilu_compute(small_n, small_n, *tridiag(small_n))
+    for pc, n in ((big, big_n), (small, small_n), (big, big_n)):
+        b = rng.standard_normal(n)
+        x = pc.solve_host(b)
+        Ax = 4.0 * x
+        Ax[1:] -= x[:-1]
+        Ax[:-1] -= x[1:]
+        assert relerr(Ax, b) < 1e-12  # the complete LU of a tridiagonal matrix: the sweeps solve the system
+    big.destroy()
+    small.destroy()
+
+
+@pytest.mark.gpu
 def test_fastsolver_gmres_enable_preconditioner(gilu, port, capsys):
     sys.path.insert(0, os.path.join(ROOT, "algotoolkit_b200"))
     import fastsolver as fs
