@@ -334,9 +334,13 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
     // peer-memory mode and the persistent one-launch loop: every rank must agree (they change who waits for whom)
     bool peer = false;
     const bool all_aligned = (n % 2 == 0) && aligned16(x) && aligned16(r) && aligned16(p) && aligned16(b);
+    // Persistent one-launch loop: the default on distributed contexts, where it removes two kernel boundaries, two
+    // last-CTA elections and every NCCL call from the iteration.  On one GPU the CUDA-graph loop of two kernels is ~1 %
+    // faster at 512^3 (the hardware CTA scheduler balances 8192 small CTAs better than a static split of 1024 tiles over
+    // 148 SMs), so there it is opt-in: ATK_CG_PERSISTENT=1 / 0 forces either.
     const char* env_persistent = std::getenv("ATK_CG_PERSISTENT");
-    bool persistent = fused && !onchip && max_iter > 0 && all_aligned && !(env_persistent && env_persistent[0] == '0') &&
-                      op->cg_persistent_blocks() > 0;
+    const bool want_persistent = env_persistent ? env_persistent[0] != '0' : ctx->world > 1;
+    bool persistent = fused && !onchip && max_iter > 0 && all_aligned && want_persistent && op->cg_persistent_blocks() > 0;
     if (fused && ctx->world > 1) {
         const char* force_nccl = std::getenv("ATK_CG_FORCE_NCCL");
         const int peer_ok = op->peer_capable() && (n % 2 == 0) && aligned16(x) && aligned16(r) && aligned16(p) &&

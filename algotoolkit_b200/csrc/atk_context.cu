@@ -187,6 +187,130 @@ void Context::arena_give(void* ptr) {
         if (a.ptr == ptr) a.busy = false;
 }
 
+// ------------------------------------------------------------------------------------------ PeerHalo
+namespace {
+__global__ void __launch_bounds__(256) halo_push_kernel(const double* __restrict__ to_prev, size_t n_to_prev,
+                                                        const double* __restrict__ to_next, size_t n_to_next,
+                                                        double* __restrict__ prev_dst, double* __restrict__ next_dst,
+                                                        unsigned long long* prev_flag, unsigned long long* next_flag,
+                                                        unsigned long long seq, unsigned* ticket) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    auto copy = [&](const double* src, double* dst, size_t n) {
+        if (!dst || n == 0) return;
+        if ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) {
+            const size_t n2 = n >> 1;
+            for (size_t i = t; i < n2; i += stride) reinterpret_cast<double2*>(dst)[i] = reinterpret_cast<const double2*>(src)[i];
+            if ((n & 1) && t == 0) dst[n - 1] = src[n - 1];
+        } else {
+            for (size_t i = t; i < n; i += stride) dst[i] = src[i];
+        }
+    };
+    copy(to_prev, prev_dst, n_to_prev);
+    copy(to_next, next_dst, n_to_next);
+    __threadfence_system();  // this thread's NVLink stores are performed before its CTA takes a ticket
+    if (last_block_done(ticket)) {
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (prev_flag) st_release_sys(prev_flag, seq);
+            if (next_flag) st_release_sys(next_flag, seq);
+        }
+    }
+}
+__global__ void halo_wait_kernel(const unsigned long long* flags, int has_prev, int has_next, unsigned long long seq) {
+    const int lane = threadIdx.x;
+    if ((lane == 0 && has_prev) || (lane == 1 && has_next)) {
+        unsigned spins = 0;
+        unsigned long long t0 = 0;
+        while (ld_acquire_sys(flags + lane) < seq) {
+            if ((++spins & 0xfffu) == 0) {
+                const unsigned long long now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                if (now - t0 > kPeerWaitNs) asm volatile("trap;");  // a neighbour died or fell out of step: fail loudly
+            }
+        }
+    }
+}
+}  // namespace
+
+void PeerHalo::setup(Context* c, size_t lo, size_t hi) {
+    ctx = c;
+    cap_lo = lo;
+    cap_hi = hi;
+    ready = false;
+    if (c->world == 1 || !c->p2p) return;
+    struct Caps { unsigned long long lo, hi; } mine{lo, hi};
+    std::vector<Caps> all((size_t)c->world);
+    allgather_host_bytes(c, &mine, all.data(), sizeof(Caps));
+    // same arena size on every rank keeps recycled arenas interchangeable; the flag words sit behind the buffers
+    arena = static_cast<double*>(c->arena_take(sizeof(double) * arena_doubles(lo, hi)));
+    ATK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    std::vector<void*> peers;
+    std::vector<int> want;
+    if (c->rank > 0) want.push_back(c->rank - 1);
+    if (c->rank + 1 < c->world) want.push_back(c->rank + 1);
+    ipc_share(c, arena, peers, want);
+    if (c->rank > 0) {
+        prev_arena = static_cast<double*>(peers[(size_t)c->rank - 1]);
+        prev_cap_lo = all[(size_t)c->rank - 1].lo;
+        prev_cap_hi = all[(size_t)c->rank - 1].hi;
+    }
+    if (c->rank + 1 < c->world) {
+        next_arena = static_cast<double*>(peers[(size_t)c->rank + 1]);
+        next_cap_lo = all[(size_t)c->rank + 1].lo;
+        next_cap_hi = all[(size_t)c->rank + 1].hi;
+    }
+    ATK_CUDA_CHECK(cudaMalloc(&d_ticket, sizeof(unsigned)));
+    ATK_CUDA_CHECK(cudaMemset(d_ticket, 0, sizeof(unsigned)));
+    seq = 0;
+    ready = true;
+}
+
+void PeerHalo::release() {
+    if (!ctx) return;
+    ctx->ipc_close(prev_arena);
+    ctx->ipc_close(next_arena);
+    if (arena) ctx->arena_give(arena);
+    cudaFree(d_ticket);
+    arena = prev_arena = next_arena = nullptr;
+    d_ticket = nullptr;
+    ready = false;
+}
+
+void PeerHalo::push(const double* to_prev, size_t n_to_prev, const double* to_next, size_t n_to_next) {
+    Context* c = ctx;
+    ++seq;
+    const size_t par = (size_t)(seq & 1);
+    // the previous rank receives into its "hi" buffer of this parity, the next rank into its "lo" buffer
+    double* prev_dst = prev_arena ? prev_arena + par * (prev_cap_lo + prev_cap_hi) + prev_cap_lo : nullptr;
+    double* next_dst = next_arena ? next_arena + par * (next_cap_lo + next_cap_hi) : nullptr;
+    unsigned long long* prev_flag =
+        prev_arena ? reinterpret_cast<unsigned long long*>(prev_arena + flag_offset(prev_cap_lo, prev_cap_hi)) + 1 : nullptr;
+    unsigned long long* next_flag =
+        next_arena ? reinterpret_cast<unsigned long long*>(next_arena + flag_offset(next_cap_lo, next_cap_hi)) + 0 : nullptr;
+    ATK_REQUIRE(n_to_prev <= (prev_arena ? prev_cap_hi : n_to_prev) && n_to_next <= (next_arena ? next_cap_lo : n_to_next),
+                ATK_ERR_INVALID_ARGUMENT, "peer halo: more entries than the neighbour's buffer holds");
+    ATK_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+    ATK_CUDA_CHECK(cudaStreamWaitEvent(c->comm_stream, c->ev_fork, 0));
+    const size_t work = std::max(n_to_prev, n_to_next) / 2 + 1;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((work + 255) / 256, 64));
+    halo_push_kernel<<<grid, 256, 0, c->comm_stream>>>(to_prev, n_to_prev, to_next, n_to_next, prev_dst, next_dst, prev_flag, next_flag,
+                                                      seq, d_ticket);
+    ATK_CUDA_CHECK(cudaGetLastError());
+    count_launch(c);
+    ATK_CUDA_CHECK(cudaEventRecord(c->ev_join, c->comm_stream));
+}
+
+void PeerHalo::wait() {
+    Context* c = ctx;
+    // our own push must have left before the caller may overwrite x; the neighbours' entries must have landed
+    ATK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(arena + flag_offset(cap_lo, cap_hi));
+    halo_wait_kernel<<<1, 32, 0, c->stream>>>(flags, prev_arena ? 1 : 0, next_arena ? 1 : 0, seq);
+    ATK_CUDA_CHECK(cudaGetLastError());
+    count_launch(c);
+}
+
 void Context::ipc_close(void* mapped) {
     if (!mapped) return;
     auto it = std::find(ipc_opened.begin(), ipc_opened.end(), mapped);
@@ -386,7 +510,11 @@ static void init_context(Context& c, int device) {
     ATK_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     c.sm_count = prop.multiProcessorCount;
     ATK_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    ATK_CUDA_CHECK(cudaStreamCreateWithFlags(&c.comm_stream, cudaStreamNonBlocking));
+    {  // communication stream at the highest priority: its small push kernels must not queue behind a full compute grid
+        int prio_lo = 0, prio_hi = 0;
+        ATK_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        ATK_CUDA_CHECK(cudaStreamCreateWithPriority(&c.comm_stream, cudaStreamNonBlocking, prio_hi));
+    }
     ATK_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
     ATK_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
     ATK_CUDA_CHECK(cudaEventCreate(&c.ev_t0));

@@ -199,7 +199,16 @@ struct MgsArgs {
     int sequential;
     double skip_below;   // V[j+1] is left untouched when ||w|| < skip_below (the reference breaks before assigning it)
     int* stop;           // optional {stopped, step}: set by the step whose norm ends the cycle; later steps return at once
+    // distributed contexts in peer-memory mode: every dependent reduction is per-CTA partial -> arrival counter -> CTA 0
+    // adds the partials in CTA order and stores the rank's sum into EVERY rank's packed {value half | sequence} words
+    // (NVLink stores) -> every CTA of every rank polls its local words and adds the rank sums in rank order.  ~4 us per
+    // projection instead of a kernel boundary, an NCCL all-gather and a second kernel.
+    int world, rank;
+    unsigned long long* ll;               // local packed words
+    unsigned long long* const* peer_ll;   // every rank's packed words as mapped here
+    unsigned long long seq_base;          // this launch uses sequence numbers seq_base + 1 .. seq_base + j + 1
 };
+constexpr int kMgsLlSlot = 2;  // packed-word slots 2 and 3 (0 and 1 belong to the CG loops)
 
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
     __syncthreads();
@@ -249,15 +258,75 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
     const unsigned G = gridDim.x;
 
     // h from a per-thread partial: fixed block tree, then (several CTAs) barrier + fixed-order sum of the CTA partials
+    __shared__ double rank_vals[kMaxRanks];
     auto finish_tree = [&](double acc, int i) -> double {
         const double bs = block_sum<BLOCK>(acc);
-        if (G == 1) return bs;
+        if (G == 1 && a.world == 1) return bs;
         double* part = a.partials + (size_t)(i & 1) * G;
-        if (threadIdx.x == 0) part[blockIdx.x] = bs;
-        grid_barrier(a.bar, target);
-        double s = 0.0;
-        for (unsigned q = threadIdx.x; q < G; q += BLOCK) s = add_rn(s, __ldcg(part + q));
-        return block_sum<BLOCK>(s);
+        if (a.world == 1) {
+            if (threadIdx.x == 0) part[blockIdx.x] = bs;
+            grid_barrier(a.bar, target);
+            double s = 0.0;
+            for (unsigned q = threadIdx.x; q < G; q += BLOCK) s = add_rn(s, __ldcg(part + q));
+            return block_sum<BLOCK>(s);
+        }
+        // ---- distributed: arrive, CTA 0 publishes the rank's sum to every rank, everyone polls its local words
+        const int slot = kMgsLlSlot + (i & 1);
+        const unsigned long long seq = a.seq_base + (unsigned long long)i + 1ull;
+        target += G;
+        if (threadIdx.x == 0) {
+            __stcg(part + blockIdx.x, bs);
+            __threadfence();
+            atomicAdd(a.bar, 1u);
+        }
+        if (blockIdx.x == 0) {
+            if (threadIdx.x == 0) {
+                unsigned spins = 0;
+                unsigned long long t0 = 0;
+                while (*reinterpret_cast<volatile unsigned*>(a.bar) < target) {
+                    if ((++spins & 0xfffu) == 0) {
+                        const unsigned long long now = global_timer_ns();
+                        if (t0 == 0) t0 = now;
+                        if (now - t0 > kPeerWaitNs) asm volatile("trap;");
+                    }
+                }
+                __threadfence();
+            }
+            __syncthreads();
+            double s = 0.0;
+            for (unsigned q = threadIdx.x; q < G; q += BLOCK) s = add_rn(s, __ldcg(part + q));
+            const double total = block_sum<BLOCK>(s);
+            if (threadIdx.x < 32 && (int)threadIdx.x < a.world) {
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(total);
+                const unsigned long long tag = (seq & 0xffffffffull) << 32;
+                unsigned long long* dst = ((int)threadIdx.x == a.rank ? a.ll : a.peer_ll[threadIdx.x]) + (size_t)(slot * kMaxRanks + a.rank) * 2;
+                st_relaxed_sys(dst, (bits & 0xffffffffull) | tag);
+                st_relaxed_sys(dst + 1, (bits >> 32) | tag);
+            }
+        }
+        if (threadIdx.x < 32 && (int)threadIdx.x < a.world) {
+            const unsigned long long* src = a.ll + (size_t)(slot * kMaxRanks + threadIdx.x) * 2;
+            const unsigned long long tag = seq & 0xffffffffull;
+            unsigned long long w0, w1;
+            unsigned spins = 0;
+            unsigned long long t0 = 0;
+            for (;;) {
+                w0 = ld_relaxed_sys(src);
+                w1 = ld_relaxed_sys(src + 1);
+                if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
+                if ((++spins & 0xfffu) == 0) {
+                    const unsigned long long now = global_timer_ns();
+                    if (t0 == 0) t0 = now;
+                    if (now - t0 > kPeerWaitNs) asm volatile("trap;");  // a rank died or fell out of step: fail loudly
+                }
+            }
+            rank_vals[threadIdx.x] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+        }
+        __syncthreads();
+        double h = rank_vals[0];
+        for (int q = 1; q < a.world; ++q) h = add_rn(h, rank_vals[q]);
+        __syncthreads();  // rank_vals is rewritten by the next projection
+        return h;
     };
 
     if constexpr (REG) {
@@ -327,31 +396,97 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
         double* stage = wsm + a.chunk;
         for (int64_t e = threadIdx.x; e < len; e += BLOCK) wsm[e] = a.w[c0 + e];
         __syncthreads();
-        for (int i = 0; i <= a.j; ++i) {
-            // i < j: projection against V[i];  i == j: the norm of what is left
-            const double* v = (i < a.j) ? a.V + (int64_t)i * a.ldv + c0 : nullptr;
-            double h;
-            if (a.sequential) {  // single CTA
+        if (a.sequential) {  // single CTA, reference-ordered sums: separate dot and update passes
+            for (int i = 0; i <= a.j; ++i) {
+                const double* v = (i < a.j) ? a.V + (int64_t)i * a.ldv + c0 : nullptr;
+                double h;
                 if (i < a.j) h = sequential_sum(len, stage, &bcast, [&](int64_t e) { return mul_rn(v[e], wsm[e]); });
                 else h = sequential_sum(len, stage, &bcast, [&](int64_t e) { return mul_rn(wsm[e], wsm[e]); });
-            } else {
-                double acc = 0.0;
-                if (i < a.j) for (int64_t e = threadIdx.x; e < len; e += BLOCK) acc = add_rn(acc, mul_rn(v[e], wsm[e]));
-                else for (int64_t e = threadIdx.x; e < len; e += BLOCK) acc = add_rn(acc, mul_rn(wsm[e], wsm[e]));
-                h = finish_tree(acc, i);
-            }
-            if (i < a.j) {
-                if (blockIdx.x == 0 && threadIdx.x == 0) a.h_out[i] = h;                                          // H(i,j)   (:75)
-                for (int64_t e = threadIdx.x; e < len; e += BLOCK) wsm[e] = sub_rn(wsm[e], mul_rn(v[e], h));      // (:76)
-                __syncthreads();
-            } else {
-                const double nrm = sqrt(h);                                                                       // (:79)
-                if (blockIdx.x == 0 && threadIdx.x == 0) {
-                    a.h_out[a.j] = nrm;
-                    if (a.stop && (nrm == 0.0 || nrm < a.skip_below)) { a.stop[1] = a.j; a.stop[0] = 1; }
+                if (i < a.j) {
+                    if (blockIdx.x == 0 && threadIdx.x == 0) a.h_out[i] = h;                                          // H(i,j)   (:75)
+                    for (int64_t e = threadIdx.x; e < len; e += BLOCK) wsm[e] = sub_rn(wsm[e], mul_rn(v[e], h));      // (:76)
+                    __syncthreads();
+                } else {
+                    const double nrm = sqrt(h);                                                                       // (:79)
+                    if (blockIdx.x == 0 && threadIdx.x == 0) {
+                        a.h_out[a.j] = nrm;
+                        if (a.stop && (nrm == 0.0 || nrm < a.skip_below)) { a.stop[1] = a.j; a.stop[0] = 1; }
+                    }
+                    if (nrm != 0.0 && !(nrm < a.skip_below))
+                        for (int64_t e = threadIdx.x; e < len; e += BLOCK) a.vnext[c0 + e] = __ddiv_rn(wsm[e], nrm);  // (:86)
                 }
-                if (nrm != 0.0 && !(nrm < a.skip_below))
-                    for (int64_t e = threadIdx.x; e < len; e += BLOCK) a.vnext[c0 + e] = __ddiv_rn(wsm[e], nrm);  // (:86)
+            }
+        } else {
+            // Tree sums: ONE pass per projection.  Pass i applies the update of projection i-1 (w -= V[i-1]*h_(i-1), the
+            // column is still in L2) and forms the products with V[i] (streamed from HBM) on the updated values - the same
+            // per-element arithmetic in the same order as separate passes, with every thread touching only its own entries
+            // of w.  16-byte accesses when the columns allow it; four independent loads in flight per thread and array.
+            const bool vec = ((a.ldv & 1) == 0) && ((c0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.V) & 15u) == 0);
+            double hprev = 0.0;
+            for (int i = 0; i <= a.j; ++i) {
+                const double* vp = (i > 0) ? a.V + (int64_t)(i - 1) * a.ldv + c0 : nullptr;
+                const double* vc = (i < a.j) ? a.V + (int64_t)i * a.ldv + c0 : nullptr;
+                double acc = 0.0;
+                if (vec) {
+                    const int64_t len2 = len >> 1;
+                    double acc1 = 0.0;
+                    double2* w2 = reinterpret_cast<double2*>(wsm);
+                    auto one = [&](int64_t e, const double2 pv, const double2 cv) {
+                        double2 wv = w2[e];
+                        if (vp) {
+                            wv.x = sub_rn(wv.x, mul_rn(pv.x, hprev));
+                            wv.y = sub_rn(wv.y, mul_rn(pv.y, hprev));
+                            w2[e] = wv;
+                        }
+                        acc = add_rn(acc, vc ? mul_rn(cv.x, wv.x) : mul_rn(wv.x, wv.x));
+                        acc1 = add_rn(acc1, vc ? mul_rn(cv.y, wv.y) : mul_rn(wv.y, wv.y));
+                    };
+                    const double2 z2 = make_double2(0.0, 0.0);
+                    auto ldp = [&](int64_t e) -> double2 { return vp ? __ldcg(reinterpret_cast<const double2*>(vp) + e) : z2; };
+                    auto ldc = [&](int64_t e) -> double2 { return vc ? __ldcs(reinterpret_cast<const double2*>(vc) + e) : z2; };
+                    int64_t e = threadIdx.x;
+                    for (; e + 3 * BLOCK < len2; e += 4 * BLOCK) {
+                        const double2 p0 = ldp(e), p1 = ldp(e + BLOCK), p2 = ldp(e + 2 * BLOCK), p3 = ldp(e + 3 * BLOCK);
+                        const double2 q0 = ldc(e), q1 = ldc(e + BLOCK), q2 = ldc(e + 2 * BLOCK), q3 = ldc(e + 3 * BLOCK);
+                        one(e, p0, q0);
+                        one(e + BLOCK, p1, q1);
+                        one(e + 2 * BLOCK, p2, q2);
+                        one(e + 3 * BLOCK, p3, q3);
+                    }
+                    for (; e < len2; e += BLOCK) one(e, ldp(e), ldc(e));
+                    acc = add_rn(acc, acc1);
+                    if ((len & 1) && threadIdx.x == 0) {
+                        const int64_t t = len - 1;
+                        double wv = wsm[t];
+                        if (vp) {
+                            wv = sub_rn(wv, mul_rn(vp[t], hprev));
+                            wsm[t] = wv;
+                        }
+                        acc = add_rn(acc, vc ? mul_rn(vc[t], wv) : mul_rn(wv, wv));
+                    }
+                } else {
+                    for (int64_t e = threadIdx.x; e < len; e += BLOCK) {
+                        double wv = wsm[e];
+                        if (vp) {
+                            wv = sub_rn(wv, mul_rn(vp[e], hprev));
+                            wsm[e] = wv;
+                        }
+                        acc = add_rn(acc, vc ? mul_rn(vc[e], wv) : mul_rn(wv, wv));
+                    }
+                }
+                const double h = finish_tree(acc, i);
+                if (i < a.j) {
+                    if (blockIdx.x == 0 && threadIdx.x == 0) a.h_out[i] = h;  // H(i,j)   (:75)
+                    hprev = h;
+                } else {
+                    const double nrm = sqrt(h);  // (:79)
+                    if (blockIdx.x == 0 && threadIdx.x == 0) {
+                        a.h_out[a.j] = nrm;
+                        if (a.stop && (nrm == 0.0 || nrm < a.skip_below)) { a.stop[1] = a.j; a.stop[0] = 1; }
+                    }
+                    if (nrm != 0.0 && !(nrm < a.skip_below))  // (finish_tree ended with a block-wide barrier: w is complete)
+                        for (int64_t e = threadIdx.x; e < len; e += BLOCK) a.vnext[c0 + e] = __ddiv_rn(wsm[e], nrm);  // (:86)
+                }
             }
         }
     }
@@ -383,8 +518,18 @@ struct PersistentMgs {
         cudaFree(d_part);
     }
     void setup(Context* ctx, int64_t n, int max_steps) {
-        if (ctx->world != 1 || n <= 0 || std::getenv("ATK_GMRES_NO_PERSISTENT")) return;
+        int mine = try_setup(ctx, n, max_steps) ? 1 : 0;
+        if (ctx->world > 1) {  // every rank must take the same path: the kernels wait for each other
+            std::vector<int> all((size_t)ctx->world);
+            allgather_host_bytes(ctx, &mine, all.data(), sizeof(int));
+            for (int v : all) mine = mine && v;
+        }
+        usable = mine != 0;
+    }
+    bool try_setup(Context* ctx, int64_t n, int max_steps) {
+        if (n <= 0 || std::getenv("ATK_GMRES_NO_PERSISTENT")) return false;
         const bool seq = ctx->reduction == ATK_REDUCE_SEQUENTIAL;
+        if (ctx->world > 1 && (!ctx->p2p || seq)) return false;  // distributed: peer-memory mode, tree sums only
         int64_t c = seq ? n : std::max<int64_t>(2048, (n + ctx->sm_count - 1) / ctx->sm_count);
         c = (c + 1) & ~(int64_t)1;
         const int64_t rows = std::min(c, n);
@@ -394,7 +539,7 @@ struct PersistentMgs {
         kernel = mgs_kernel_for(block, reg);
         int max_smem = 0;
         ATK_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-        if (sm + 1024 > (size_t)max_smem) return;
+        if (sm + 1024 > (size_t)max_smem) return false;
         // per function and process-wide: always the device maximum, so that a later, smaller solve cannot lower the limit
         // under a live, larger one (two GMRES objects of different sizes)
         cudaFuncAttributes fa;
@@ -404,21 +549,25 @@ struct PersistentMgs {
         int per_sm = 0;
         ATK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, sm));
         const int g = (int)((n + c - 1) / c);
-        if (per_sm < 1 || g > per_sm * ctx->sm_count) return;
+        if (per_sm < 1 || g > per_sm * ctx->sm_count) return false;
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        if (!coop) return false;
         grid = g;
         chunk = c;
         smem = sm;
         n_bars = max_steps + 1;
         ATK_CUDA_CHECK(cudaMalloc(&d_bar, sizeof(unsigned) * (size_t)n_bars));
         ATK_CUDA_CHECK(cudaMalloc(&d_part, sizeof(double) * 2 * (size_t)g));
-        usable = true;
+        return true;
     }
     void reset_barriers(cudaStream_t st) { ATK_CUDA_CHECK(cudaMemsetAsync(d_bar, 0, sizeof(unsigned) * (size_t)n_bars, st)); }
     // projections of w against columns [0, ncols) of V, then the norm and V_next = w / norm; h_out[0..ncols] on the device
     void launch(Context* ctx, int64_t n, int ncols, int step, const double* V, int64_t ldv, const double* w, double* vnext,
                 double* h_out, double skip_below, int* stop = nullptr) {
         MgsArgs ma{n, ncols, V, ldv, w, vnext, h_out, d_part, d_bar + step, chunk, ctx->reduction == ATK_REDUCE_SEQUENTIAL ? 1 : 0,
-                   skip_below, stop};
+                   skip_below, stop, ctx->world, ctx->rank, ctx->d_ll, ctx->d_peer_ll, ctx->epoch};
+        if (ctx->world > 1) ctx->epoch += (unsigned long long)ncols + 2ull;  // same advance on every rank
         void* kargs[] = {&ma};
         ATK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(block), kargs, smem, ctx->stream));
         count_launch(ctx);

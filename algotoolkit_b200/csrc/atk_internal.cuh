@@ -106,6 +106,12 @@ struct Context {
     void ws_release(void* ptr);     // back to the cache
     void ws_trim();                 // cudaFree every idle block
 
+    // true while ctx->stream is being captured into a CUDA graph (the generic CG loop captures one iteration): work whose
+    // kernel arguments change from call to call (PeerHalo sequence numbers) must then take its capturable NCCL form
+    bool capturing() const {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        return cudaStreamIsCapturing(stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone;
+    }
     double* slot(int s) const { return d_gather + (size_t)s * kMaxRanks; }
     int reduce_grid() const { return sm_count * 4; }
 };
@@ -146,6 +152,36 @@ void allgather_host_bytes(Context* ctx, const void* send, void* recv, size_t byt
 // to ranks rank-1 / rank+1 and receive `from_prev` / `from_next` from them; a count of 0 skips that transfer.
 void exchange_ranges(Context* ctx, const double* to_prev, size_t n_to_prev, const double* to_next, size_t n_to_next,
                      double* from_prev, size_t n_from_prev, double* from_next, size_t n_from_next, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------ peer-memory halo exchange
+// Neighbour exchange of an operator apply without NCCL (distributed contexts with Context::p2p): every rank exports one
+// arena [lo0 | hi0 | lo1 | hi1 | flags]; an apply PUSHES its boundary entries straight into the neighbours' buffers of the
+// current parity with NVLink stores (one small kernel on the high-priority communication stream, system fence, the CTA
+// that finishes last releases a sequence number into the neighbours' flag words) while the rows that need no remote
+// entry are computed; a one-warp wait kernel on the compute stream then spins on the LOCAL flags before the boundary rows
+// run.  Two parities suffice: a rank can only push apply n+2 after it has seen its neighbour's flag n+1, which the
+// neighbour released after its own reads of apply n.
+struct PeerHalo {
+    Context* ctx = nullptr;
+    size_t cap_lo = 0, cap_hi = 0;   // doubles received from the previous / next rank per apply
+    double* arena = nullptr;         // exported allocation
+    double* prev_arena = nullptr;    // neighbours' arenas mapped here
+    double* next_arena = nullptr;
+    size_t prev_cap_lo = 0, prev_cap_hi = 0, next_cap_lo = 0, next_cap_hi = 0;
+    unsigned* d_ticket = nullptr;
+    unsigned long long seq = 0;      // applies so far (identical on every rank: applies are collective)
+    bool ready = false;
+    static size_t flag_offset(size_t lo, size_t hi) { return (2 * (lo + hi) + 15) / 16 * 16; }  // in doubles
+    static size_t arena_doubles(size_t lo, size_t hi) { return flag_offset(lo, hi) + 16; }
+    void setup(Context* c, size_t lo, size_t hi);  // collective over all ranks
+    void release();
+    // entries for the previous rank (its "hi" side) and the next rank (its "lo" side); runs on ctx->comm_stream after
+    // everything enqueued on ctx->stream so far, and starts the next apply (parity flips)
+    void push(const double* to_prev, size_t n_to_prev, const double* to_next, size_t n_to_next);
+    void wait();  // on ctx->stream: returns (on the device) once both neighbours' entries of this apply have landed
+    const double* lo() const { return arena + (seq & 1) * (cap_lo + cap_hi); }
+    const double* hi() const { return arena + (seq & 1) * (cap_lo + cap_hi) + cap_lo; }
+};
 
 // ------------------------------------------------------------------------------------------ fused CG state
 // Device-resident scalars of the fused two-kernel CG iteration (atk_cg.cu drives it, the operator supplies KA).

@@ -18,6 +18,8 @@
 // Algorithmic traffic per SpMV: 12*nnz + 4*(n+1) + 8*m + 8*n bytes.
 #include <algorithm>
 
+#include <string>
+
 #include "atk_internal.cuh"
 
 namespace atk {
@@ -516,8 +518,9 @@ struct AssembledMatrix : public Operator {
     bool dist = false;
     int h_lo = 0, h_hi = 0;            // entries needed from the previous / next rank
     int send_prev = 0, send_next = 0;  // entries the previous / next rank needs from this one
-    double* halo_lo = nullptr;
+    double* halo_lo = nullptr;         // receive buffers of the NCCL exchange
     double* halo_hi = nullptr;
+    PeerHalo ph;                       // peer-memory exchange (Context::p2p): entries stored straight into the neighbours
     int col_shift = 0;                 // local column + col_shift = global column
     int s_int_begin = 0, s_int_end = 0;  // slices whose rows touch no received entry: they run while the exchange is in flight
 
@@ -525,6 +528,7 @@ struct AssembledMatrix : public Operator {
         cudaFree(row_ptr); cudaFree(csr_col); cudaFree(csr_val);
         cudaFree(wscan); cudaFree(perm); cudaFree(sell_col); cudaFree(sell_val); cudaFree(blk_row);
         cudaFree(halo_lo); cudaFree(halo_hi);
+        ph.release();
     }
     bool has_csr() const override { return true; }
     void export_csr(int* h_row_ptr, int* h_col, double* h_val) const override {
@@ -542,7 +546,11 @@ struct AssembledMatrix : public Operator {
         double* dot_out = dot_slot >= 0 ? c->slot(dot_slot) + c->rank : nullptr;
         const int grid = c->sm_count * 8;
         if (format == ATK_FORMAT_SELL) {
-            const DistX dx{halo_lo, halo_hi, h_lo, n_rows};
+            const char* comm = std::getenv("ATK_COMM");
+            const bool peer_push = dist && ph.ready && !(comm && std::string(comm) == "nccl") && !c->capturing();
+            if (peer_push)  // pushes this apply's entries to the neighbours and flips to the receive buffers of its parity
+                ph.push(x, (size_t)send_prev, x + (n_rows - send_next), (size_t)send_next);
+            const DistX dx{peer_push ? ph.lo() : halo_lo, peer_push ? ph.hi() : halo_hi, h_lo, n_rows};
             const bool dot = dot_slot >= 0;
             int pbase = 0;
             // (measured at 2 GPUs, 256^3: the persistent grid of the interior piece fills every SM, so the one-CTA transfer
@@ -567,14 +575,17 @@ struct AssembledMatrix : public Operator {
                 piece(0, n_slices, true);
             } else {
                 // neighbour entries on the communication stream while the slices that need none of them run
-                ATK_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
-                ATK_CUDA_CHECK(cudaStreamWaitEvent(c->comm_stream, c->ev_fork, 0));
-                exchange_ranges(c, x, (size_t)send_prev, x + (n_rows - send_next), (size_t)send_next, halo_lo, (size_t)h_lo, halo_hi,
-                                (size_t)h_hi, c->comm_stream);
-                ATK_CUDA_CHECK(cudaEventRecord(c->ev_join, c->comm_stream));
+                if (!peer_push) {
+                    ATK_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+                    ATK_CUDA_CHECK(cudaStreamWaitEvent(c->comm_stream, c->ev_fork, 0));
+                    exchange_ranges(c, x, (size_t)send_prev, x + (n_rows - send_next), (size_t)send_next, halo_lo, (size_t)h_lo,
+                                    halo_hi, (size_t)h_hi, c->comm_stream);
+                    ATK_CUDA_CHECK(cudaEventRecord(c->ev_join, c->comm_stream));
+                }
                 const bool has_lo = s_int_begin > 0, has_hi = s_int_end < n_slices;
                 piece(s_int_begin, s_int_end, !has_lo && !has_hi, true);
-                ATK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+                if (peer_push) ph.wait();
+                else ATK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
                 piece(0, s_int_begin, !has_hi);
                 piece(s_int_end, n_slices, true);
             }
@@ -781,6 +792,7 @@ static Operator* build_from_device_csc(Context* ctx, int n_rows, int n_cols, int
             A->send_next = ctx->rank + 1 < ctx->world ? all[(size_t)ctx->rank + 1].h_lo : 0;
             A->halo_lo = dalloc<double>((size_t)A->h_lo);
             A->halo_hi = dalloc<double>((size_t)A->h_hi);
+            A->ph.setup(ctx, (size_t)A->h_lo, (size_t)A->h_hi);  // collective; no-op unless the GPUs can map each other
             A->col_shift = row_lo - A->h_lo;
             if (nnz_loc > 0 && A->col_shift != 0) {
                 shift_cols_kernel<<<grid_for(nnz_loc, 256, cap), 256, 0, st>>>(nnz_loc, A->col_shift, A->csr_col);

@@ -17,6 +17,7 @@
 // exchange_halo() fills on the communication stream while the interior planes are being computed.
 #include <algorithm>
 #include <cstdlib>
+#include <string>
 
 #include "atk_internal.cuh"
 
@@ -1462,8 +1463,11 @@ void allow_fused_smem() {
 
 struct Stencil7 : public Operator {
     StencilGeom g;
-    double* halo_lo = nullptr;
-    double* halo_hi = nullptr;
+    double* nccl_halo_lo = nullptr;  // receive buffers of the NCCL exchange
+    double* nccl_halo_hi = nullptr;
+    const double* halo_lo = nullptr;  // the halo planes the kernels of the current apply read
+    const double* halo_hi = nullptr;
+    PeerHalo ph;                      // peer-memory exchange of the plain apply (Context::p2p)
     int kc = 64;
     int tile = 4;  // 0: 32x8 threads (64x8 points), 1: 64x4 (128x4), 2: 32x16 (64x16), 3: 64x8 (128x8)
 
@@ -1482,8 +1486,9 @@ struct Stencil7 : public Operator {
     ~Stencil7() override {
         cudaFree(oc_part);
         cudaFree(ps_part);
-        cudaFree(halo_lo);
-        cudaFree(halo_hi);
+        cudaFree(nccl_halo_lo);
+        cudaFree(nccl_halo_hi);
+        ph.release();
         cudaFree(fsend);
         // the neighbours may still have this rank's halo arena mapped: unmap theirs now, free ours with the context
         ctx->ipc_close(nb_lo_arena);
@@ -1823,6 +1828,10 @@ struct Stencil7 : public Operator {
         }
     }
 
+    static bool apply_over_nccl() {
+        const char* e = std::getenv("ATK_COMM");
+        return e && std::string(e) == "nccl";
+    }
     void apply(const double* x, double* y, int dot_slot, const int* skip_flag) override {
         Context* c = ctx;
         const bool dot = dot_slot >= 0;
@@ -1833,13 +1842,23 @@ struct Stencil7 : public Operator {
         } else {
             // halo exchange on the communication stream, overlapped with the planes that do not need it
             const size_t plane = (size_t)g.nx * g.ny;
-            ATK_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
-            ATK_CUDA_CHECK(cudaStreamWaitEvent(c->comm_stream, c->ev_fork, 0));
-            exchange_halo(c, x, x + (size_t)(g.nz_loc - 1) * plane, halo_lo, halo_hi, plane, c->comm_stream);
-            ATK_CUDA_CHECK(cudaEventRecord(c->ev_join, c->comm_stream));
+            const bool peer_push = ph.ready && !apply_over_nccl() && !c->capturing();
+            if (peer_push) {  // boundary planes stored straight into the neighbours' buffers over NVLink, flag released
+                ph.push(x, plane, x + (size_t)(g.nz_loc - 1) * plane, plane);
+                halo_lo = ph.lo();
+                halo_hi = ph.hi();
+            } else {
+                halo_lo = nccl_halo_lo;
+                halo_hi = nccl_halo_hi;
+                ATK_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+                ATK_CUDA_CHECK(cudaStreamWaitEvent(c->comm_stream, c->ev_fork, 0));
+                exchange_halo(c, x, x + (size_t)(g.nz_loc - 1) * plane, nccl_halo_lo, nccl_halo_hi, plane, c->comm_stream);
+                ATK_CUDA_CHECK(cudaEventRecord(c->ev_join, c->comm_stream));
+            }
             int nb_int = 0, nb_lo = 0, nb_hi = 0;
             if (g.nz_loc > 2) launch_tile(x, y, 1, g.nz_loc - 1, dot, 0, false, dot_out, skip_flag, &nb_int);
-            ATK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+            if (peer_push) ph.wait();
+            else ATK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
             if (g.nz_loc >= 2) {
                 launch_tile(x, y, 0, 1, dot, nb_int, false, dot_out, skip_flag, &nb_lo);
                 launch_tile(x, y, g.nz_loc - 1, g.nz_loc, dot, nb_int + nb_lo, true, dot_out, skip_flag, &nb_hi);
@@ -2028,11 +2047,15 @@ __global__ void __launch_bounds__(TX* TY) stencil27_smem_kernel(StencilGeom g, C
 struct Stencil27 : public Operator {
     StencilGeom g;
     Coef27 cf;
-    double* halo_lo = nullptr;
-    double* halo_hi = nullptr;
+    double* nccl_halo_lo = nullptr;
+    double* nccl_halo_hi = nullptr;
+    const double* halo_lo = nullptr;  // the halo planes the kernels of the current apply read
+    const double* halo_hi = nullptr;
+    PeerHalo ph;
     ~Stencil27() override {
-        cudaFree(halo_lo);
-        cudaFree(halo_hi);
+        cudaFree(nccl_halo_lo);
+        cudaFree(nccl_halo_hi);
+        ph.release();
     }
     int kc27 = 64;  // planes per chunk of the shared-memory kernel (ATK_STENCIL27_KC)
     void launch(const double* x, double* y, int k_lo, int k_hi) {
@@ -2069,12 +2092,23 @@ struct Stencil27 : public Operator {
             launch(x, y, 0, g.nz_loc);
         } else {
             const size_t plane = (size_t)g.nx * g.ny;
-            ATK_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
-            ATK_CUDA_CHECK(cudaStreamWaitEvent(c->comm_stream, c->ev_fork, 0));
-            exchange_halo(c, x, x + (size_t)(g.nz_loc - 1) * plane, halo_lo, halo_hi, plane, c->comm_stream);
-            ATK_CUDA_CHECK(cudaEventRecord(c->ev_join, c->comm_stream));
+            const char* comm = std::getenv("ATK_COMM");
+            const bool peer_push = ph.ready && !(comm && std::string(comm) == "nccl") && !c->capturing();
+            if (peer_push) {
+                ph.push(x, plane, x + (size_t)(g.nz_loc - 1) * plane, plane);
+                halo_lo = ph.lo();
+                halo_hi = ph.hi();
+            } else {
+                halo_lo = nccl_halo_lo;
+                halo_hi = nccl_halo_hi;
+                ATK_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+                ATK_CUDA_CHECK(cudaStreamWaitEvent(c->comm_stream, c->ev_fork, 0));
+                exchange_halo(c, x, x + (size_t)(g.nz_loc - 1) * plane, nccl_halo_lo, nccl_halo_hi, plane, c->comm_stream);
+                ATK_CUDA_CHECK(cudaEventRecord(c->ev_join, c->comm_stream));
+            }
             launch(x, y, 1, g.nz_loc - 1);  // planes that need no halo run while the exchange is in flight
-            ATK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+            if (peer_push) ph.wait();
+            else ATK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
             launch(x, y, 0, 1);
             if (g.nz_loc > 1) launch(x, y, g.nz_loc - 1, g.nz_loc);
         }
@@ -2111,10 +2145,11 @@ Operator* make_stencil7(Context* ctx, int nx, int ny, int nz, double cx, double 
     if (const char* e = std::getenv("ATK_STENCIL_TMA")) S->use_tma = std::atoi(e) != 0;
     try {
         if (ctx->world > 1) {
-            ATK_CUDA_CHECK(cudaMalloc(&S->halo_lo, sizeof(double) * (size_t)plane));
-            ATK_CUDA_CHECK(cudaMalloc(&S->halo_hi, sizeof(double) * (size_t)plane));
-            ATK_CUDA_CHECK(cudaMemset(S->halo_lo, 0, sizeof(double) * (size_t)plane));
-            ATK_CUDA_CHECK(cudaMemset(S->halo_hi, 0, sizeof(double) * (size_t)plane));
+            ATK_CUDA_CHECK(cudaMalloc(&S->nccl_halo_lo, sizeof(double) * (size_t)plane));
+            ATK_CUDA_CHECK(cudaMalloc(&S->nccl_halo_hi, sizeof(double) * (size_t)plane));
+            ATK_CUDA_CHECK(cudaMemset(S->nccl_halo_lo, 0, sizeof(double) * (size_t)plane));
+            ATK_CUDA_CHECK(cudaMemset(S->nccl_halo_hi, 0, sizeof(double) * (size_t)plane));
+            S->ph.setup(ctx, (size_t)plane, (size_t)plane);  // collective; no-op unless the GPUs can map each other
             ATK_CUDA_CHECK(cudaMalloc(&S->fsend, sizeof(double) * 4 * (size_t)plane));
             if (ctx->p2p) {
                 S->frecv = static_cast<double*>(ctx->arena_take(sizeof(double) * 6 * (size_t)plane));
@@ -2165,10 +2200,11 @@ Operator* make_stencil27(Context* ctx, int nx, int ny, int nz, const double* coe
     S->nnz = nnz;
     try {
         if (ctx->world > 1) {
-            ATK_CUDA_CHECK(cudaMalloc(&S->halo_lo, sizeof(double) * (size_t)plane));
-            ATK_CUDA_CHECK(cudaMalloc(&S->halo_hi, sizeof(double) * (size_t)plane));
-            ATK_CUDA_CHECK(cudaMemset(S->halo_lo, 0, sizeof(double) * (size_t)plane));
-            ATK_CUDA_CHECK(cudaMemset(S->halo_hi, 0, sizeof(double) * (size_t)plane));
+            ATK_CUDA_CHECK(cudaMalloc(&S->nccl_halo_lo, sizeof(double) * (size_t)plane));
+            ATK_CUDA_CHECK(cudaMalloc(&S->nccl_halo_hi, sizeof(double) * (size_t)plane));
+            ATK_CUDA_CHECK(cudaMemset(S->nccl_halo_lo, 0, sizeof(double) * (size_t)plane));
+            ATK_CUDA_CHECK(cudaMemset(S->nccl_halo_hi, 0, sizeof(double) * (size_t)plane));
+            S->ph.setup(ctx, (size_t)plane, (size_t)plane);
         }
     } catch (...) {
         delete S;

@@ -757,6 +757,28 @@ def test_gmres_op27_larger_systems_vs_reference(ctx, port, key):
         assert digest(seq["x"]) == g["x_sha256"] and list(seq["resid"]) == g["resid"]
 
 
+@pytest.mark.parametrize("dims", [(96, 96, 96), (95, 97, 96)])
+def test_gmres_persistent_step_with_w_in_shared_memory(ctx, dims, monkeypatch):
+    """Slices above 4096 rows per CTA keep w in shared memory and fuse the update of projection i-1 with the products of
+    projection i (16-byte accesses when the column stride is even, scalar otherwise): must agree with the per-projection
+    kernels and with the batched form to 1e-10."""
+    from algotoolkit_b200 import synthetic
+
+    nx, ny, nz = dims
+    rows = nx * ny * nz
+    op = ctx.operator_stencil27(nx, ny, nz, synthetic.stencil27_coefficients())
+    b = op.apply_numpy(synthetic.u01_array(777, 0, rows))
+    pers = ctx.gmres_solve_host(op, b, np.zeros(rows), 2, 24, 1e-6)
+    assert pers["kernel_launches"] < 2 * (24 * 3 + 20)  # one step kernel per Arnoldi step, not one pair per projection
+    monkeypatch.setenv("ATK_GMRES_NO_PERSISTENT", "1")
+    plain = ctx.gmres_solve_host(op, b, np.zeros(rows), 2, 24, 1e-6)
+    bat = ctx.gmres_solve_host(op, b, np.zeros(rows), 2, 24, 1e-6, ortho=capi.GMRES_MGS_BATCHED)
+    for other in (plain, bat):
+        assert np.allclose(pers["resid"], other["resid"], rtol=REL, atol=0.0)
+        assert relerr(pers["x"], other["x"]) < REL
+    op.destroy()
+
+
 # ------------------------------------------------------------------------------------------------ CSR format kernels
 def test_csr_stream_is_bit_exact_and_vector_kernel_still_covered(ctx, port, monkeypatch):
     """CSR format: short rows -> CSR-stream (per-row ascending sums: bit-identical to the CSC matvec, empty rows, rows
