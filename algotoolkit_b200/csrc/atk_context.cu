@@ -260,8 +260,8 @@ void PeerHalo::setup(Context* c, size_t lo, size_t hi) {
         next_cap_lo = all[(size_t)c->rank + 1].lo;
         next_cap_hi = all[(size_t)c->rank + 1].hi;
     }
-    ATK_CUDA_CHECK(cudaMalloc(&d_ticket, sizeof(unsigned)));
-    ATK_CUDA_CHECK(cudaMemset(d_ticket, 0, sizeof(unsigned)));
+    ATK_CUDA_CHECK(cudaMalloc(&d_ticket, sizeof(unsigned) * 4));
+    ATK_CUDA_CHECK(cudaMemset(d_ticket, 0, sizeof(unsigned) * 4));
     seq = 0;
     ready = true;
 }
@@ -277,17 +277,27 @@ void PeerHalo::release() {
     ready = false;
 }
 
-void PeerHalo::push(const double* to_prev, size_t n_to_prev, const double* to_next, size_t n_to_next) {
-    Context* c = ctx;
+PeerHalo::Targets PeerHalo::begin() {
     ++seq;
     const size_t par = (size_t)(seq & 1);
+    Targets t;
     // the previous rank receives into its "hi" buffer of this parity, the next rank into its "lo" buffer
-    double* prev_dst = prev_arena ? prev_arena + par * (prev_cap_lo + prev_cap_hi) + prev_cap_lo : nullptr;
-    double* next_dst = next_arena ? next_arena + par * (next_cap_lo + next_cap_hi) : nullptr;
-    unsigned long long* prev_flag =
-        prev_arena ? reinterpret_cast<unsigned long long*>(prev_arena + flag_offset(prev_cap_lo, prev_cap_hi)) + 1 : nullptr;
-    unsigned long long* next_flag =
-        next_arena ? reinterpret_cast<unsigned long long*>(next_arena + flag_offset(next_cap_lo, next_cap_hi)) + 0 : nullptr;
+    t.prev_dst = prev_arena ? prev_arena + par * (prev_cap_lo + prev_cap_hi) + prev_cap_lo : nullptr;
+    t.next_dst = next_arena ? next_arena + par * (next_cap_lo + next_cap_hi) : nullptr;
+    t.prev_flag = prev_arena ? reinterpret_cast<unsigned long long*>(prev_arena + flag_offset(prev_cap_lo, prev_cap_hi)) + 1 : nullptr;
+    t.next_flag = next_arena ? reinterpret_cast<unsigned long long*>(next_arena + flag_offset(next_cap_lo, next_cap_hi)) + 0 : nullptr;
+    t.my_flags = reinterpret_cast<const unsigned long long*>(arena + flag_offset(cap_lo, cap_hi));
+    t.seq = seq;
+    return t;
+}
+
+void PeerHalo::push(const double* to_prev, size_t n_to_prev, const double* to_next, size_t n_to_next) {
+    Context* c = ctx;
+    const Targets tg = begin();
+    double* prev_dst = tg.prev_dst;
+    double* next_dst = tg.next_dst;
+    unsigned long long* prev_flag = tg.prev_flag;
+    unsigned long long* next_flag = tg.next_flag;
     ATK_REQUIRE(n_to_prev <= (prev_arena ? prev_cap_hi : n_to_prev) && n_to_next <= (next_arena ? next_cap_lo : n_to_next),
                 ATK_ERR_INVALID_ARGUMENT, "peer halo: more entries than the neighbour's buffer holds");
     ATK_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));

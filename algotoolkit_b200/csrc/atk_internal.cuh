@@ -178,6 +178,18 @@ struct PeerHalo {
     // entries for the previous rank (its "hi" side) and the next rank (its "lo" side); runs on ctx->comm_stream after
     // everything enqueued on ctx->stream so far, and starts the next apply (parity flips)
     void push(const double* to_prev, size_t n_to_prev, const double* to_next, size_t n_to_next);
+    // For operators whose own kernel does the stores and the waiting: starts the next apply (parity flips) and returns
+    // where its entries go, which flag words to release / poll, and the sequence number.  d_ticket[1], [2] are free for
+    // that kernel's arrival counters.
+    struct Targets {
+        double* prev_dst;
+        double* next_dst;
+        unsigned long long* prev_flag;
+        unsigned long long* next_flag;
+        const unsigned long long* my_flags;
+        unsigned long long seq;
+    };
+    Targets begin();
     void wait();  // on ctx->stream: returns (on the device) once both neighbours' entries of this apply have landed
     const double* lo() const { return arena + (seq & 1) * (cap_lo + cap_hi); }
     const double* hi() const { return arena + (seq & 1) * (cap_lo + cap_hi) + cap_lo; }

@@ -578,12 +578,38 @@ __global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_smem_kernel(StencilG
 // y = A x (+ partial sums of x.y) with the same data path as KA: x planes stream through a 4-deep ring of
 // shared-memory tiles filled by cp.async three planes ahead; k-1 / k / k+1 centre values live in registers.
 // Used when nx is even and x, y are 16-byte aligned; the register-marching kernel above is the general fallback.
-template <int TX, int TY, bool DOT>
+// PEER (distributed contexts in peer-memory mode): the WHOLE slab in one launch.  The CTAs whose chunk holds the slab's first
+// / last plane are scheduled first; each stores its tile of that plane straight into the neighbour's halo buffer (NVLink),
+// the last of them to finish releases the apply's sequence number into the neighbour's flag word, and each then waits on
+// its LOCAL flag for the neighbour's plane before it marches.  No exchange kernel, no NCCL call, no second stream.
+struct PeerApply {
+    double* prev_dst = nullptr;            // previous rank's "hi" halo buffer of this apply's parity (null: no such rank)
+    double* next_dst = nullptr;            // next rank's "lo" halo buffer
+    unsigned long long* prev_flag = nullptr;
+    unsigned long long* next_flag = nullptr;
+    const unsigned long long* my_flags = nullptr;  // [0] set by the previous rank, [1] by the next rank
+    unsigned* tickets = nullptr;           // [2] self-resetting arrival counters (lo side, hi side)
+    unsigned long long seq = 0;
+};
+__device__ __forceinline__ void peer_flag_wait(const unsigned long long* flag, unsigned long long seq) {
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    while (ld_acquire_sys(flag) < seq) {
+        if ((++spins & 0xfffu) == 0) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > kPeerWaitNs) asm volatile("trap;");  // the neighbour died or fell out of step: fail loudly
+        }
+    }
+}
+
+template <int TX, int TY, bool DOT, bool PEER = false>
 __global__ void __launch_bounds__(TX* TY) stencil7_smem_kernel(StencilGeom g, const double* __restrict__ x, double* __restrict__ y,
                                                                 const double* __restrict__ halo_lo,
                                                                 const double* __restrict__ halo_hi, int k_lo, int k_hi, int kc,
                                                                 double* partials, int partial_base, unsigned* ticket,
-                                                                double* dot_out, int dot_final, const int* skip_flag) {
+                                                                double* dot_out, int dot_final, const int* skip_flag,
+                                                                PeerApply pa = PeerApply()) {
     constexpr int DEPTH = 4;
     constexpr int W = 2 * TX + 4;
     constexpr int STAGE = (TY + 2) * W;  // doubles per ring stage
@@ -599,11 +625,49 @@ __global__ void __launch_bounds__(TX* TY) stencil7_smem_kernel(StencilGeom g, co
     const int j_lo = blockIdx.y * TY;
     const int i0 = i_lo + 2 * tx;
     const int j = j_lo + ty;
-    const int kb = k_lo + blockIdx.z * kc;
+    int zc = blockIdx.z;
+    if constexpr (PEER) {  // chunk order: first, last, then the ones in between (CTAs are scheduled in ascending blockIdx.z)
+        const int nzc = gridDim.z;
+        zc = (zc == 0) ? 0 : (zc == 1 ? nzc - 1 : zc - 1);
+    }
+    const int kb = k_lo + zc * kc;
     const int ke = min(kb + kc, k_hi);
     const bool active = (i0 < g.nx) && (j < g.ny);
     const int64_t sxy = (int64_t)g.nx * g.ny;
     double dacc = 0.0;
+    if constexpr (PEER) {
+        if (kb < ke) {
+            const bool has_first = kb == 0, has_last = ke == g.nz_loc;
+            const int64_t row = (int64_t)j * g.nx + i0;
+            if (active) {
+                if (has_first && pa.prev_dst) *reinterpret_cast<double2*>(pa.prev_dst + row) = *reinterpret_cast<const double2*>(x + row);
+                if (has_last && pa.next_dst)
+                    *reinterpret_cast<double2*>(pa.next_dst + row) = *reinterpret_cast<const double2*>(x + (int64_t)(g.nz_loc - 1) * sxy + row);
+            }
+            if ((has_first && pa.prev_dst) || (has_last && pa.next_dst)) {
+                __threadfence_system();  // this thread's NVLink stores are performed ...
+                __syncthreads();         // ... before thread 0 announces the tile
+                if (tx == 0 && ty == 0) {
+                    const unsigned n_tiles = gridDim.x * gridDim.y;
+                    if (has_first && pa.prev_dst && atomicInc(pa.tickets, n_tiles - 1) == n_tiles - 1) {
+                        __threadfence_system();
+                        st_release_sys(pa.prev_flag, pa.seq);
+                    }
+                    if (has_last && pa.next_dst && atomicInc(pa.tickets + 1, n_tiles - 1) == n_tiles - 1) {
+                        __threadfence_system();
+                        st_release_sys(pa.next_flag, pa.seq);
+                    }
+                }
+            }
+            if ((has_first && g.k_off > 0) || (has_last && g.k_off + g.nz_loc < g.nz)) {
+                if (tx == 0 && ty == 0) {
+                    if (has_first && g.k_off > 0) peer_flag_wait(pa.my_flags, pa.seq);
+                    if (has_last && g.k_off + g.nz_loc < g.nz) peer_flag_wait(pa.my_flags + 1, pa.seq);
+                }
+                __syncthreads();
+            }
+        }
+    }
     if (kb < ke) {
         // Planes kb-1 .. ke are read; those outside the global grid do not exist.  Plane k lives in ring stage
         // (k - kb + 1) mod DEPTH.  The steady-state loop is kept lean - this kernel was issue-bound (ncu: 76 % issue-active,
@@ -1828,6 +1892,37 @@ struct Stencil7 : public Operator {
         }
     }
 
+    template <int TX, int TY>
+    void launch_peer(const double* x, double* y, bool dot, double* dot_out, const int* skip_flag, const PeerApply& pa) {
+        Context* c = ctx;
+        const int planes = g.nz_loc;
+        const int kcc = chunk_planes(kc, planes, ((g.nx + 2 * TX - 1) / (2 * TX)) * ((g.ny + TY - 1) / TY));
+        dim3 grid((g.nx + 2 * TX - 1) / (2 * TX), (g.ny + TY - 1) / TY, (planes + kcc - 1) / kcc);
+        dim3 block(TX, TY, 1);
+        const int nblocks = (int)(grid.x * grid.y * grid.z);
+        ATK_REQUIRE(nblocks <= kMaxPartials, ATK_ERR_INVALID_ARGUMENT, "stencil grid exceeds the partial-sum scratch");
+        constexpr size_t smem = (size_t)4 * (TY + 2) * (2 * TX + 4) * sizeof(double) + kRingShift * sizeof(double);
+        if (dot)
+            stencil7_smem_kernel<TX, TY, true, true><<<grid, block, smem, c->stream>>>(g, x, y, halo_lo, halo_hi, 0, planes, kcc,
+                                                                                        c->d_partials, 0, c->d_tickets + 2, dot_out, 1,
+                                                                                        skip_flag, pa);
+        else
+            stencil7_smem_kernel<TX, TY, false, true><<<grid, block, smem, c->stream>>>(g, x, y, halo_lo, halo_hi, 0, planes, kcc,
+                                                                                         c->d_partials, 0, c->d_tickets + 2, dot_out, 1,
+                                                                                         skip_flag, pa);
+        ATK_CUDA_CHECK(cudaGetLastError());
+        count_launch(c);
+    }
+    void launch_peer_tile(const double* x, double* y, bool dot, double* dot_out, const int* skip_flag, const PeerApply& pa) {
+        switch (tile) {
+            case 1: launch_peer<64, 4>(x, y, dot, dot_out, skip_flag, pa); break;
+            case 2: launch_peer<32, 16>(x, y, dot, dot_out, skip_flag, pa); break;
+            case 3: launch_peer<64, 8>(x, y, dot, dot_out, skip_flag, pa); break;
+            case 0: launch_peer<32, 8>(x, y, dot, dot_out, skip_flag, pa); break;
+            case 5: launch_peer<64, 2>(x, y, dot, dot_out, skip_flag, pa); break;
+            default: launch_peer<32, 4>(x, y, dot, dot_out, skip_flag, pa); break;
+        }
+    }
     static bool apply_over_nccl() {
         const char* e = std::getenv("ATK_COMM");
         return e && std::string(e) == "nccl";
@@ -1843,6 +1938,25 @@ struct Stencil7 : public Operator {
             // halo exchange on the communication stream, overlapped with the planes that do not need it
             const size_t plane = (size_t)g.nx * g.ny;
             const bool peer_push = ph.ready && !apply_over_nccl() && !c->capturing();
+            const bool vec_ok = (g.nx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) &&
+                                ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
+            if (peer_push && vec_ok && fsmem && !use_tma && !std::getenv("ATK_APPLY_SPLIT")) {
+                // one launch for the whole slab: its boundary CTAs do the neighbour stores and the waiting themselves
+                const PeerHalo::Targets tg = ph.begin();
+                halo_lo = ph.lo();
+                halo_hi = ph.hi();
+                PeerApply pa;
+                pa.prev_dst = tg.prev_dst;
+                pa.next_dst = tg.next_dst;
+                pa.prev_flag = tg.prev_flag;
+                pa.next_flag = tg.next_flag;
+                pa.my_flags = tg.my_flags;
+                pa.tickets = ph.d_ticket + 1;
+                pa.seq = tg.seq;
+                launch_peer_tile(x, y, dot, dot_out, skip_flag, pa);
+                if (dot) allgather_slot(c, dot_slot, c->stream);
+                return;
+            }
             if (peer_push) {  // boundary planes stored straight into the neighbours' buffers over NVLink, flag released
                 ph.push(x, plane, x + (size_t)(g.nz_loc - 1) * plane, plane);
                 halo_lo = ph.lo();
@@ -1917,10 +2031,11 @@ __global__ void __launch_bounds__(256) stencil27_kernel(StencilGeom g, Coef27 cf
 
 // DENSE: all 27 coefficients are non-zero (the config-5 operator), so the per-tap zero tests are compiled out - the kernel
 // is issue-bound (ncu: 79 % issue-active, FP64 pipe 50 %).
-template <int TX, int TY, bool DENSE>
+template <int TX, int TY, bool DENSE, bool PEER = false>
 __global__ void __launch_bounds__(TX* TY) stencil27_smem_kernel(StencilGeom g, Coef27 cf, const double* __restrict__ x,
                                                                  double* __restrict__ y, const double* __restrict__ halo_lo,
-                                                                 const double* __restrict__ halo_hi, int k_lo, int k_hi, int kc) {
+                                                                 const double* __restrict__ halo_hi, int k_lo, int k_hi, int kc,
+                                                                 PeerApply pa = PeerApply()) {
     constexpr int DEPTH = 4;
     constexpr int W = 2 * TX + 4;
     constexpr int STAGE = (TY + 2) * W;
@@ -1936,11 +2051,47 @@ __global__ void __launch_bounds__(TX* TY) stencil27_smem_kernel(StencilGeom g, C
     const int j_lo = blockIdx.y * TY;
     const int i0 = i_lo + 2 * tx;
     const int j = j_lo + ty;
-    const int kb = k_lo + blockIdx.z * kc;
+    int zc = blockIdx.z;
+    if constexpr (PEER) {  // chunk order: first, last, then the ones in between (see stencil7_smem_kernel)
+        const int nzc = gridDim.z;
+        zc = (zc == 0) ? 0 : (zc == 1 ? nzc - 1 : zc - 1);
+    }
+    const int kb = k_lo + zc * kc;
     const int ke = min(kb + kc, k_hi);
     if (kb >= ke) return;
     const bool active = (i0 < g.nx) && (j < g.ny);
     const int64_t sxy = (int64_t)g.nx * g.ny;
+    if constexpr (PEER) {  // boundary CTAs: store the tile of the first / last plane into the neighbour, release, wait
+        const bool has_first = kb == 0, has_last = ke == g.nz_loc;
+        const int64_t row = (int64_t)j * g.nx + i0;
+        if (active) {
+            if (has_first && pa.prev_dst) *reinterpret_cast<double2*>(pa.prev_dst + row) = *reinterpret_cast<const double2*>(x + row);
+            if (has_last && pa.next_dst)
+                *reinterpret_cast<double2*>(pa.next_dst + row) = *reinterpret_cast<const double2*>(x + (int64_t)(g.nz_loc - 1) * sxy + row);
+        }
+        if ((has_first && pa.prev_dst) || (has_last && pa.next_dst)) {
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned n_tiles = gridDim.x * gridDim.y;
+                if (has_first && pa.prev_dst && atomicInc(pa.tickets, n_tiles - 1) == n_tiles - 1) {
+                    __threadfence_system();
+                    st_release_sys(pa.prev_flag, pa.seq);
+                }
+                if (has_last && pa.next_dst && atomicInc(pa.tickets + 1, n_tiles - 1) == n_tiles - 1) {
+                    __threadfence_system();
+                    st_release_sys(pa.next_flag, pa.seq);
+                }
+            }
+        }
+        if ((has_first && g.k_off > 0) || (has_last && g.k_off + g.nz_loc < g.nz)) {
+            if (tid == 0) {
+                if (has_first && g.k_off > 0) peer_flag_wait(pa.my_flags, pa.seq);
+                if (has_last && g.k_off + g.nz_loc < g.nz) peer_flag_wait(pa.my_flags + 1, pa.seq);
+            }
+            __syncthreads();
+        }
+    }
     // everything that is never a copy destination (rows / columns outside the grid) stays zero for the whole kernel
     for (int e = tid; e < DEPTH * STAGE; e += NT) ring[e] = 0.0;
     __syncthreads();
@@ -2058,10 +2209,32 @@ struct Stencil27 : public Operator {
         ph.release();
     }
     int kc27 = 64;  // planes per chunk of the shared-memory kernel (ATK_STENCIL27_KC)
-    void launch(const double* x, double* y, int k_lo, int k_hi) {
+    bool vec_ok(const double* x, const double* y) const {
+        return (g.nx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15u) == 0) &&
+               !std::getenv("ATK_STENCIL27_SIMPLE");
+    }
+    void launch(const double* x, double* y, int k_lo, int k_hi, const PeerApply* pa = nullptr) {
         if (k_hi <= k_lo) return;
-        const bool vec = (g.nx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(y) & 15u) == 0) && !std::getenv("ATK_STENCIL27_SIMPLE");
+        const bool vec = vec_ok(x, y);
+        if (vec && pa) {  // the whole slab in one launch, neighbour stores and waits inside (see stencil7_smem_kernel PEER)
+            constexpr int TX = 32, TY = 4;
+            const int tiles = ((g.nx + 2 * TX - 1) / (2 * TX)) * ((g.ny + TY - 1) / TY);
+            int kcc = std::min(kc27, k_hi - k_lo);
+            while (kcc > 8 && (int64_t)tiles * ((k_hi - k_lo + kcc - 1) / kcc) < (int64_t)ctx->sm_count * 8) kcc = (kcc + 1) / 2;
+            dim3 grid((g.nx + 2 * TX - 1) / (2 * TX), (g.ny + TY - 1) / TY, (k_hi - k_lo + kcc - 1) / kcc);
+            constexpr size_t smem = (size_t)4 * (TY + 2) * (2 * TX + 4) * sizeof(double) + kRingShift * sizeof(double);
+            bool dense = true;
+            for (int t = 0; t < 27; ++t) dense = dense && cf.v[t] != 0.0;
+            if (dense)
+                stencil27_smem_kernel<TX, TY, true, true><<<grid, dim3(TX, TY, 1), smem, ctx->stream>>>(g, cf, x, y, halo_lo, halo_hi, k_lo,
+                                                                                                        k_hi, kcc, *pa);
+            else
+                stencil27_smem_kernel<TX, TY, false, true><<<grid, dim3(TX, TY, 1), smem, ctx->stream>>>(g, cf, x, y, halo_lo, halo_hi,
+                                                                                                         k_lo, k_hi, kcc, *pa);
+            ATK_CUDA_CHECK(cudaGetLastError());
+            count_launch(ctx);
+            return;
+        }
         if (vec) {
             constexpr int TX = 32, TY = 4;
             const int tiles = ((g.nx + 2 * TX - 1) / (2 * TX)) * ((g.ny + TY - 1) / TY);
@@ -2094,6 +2267,22 @@ struct Stencil27 : public Operator {
             const size_t plane = (size_t)g.nx * g.ny;
             const char* comm = std::getenv("ATK_COMM");
             const bool peer_push = ph.ready && !(comm && std::string(comm) == "nccl") && !c->capturing();
+            if (peer_push && vec_ok(x, y) && !std::getenv("ATK_APPLY_SPLIT")) {
+                const PeerHalo::Targets tg = ph.begin();
+                halo_lo = ph.lo();
+                halo_hi = ph.hi();
+                PeerApply pa;
+                pa.prev_dst = tg.prev_dst;
+                pa.next_dst = tg.next_dst;
+                pa.prev_flag = tg.prev_flag;
+                pa.next_flag = tg.next_flag;
+                pa.my_flags = tg.my_flags;
+                pa.tickets = ph.d_ticket + 1;
+                pa.seq = tg.seq;
+                launch(x, y, 0, g.nz_loc, &pa);
+                if (dot_slot >= 0) launch_dot(c, n_rows_local, x, y, dot_slot, skip_flag);
+                return;
+            }
             if (peer_push) {
                 ph.push(x, plane, x + (size_t)(g.nz_loc - 1) * plane, plane);
                 halo_lo = ph.lo();
