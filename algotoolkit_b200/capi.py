@@ -76,7 +76,7 @@ EXPORTS = [
     "atk_context_create_distributed", "atk_context_destroy", "atk_context_rank", "atk_context_set_reduction",
     "atk_context_synchronize", "atk_context_launch_count", "atk_malloc", "atk_free", "atk_memcpy_h2d", "atk_memcpy_d2h",
     "atk_memcpy_d2d", "atk_memset_zero", "atk_host_alloc", "atk_host_free", "atk_host_numa_node", "atk_dot", "atk_nrm2", "atk_vec_scale",
-    "atk_vec_div", "atk_vec_add", "atk_vec_sub", "atk_vec_axpy", "atk_vec_axmy", "atk_operator_from_csc",
+    "atk_vec_div", "atk_vec_add", "atk_vec_sub", "atk_vec_axpy", "atk_vec_axmy", "atk_operator_from_csc", "atk_operator_from_csc_rows",
     "atk_operator_stencil7", "atk_operator_poisson_assembled", "atk_operator_stencil27", "atk_operator_stencil27_assembled", "atk_slab_partition",
     "atk_operator_destroy",
     "atk_operator_shape", "atk_operator_row_range", "atk_operator_export_csr", "atk_operator_apply", "atk_cg_solve",
@@ -127,6 +127,7 @@ def load():
         "atk_vec_axpy": [_vp, i64, _vp, _vp, C.c_double, _vp],
         "atk_vec_axmy": [_vp, i64, _vp, _vp, C.c_double, _vp],
         "atk_operator_from_csc": [_vp, C.c_int, C.c_int, i64, _vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)],
+        "atk_operator_from_csc_rows": [_vp, C.c_int, C.c_int, C.c_int, C.c_int, i64, _vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)],
         "atk_operator_stencil7": [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(_vp)],
         "atk_operator_poisson_assembled": [_vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                            C.POINTER(_vp)],
@@ -375,6 +376,16 @@ class Context:
         h = _vp()
         _check(self.L.atk_operator_from_csc(self.h, n_rows, n_cols, vals.size, _np_ptr(col_ptr), _np_ptr(row_idx),
                                             _np_ptr(vals), 0, fmt, C.byref(h)))
+        return Operator(self, h)
+
+    def operator_from_csc_rows(self, n_rows, n_cols, row_begin, row_end, col_ptr, row_idx, vals, fmt=FORMAT_SELL) -> Operator:
+        """This rank's row slice [row_begin, row_end) of a CSC matrix (global row numbers in row_idx)."""
+        col_ptr = np.ascontiguousarray(col_ptr, np.int32)
+        row_idx = np.ascontiguousarray(row_idx, np.int32)
+        vals = np.ascontiguousarray(vals, np.float64)
+        h = _vp()
+        _check(self.L.atk_operator_from_csc_rows(self.h, n_rows, n_cols, row_begin, row_end, vals.size, _np_ptr(col_ptr),
+                                                 _np_ptr(row_idx), _np_ptr(vals), 0, fmt, C.byref(h)))
         return Operator(self, h)
 
     def operator_stencil7(self, nx, ny, nz, cx, cy, cz) -> Operator:

@@ -237,6 +237,15 @@ int atk_operator_from_csc(atk_context_t ctx, int n_rows, int n_cols, int64_t nnz
         wrap_operator(out, atk::make_operator_from_csc(C(ctx), n_rows, n_cols, nnz, col_ptr, row_idx, vals, on_device != 0, format));
     });
 }
+int atk_operator_from_csc_rows(atk_context_t ctx, int n_rows, int n_cols, int row_begin, int row_end, int64_t nnz,
+                               const int* col_ptr, const int* row_idx, const double* vals, int on_device, atk_format format,
+                               atk_operator_t* out) {
+    return guarded([&] {
+        ATK_REQUIRE(out, ATK_ERR_INVALID_ARGUMENT, "null pointer");
+        wrap_operator(out, atk::make_operator_from_csc_rows(C(ctx), n_rows, n_cols, row_begin, row_end, nnz, col_ptr, row_idx, vals,
+                                                            on_device != 0, format));
+    });
+}
 int atk_operator_stencil7(atk_context_t ctx, int nx, int ny, int nz, double cx, double cy, double cz, atk_operator_t* out) {
     return guarded([&] {
         ATK_REQUIRE(out, ATK_ERR_INVALID_ARGUMENT, "null pointer");

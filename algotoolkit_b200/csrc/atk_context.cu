@@ -321,6 +321,221 @@ void PeerHalo::wait() {
     count_launch(c);
 }
 
+// ------------------------------------------------------------------------------------------ PeerGather
+namespace {
+struct GatherTable {
+    double* dst[kMaxRanks];               // where destination d's entries go (null: nothing to send to that partner)
+    int begin[kMaxRanks + 1];             // destination d serves send_idx[begin[d] .. begin[d+1])
+    unsigned long long* flag[kMaxRanks];  // flag word to release per partner (null: none)
+    int n_dst;
+};
+__global__ void __launch_bounds__(256) gather_push_kernel(const double* __restrict__ x, const int* __restrict__ idx, GatherTable tb,
+                                                          unsigned long long seq, unsigned* ticket, int release) {
+    const int total = tb.begin[tb.n_dst];
+    const int stride = gridDim.x * blockDim.x;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        int d = 0;
+        while (t >= tb.begin[d + 1]) ++d;
+        tb.dst[d][t - tb.begin[d]] = x[idx[t]];
+    }
+    if (!release) return;
+    __threadfence_system();
+    if (last_block_done(ticket)) {
+        if (threadIdx.x < tb.n_dst && tb.flag[threadIdx.x]) {
+            __threadfence_system();
+            st_release_sys(tb.flag[threadIdx.x], seq);
+        }
+    }
+}
+struct WaitTable {
+    const unsigned long long* flag[kMaxRanks];
+    int n;
+};
+__global__ void gather_wait_kernel(WaitTable wt, unsigned long long seq) {
+    const int lane = threadIdx.x;
+    if (lane < wt.n) {
+        unsigned spins = 0;
+        unsigned long long t0 = 0;
+        while (ld_acquire_sys(wt.flag[lane]) < seq) {
+            if ((++spins & 0xfffu) == 0) {
+                const unsigned long long now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                if (now - t0 > kPeerWaitNs) asm volatile("trap;");  // a partner died or fell out of step: fail loudly
+            }
+        }
+    }
+}
+__global__ void shift_idx_kernel(int n, int shift, int* __restrict__ idx) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) idx[t] -= shift;
+}
+}  // namespace
+
+void PeerGather::setup(Context* c, const int* d_ext_cols, int n_ext_, const std::vector<int>& ext_cols_host,
+                       const std::vector<std::pair<int, int>>& blocks) {
+    ctx = c;
+    n_ext = n_ext_;
+    const int W = c->world, me = c->rank;
+    recv_count.assign((size_t)W, 0);
+    recv_off.assign((size_t)W + 1, 0);
+    for (int q = 0; q < W; ++q) {  // ext_cols is ascending and the blocks are contiguous: each owner's entries form a run
+        const auto lo = std::lower_bound(ext_cols_host.begin(), ext_cols_host.end(), blocks[(size_t)q].first);
+        const auto hi = std::lower_bound(ext_cols_host.begin(), ext_cols_host.end(), blocks[(size_t)q].second);
+        recv_count[(size_t)q] = (int)(hi - lo);
+        recv_off[(size_t)q] = (int)(lo - ext_cols_host.begin());
+    }
+    recv_off[(size_t)W] = n_ext;
+    ATK_REQUIRE(recv_count[(size_t)me] == 0, ATK_ERR_INVALID_ARGUMENT, "internal: an own column was classified as external");
+    // need[p][q]: entries rank p receives from rank q
+    std::vector<int> row(kMaxRanks, 0), need((size_t)W * kMaxRanks, 0);
+    for (int q = 0; q < W; ++q) row[(size_t)q] = recv_count[(size_t)q];
+    allgather_host_bytes(c, row.data(), need.data(), sizeof(int) * kMaxRanks);
+    send_count.assign((size_t)W, 0);
+    send_off.assign((size_t)W + 1, 0);
+    peer_n_ext.assign((size_t)W, 0);
+    off_in_peer.assign((size_t)W, 0);
+    for (int p = 0; p < W; ++p) {
+        send_count[(size_t)p] = need[(size_t)p * kMaxRanks + me];
+        send_off[(size_t)p + 1] = send_off[(size_t)p] + send_count[(size_t)p];
+        size_t tot = 0, before = 0;
+        for (int q = 0; q < W; ++q) {
+            if (q < me) before += (size_t)need[(size_t)p * kMaxRanks + q];
+            tot += (size_t)need[(size_t)p * kMaxRanks + q];
+        }
+        peer_n_ext[(size_t)p] = tot;
+        off_in_peer[(size_t)p] = before;
+    }
+    n_send = send_off[(size_t)W];
+    partners.clear();
+    for (int p = 0; p < W; ++p)
+        if (p != me && (send_count[(size_t)p] > 0 || recv_count[(size_t)p] > 0)) partners.push_back(p);
+    ATK_REQUIRE((int)partners.size() <= kMaxRanks, ATK_ERR_INVALID_ARGUMENT, "too many partner ranks");
+    // every owner learns WHICH of its entries each requester wants: the requesters' column lists travel over NCCL
+    ATK_CUDA_CHECK(cudaMalloc(&d_send_idx, sizeof(int) * (size_t)std::max(n_send, 1)));
+    ATK_CUDA_CHECK(cudaMalloc(&d_pack, sizeof(double) * (size_t)std::max(n_send, 1)));
+    ATK_CUDA_CHECK(cudaMalloc(&nccl_ext, sizeof(double) * (size_t)std::max(n_ext, 1)));
+    {
+        ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+        nccl_check(g_nccl.GroupStart(), "ncclGroupStart");
+        for (int q = 0; q < W; ++q) {
+            if (q == me) continue;
+            if (recv_count[(size_t)q] > 0)
+                nccl_check(g_nccl.Send(d_ext_cols + recv_off[(size_t)q], (size_t)recv_count[(size_t)q], ncclInt, q, comm, c->stream), "ncclSend");
+            if (send_count[(size_t)q] > 0)
+                nccl_check(g_nccl.Recv(d_send_idx + send_off[(size_t)q], (size_t)send_count[(size_t)q], ncclInt, q, comm, c->stream), "ncclRecv");
+        }
+        nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd");
+        if (n_send > 0) {
+            shift_idx_kernel<<<(n_send + 255) / 256, 256, 0, c->stream>>>(n_send, blocks[(size_t)me].first, d_send_idx);
+            count_launch(c);
+        }
+        ATK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    peer_ready = false;
+    peer_arena.assign((size_t)W, nullptr);
+    if (c->p2p) {
+        arena = static_cast<double*>(c->arena_take(sizeof(double) * (flag_offset((size_t)n_ext) + kMaxRanks)));
+        ATK_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        std::vector<void*> peers;
+        // ipc_share maps "all ranks" when the want-list is empty: a rank without partners asks for itself only
+        std::vector<int> want = partners.empty() ? std::vector<int>{me} : partners;
+        ipc_share(c, arena, peers, want);
+        for (int p : partners) peer_arena[(size_t)p] = static_cast<double*>(peers[(size_t)p]);
+        ATK_CUDA_CHECK(cudaMalloc(&d_ticket, sizeof(unsigned)));
+        ATK_CUDA_CHECK(cudaMemset(d_ticket, 0, sizeof(unsigned)));
+        peer_ready = true;
+    }
+    seq = 0;
+}
+
+void PeerGather::release() {
+    if (!ctx) return;
+    for (double* p : peer_arena) ctx->ipc_close(p);
+    peer_arena.clear();
+    if (arena) ctx->arena_give(arena);
+    arena = nullptr;
+    cudaFree(d_ticket);
+    cudaFree(d_send_idx);
+    cudaFree(d_pack);
+    cudaFree(nccl_ext);
+    d_ticket = nullptr;
+    d_send_idx = nullptr;
+    d_pack = nccl_ext = nullptr;
+    peer_ready = false;
+}
+
+const double* PeerGather::begin(const double* x) {
+    Context* c = ctx;
+    const char* comm_env = std::getenv("ATK_COMM");
+    const bool peer = peer_ready && !(comm_env && std::string(comm_env) == "nccl") && !c->capturing();
+    last_was_peer = peer;
+    ATK_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+    ATK_CUDA_CHECK(cudaStreamWaitEvent(c->comm_stream, c->ev_fork, 0));
+    GatherTable tb;
+    const double* result = nullptr;
+    if (peer) {
+        ++seq;
+        const size_t par = (size_t)(seq & 1);
+        tb.n_dst = (int)partners.size();
+        int pos = 0;
+        tb.begin[0] = 0;
+        // d_send_idx is grouped by destination RANK; the partners are in ascending rank order, and ranks that are no
+        // partners have nothing to receive, so walking the partners in order walks d_send_idx in order
+        for (int d = 0; d < tb.n_dst; ++d) {
+            const int p = partners[(size_t)d];
+            ATK_REQUIRE(send_off[(size_t)p] == pos, ATK_ERR_RUNTIME, "internal: send list order");
+            double* pa = peer_arena[(size_t)p];
+            tb.dst[d] = send_count[(size_t)p] > 0 ? pa + par * peer_n_ext[(size_t)p] + off_in_peer[(size_t)p] : nullptr;
+            tb.flag[d] = reinterpret_cast<unsigned long long*>(pa + flag_offset(peer_n_ext[(size_t)p])) + c->rank;
+            pos += send_count[(size_t)p];
+            tb.begin[d + 1] = pos;
+        }
+        const int grid = std::max(1, std::min((n_send + 255) / 256, 128));
+        gather_push_kernel<<<grid, 256, 0, c->comm_stream>>>(x, d_send_idx, tb, seq, d_ticket, 1);
+        ATK_CUDA_CHECK(cudaGetLastError());
+        count_launch(c);
+        result = arena + par * (size_t)n_ext;
+    } else {
+        tb.n_dst = 1;
+        tb.dst[0] = d_pack;
+        tb.begin[0] = 0;
+        tb.begin[1] = n_send;
+        tb.flag[0] = nullptr;
+        if (n_send > 0) {
+            const int grid = std::max(1, std::min((n_send + 255) / 256, 128));
+            gather_push_kernel<<<grid, 256, 0, c->comm_stream>>>(x, d_send_idx, tb, 0ull, nullptr, 0);
+            ATK_CUDA_CHECK(cudaGetLastError());
+            count_launch(c);
+        }
+        ncclComm_t comm = (ncclComm_t)c->nccl_comm;
+        nccl_check(g_nccl.GroupStart(), "ncclGroupStart");
+        for (int q : partners) {
+            if (send_count[(size_t)q] > 0)
+                nccl_check(g_nccl.Send(d_pack + send_off[(size_t)q], (size_t)send_count[(size_t)q], ncclDouble, q, comm, c->comm_stream), "ncclSend");
+            if (recv_count[(size_t)q] > 0)
+                nccl_check(g_nccl.Recv(nccl_ext + recv_off[(size_t)q], (size_t)recv_count[(size_t)q], ncclDouble, q, comm, c->comm_stream), "ncclRecv");
+        }
+        nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd");
+        result = nccl_ext;
+    }
+    ATK_CUDA_CHECK(cudaEventRecord(c->ev_join, c->comm_stream));
+    return result;
+}
+
+void PeerGather::wait() {
+    Context* c = ctx;
+    ATK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    if (last_was_peer && !partners.empty()) {
+        WaitTable wt;
+        wt.n = (int)partners.size();
+        const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(arena + flag_offset((size_t)n_ext));
+        for (int d = 0; d < wt.n; ++d) wt.flag[d] = flags + partners[(size_t)d];
+        gather_wait_kernel<<<1, 32, 0, c->stream>>>(wt, seq);
+        ATK_CUDA_CHECK(cudaGetLastError());
+        count_launch(c);
+    }
+}
+
 void Context::ipc_close(void* mapped) {
     if (!mapped) return;
     auto it = std::find(ipc_opened.begin(), ipc_opened.end(), mapped);

@@ -474,6 +474,11 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
                         acc = add_rn(acc, vc ? mul_rn(vc[e], wv) : mul_rn(wv, wv));
                     }
                 }
+                if (i + 1 < a.j) {  // the next column's slice starts its way from HBM into L2 while the sum is in flight
+                    const char* nx = reinterpret_cast<const char*>(a.V + (int64_t)(i + 1) * a.ldv + c0);
+                    for (int64_t o = (int64_t)threadIdx.x * 128; o < len * 8; o += (int64_t)BLOCK * 128)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+                }
                 const double h = finish_tree(acc, i);
                 if (i < a.j) {
                     if (blockIdx.x == 0 && threadIdx.x == 0) a.h_out[i] = h;  // H(i,j)   (:75)

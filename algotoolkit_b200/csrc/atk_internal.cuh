@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <exception>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/atk_cuda.h"
@@ -195,6 +196,46 @@ struct PeerHalo {
     const double* hi() const { return arena + (seq & 1) * (cap_lo + cap_hi) + cap_lo; }
 };
 
+// ------------------------------------------------------------------------------------------ general gather exchange
+// Row-block partitioned assembled operators with ARBITRARY sparsity (SparseObj.hpp:131-152 takes any pattern): a rank's
+// rows may reference columns owned by any other rank.  Local column numbering is [own block | external entries in
+// ascending global column order]; per apply every owner gathers the entries each requester needs from its x block and
+//   peer mode: stores them straight into the requester's receive buffer of the apply's parity (NVLink stores, one kernel
+//              for all destinations), fences, and the CTA that finishes last releases the sequence number into the flag
+//              word it owns in every PARTNER's arena (partner = traffic in either direction, so the two-parity
+//              write-after-read argument of PeerHalo holds pairwise);
+//   NCCL mode: packs them and exchanges the packed ranges with grouped ncclSend / ncclRecv (also while a CUDA graph is
+//              being captured).
+struct PeerGather {
+    Context* ctx = nullptr;
+    int n_ext = 0;                          // external entries this rank receives per apply
+    int n_send = 0;                         // entries this rank serves per apply (all destinations)
+    std::vector<int> recv_count, recv_off;  // per source rank: how many, and where in the receive buffer
+    std::vector<int> send_count, send_off;  // per destination rank: how many, and where in d_send_idx / d_pack
+    std::vector<int> partners;
+    int* d_send_idx = nullptr;              // [n_send] local row indices, grouped by destination rank
+    double* d_pack = nullptr;               // [n_send] NCCL mode: packed entries
+    double* nccl_ext = nullptr;             // [n_ext]  NCCL mode: receive buffer
+    double* arena = nullptr;                // peer mode, exported: [buf parity 0 | buf parity 1 | flags (kMaxRanks words)]
+    std::vector<double*> peer_arena;        // partners' arenas mapped here
+    std::vector<size_t> peer_n_ext;         // their n_ext (layout of their arenas)
+    std::vector<size_t> off_in_peer;        // where this rank's entries start inside partner p's receive buffer
+    unsigned* d_ticket = nullptr;
+    unsigned long long seq = 0;
+    bool peer_ready = false;
+    bool last_was_peer = false;
+    static size_t flag_offset(size_t n) { return (2 * n + 15) / 16 * 16; }
+    // ext_cols: this rank's external global columns, ascending (device, n_ext_ entries; a valid allocation even when empty);
+    // blocks: [row_begin, row_end) of every rank.  Collective.
+    void setup(Context* c, const int* d_ext_cols, int n_ext_, const std::vector<int>& ext_cols_host,
+               const std::vector<std::pair<int, int>>& blocks);
+    void release();
+    // starts the exchange of an apply after everything enqueued on ctx->stream so far; returns the buffer the external
+    // entries of THIS apply arrive in (valid for the kernels launched after wait())
+    const double* begin(const double* x);
+    void wait();
+};
+
 // ------------------------------------------------------------------------------------------ fused CG state
 // Device-resident scalars of the fused two-kernel CG iteration (atk_cg.cu drives it, the operator supplies KA).
 struct CgFusedState {
@@ -266,6 +307,8 @@ inline void slab_partition(int nz, int rank, int world, int* k_begin, int* k_end
 
 Operator* make_operator_from_csc(Context* ctx, int n_rows, int n_cols, int64_t nnz, const int* col_ptr, const int* row_idx,
                                  const double* vals, bool on_device, atk_format format);
+Operator* make_operator_from_csc_rows(Context* ctx, int n_rows_global, int n_cols, int row_begin, int row_end, int64_t nnz,
+                                      const int* col_ptr, const int* row_idx, const double* vals, bool on_device, atk_format format);
 Operator* make_stencil7(Context* ctx, int nx, int ny, int nz, double cx, double cy, double cz);
 Operator* make_poisson_assembled(Context* ctx, int nx, int ny, int nz, double cx, double cy, double cz, atk_format format);
 Operator* make_stencil27(Context* ctx, int nx, int ny, int nz, const double* coef);

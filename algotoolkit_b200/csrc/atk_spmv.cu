@@ -514,21 +514,17 @@ struct AssembledMatrix : public Operator {
     // CSR-stream (CSR format, short rows)
     int* blk_row = nullptr;  // [stream_blocks + 1]
     int stream_blocks = 0;   // 0: rows too long for the stream kernel -> CSR-vector
-    // row-block partition on a distributed context (SELL only): local columns = [h_lo received | n_rows own | h_hi received]
+    // row-block partition on a distributed context (SELL only), any sparsity: local columns = [n_rows own | n_ext external
+    // entries in ascending global column order]; the external entries of an apply arrive through PeerGather
     bool dist = false;
-    int h_lo = 0, h_hi = 0;            // entries needed from the previous / next rank
-    int send_prev = 0, send_next = 0;  // entries the previous / next rank needs from this one
-    double* halo_lo = nullptr;         // receive buffers of the NCCL exchange
-    double* halo_hi = nullptr;
-    PeerHalo ph;                       // peer-memory exchange (Context::p2p): entries stored straight into the neighbours
-    int col_shift = 0;                 // local column + col_shift = global column
-    int s_int_begin = 0, s_int_end = 0;  // slices whose rows touch no received entry: they run while the exchange is in flight
+    PeerGather pg;
+    std::vector<int> ext_cols_host;      // global column of every external entry (for export)
+    int s_int_begin = 0, s_int_end = 0;  // slices whose rows touch no external entry: they run while the exchange is in flight
 
     ~AssembledMatrix() override {
         cudaFree(row_ptr); cudaFree(csr_col); cudaFree(csr_val);
         cudaFree(wscan); cudaFree(perm); cudaFree(sell_col); cudaFree(sell_val); cudaFree(blk_row);
-        cudaFree(halo_lo); cudaFree(halo_hi);
-        ph.release();
+        pg.release();
     }
     bool has_csr() const override { return true; }
     void export_csr(int* h_row_ptr, int* h_col, double* h_val) const override {
@@ -536,8 +532,9 @@ struct AssembledMatrix : public Operator {
         if (nnz > 0) {
             ATK_CUDA_CHECK(cudaMemcpy(h_col, csr_col, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToHost));
             ATK_CUDA_CHECK(cudaMemcpy(h_val, csr_val, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost));
-            if (col_shift != 0)
-                for (int64_t k = 0; k < nnz; ++k) h_col[k] += col_shift;  // back to global column indices
+            if (dist)  // back to global column indices
+                for (int64_t k = 0; k < nnz; ++k)
+                    h_col[k] = h_col[k] < n_rows ? h_col[k] + (int)row_begin : ext_cols_host[(size_t)(h_col[k] - n_rows)];
         }
     }
 
@@ -546,11 +543,9 @@ struct AssembledMatrix : public Operator {
         double* dot_out = dot_slot >= 0 ? c->slot(dot_slot) + c->rank : nullptr;
         const int grid = c->sm_count * 8;
         if (format == ATK_FORMAT_SELL) {
-            const char* comm = std::getenv("ATK_COMM");
-            const bool peer_push = dist && ph.ready && !(comm && std::string(comm) == "nccl") && !c->capturing();
-            if (peer_push)  // pushes this apply's entries to the neighbours and flips to the receive buffers of its parity
-                ph.push(x, (size_t)send_prev, x + (n_rows - send_next), (size_t)send_next);
-            const DistX dx{peer_push ? ph.lo() : halo_lo, peer_push ? ph.hi() : halo_hi, h_lo, n_rows};
+            // distributed: the owners start sending the external entries of this apply (communication stream)
+            const double* ext = dist ? pg.begin(x) : nullptr;
+            const DistX dx{nullptr, ext, 0, n_rows};
             const bool dot = dot_slot >= 0;
             int pbase = 0;
             // (measured at 2 GPUs, 256^3: the persistent grid of the interior piece fills every SM, so the one-CTA transfer
@@ -574,18 +569,10 @@ struct AssembledMatrix : public Operator {
             if (!dist) {
                 piece(0, n_slices, true);
             } else {
-                // neighbour entries on the communication stream while the slices that need none of them run
-                if (!peer_push) {
-                    ATK_CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
-                    ATK_CUDA_CHECK(cudaStreamWaitEvent(c->comm_stream, c->ev_fork, 0));
-                    exchange_ranges(c, x, (size_t)send_prev, x + (n_rows - send_next), (size_t)send_next, halo_lo, (size_t)h_lo,
-                                    halo_hi, (size_t)h_hi, c->comm_stream);
-                    ATK_CUDA_CHECK(cudaEventRecord(c->ev_join, c->comm_stream));
-                }
+                // the slices that need no external entry run while the exchange is in flight
                 const bool has_lo = s_int_begin > 0, has_hi = s_int_end < n_slices;
                 piece(s_int_begin, s_int_end, !has_lo && !has_hi, true);
-                if (peer_push) ph.wait();
-                else ATK_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+                pg.wait();
                 piece(0, s_int_begin, !has_hi);
                 piece(s_int_end, n_slices, true);
             }
@@ -647,43 +634,54 @@ __global__ void slice_row_ptr_kernel(int n_loc, int r0, const int* __restrict__ 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= n_loc) row_ptr[i] = g_row_ptr[r0 + i] - g_row_ptr[r0];
 }
-__global__ void col_range_kernel(int64_t nnz, const int* __restrict__ col, int* __restrict__ min_max) {
-    int lo = 0x7fffffff, hi = -1;
+// flag[c] = 1 for every column outside [row_lo, row_hi) that a local entry references
+__global__ void mark_ext_kernel(int64_t nnz, const int* __restrict__ col, int row_lo, int row_hi, int* __restrict__ flag) {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) {
         const int c = col[k];
-        lo = min(lo, c);
-        hi = max(hi, c);
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMin(min_max, lo);
-        atomicMax(min_max + 1, hi);
+        if (c < row_lo || c >= row_hi) flag[c] = 1;
     }
 }
-// rows [0, out[0]) may read entries received from the previous rank, rows [out[1], n) entries from the next one
-// (columns are ascending inside a row, so its first / last entry decide); out starts as {0, n_rows}
-__global__ void halo_rows_kernel(int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col, int h_lo, int n_mid,
-                                 int* __restrict__ out) {
+__global__ void compact_ext_kernel(int n_cols, const int* __restrict__ flag, const int* __restrict__ pos, int* __restrict__ ext_cols) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_cols && flag[c]) ext_cols[pos[c]] = c;
+}
+// global column -> local column: own block first, then the external entries in ascending global order
+__global__ void renumber_cols_kernel(int64_t nnz, int row_lo, int row_hi, int n_loc, const int* __restrict__ pos, int* __restrict__ col) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) {
+        const int c = col[k];
+        col[k] = (c >= row_lo && c < row_hi) ? c - row_lo : n_loc + pos[c];
+    }
+}
+// rows that reference an external entry: those in the lower half push out[0] up past them, those in the upper half pull
+// out[1] down to them, so that rows [out[0], out[1]) reference none (out starts as {0, n_rows})
+__global__ void ext_rows_kernel(int n_rows, const int* __restrict__ row_ptr, const int* __restrict__ col, int n_loc,
+                                int* __restrict__ out) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
-    const int b = row_ptr[r], e = row_ptr[r + 1];
-    if (e <= b) return;
-    if (col[b] < h_lo) atomicMax(out, r + 1);
-    if (col[e - 1] >= h_lo + n_mid) atomicMin(out + 1, r);
+    bool ext = false;
+    for (int k = row_ptr[r]; k < row_ptr[r + 1]; ++k) ext = ext || col[k] >= n_loc;
+    if (!ext) return;
+    if (r < n_rows / 2) atomicMax(out, r + 1);
+    else atomicMin(out + 1, r);
 }
-__global__ void shift_cols_kernel(int64_t nnz, int shift, int* __restrict__ col) {
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) col[k] -= shift;
+__global__ void shift_rows_kernel(int64_t nnz, int shift, const int* __restrict__ in, int* __restrict__ out, int n_loc,
+                                  int* __restrict__ bad) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) {
+        const int r = in[k] - shift;
+        if (r < 0 || r >= n_loc) atomicOr(bad, 1);
+        out[k] = r;
+    }
 }
 
 // row_lo / row_hi: the row block of this rank on a distributed context (row_hi < 0: balanced blocks of rows)
+// rows_are_slice: the CSC arrays hold ONLY the entries of rows [row_lo, row_hi), their row indices already relative to
+// row_lo (n_rows is then the global row count and the conversion works on row_hi - row_lo local rows).
 static Operator* build_from_device_csc(Context* ctx, int n_rows, int n_cols, int64_t nnz, const int* d_col_ptr,
                                        const int* d_row_idx, const double* d_vals, atk_format format, int row_lo = 0,
-                                       int row_hi = -1) {
+                                       int row_hi = -1, bool rows_are_slice = false) {
     ATK_REQUIRE(nnz >= 0 && nnz < (int64_t)0x7fffffff, ATK_ERR_INVALID_ARGUMENT, "nnz must be below 2^31");
     const bool dist = ctx->world > 1;
+    const int n_rows_global = n_rows;
     if (dist) {
         ATK_REQUIRE(format == ATK_FORMAT_SELL, ATK_ERR_INVALID_ARGUMENT, "distributed assembled operators use the SELL format");
         ATK_REQUIRE(n_rows == n_cols, ATK_ERR_INVALID_ARGUMENT, "distributed assembled operators must be square");
@@ -691,7 +689,12 @@ static Operator* build_from_device_csc(Context* ctx, int n_rows, int n_cols, int
         // reduction slot that the all-gather then feeds into p.Ap on every rank
         ATK_REQUIRE(n_rows >= ctx->world, ATK_ERR_INVALID_ARGUMENT, "distributed assembled operator: fewer rows than ranks");
         if (row_hi < 0) slab_partition(n_rows, ctx->rank, ctx->world, &row_lo, &row_hi);
-        ATK_REQUIRE(row_hi > row_lo, ATK_ERR_INVALID_ARGUMENT, "distributed assembled operator: empty row block");
+        ATK_REQUIRE(row_hi > row_lo && row_lo >= 0 && row_hi <= n_rows, ATK_ERR_INVALID_ARGUMENT,
+                    "distributed assembled operator: empty or out-of-range row block");
+        if (rows_are_slice) n_rows = row_hi - row_lo;  // the conversion below sees the local rows only
+    } else {
+        ATK_REQUIRE(!rows_are_slice || (row_lo == 0 && row_hi == n_rows), ATK_ERR_INVALID_ARGUMENT,
+                    "a single-GPU context owns every row");
     }
     auto* A = new AssembledMatrix();
     try {
@@ -742,68 +745,79 @@ static Operator* build_from_device_csc(Context* ctx, int n_rows, int n_cols, int
         ATK_CUDA_CHECK(cudaStreamSynchronize(st));
         cudaFree(fill); cudaFree(col_of_pos); cudaFree(pos_of_slot); cudaFree(bad);
 
-        // ---- distributed context: keep rows [row_lo, row_hi) and renumber the columns they reach
+        // ---- distributed context: keep rows [row_lo, row_hi); local columns = [own block | external entries]
         if (dist) {
             const int n_loc = row_hi - row_lo;
-            int e0 = 0, e1 = 0;
-            ATK_CUDA_CHECK(cudaMemcpy(&e0, A->row_ptr + row_lo, sizeof(int), cudaMemcpyDeviceToHost));
-            ATK_CUDA_CHECK(cudaMemcpy(&e1, A->row_ptr + row_hi, sizeof(int), cudaMemcpyDeviceToHost));
-            const int64_t nnz_loc = (int64_t)e1 - e0;
-            int* rp = dalloc<int>((size_t)n_loc + 1);
-            int* cl = dalloc<int>((size_t)nnz_loc);
-            double* vl = dalloc<double>((size_t)nnz_loc);
-            int* d_mm = dalloc<int>(2);
-            const int init_mm[2] = {0x7fffffff, -1};
-            int h_mm[2] = {0, -1};
-            try {
-                slice_row_ptr_kernel<<<(n_loc + 1 + 255) / 256, 256, 0, st>>>(n_loc, row_lo, A->row_ptr, rp);
-                if (nnz_loc > 0) {
-                    ATK_CUDA_CHECK(cudaMemcpyAsync(cl, A->csr_col + e0, sizeof(int) * (size_t)nnz_loc, cudaMemcpyDeviceToDevice, st));
-                    ATK_CUDA_CHECK(cudaMemcpyAsync(vl, A->csr_val + e0, sizeof(double) * (size_t)nnz_loc, cudaMemcpyDeviceToDevice, st));
+            int64_t nnz_loc = nnz;
+            if (!rows_are_slice) {  // every rank converted the whole matrix: cut this rank's rows out of it
+                int e0 = 0, e1 = 0;
+                ATK_CUDA_CHECK(cudaMemcpy(&e0, A->row_ptr + row_lo, sizeof(int), cudaMemcpyDeviceToHost));
+                ATK_CUDA_CHECK(cudaMemcpy(&e1, A->row_ptr + row_hi, sizeof(int), cudaMemcpyDeviceToHost));
+                nnz_loc = (int64_t)e1 - e0;
+                int* rp = dalloc<int>((size_t)n_loc + 1);
+                int* cl = dalloc<int>((size_t)nnz_loc);
+                double* vl = dalloc<double>((size_t)nnz_loc);
+                try {
+                    slice_row_ptr_kernel<<<(n_loc + 1 + 255) / 256, 256, 0, st>>>(n_loc, row_lo, A->row_ptr, rp);
+                    if (nnz_loc > 0) {
+                        ATK_CUDA_CHECK(cudaMemcpyAsync(cl, A->csr_col + e0, sizeof(int) * (size_t)nnz_loc, cudaMemcpyDeviceToDevice, st));
+                        ATK_CUDA_CHECK(cudaMemcpyAsync(vl, A->csr_val + e0, sizeof(double) * (size_t)nnz_loc, cudaMemcpyDeviceToDevice, st));
+                    }
+                    ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+                    count_launch(ctx);
+                } catch (...) {
+                    cudaFree(rp); cudaFree(cl); cudaFree(vl);
+                    throw;
                 }
-                ATK_CUDA_CHECK(cudaMemcpyAsync(d_mm, init_mm, sizeof(init_mm), cudaMemcpyHostToDevice, st));
-                if (nnz_loc > 0) col_range_kernel<<<grid_for(nnz_loc, 256, cap), 256, 0, st>>>(nnz_loc, cl, d_mm);
-                ATK_CUDA_CHECK(cudaMemcpyAsync(h_mm, d_mm, sizeof(h_mm), cudaMemcpyDeviceToHost, st));
+                cudaFree(A->row_ptr); cudaFree(A->csr_col); cudaFree(A->csr_val);
+                A->row_ptr = rp;
+                A->csr_col = cl;
+                A->csr_val = vl;
+            }
+            A->dist = true;
+            // the row blocks of all ranks must tile [0, n) in rank order
+            struct Blk { int lo, hi; } mine{row_lo, row_hi};
+            std::vector<Blk> all((size_t)ctx->world);
+            allgather_host_bytes(ctx, &mine, all.data(), sizeof(Blk));
+            std::vector<std::pair<int, int>> blocks;
+            for (int q = 0; q < ctx->world; ++q) {
+                const bool ok = all[(size_t)q].lo == (q == 0 ? 0 : all[(size_t)q - 1].hi) &&
+                                (q + 1 < ctx->world || all[(size_t)q].hi == n_rows_global);
+                ATK_REQUIRE(ok, ATK_ERR_INVALID_ARGUMENT, "distributed assembled operator: the ranks' row blocks do not tile the matrix");
+                blocks.emplace_back(all[(size_t)q].lo, all[(size_t)q].hi);
+            }
+            // external columns: flag, scan, compact (ascending), renumber
+            int* flag = dalloc<int>((size_t)n_cols + 1);
+            int* pos = dalloc<int>((size_t)n_cols + 1);
+            int* ext_cols = nullptr;
+            int n_ext = 0;
+            try {
+                ATK_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int) * ((size_t)n_cols + 1), st));
+                if (nnz_loc > 0) mark_ext_kernel<<<grid_for(nnz_loc, 256, cap), 256, 0, st>>>(nnz_loc, A->csr_col, row_lo, row_hi, flag);
+                exclusive_scan_i32(ctx, flag, pos, (int64_t)n_cols + 1);
+                ATK_CUDA_CHECK(cudaMemcpyAsync(&n_ext, pos + n_cols, sizeof(int), cudaMemcpyDeviceToHost, st));
                 ATK_CUDA_CHECK(cudaStreamSynchronize(st));
-                count_launch(ctx, 2);
+                ext_cols = dalloc<int>((size_t)n_ext);
+                if (n_ext > 0) compact_ext_kernel<<<(n_cols + 255) / 256, 256, 0, st>>>(n_cols, flag, pos, ext_cols);
+                if (nnz_loc > 0)
+                    renumber_cols_kernel<<<grid_for(nnz_loc, 256, cap), 256, 0, st>>>(nnz_loc, row_lo, row_hi, n_loc, pos, A->csr_col);
+                count_launch(ctx, 3);
+                A->ext_cols_host.resize((size_t)n_ext);
+                if (n_ext > 0)
+                    ATK_CUDA_CHECK(cudaMemcpyAsync(A->ext_cols_host.data(), ext_cols, sizeof(int) * (size_t)n_ext, cudaMemcpyDeviceToHost, st));
+                ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+                A->pg.setup(ctx, ext_cols, n_ext, A->ext_cols_host, blocks);
             } catch (...) {
-                cudaFree(rp); cudaFree(cl); cudaFree(vl); cudaFree(d_mm);
+                cudaFree(flag); cudaFree(pos); cudaFree(ext_cols);
                 throw;
             }
-            cudaFree(d_mm);
-            cudaFree(A->row_ptr); cudaFree(A->csr_col); cudaFree(A->csr_val);
-            A->row_ptr = rp;
-            A->csr_col = cl;
-            A->csr_val = vl;
-            A->dist = true;
-            A->h_lo = nnz_loc > 0 ? std::max(0, row_lo - h_mm[0]) : 0;
-            A->h_hi = nnz_loc > 0 ? std::max(0, h_mm[1] - (row_hi - 1)) : 0;
-            // every rank learns what its neighbours need, and checks that nobody reaches past an adjacent block
-            struct Need { int h_lo, h_hi, n_loc, pad; } mine{A->h_lo, A->h_hi, n_loc, 0};
-            std::vector<Need> all((size_t)ctx->world);
-            allgather_host_bytes(ctx, &mine, all.data(), sizeof(Need));
-            for (int q = 0; q < ctx->world; ++q) {
-                const bool ok = (q == 0 ? all[q].h_lo == 0 : all[q].h_lo <= all[q - 1].n_loc) &&
-                                (q == ctx->world - 1 ? all[q].h_hi == 0 : all[q].h_hi <= all[q + 1].n_loc);
-                ATK_REQUIRE(ok, ATK_ERR_INVALID_ARGUMENT,
-                            "distributed assembled operator: a row block reaches columns beyond the adjacent rank's block");
-            }
-            A->send_prev = ctx->rank > 0 ? all[(size_t)ctx->rank - 1].h_hi : 0;
-            A->send_next = ctx->rank + 1 < ctx->world ? all[(size_t)ctx->rank + 1].h_lo : 0;
-            A->halo_lo = dalloc<double>((size_t)A->h_lo);
-            A->halo_hi = dalloc<double>((size_t)A->h_hi);
-            A->ph.setup(ctx, (size_t)A->h_lo, (size_t)A->h_hi);  // collective; no-op unless the GPUs can map each other
-            A->col_shift = row_lo - A->h_lo;
-            if (nnz_loc > 0 && A->col_shift != 0) {
-                shift_cols_kernel<<<grid_for(nnz_loc, 256, cap), 256, 0, st>>>(nnz_loc, A->col_shift, A->csr_col);
-                count_launch(ctx);
-            }
-            if (n_loc > 0) {
+            cudaFree(flag); cudaFree(pos); cudaFree(ext_cols);
+            {   // rows [a, b) reference no external entry: their slices run while the exchange is in flight
                 int* d_hr = dalloc<int>(2);
                 const int init_hr[2] = {0, n_loc};
                 int h_hr[2] = {0, n_loc};
                 ATK_CUDA_CHECK(cudaMemcpyAsync(d_hr, init_hr, sizeof(init_hr), cudaMemcpyHostToDevice, st));
-                halo_rows_kernel<<<(n_loc + 255) / 256, 256, 0, st>>>(n_loc, A->row_ptr, A->csr_col, A->h_lo, n_loc, d_hr);
+                ext_rows_kernel<<<(n_loc + 255) / 256, 256, 0, st>>>(n_loc, A->row_ptr, A->csr_col, n_loc, d_hr);
                 ATK_CUDA_CHECK(cudaMemcpyAsync(h_hr, d_hr, sizeof(h_hr), cudaMemcpyDeviceToHost, st));
                 ATK_CUDA_CHECK(cudaStreamSynchronize(st));
                 cudaFree(d_hr);
@@ -892,6 +906,57 @@ static Operator* build_from_device_csc(Context* ctx, int n_rows, int n_cols, int
         throw;
     }
     return A;
+}
+
+// A rank's ROW SLICE of a CSC matrix: only the entries of rows [row_begin, row_end) (global row numbers), col_ptr over all
+// columns.  No rank ever holds the whole matrix.
+Operator* make_operator_from_csc_rows(Context* ctx, int n_rows_global, int n_cols, int row_begin, int row_end, int64_t nnz,
+                                      const int* col_ptr, const int* row_idx, const double* vals, bool on_device, atk_format format) {
+    ATK_REQUIRE(n_rows_global >= 0 && n_cols >= 0 && nnz >= 0 && nnz < (int64_t)0x7fffffff, ATK_ERR_INVALID_ARGUMENT,
+                "bad matrix dimensions");
+    ATK_REQUIRE(col_ptr != nullptr, ATK_ERR_INVALID_ARGUMENT, "col_ptr is null");
+    ATK_REQUIRE(row_begin >= 0 && row_end > row_begin && row_end <= n_rows_global, ATK_ERR_INVALID_ARGUMENT, "bad row block");
+    const int n_loc = row_end - row_begin;
+    int *d_cp = nullptr, *d_ri = nullptr, *d_rl = nullptr, *d_bad = nullptr;
+    double* d_v = nullptr;
+    Operator* op = nullptr;
+    auto cleanup = [&] {
+        if (!on_device) { cudaFree(d_cp); cudaFree(d_ri); cudaFree(d_v); }
+        cudaFree(d_rl); cudaFree(d_bad);
+    };
+    try {
+        cudaStream_t st = ctx->stream;
+        if (on_device) {
+            d_cp = const_cast<int*>(col_ptr); d_ri = const_cast<int*>(row_idx); d_v = const_cast<double*>(vals);
+        } else {
+            d_cp = dalloc<int>((size_t)n_cols + 1);
+            d_ri = dalloc<int>((size_t)nnz);
+            d_v = dalloc<double>((size_t)nnz);
+            ATK_CUDA_CHECK(cudaMemcpyAsync(d_cp, col_ptr, sizeof(int) * ((size_t)n_cols + 1), cudaMemcpyHostToDevice, st));
+            if (nnz > 0) {
+                ATK_CUDA_CHECK(cudaMemcpyAsync(d_ri, row_idx, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+                ATK_CUDA_CHECK(cudaMemcpyAsync(d_v, vals, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+            }
+        }
+        d_rl = dalloc<int>((size_t)nnz);
+        d_bad = dalloc<int>(1);
+        ATK_CUDA_CHECK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+        if (nnz > 0) {
+            shift_rows_kernel<<<grid_for(nnz, 256, ctx->sm_count * 16), 256, 0, st>>>(nnz, row_begin, d_ri, d_rl, n_loc, d_bad);
+            count_launch(ctx);
+        }
+        int h_bad = 0;
+        ATK_CUDA_CHECK(cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+        ATK_CUDA_CHECK(cudaStreamSynchronize(st));
+        ATK_REQUIRE(!h_bad, ATK_ERR_OUT_OF_RANGE, "Index out of range");  // a row outside the rank's block
+        if (ctx->world == 1) op = build_from_device_csc(ctx, n_rows_global, n_cols, nnz, d_cp, d_rl, d_v, format);
+        else op = build_from_device_csc(ctx, n_rows_global, n_cols, nnz, d_cp, d_rl, d_v, format, row_begin, row_end, true);
+    } catch (...) {
+        cleanup();
+        throw;
+    }
+    cleanup();
+    return op;
 }
 
 Operator* make_operator_from_csc(Context* ctx, int n_rows, int n_cols, int64_t nnz, const int* col_ptr, const int* row_idx,

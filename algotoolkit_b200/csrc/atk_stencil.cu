@@ -625,44 +625,49 @@ __global__ void __launch_bounds__(TX* TY) stencil7_smem_kernel(StencilGeom g, co
     const int j_lo = blockIdx.y * TY;
     const int i0 = i_lo + 2 * tx;
     const int j = j_lo + ty;
+    // PEER: blockIdx.z == 0 is a slice of push-only CTAs (one per xy tile): each stores its tile of the slab's first and last
+    // plane into the neighbours, fences, and the last one to finish releases the sequence number into the neighbours' flag
+    // words; they never wait.  The chunks follow with the two boundary chunks LAST (CTAs are dispatched in ascending block
+    // order): by the time a boundary CTA spins on its local flag every push CTA of this launch has been dispatched, so a
+    // waiting CTA can never keep a pushing one off the SMs, whatever the grid size.
     int zc = blockIdx.z;
-    if constexpr (PEER) {  // chunk order: first, last, then the ones in between (CTAs are scheduled in ascending blockIdx.z)
-        const int nzc = gridDim.z;
-        zc = (zc == 0) ? 0 : (zc == 1 ? nzc - 1 : zc - 1);
+    const int64_t sxy = (int64_t)g.nx * g.ny;
+    const bool active = (i0 < g.nx) && (j < g.ny);
+    if constexpr (PEER) {
+        if (zc == 0) {
+            const int64_t row = (int64_t)j * g.nx + i0;
+            if (active) {
+                if (pa.prev_dst) *reinterpret_cast<double2*>(pa.prev_dst + row) = *reinterpret_cast<const double2*>(x + row);
+                if (pa.next_dst)
+                    *reinterpret_cast<double2*>(pa.next_dst + row) = *reinterpret_cast<const double2*>(x + (int64_t)(g.nz_loc - 1) * sxy + row);
+            }
+            __threadfence_system();  // this thread's NVLink stores are performed ...
+            __syncthreads();         // ... before thread 0 announces the tile
+            if (tx == 0 && ty == 0) {
+                const unsigned n_tiles = gridDim.x * gridDim.y;
+                if (atomicInc(pa.tickets, n_tiles - 1) == n_tiles - 1) {
+                    __threadfence_system();
+                    if (pa.prev_flag) st_release_sys(pa.prev_flag, pa.seq);
+                    if (pa.next_flag) st_release_sys(pa.next_flag, pa.seq);
+                }
+            }
+            if constexpr (!DOT) return;
+        }
+        // chunks: the inner ones first, then the one with the first plane, then the one with the last plane
+        const int nchunk = (int)gridDim.z - 1;
+        const int q = zc - 1;
+        zc = (zc == 0) ? nchunk /* no planes: kb >= ke below */ : (nchunk >= 2 ? (q < nchunk - 2 ? q + 1 : (q == nchunk - 2 ? 0 : nchunk - 1)) : q);
     }
     const int kb = k_lo + zc * kc;
     const int ke = min(kb + kc, k_hi);
-    const bool active = (i0 < g.nx) && (j < g.ny);
-    const int64_t sxy = (int64_t)g.nx * g.ny;
     double dacc = 0.0;
     if constexpr (PEER) {
         if (kb < ke) {
-            const bool has_first = kb == 0, has_last = ke == g.nz_loc;
-            const int64_t row = (int64_t)j * g.nx + i0;
-            if (active) {
-                if (has_first && pa.prev_dst) *reinterpret_cast<double2*>(pa.prev_dst + row) = *reinterpret_cast<const double2*>(x + row);
-                if (has_last && pa.next_dst)
-                    *reinterpret_cast<double2*>(pa.next_dst + row) = *reinterpret_cast<const double2*>(x + (int64_t)(g.nz_loc - 1) * sxy + row);
-            }
-            if ((has_first && pa.prev_dst) || (has_last && pa.next_dst)) {
-                __threadfence_system();  // this thread's NVLink stores are performed ...
-                __syncthreads();         // ... before thread 0 announces the tile
+            const bool need_lo = kb == 0 && g.k_off > 0, need_hi = ke == g.nz_loc && g.k_off + g.nz_loc < g.nz;
+            if (need_lo || need_hi) {
                 if (tx == 0 && ty == 0) {
-                    const unsigned n_tiles = gridDim.x * gridDim.y;
-                    if (has_first && pa.prev_dst && atomicInc(pa.tickets, n_tiles - 1) == n_tiles - 1) {
-                        __threadfence_system();
-                        st_release_sys(pa.prev_flag, pa.seq);
-                    }
-                    if (has_last && pa.next_dst && atomicInc(pa.tickets + 1, n_tiles - 1) == n_tiles - 1) {
-                        __threadfence_system();
-                        st_release_sys(pa.next_flag, pa.seq);
-                    }
-                }
-            }
-            if ((has_first && g.k_off > 0) || (has_last && g.k_off + g.nz_loc < g.nz)) {
-                if (tx == 0 && ty == 0) {
-                    if (has_first && g.k_off > 0) peer_flag_wait(pa.my_flags, pa.seq);
-                    if (has_last && g.k_off + g.nz_loc < g.nz) peer_flag_wait(pa.my_flags + 1, pa.seq);
+                    if (need_lo) peer_flag_wait(pa.my_flags, pa.seq);
+                    if (need_hi) peer_flag_wait(pa.my_flags + 1, pa.seq);
                 }
                 __syncthreads();
             }
@@ -1228,9 +1233,9 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
                 unsigned spins = 0;
                 unsigned long long t0 = 0;
                 bool ok = true;
-                for (;;) {
-                    w0 = ld_relaxed_sys(src);
-                    w1 = ld_relaxed_sys(src + 1);
+                for (;;) {  // acquire loads: the halo planes the neighbours stored before they published are visible after it
+                    w0 = ld_acquire_sys(src);
+                    w1 = ld_acquire_sys(src + 1);
                     if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
                     if ((++spins & 0xfffu) == 0) {
                         const unsigned long long now = global_timer_ns();
@@ -1242,12 +1247,7 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
                         }
                     }
                 }
-                if (ok) {  // the words can only change again after this CTA has arrived at the next reduction
-                    w0 = ld_acquire_sys(src);
-                    w1 = ld_acquire_sys(src + 1);
-                } else {
-                    s_abort = 1;
-                }
+                if (!ok) s_abort = 1;
                 rank_vals[tid] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
             }
         }
@@ -1896,8 +1896,12 @@ struct Stencil7 : public Operator {
     void launch_peer(const double* x, double* y, bool dot, double* dot_out, const int* skip_flag, const PeerApply& pa) {
         Context* c = ctx;
         const int planes = g.nz_loc;
-        const int kcc = chunk_planes(kc, planes, ((g.nx + 2 * TX - 1) / (2 * TX)) * ((g.ny + TY - 1) / TY));
-        dim3 grid((g.nx + 2 * TX - 1) / (2 * TX), (g.ny + TY - 1) / TY, (planes + kcc - 1) / kcc);
+        // at least four chunks where the slab allows it, so that the inner ones are computed while the boundary planes are
+        // still crossing NVLink; plus the slice of push-only CTAs (blockIdx.z == 0)
+        int kcc = chunk_planes(kc, planes, ((g.nx + 2 * TX - 1) / (2 * TX)) * ((g.ny + TY - 1) / TY));
+        kcc = std::max(1, std::min(kcc, std::max(8, (planes + 3) / 4)));
+        if (const char* e = std::getenv("ATK_PEER_APPLY_KC")) kcc = std::max(1, std::min(std::atoi(e), planes));
+        dim3 grid((g.nx + 2 * TX - 1) / (2 * TX), (g.ny + TY - 1) / TY, (planes + kcc - 1) / kcc + 1);
         dim3 block(TX, TY, 1);
         const int nblocks = (int)(grid.x * grid.y * grid.z);
         ATK_REQUIRE(nblocks <= kMaxPartials, ATK_ERR_INVALID_ARGUMENT, "stencil grid exceeds the partial-sum scratch");
@@ -2052,42 +2056,41 @@ __global__ void __launch_bounds__(TX* TY) stencil27_smem_kernel(StencilGeom g, C
     const int i0 = i_lo + 2 * tx;
     const int j = j_lo + ty;
     int zc = blockIdx.z;
-    if constexpr (PEER) {  // chunk order: first, last, then the ones in between (see stencil7_smem_kernel)
-        const int nzc = gridDim.z;
-        zc = (zc == 0) ? 0 : (zc == 1 ? nzc - 1 : zc - 1);
-    }
-    const int kb = k_lo + zc * kc;
-    const int ke = min(kb + kc, k_hi);
-    if (kb >= ke) return;
     const bool active = (i0 < g.nx) && (j < g.ny);
     const int64_t sxy = (int64_t)g.nx * g.ny;
-    if constexpr (PEER) {  // boundary CTAs: store the tile of the first / last plane into the neighbour, release, wait
-        const bool has_first = kb == 0, has_last = ke == g.nz_loc;
-        const int64_t row = (int64_t)j * g.nx + i0;
-        if (active) {
-            if (has_first && pa.prev_dst) *reinterpret_cast<double2*>(pa.prev_dst + row) = *reinterpret_cast<const double2*>(x + row);
-            if (has_last && pa.next_dst)
-                *reinterpret_cast<double2*>(pa.next_dst + row) = *reinterpret_cast<const double2*>(x + (int64_t)(g.nz_loc - 1) * sxy + row);
-        }
-        if ((has_first && pa.prev_dst) || (has_last && pa.next_dst)) {
+    if constexpr (PEER) {  // push-only CTAs first, boundary chunks last: see stencil7_smem_kernel
+        if (zc == 0) {
+            const int64_t row = (int64_t)j * g.nx + i0;
+            if (active) {
+                if (pa.prev_dst) *reinterpret_cast<double2*>(pa.prev_dst + row) = *reinterpret_cast<const double2*>(x + row);
+                if (pa.next_dst)
+                    *reinterpret_cast<double2*>(pa.next_dst + row) = *reinterpret_cast<const double2*>(x + (int64_t)(g.nz_loc - 1) * sxy + row);
+            }
             __threadfence_system();
             __syncthreads();
             if (tid == 0) {
                 const unsigned n_tiles = gridDim.x * gridDim.y;
-                if (has_first && pa.prev_dst && atomicInc(pa.tickets, n_tiles - 1) == n_tiles - 1) {
+                if (atomicInc(pa.tickets, n_tiles - 1) == n_tiles - 1) {
                     __threadfence_system();
-                    st_release_sys(pa.prev_flag, pa.seq);
-                }
-                if (has_last && pa.next_dst && atomicInc(pa.tickets + 1, n_tiles - 1) == n_tiles - 1) {
-                    __threadfence_system();
-                    st_release_sys(pa.next_flag, pa.seq);
+                    if (pa.prev_flag) st_release_sys(pa.prev_flag, pa.seq);
+                    if (pa.next_flag) st_release_sys(pa.next_flag, pa.seq);
                 }
             }
+            return;
         }
-        if ((has_first && g.k_off > 0) || (has_last && g.k_off + g.nz_loc < g.nz)) {
+        const int nchunk = (int)gridDim.z - 1;
+        const int q = zc - 1;
+        zc = nchunk >= 2 ? (q < nchunk - 2 ? q + 1 : (q == nchunk - 2 ? 0 : nchunk - 1)) : q;
+    }
+    const int kb = k_lo + zc * kc;
+    const int ke = min(kb + kc, k_hi);
+    if (kb >= ke) return;
+    if constexpr (PEER) {
+        const bool need_lo = kb == 0 && g.k_off > 0, need_hi = ke == g.nz_loc && g.k_off + g.nz_loc < g.nz;
+        if (need_lo || need_hi) {
             if (tid == 0) {
-                if (has_first && g.k_off > 0) peer_flag_wait(pa.my_flags, pa.seq);
-                if (has_last && g.k_off + g.nz_loc < g.nz) peer_flag_wait(pa.my_flags + 1, pa.seq);
+                if (need_lo) peer_flag_wait(pa.my_flags, pa.seq);
+                if (need_hi) peer_flag_wait(pa.my_flags + 1, pa.seq);
             }
             __syncthreads();
         }
@@ -2221,7 +2224,8 @@ struct Stencil27 : public Operator {
             const int tiles = ((g.nx + 2 * TX - 1) / (2 * TX)) * ((g.ny + TY - 1) / TY);
             int kcc = std::min(kc27, k_hi - k_lo);
             while (kcc > 8 && (int64_t)tiles * ((k_hi - k_lo + kcc - 1) / kcc) < (int64_t)ctx->sm_count * 8) kcc = (kcc + 1) / 2;
-            dim3 grid((g.nx + 2 * TX - 1) / (2 * TX), (g.ny + TY - 1) / TY, (k_hi - k_lo + kcc - 1) / kcc);
+            kcc = std::max(1, std::min(kcc, std::max(8, (k_hi - k_lo + 3) / 4)));  // inner chunks run during the handshake
+            dim3 grid((g.nx + 2 * TX - 1) / (2 * TX), (g.ny + TY - 1) / TY, (k_hi - k_lo + kcc - 1) / kcc + 1);  // + push-only slice
             constexpr size_t smem = (size_t)4 * (TY + 2) * (2 * TX + 4) * sizeof(double) + kRingShift * sizeof(double);
             bool dense = true;
             for (int t = 0; t < 27; ++t) dense = dense && cf.v[t] != 0.0;

@@ -116,11 +116,20 @@ int atk_vec_axmy(atk_context_t ctx, int64_t n, const double* x, const double* y,
  * col_ptr after finalize(), :76-100) and converts them ON THE DEVICE to CSR (stable in column order) and then to
  * the requested format.  `on_device` != 0 means the three arrays are already device pointers.
  * On a distributed context (SELL format, square matrices): every rank passes the WHOLE matrix and keeps a balanced block
- * of rows (atk_operator_row_range tells which; the grid operators below keep whole z-planes); a row block may reach
- * columns of the two adjacent blocks only (ATK_ERR_INVALID_ARGUMENT otherwise); vectors are the local row blocks. */
+ * of rows (atk_operator_row_range tells which; the grid operators below keep whole z-planes); vectors are the local row
+ * blocks.  ANY sparsity is accepted, as in the reference matvec: a rank's rows may reference columns owned by any other
+ * rank; the owners gather those entries and store them into the requester's memory (NVLink peer stores + sequence flags,
+ * grouped ncclSend/ncclRecv where the GPUs cannot map each other) while the rows that need none of them are computed. */
 int atk_operator_from_csc(atk_context_t ctx, int n_rows, int n_cols, int64_t nnz, const int* col_ptr,
                           const int* row_idx, const double* vals, int on_device, atk_format format,
                           atk_operator_t* out);
+/* The same from a ROW SLICE per rank, so that no rank ever holds the whole matrix: the CSC arrays contain only the entries
+ * of rows [row_begin, row_end) (global row numbers in row_idx, col_ptr over all n_cols columns, nnz = entries of the
+ * slice).  The ranks' blocks must tile [0, n_rows) in rank order (ATK_ERR_INVALID_ARGUMENT otherwise; a row outside the
+ * block is ATK_ERR_OUT_OF_RANGE).  On a single-GPU context the slice must be the whole matrix. */
+int atk_operator_from_csc_rows(atk_context_t ctx, int n_rows, int n_cols, int row_begin, int row_end, int64_t nnz,
+                               const int* col_ptr, const int* row_idx, const double* vals, int on_device, atk_format format,
+                               atk_operator_t* out);
 /* Matrix-free operator of Poisson3DSolver::buildLaplacianMatrix (src/PDEs/FDM/Poisson.hpp:49-95): identity on the
  * Dirichlet shell, 7 taps (cz,cy,cx,cc=-2(cx+cy+cz),cx,cy,cz) inside, idx = i + j*nx + k*nx*ny (:98-100).
  * On a distributed context the operator is the rank's z-slab (planes [k_begin,k_end) of nz, balanced split). */

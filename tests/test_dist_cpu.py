@@ -144,10 +144,25 @@ def test_slab_partition_properties():
 
 
 # ------------------------------------------------------------------------------------------------ row-block operators
-def _rowblock_worker(rank, world, port, n, seed, out_dir):
-    """Host-side model of the row-block protocol of distributed assembled operators (atk_spmv.cu): slice the rows, find
-    how far the columns reach into the adjacent blocks, renumber into [received-lo | own | received-hi], exchange the two
-    neighbour ranges, multiply.  Sends / receives mirror exchange_ranges()."""
+def _rowblock_matrix(n, seed, banded):
+    rng = np.random.default_rng(seed)  # the same matrix and vector on every rank
+    D = np.zeros((n, n))
+    if banded:
+        for dgl in range(-6, 5):
+            idx = np.arange(max(0, -dgl), min(n, n - dgl))
+            D[idx, idx + dgl] = rng.standard_normal(idx.size) * (rng.random(idx.size) < 0.8)
+    else:  # arbitrary sparsity: every rank's rows reach columns of every other rank
+        D = np.where(rng.random((n, n)) < 0.12, rng.standard_normal((n, n)), 0.0)
+        D[np.arange(n), np.arange(n)] = 3.0
+        D[n // 3] = 0.0  # an empty row
+    return D, rng.standard_normal(n)
+
+
+def _rowblock_worker(rank, world, port, n, seed, banded, out_dir):
+    """Host-side model of the general row-block protocol of distributed assembled operators (atk_spmv.cu, PeerGather in
+    atk_context.cu): slice the rows; the external columns in ascending order; local numbering [own block | external];
+    all-gather of the need matrix; the requesters' column lists travel to the owners; per apply every owner gathers
+    what each requester needs and sends it; multiply in the stored (ascending global column) order."""
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -155,71 +170,70 @@ def _rowblock_worker(rank, world, port, n, seed, out_dir):
 
     from algotoolkit_b200 import capi
 
-    rng = np.random.default_rng(seed)  # the same matrix and vector on every rank
-    D = np.zeros((n, n))
-    for dgl in range(-6, 5):
-        idx = np.arange(max(0, -dgl), min(n, n - dgl))
-        D[idx, idx + dgl] = rng.standard_normal(idx.size) * (rng.random(idx.size) < 0.8)
+    D, x = _rowblock_matrix(n, seed, banded)
     A = sp.csr_matrix(D)
-    x = rng.standard_normal(n)
-    r0, r1 = capi.slab_partition(n, rank, world)
+    A.sort_indices()
+    blocks = [capi.slab_partition(n, q, world) for q in range(world)]
+    r0, r1 = blocks[rank]
     n_loc = r1 - r0
     loc = A[r0:r1]
     cols = loc.indices
-    h_lo = max(0, r0 - int(cols.min())) if cols.size else 0
-    h_hi = max(0, int(cols.max()) - (r1 - 1)) if cols.size else 0
-    need = torch.tensor([h_lo, h_hi, n_loc], dtype=torch.int64)
-    allneed = [torch.zeros(3, dtype=torch.int64) for _ in range(world)]
-    dist.all_gather(allneed, need)
-    allneed = [t.tolist() for t in allneed]
-    for q in range(world):  # nobody reaches past an adjacent block
-        assert (allneed[q][0] == 0 if q == 0 else allneed[q][0] <= allneed[q - 1][2])
-        assert (allneed[q][1] == 0 if q == world - 1 else allneed[q][1] <= allneed[q + 1][2])
-    send_prev = allneed[rank - 1][1] if rank > 0 else 0
-    send_next = allneed[rank + 1][0] if rank + 1 < world else 0
+    ext = np.unique(cols[(cols < r0) | (cols >= r1)])                      # ascending external columns
+    recv_count = [int(((ext >= a) & (ext < b)).sum()) for a, b in blocks]  # contiguous runs of `ext`, by owner
+    recv_off = np.concatenate([[0], np.cumsum(recv_count)])
+    assert recv_count[rank] == 0
+    rows = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(rows, torch.tensor(recv_count, dtype=torch.int64))
+    need = np.array([t.tolist() for t in rows])                            # need[p][q]: p receives from q
+    send_count = need[:, rank]
+    # the column lists go to their owners (ncclSend / ncclRecv of ints in the library)
+    reqs, send_idx = [], {}
+    for q in range(world):
+        if q == rank:
+            continue
+        if recv_count[q]:
+            reqs.append(dist.isend(torch.from_numpy(ext[recv_off[q]:recv_off[q + 1]].astype(np.int64)), q))
+        if send_count[q]:
+            send_idx[q] = torch.zeros(int(send_count[q]), dtype=torch.int64)
+            reqs.append(dist.irecv(send_idx[q], q))
+    for r in reqs:
+        r.wait()
+    # ---- one apply: owners gather and send, requesters receive into [external] at the owner's offset
     x_loc = x[r0:r1].copy()
-    halo_lo, halo_hi = torch.zeros(h_lo, dtype=torch.float64), torch.zeros(h_hi, dtype=torch.float64)
+    x_ext = torch.zeros(ext.size, dtype=torch.float64)
     reqs = []
-    if rank > 0:
-        if send_prev:
-            reqs.append(dist.isend(torch.from_numpy(x_loc[:send_prev].copy()), rank - 1))
-        if h_lo:
-            reqs.append(dist.irecv(halo_lo, rank - 1))
-    if rank + 1 < world:
-        if send_next:
-            reqs.append(dist.isend(torch.from_numpy(x_loc[n_loc - send_next:].copy()), rank + 1))
-        if h_hi:
-            reqs.append(dist.irecv(halo_hi, rank + 1))
-    for q in reqs:
-        q.wait()
-    x_ext = np.concatenate([halo_lo.numpy(), x_loc, halo_hi.numpy()])
-    shift = r0 - h_lo
-    loc_ext = sp.csr_matrix((loc.data, loc.indices - shift, loc.indptr), shape=(n_loc, h_lo + n_loc + h_hi))
+    for q in range(world):
+        if q == rank:
+            continue
+        if send_count[q]:
+            reqs.append(dist.isend(torch.from_numpy(x_loc[send_idx[q].numpy() - r0].copy()), q))
+        if recv_count[q]:
+            reqs.append(dist.irecv(x_ext[recv_off[q]:recv_off[q + 1]], q))
+    for r in reqs:
+        r.wait()
+    x_all = np.concatenate([x_loc, x_ext.numpy()])
+    local_col = np.where((cols >= r0) & (cols < r1), cols - r0, n_loc + np.searchsorted(ext, cols))
     y = np.zeros(n_loc)
-    for i in range(n_loc):  # ascending-column sums from 0.0, as the SELL kernel adds them
+    for i in range(n_loc):  # entries stay in ascending GLOBAL column order, whatever their local number
         acc = 0.0
-        for k in range(loc_ext.indptr[i], loc_ext.indptr[i + 1]):
-            acc = acc + loc_ext.data[k] * x_ext[loc_ext.indices[k]]
+        for k in range(loc.indptr[i], loc.indptr[i + 1]):
+            acc = acc + loc.data[k] * x_all[local_col[k]]
         y[i] = acc
     np.save(os.path.join(out_dir, f"y_{rank}.npy"), y)
-    np.save(os.path.join(out_dir, f"rb_{rank}.npy"), np.array([r0, r1, h_lo, h_hi, send_prev, send_next]))
+    np.save(os.path.join(out_dir, f"need_{rank}.npy"), need)
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n", [(2, 41), (3, 64)])
-def test_rowblock_spmv_protocol_matches_global_product(tmp_path, world, n):
+@pytest.mark.parametrize("world,n,banded", [(2, 41, True), (3, 64, True), (2, 37, False), (3, 50, False)])
+def test_rowblock_spmv_protocol_matches_global_product(tmp_path, world, n, banded):
     import scipy.sparse as sp
 
     seed = 31
-    mp.spawn(_rowblock_worker, args=(world, _free_port(), n, seed, str(tmp_path)), nprocs=world, join=True)
-    rng = np.random.default_rng(seed)
-    D = np.zeros((n, n))
-    for dgl in range(-6, 5):
-        idx = np.arange(max(0, -dgl), min(n, n - dgl))
-        D[idx, idx + dgl] = rng.standard_normal(idx.size) * (rng.random(idx.size) < 0.8)
+    mp.spawn(_rowblock_worker, args=(world, _free_port(), n, seed, banded, str(tmp_path)), nprocs=world, join=True)
+    D, x = _rowblock_matrix(n, seed, banded)
     A = sp.csr_matrix(D)
-    x = rng.standard_normal(n)
+    A.sort_indices()
     want = np.zeros(n)
     for i in range(n):
         acc = 0.0
@@ -228,8 +242,7 @@ def test_rowblock_spmv_protocol_matches_global_product(tmp_path, world, n):
         want[i] = acc
     y = np.concatenate([np.load(tmp_path / f"y_{r}.npy") for r in range(world)])
     assert np.array_equal(y, want)  # same per-row sequence of operations -> same bits
-    meta = [np.load(tmp_path / f"rb_{r}.npy") for r in range(world)]
-    assert meta[0][0] == 0 and meta[-1][1] == n and meta[0][2] == 0 and meta[-1][3] == 0
-    for r in range(world - 1):
-        assert meta[r][1] == meta[r + 1][0]
-        assert meta[r][5] == meta[r + 1][2] and meta[r + 1][4] == meta[r][3]  # what one sends is what the other needs
+    needs = [np.load(tmp_path / f"need_{r}.npy") for r in range(world)]
+    assert all(np.array_equal(needs[0], m) for m in needs)  # every rank derived the same need matrix
+    if not banded:
+        assert (needs[0] + np.eye(world, dtype=int) > 0).all()  # truly all-to-all

@@ -105,6 +105,44 @@ cpb = np.cumsum(cpb).astype(np.int32)
 opb = ctx.operator_from_csc(nb, nb, cpb, rb.astype(np.int32), Db[rb, cb], capi.FORMAT_SELL)
 xb = rngb.standard_normal(nb)
 yb = gather(opb.apply_numpy(xb[opb.row_begin: opb.row_begin + opb.n_rows_local]))
+# a matrix with ARBITRARY sparsity (every rank's rows reach columns of every other rank; an empty row; SPD so that CG
+# makes sense): through the whole-matrix entry and through the row-slice entry, peer stores and NCCL
+ng = 64 * world + 11
+rngg = np.random.default_rng(17)
+Dg = np.where(rngg.random((ng, ng)) < 0.06, rngg.standard_normal((ng, ng)), 0.0)
+Dg = Dg + Dg.T
+Dg[np.arange(ng), np.arange(ng)] = np.abs(Dg).sum(1) + 1.0
+Dg[5, :] = 0.0
+Dg[:, 5] = 0.0
+Dg[5, 5] = 2.0
+cg_, rg_ = np.nonzero(Dg.T)  # column-major order = CSC order
+cpg = np.zeros(ng + 1, np.int32)
+np.add.at(cpg, cg_ + 1, 1)
+cpg = np.cumsum(cpg).astype(np.int32)
+vg = Dg[rg_, cg_]
+xg = rngg.standard_normal(ng)
+bg = rngg.standard_normal(ng)
+opg = ctx.operator_from_csc(ng, ng, cpg, rg_.astype(np.int32), vg, capi.FORMAT_SELL)
+g0, g1 = opg.row_begin, opg.row_begin + opg.n_rows_local
+yg = gather(opg.apply_numpy(xg[g0:g1]))
+os.environ["ATK_COMM"] = "nccl"
+yg_nccl = gather(opg.apply_numpy(xg[g0:g1]))
+os.environ.pop("ATK_COMM")
+yg2 = gather(opg.apply_numpy(xg[g0:g1]))  # and back to peer stores: the sequence numbers of the two modes are independent
+os.environ["ATK_CG_FUSED"] = "0"
+resg = ctx.cg_solve_host(opg, bg[g0:g1], 8)
+xgs = gather(resg["x"])
+rpg, cig, vvg = opg.export_csr()
+# row slice: uneven blocks chosen by the caller, only the rank's own entries are passed
+cuts = [0] + [int(ng * (q + 1) / world) - (3 if q % 2 == 0 and q + 1 < world else 0) for q in range(world)]
+s0, s1 = cuts[rank], cuts[rank + 1]
+msk = (rg_ >= s0) & (rg_ < s1)
+cps = np.zeros(ng + 1, np.int32)
+np.add.at(cps, cg_[msk] + 1, 1)
+cps = np.cumsum(cps).astype(np.int32)
+ops_ = ctx.operator_from_csc_rows(ng, ng, s0, s1, cps, rg_[msk].astype(np.int32), vg[msk], capi.FORMAT_SELL)
+assert (ops_.row_begin, ops_.n_rows_local) == (s0, s1 - s0)
+ys = gather(ops_.apply_numpy(xg[s0:s1]))
 if rank == 0:
     from oracle.pyoracle import Port
 
@@ -147,6 +185,22 @@ if rank == 0:
     Ab = P.csc_from_triplets(nb, nb, rb, cb, Db[rb, cb])
     print("banded matrix via from_csc, row blocks, apply bit-exact:", np.array_equal(yb, P.spmv(Ab, xb)))
     ok &= np.array_equal(yb, P.spmv(Ab, xb))
+    Ag = P.csc_from_triplets(ng, ng, rg_, cg_, vg)
+    yg_ref = P.spmv(Ag, xg)
+    print("general sparsity, whole-matrix entry, apply bit-exact (peer stores / NCCL / peer again):", np.array_equal(yg, yg_ref),
+          np.array_equal(yg_nccl, yg_ref), np.array_equal(yg2, yg_ref), " row-slice entry:", np.array_equal(ys, yg_ref))
+    ok &= np.array_equal(yg, yg_ref) and np.array_equal(yg_nccl, yg_ref) and np.array_equal(yg2, yg_ref) and np.array_equal(ys, yg_ref)
+    orag = P.cg(Ag, bg, 8)
+    exg = np.linalg.norm(xgs - orag["x"]) / np.linalg.norm(orag["x"])
+    print(f"CG on the general distributed operator: iters {resg['iters']} (oracle {orag['iters']}) relerr x {exg:.2e}")
+    ok &= resg["iters"] == orag["iters"] and exg < 1e-10
+    # exported CSR of rank 0's block: global column numbers again
+    want_rows = Dg[g0:g1]
+    got = np.zeros_like(want_rows)
+    for i in range(g1 - g0):
+        got[i, cig[rpg[i]:rpg[i + 1]]] = vvg[rpg[i]:rpg[i + 1]]
+    print("export_csr of a distributed block returns global columns:", np.array_equal(got, want_rows))
+    ok &= np.array_equal(got, want_rows)
     ora2 = P.cg(None, b, 7, state=(ora["x"], ora["r"], ora["p"]), stencil=(nx, ny, nz, cx, cy, cz))
     ec = np.linalg.norm(x_cont - ora2["x"]) / np.linalg.norm(ora2["x"])
     print(f"continued solve (+7 iterations): iters {res2['iters']} peer {res2['peer']} relerr x {ec:.2e}")
