@@ -45,7 +45,17 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, checked: bool = False) -> str:
+    """checked=True builds libatk_cuda_checked.so with -DATK_CHECKED (device-side assertions on tile / halo indices and on
+    the peer protocols' sequence numbers); ATK_LIB=checked makes capi load it."""
+    global OBJ, LIB
+    if checked:
+        OBJ = os.path.join(HERE, "build_checked")
+        LIB = os.path.join(HERE, "libatk_cuda_checked.so")
+    else:
+        OBJ = os.path.join(HERE, "build")
+        LIB = os.path.join(HERE, "libatk_cuda.so")
+    flags = NVCC_FLAGS + (["-DATK_CHECKED"] if checked else [])
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(INCLUDE, "atk_cuda.h"))
@@ -59,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, obj = job
-        cmd = [NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [NVCC] + flags + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return job, r
 
@@ -85,5 +95,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, checked="--checked" in sys.argv)
     print(path)

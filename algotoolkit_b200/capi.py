@@ -12,7 +12,8 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libatk_cuda.so")
+# ATK_LIB=checked loads the build with device-side assertions (python -m algotoolkit_b200.build --checked)
+LIB_PATH = os.path.join(_HERE, "libatk_cuda_checked.so" if os.environ.get("ATK_LIB") == "checked" else "libatk_cuda.so")
 
 ATK_OK, ATK_ERR_INVALID_ARGUMENT, ATK_ERR_RUNTIME, ATK_ERR_OUT_OF_RANGE, ATK_ERR_CUDA, ATK_ERR_NCCL, ATK_ERR_NOMEM = range(7)
 REDUCE_TREE, REDUCE_SEQUENTIAL = 0, 1

@@ -318,6 +318,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r, double* p, int max_iter,
               atk_cg_info* info) {
     ATK_REQUIRE(op && b && x && r && p && info, ATK_ERR_INVALID_ARGUMENT, "null argument to cg_solve");
+    ATK_NVTX("atk::cg_solve");
     ATK_REQUIRE(op->n_cols == op->n_rows_local * 1 || ctx->world > 1, ATK_ERR_INVALID_ARGUMENT, "Dimension mismatch");
     const int64_t n = op->n_rows_local;
     cudaStream_t st = ctx->stream;

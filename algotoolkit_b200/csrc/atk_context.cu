@@ -760,6 +760,9 @@ static void init_context(Context& c, int device) {
     c.d_ll = c.d_flags + (size_t)kNumSlots * kMaxRanks;
     ATK_CUDA_CHECK(cudaMemset(c.d_tickets, 0, sizeof(unsigned) * kNumTickets));
     ATK_CUDA_CHECK(cudaMemset(c.d_gather, 0, arena));
+    // ATK_EPOCH_SEED: start value of the sequence-number base (stress tests seed it just below 2^32 so that the 32-bit
+    // tags of the packed words wrap during the run); must be the same on every rank
+    if (const char* e = std::getenv("ATK_EPOCH_SEED")) c.epoch = std::strtoull(e, nullptr, 0);
     ATK_CUDA_CHECK(cudaMallocHost(&c.h_pinned, sizeof(double) * 64));
     ATK_CUDA_CHECK(cudaMallocHost(&c.h_flags, sizeof(int) * kHostFlags));
     ATK_CUDA_CHECK(cudaDeviceSynchronize());

@@ -68,6 +68,7 @@ __global__ void gd_decide_kernel(GdState* st, const double* slot_rr, const doubl
 }  // namespace
 
 void gd_solve(Context* ctx, Operator* op, const double* b, double* x, int max_iter, double tol, atk_gd_info* info) {
+    ATK_NVTX("atk::gd_solve");
     ATK_REQUIRE(op && b && x && info, ATK_ERR_INVALID_ARGUMENT, "null argument to gd_solve");
     const int64_t n = op->n_rows_local;
     cudaStream_t st = ctx->stream;

@@ -599,6 +599,7 @@ struct Givens {
 void gmres_solve(Context* ctx, Operator* op, Preconditioner* pc, const double* b, double* x, int64_t n_x, int max_iter,
                  int krylov_dim, double tol, atk_gmres_ortho ortho, atk_gmres_callback cb, void* user, atk_gmres_info* info) {
     ATK_REQUIRE(op && b && x && info, ATK_ERR_INVALID_ARGUMENT, "null argument to gmres_solve");
+    ATK_NVTX("atk::gmres_solve");
     const int64_t n = op->n_rows_local;
     const int64_t n_global = op->n_cols;
     // GMRES.hpp:28-37
@@ -858,6 +859,7 @@ void gmres_solve(Context* ctx, Operator* op, Preconditioner* pc, const double* b
 // writes are touched.  *breakdown = i of the breakdown, or -1.
 void arnoldi(Context* ctx, Operator* op, double* Q, int64_t ldq, int m, double* H, double tol, int* breakdown) {
     ATK_REQUIRE(op && Q && H && breakdown && m >= 1, ATK_ERR_INVALID_ARGUMENT, "bad argument to arnoldi");
+    ATK_NVTX("atk::arnoldi");
     const int64_t n = op->n_rows_local;
     ATK_REQUIRE(ldq >= n, ATK_ERR_INVALID_ARGUMENT, "Q columns overlap");
     cudaStream_t st = ctx->stream;

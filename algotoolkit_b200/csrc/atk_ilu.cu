@@ -245,6 +245,7 @@ struct IluPreconditioner final : Preconditioner {
 Preconditioner* make_ilu(Context* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* col_ptr, const int32_t* row_idx,
                          const double* vals) {
     ATK_REQUIRE(ctx->world == 1, ATK_ERR_INVALID_ARGUMENT, "the ILU preconditioner is built on single-GPU contexts only");
+    ATK_NVTX("atk::ilu_compute");
     ATK_REQUIRE(n_rows == n_cols, ATK_ERR_INVALID_ARGUMENT, "Matrix must be square for ILU factorization");  // :24-26
     ATK_REQUIRE(n_rows >= 0 && nnz >= 0 && (n_rows == 0 || (col_ptr && (nnz == 0 || (row_idx && vals)))), ATK_ERR_INVALID_ARGUMENT,
                 "bad CSC arrays");

@@ -22,7 +22,34 @@
 
 #include "../../include/atk_cuda.h"
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost nothing unless a profiler is attached
+
 namespace atk {
+
+// One NVTX range per solver call and per kernel class (nsys / ncu --nvtx group the launches by it).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define ATK_NVTX(name) ::atk::NvtxRange atk_nvtx_range_##__LINE__(name)
+
+// Checked build (python -m algotoolkit_b200.build --checked -> libatk_cuda_checked.so, ATK_LIB=checked selects it): device-side
+// assertions on tile / halo indices and on the sequence numbers of the peer protocols; a violation prints and traps.
+#ifdef ATK_CHECKED
+#define ATK_DEVICE_ASSERT(cond)                                                                        \
+    do {                                                                                               \
+        if (!(cond)) {                                                                                 \
+            printf("ATK_CHECKED: %s failed at %s:%d (block %d thread %d)\n", #cond, __FILE__, __LINE__, \
+                   (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)),               \
+                   (int)(threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)));         \
+            asm volatile("trap;");                                                                     \
+        }                                                                                              \
+    } while (0)
+#else
+#define ATK_DEVICE_ASSERT(cond) ((void)0)
+#endif
 
 // ------------------------------------------------------------------------------------------ errors
 struct Error : public std::exception {

@@ -539,6 +539,7 @@ struct AssembledMatrix : public Operator {
     }
 
     void apply(const double* x, double* y, int dot_slot, const int* skip_flag) override {
+        ATK_NVTX(format == ATK_FORMAT_SELL ? "atk::spmv_sell32" : "atk::spmv_csr");
         Context* c = ctx;
         double* dot_out = dot_slot >= 0 ? c->slot(dot_slot) + c->rank : nullptr;
         const int grid = c->sm_count * 8;
@@ -681,6 +682,7 @@ static Operator* build_from_device_csc(Context* ctx, int n_rows, int n_cols, int
                                        int row_hi = -1, bool rows_are_slice = false) {
     ATK_REQUIRE(nnz >= 0 && nnz < (int64_t)0x7fffffff, ATK_ERR_INVALID_ARGUMENT, "nnz must be below 2^31");
     const bool dist = ctx->world > 1;
+    ATK_NVTX("atk::csc_to_device_format");
     const int n_rows_global = n_rows;
     if (dist) {
         ATK_REQUIRE(format == ATK_FORMAT_SELL, ATK_ERR_INVALID_ARGUMENT, "distributed assembled operators use the SELL format");

@@ -1237,6 +1237,8 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
                     w0 = ld_acquire_sys(src);
                     w1 = ld_acquire_sys(src + 1);
                     if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
+                    // a word two or more phases AHEAD of this rank would mean a peer overwrote a value nobody here has read
+                    ATK_DEVICE_ASSERT((unsigned)((w0 >> 32) - tag) >= 0x80000000u || (unsigned)((w0 >> 32) - tag) == 0u || (w0 >> 32) == 0ull);
                     if ((++spins & 0xfffu) == 0) {
                         const unsigned long long now = global_timer_ns();
                         if (t0 == 0) t0 = now;
@@ -1333,12 +1335,15 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
                     c_ok[q] = e < NCH && !corner && gj >= 0 && gj < g.ny && gi >= 0 && gi < g.nx;
                     c_sm[q] = 8u * (unsigned)(jj * W + 2 * c);
                     c_off[q] = gj * g.nx + gi;
+                    ATK_DEVICE_ASSERT(!c_ok[q] || (c_off[q] >= 0 && (int64_t)c_off[q] + 1 < sxy && c_sm[q] + 16u <= (unsigned)(STAGE * 8)));
                 }
+                ATK_DEVICE_ASSERT(kb >= 0 && kb < ke && ke <= g.nz_loc && tyi < a.tiles_y && chunk >= 0);
                 auto issue_plane = [&](int k) {
                     if (k >= k_first && k <= k_last) {
                         const unsigned so = (unsigned)((k - kb + 1) & (DEPTH - 1)) * (unsigned)(STAGE * 8);
                         const double* rp = k < 0 ? a.r_halo_lo : (k >= g.nz_loc ? a.r_halo_hi : a.r + (int64_t)k * sxy);
                         const double* pp = k < 0 ? p_halo_lo : (k >= g.nz_loc ? p_halo_hi : ps + (int64_t)k * sxy);
+                        ATK_DEVICE_ASSERT(k >= -1 && k <= g.nz_loc && rp != nullptr && pp != nullptr);  // a halo plane is only read where a neighbour exists
 #pragma unroll
                         for (int q = 0; q < Q; ++q)
                             if (c_ok[q]) {
@@ -1660,6 +1665,7 @@ struct Stencil7 : public Operator {
                        double* pAp_trace, double* rs_trace, int trace_cap, unsigned long long epoch, unsigned long long* stamps,
                        int stamp_cap) override {
         ATK_REQUIRE(ps_grid > 0, ATK_ERR_INVALID_ARGUMENT, "persistent CG loop not available for this operator");
+        ATK_NVTX("atk::cg_persistent_kernel");
         constexpr int TX = 32, TY = 4;
         Context* c = ctx;
         const size_t plane = (size_t)g.nx * g.ny;
@@ -1932,6 +1938,7 @@ struct Stencil7 : public Operator {
         return e && std::string(e) == "nccl";
     }
     void apply(const double* x, double* y, int dot_slot, const int* skip_flag) override {
+        ATK_NVTX("atk::stencil7_apply");
         Context* c = ctx;
         const bool dot = dot_slot >= 0;
         double* dot_out = dot ? c->slot(dot_slot) + c->rank : nullptr;
@@ -2263,6 +2270,7 @@ struct Stencil27 : public Operator {
         count_launch(ctx);
     }
     void apply(const double* x, double* y, int dot_slot, const int* skip_flag) override {
+        ATK_NVTX("atk::stencil27_apply");
         Context* c = ctx;
         (void)skip_flag;  // only the CG loop passes a skip flag, and CG on this operator goes through launch_dot below
         if (c->world == 1) {

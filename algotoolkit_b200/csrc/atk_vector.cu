@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(1024) dot_sequential_kernel(int64_t n, const d
 }  // namespace
 
 void launch_dot(Context* ctx, int64_t n, const double* x, const double* y, int slot, const int* skip_flag) {
+    ATK_NVTX("atk::dot");
     double* out = ctx->slot(slot) + ctx->rank;
     if (ctx->reduction == ATK_REDUCE_SEQUENTIAL) {
         dot_sequential_kernel<<<1, 1024, 0, ctx->stream>>>(n, x, y, out, skip_flag);
