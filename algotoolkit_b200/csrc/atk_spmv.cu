@@ -495,6 +495,88 @@ __global__ void __launch_bounds__(kStreamBlock) csr_stream_spmv_kernel(int n_blo
     }
 }
 
+// CSR-stream, second form (default): the MATRIX entries of the row run are staged in shared memory instead of the products.
+// Phase 1 copies the run's values and column indices global -> shared with 16-byte cp.async (aligned superset of the run,
+// nothing passes through registers, fully coalesced); phase 2 is thread-per-row: consecutive threads walk consecutive rows
+// through shared memory (row starts are an odd stride apart for stencil-like rows: no bank conflicts) and gather x for the
+// SAME tap position of 32 consecutive rows at a time - consecutive or near-consecutive addresses, a few sectors per warp
+// request, which is what the thread-per-entry form above lacks (~7 scattered sectors per request, LSU-bound at 53 % of
+// peak).  The row's products are added from 0.0 in ascending column order in registers: the CSC matvec's exact sequence.
+constexpr int kStream2Cap = 4096;  // entries per CTA: 32 KB of values + 16 KB of column indices
+__device__ __forceinline__ void cp_async16_g2s(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+template <bool DOT>
+__global__ void __launch_bounds__(kStreamBlock) csr_stream2_spmv_kernel(int n_blocks, int64_t nnz, const int* __restrict__ blk_row,
+                                                                        const int* __restrict__ row_ptr,
+                                                                        const int* __restrict__ csr_col,
+                                                                        const double* __restrict__ csr_val,
+                                                                        const double* __restrict__ x, double* __restrict__ y,
+                                                                        double* partials, unsigned* ticket, double* dot_out,
+                                                                        const int* skip_flag) {
+    if (skip_flag && *skip_flag) return;
+    extern __shared__ __align__(16) double smem2[];
+    double* sv = smem2;                                             // [kStream2Cap + 4]
+    int* sc = reinterpret_cast<int*>(smem2 + kStream2Cap + 4);      // [kStream2Cap + 4]
+    double dacc = 0.0;
+    const int64_t nnz4 = nnz & ~(int64_t)3;  // whole 16-byte chunks of column indices end here
+    for (int b = blockIdx.x; b < n_blocks; b += gridDim.x) {
+        const int r0 = blk_row[b], r1 = blk_row[b + 1];
+        const int e0 = row_ptr[r0], e1 = row_ptr[r1];
+        const int e0a = e0 & ~3;
+        const int n4 = (e1 - e0a + 3) >> 2;  // chunks of four entries: 16 B of indices, 32 B of values
+        for (int q = threadIdx.x; q < n4; q += kStreamBlock) {
+            const int64_t idx = (int64_t)e0a + 4 * q;
+            if (idx + 4 <= nnz4) {
+                cp_async16_g2s(sc + 4 * q, csr_col + idx);
+                cp_async16_g2s(sv + 4 * q, csr_val + idx);
+                cp_async16_g2s(sv + 4 * q + 2, csr_val + idx + 2);
+            } else {
+                for (int u = 0; u < 4; ++u)
+                    if (idx + u < nnz) {
+                        sc[4 * q + u] = csr_col[idx + u];
+                        sv[4 * q + u] = csr_val[idx + u];
+                    }
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncthreads();
+        for (int r = r0 + threadIdx.x; r < r1; r += kStreamBlock) {
+            const int k0 = row_ptr[r] - e0a, k1 = row_ptr[r + 1] - e0a;
+            double acc = 0.0;
+            constexpr int U = 8;
+            for (int kb = k0; kb < k1; kb += U) {
+                int c[U];
+                double v[U], xv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool in = kb + u < k1;
+                    c[u] = in ? sc[kb + u] : -1;
+                    v[u] = in ? sv[kb + u] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) xv[u] = x[c[u] < 0 ? 0 : c[u]];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {  // ascending column order; exact-zero x entries contribute nothing (SparseObj.hpp:141)
+                    const double t = add_rn(acc, mul_rn(v[u], xv[u]));
+                    acc = (c[u] >= 0 && xv[u] != 0.0) ? t : acc;
+                }
+            }
+            y[r] = acc;
+            if constexpr (DOT) dacc = add_rn(dacc, mul_rn(x[r], acc));
+        }
+        __syncthreads();  // the staged entries are free again
+    }
+    if constexpr (DOT) {
+        double total;
+        if (grid_sum_last_block<kStreamBlock>(dacc, partials, ticket, &total)) {
+            if (linear_thread_id() == 0) *dot_out = total;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ the operator
 struct AssembledMatrix : public Operator {
     int n_rows = 0;
@@ -580,6 +662,22 @@ struct AssembledMatrix : public Operator {
             ATK_CUDA_CHECK(cudaGetLastError());
             if (dot) allgather_slot(c, dot_slot, c->stream);
             return;
+        } else if (stream_blocks > 0 && !std::getenv("ATK_CSR_STREAM_V1")) {
+            const int g = std::min(stream_blocks, c->sm_count * 8);
+            constexpr size_t smem = (sizeof(double) + sizeof(int)) * (kStream2Cap + 4);
+            static bool opted_in = false;
+            if (!opted_in) {  // above the 48 KB default: raise the limit of both instantiations once
+                ATK_CUDA_CHECK(cudaFuncSetAttribute(csr_stream2_spmv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                ATK_CUDA_CHECK(cudaFuncSetAttribute(csr_stream2_spmv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                opted_in = true;
+            }
+            if (dot_slot >= 0)
+                csr_stream2_spmv_kernel<true><<<g, kStreamBlock, smem, c->stream>>>(stream_blocks, nnz, blk_row, row_ptr, csr_col,
+                                                                                  csr_val, x, y, c->d_partials, c->d_tickets + 1,
+                                                                                  dot_out, skip_flag);
+            else
+                csr_stream2_spmv_kernel<false><<<g, kStreamBlock, smem, c->stream>>>(stream_blocks, nnz, blk_row, row_ptr, csr_col,
+                                                                                   csr_val, x, y, nullptr, nullptr, nullptr, skip_flag);
         } else if (stream_blocks > 0) {
             const int g = std::min(stream_blocks, c->sm_count * 32);
             constexpr size_t smem = sizeof(double) * kStreamCap;

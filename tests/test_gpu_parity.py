@@ -796,7 +796,19 @@ def test_csr_stream_is_bit_exact_and_vector_kernel_still_covered(ctx, port, monk
     x[::7] = 0.0
     want = port.spmv(A, x)
     op = ctx.operator_from_csc(n_rows, n_cols, A.col_ptr, A.row_idx, A.vals, capi.FORMAT_CSR_VECTOR)
-    assert np.array_equal(op.apply_numpy(x), want)
+    assert np.array_equal(op.apply_numpy(x), want)  # row-parallel form: matrix entries staged in shared memory
+    monkeypatch.setenv("ATK_CSR_STREAM_V1", "1")
+    assert np.array_equal(op.apply_numpy(x), want)  # entry-parallel form: products staged in shared memory
+    monkeypatch.delenv("ATK_CSR_STREAM_V1")
+    # nnz not a multiple of four and a last block that ends inside the final 16-byte chunk
+    for extra in (1, 2, 3):
+        rr = np.concatenate([rows, np.full(extra, n_rows - 1)])
+        cc = np.concatenate([cols, np.arange(extra)])
+        vv = np.concatenate([vals, rng.standard_normal(extra)])
+        A3 = port.csc_from_triplets(n_rows, n_cols, rr, cc, vv)
+        op3 = ctx.operator_from_csc(n_rows, n_cols, A3.col_ptr, A3.row_idx, A3.vals, capi.FORMAT_CSR_VECTOR)
+        assert np.array_equal(op3.apply_numpy(x), port.spmv(A3, x))
+        op3.destroy()
     monkeypatch.setenv("ATK_CSR_NO_STREAM", "1")
     opv = ctx.operator_from_csc(n_rows, n_cols, A.col_ptr, A.row_idx, A.vals, capi.FORMAT_CSR_VECTOR)
     assert relerr(opv.apply_numpy(x), want) < 1e-14
