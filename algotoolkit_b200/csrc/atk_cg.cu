@@ -297,10 +297,37 @@ __global__ void __launch_bounds__(kReduceBlock) cg_fused_flush_kernel(int64_t n,
     const double rs_new = pk.on ? rs_peer : slot_sum(slot_rr, world);
     const double beta = __ddiv_rn(rs_new, st->rs_old);
     const double alpha = st->alpha;
-    for (int64_t i = t; i < n; i += stride) {
-        const double pv = pc[i];
-        x[i] = add_rn(x[i], mul_rn(pv, alpha));
-        p_user[i] = add_rn(r[i], mul_rn(pv, beta));
+    if (((n & 1) == 0) && ((reinterpret_cast<uintptr_t>(pc) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(r) |
+                            reinterpret_cast<uintptr_t>(p_user)) & 15u) == 0) {
+        // 16-byte accesses, four independent element pairs in flight per thread (40 B/row: read x, p, r; write x, p)
+        const int64_t n2 = n >> 1;
+        const double2* pc2 = reinterpret_cast<const double2*>(pc);
+        const double2* r2 = reinterpret_cast<const double2*>(r);
+        double2* x2 = reinterpret_cast<double2*>(x);
+        double2* pu2 = reinterpret_cast<double2*>(p_user);
+        auto one = [&](int64_t i, const double2 pv, const double2 rv, double2 xv) {
+            xv.x = add_rn(xv.x, mul_rn(pv.x, alpha));
+            xv.y = add_rn(xv.y, mul_rn(pv.y, alpha));
+            x2[i] = xv;
+            pu2[i] = make_double2(add_rn(rv.x, mul_rn(pv.x, beta)), add_rn(rv.y, mul_rn(pv.y, beta)));
+        };
+        int64_t i = t;
+        for (; i + 3 * stride < n2; i += 4 * stride) {
+            const double2 p0 = pc2[i], p1 = pc2[i + stride], p2 = pc2[i + 2 * stride], p3 = pc2[i + 3 * stride];
+            const double2 r0 = r2[i], r1 = r2[i + stride], r2v = r2[i + 2 * stride], r3 = r2[i + 3 * stride];
+            const double2 x0 = x2[i], x1 = x2[i + stride], x2v = x2[i + 2 * stride], x3 = x2[i + 3 * stride];
+            one(i, p0, r0, x0);
+            one(i + stride, p1, r1, x1);
+            one(i + 2 * stride, p2, r2v, x2v);
+            one(i + 3 * stride, p3, r3, x3);
+        }
+        for (; i < n2; i += stride) one(i, pc2[i], r2[i], x2[i]);
+    } else {
+        for (int64_t i = t; i < n; i += stride) {
+            const double pv = pc[i];
+            x[i] = add_rn(x[i], mul_rn(pv, alpha));
+            p_user[i] = add_rn(r[i], mul_rn(pv, beta));
+        }
     }
     if (last_block_done(ticket)) {
         if (threadIdx.x == 0) {

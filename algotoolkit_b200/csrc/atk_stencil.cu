@@ -15,6 +15,8 @@
 //
 // Distributed contexts own a z-slab [k_begin,k_end); the planes k_begin-1 and k_end come from halo buffers that
 // exchange_halo() fills on the communication stream while the interior planes are being computed.
+#include <cuda.h>  // CUtensorMap (the encode function itself is fetched with cudaGetDriverEntryPoint: no libcuda link)
+
 #include <algorithm>
 #include <cstdlib>
 #include <string>
@@ -945,6 +947,191 @@ __global__ void __launch_bounds__(TX* TY) stencil7_tma_kernel(StencilGeom g, con
     }
 }
 
+// ---------------------------------------------------------------------------------------------- KA through tensor-map TMA
+// The same fused step as stencil7_cg_fused_smem_kernel with the r and p plane tiles fetched by the TMA unit: 3-D tensor maps
+// over (nx, ny, nz) with a (2TX+4) x (TY+2) x 1 box, one cp.async.bulk.tensor.3d per array and plane issued by ONE elected
+// thread at coordinates (i_lo-2, j_lo-1, k) - columns, rows and planes outside the grid are zero-filled by the hardware -
+// completion on an mbarrier with expect_tx; nobody spends issue slots or registers on load addresses.  Single-GPU
+// contexts (ATK_FUSED_TMA=1); arithmetic identical to the LDGSTS kernel, so the results are bit-identical.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+template <int TX, int TY>
+__global__ void __launch_bounds__(TX* TY) stencil7_cg_fused_tma_kernel(const __grid_constant__ CUtensorMap tm_r,
+                                                                        const __grid_constant__ CUtensorMap tm_p0,
+                                                                        const __grid_constant__ CUtensorMap tm_p1, StencilGeom g,
+                                                                        FusedArgs a, int k_lo, int k_hi, int kc, double* partials,
+                                                                        int partial_base, unsigned* ticket, double* dot_out,
+                                                                        int is_final) {
+    constexpr int DEPTH = 4;
+    constexpr int W = 2 * TX + 4;
+    constexpr int TILE = (TY + 2) * W;                  // doubles per plane tile
+    constexpr int STAGE = (TILE * 8 + 127) / 128 * 16;  // doubles per stage: TMA destinations are 128-byte aligned
+    extern __shared__ __align__(128) double smem_raw[];
+    double* ring_r = smem_raw;
+    double* ring_p = smem_raw + DEPTH * STAGE;
+    __shared__ __align__(8) unsigned long long full[DEPTH];
+
+    CgFusedState* st = a.st;
+    if (st->done) return;
+    const int first = st->first;
+    const int cnt = st->ka_count;
+    const CUtensorMap* tm_p = (cnt & 1) ? &tm_p1 : &tm_p0;
+    double* __restrict__ pd = (cnt & 1) ? a.P0 : a.P1;
+    double rs_new = 0.0, beta = 0.0, alpha = 0.0;
+    if (!first) {
+        rs_new = slot_sum(a.slot_rr, a.world);
+        beta = __ddiv_rn(rs_new, st->rs_old);
+        alpha = st->alpha;
+    }
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i_lo = blockIdx.x * 2 * TX;
+    const int j_lo = blockIdx.y * TY;
+    const int i0 = i_lo + 2 * tx;
+    const int j = j_lo + ty;
+    const int kb = k_lo + blockIdx.z * kc;
+    const int ke = min(kb + kc, k_hi);
+    const bool active = (i0 < g.nx) && (j < g.ny);
+    const int64_t sxy = (int64_t)g.nx * g.ny;
+    const int64_t row = (int64_t)j * g.nx + i0;
+    const bool leader = (tx == 0 && ty == 0);
+    double dacc = 0.0;
+    if (leader) {
+#pragma unroll
+        for (int s = 0; s < DEPTH; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto stage_of = [&](int k) -> int { return (k - kb + 1) & (DEPTH - 1); };
+    auto issue_plane = [&](int k) {  // leader only; planes kb-1 .. ke (outside the grid: zero fill)
+        if (k > ke) return;
+        const int s = stage_of(k);
+        mbar_expect_tx(&full[s], 2u * (unsigned)(TILE * 8));
+        tma_load_3d(ring_r + s * STAGE, &tm_r, i_lo - 2, j_lo - 1, k, &full[s]);
+        tma_load_3d(ring_p + s * STAGE, tm_p, i_lo - 2, j_lo - 1, k, &full[s]);
+    };
+    unsigned phase_bits = 0;
+    auto wait_plane = [&](int k) {
+        if (k > ke) return;
+        const int s = stage_of(k);
+        mbar_wait(&full[s], (phase_bits >> s) & 1u);
+        phase_bits ^= 1u << s;
+    };
+    auto pnew = [&](double rv, double pv) -> double { return first ? pv : add_rn(rv, mul_rn(pv, beta)); };
+    auto pnew2 = [&](double2 rv, double2 pv) -> double2 { return make_double2(pnew(rv.x, pv.x), pnew(rv.y, pv.y)); };
+    auto ld2s = [](const double* q) -> double2 { return *reinterpret_cast<const double2*>(q); };
+    const int centre = (ty + 1) * W + 2 * tx + 2;
+
+    if (kb < ke) {
+        const bool j_shell = (j == 0 || j == g.ny - 1);
+        const bool a_shell_i = (i0 == 0 || i0 == g.nx - 1);
+        const bool b_shell_i = (i0 + 1 == g.nx - 1);
+        const double2 zero2 = make_double2(0.0, 0.0);
+        if (leader) {
+            issue_plane(kb - 1);
+            issue_plane(kb);
+            issue_plane(kb + 1);
+            issue_plane(kb + 2);
+        }
+        double2 xv = zero2;
+        if (active && !first) xv = *reinterpret_cast<const double2*>(a.x + (int64_t)kb * sxy + row);
+        wait_plane(kb - 1);
+        wait_plane(kb);
+        double2 pnA = zero2, pnB = zero2, pnC = zero2, poB = zero2;
+        if (active) {
+            if (g.k_off + kb - 1 >= 0) pnA = pnew2(ld2s(ring_r + centre), ld2s(ring_p + centre));
+            poB = ld2s(ring_p + STAGE + centre);
+            pnB = pnew2(ld2s(ring_r + STAGE + centre), poB);
+        }
+        for (int k = kb; k < ke; ++k) {
+            const int kg = g.k_off + k;
+            const int64_t idx = (int64_t)k * sxy + row;
+            wait_plane(k + 1);
+            __syncthreads();  // everyone is done reading plane k-1's stage: it may be refilled
+            if (leader) issue_plane(k + 3);
+            double2 xn = zero2;
+            if (active && !first && k + 1 < ke) xn = *reinterpret_cast<const double2*>(a.x + idx + sxy);
+            if (active) {
+                const int so = stage_of(k) * STAGE, sn = stage_of(k + 1) * STAGE;
+                const double* rs = ring_r + so + centre;
+                const double* pss = ring_p + so + centre;
+                double2 poC = zero2;
+                if (kg + 1 < g.nz) {
+                    poC = ld2s(ring_p + sn + centre);
+                    pnC = pnew2(ld2s(ring_r + sn + centre), poC);
+                }
+                double2 out;
+                if (j_shell || kg == 0 || kg == g.nz - 1) {
+                    out.x = shell_row(pnB.x);
+                    out.y = shell_row(pnB.y);
+                } else {
+                    const double2 jm = pnew2(ld2s(rs - W), ld2s(pss - W));
+                    const double2 jp = pnew2(ld2s(rs + W), ld2s(pss + W));
+                    if (a_shell_i) {
+                        out.x = shell_row(pnB.x);
+                    } else {
+                        const double left = pnew(rs[-1], pss[-1]);
+                        out.x = tap7(g, pnA.x, jm.x, left, pnB.x, pnB.y, jp.x, pnC.x);
+                    }
+                    if (b_shell_i) {
+                        out.y = shell_row(pnB.y);
+                    } else {
+                        const double right = pnew(rs[2], pss[2]);
+                        out.y = tap7(g, pnA.y, jm.y, pnB.x, pnB.y, right, jp.y, pnC.y);
+                    }
+                }
+                *reinterpret_cast<double2*>(a.Ap + idx) = out;
+                *reinterpret_cast<double2*>(pd + idx) = pnB;
+                dacc = add_rn(dacc, mul_rn(pnB.x, out.x));
+                dacc = add_rn(dacc, mul_rn(pnB.y, out.y));
+                if (!first) {
+                    xv.x = add_rn(xv.x, mul_rn(poB.x, alpha));  // x = x + p*alpha of the previous iteration (:60)
+                    xv.y = add_rn(xv.y, mul_rn(poB.y, alpha));
+                    *reinterpret_cast<double2*>(a.x + idx) = xv;
+                }
+                pnA = pnB;
+                pnB = pnC;
+                poB = poC;
+            }
+            xv = xn;
+        }
+        // planes requested beyond the last one computed must have landed before the CTA may exit
+        // (wait_plane(k+1) covered planes up to ke; nothing beyond ke was issued)
+    }
+    const double bs = block_sum<TX * TY>(dacc);
+    __shared__ bool is_last;
+    const unsigned nb = total_blocks();
+    if (linear_thread_id() == 0) {
+        partials[partial_base + linear_block_id()] = bs;
+        is_last = false;
+        if (is_final) {
+            __threadfence();
+            const unsigned t = atomicInc(ticket, nb - 1);
+            is_last = (t == nb - 1);
+        }
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        const double total = partials_sum<TX * TY>(partials, partial_base + nb);
+        if (linear_thread_id() == 0) {
+            *dot_out = total;
+            if (!first) {
+                if (a.rs_trace && st->it < st->trace_cap) a.rs_trace[st->it] = rs_new;
+                st->rs_old = rs_new;
+                st->it = st->it + 1;
+            }
+            st->first = 0;
+            st->ka_count = cnt + 1;
+        }
+    }
+}
+
 // packs the boundary planes of r and of the current p (selected on the device by the ping-pong parity) for the
 // halo exchange: send = [r_first | p_first | r_last | p_last]
 __global__ void __launch_bounds__(256) pack_halo_kernel(const CgFusedState* st, const double* __restrict__ r, const double* P0,
@@ -1735,6 +1922,33 @@ struct Stencil7 : public Operator {
         exchange_halo(c, fsend, fsend + 2 * plane, frecv, frecv + 2 * plane, 2 * plane, c->stream);
     }
 
+    // 3-D tensor map over one slab-sized array for the TMA variant of KA: box (2TX+4) x (TY+2) x 1, zero fill outside
+    template <int TX, int TY>
+    CUtensorMap make_tensor_map(const double* base) const {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = nullptr;
+        if (!encode) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            ATK_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+            ATK_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, ATK_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+            encode = reinterpret_cast<EncodeFn>(fn);
+        }
+        CUtensorMap tm;
+        const cuuint64_t dims[3] = {(cuuint64_t)g.nx, (cuuint64_t)g.ny, (cuuint64_t)g.nz_loc};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.nx * 8u, (cuuint64_t)g.nx * (cuuint64_t)g.ny * 8u};
+        const cuuint32_t box[3] = {(cuuint32_t)(2 * TX + 4), (cuuint32_t)(TY + 2), 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        const CUresult rc = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        ATK_REQUIRE(rc == CUDA_SUCCESS, ATK_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)rc) + ")");
+        return tm;
+    }
+    bool fused_tma = false;  // KA through tensor-map TMA (ATK_FUSED_TMA=1, single-GPU contexts)
+
     template <int TX, int TY>
     void launch_fused(const FusedArgs& fa, int k_lo, int k_hi, int partial_base, bool is_final, double* dot_out, int* blocks_out) {
         Context* c = ctx;
@@ -1748,7 +1962,22 @@ struct Stencil7 : public Operator {
         ATK_REQUIRE(partial_base + nblocks <= kMaxPartials, ATK_ERR_INVALID_ARGUMENT, "stencil grid exceeds the partial-sum scratch");
         auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
         const bool vec = (g.nx % 2 == 0) && al(fa.r) && al(fa.x) && al(fa.Ap) && al(fa.P0) && al(fa.P1);
-        if (vec && fsmem) {
+        if (vec && fsmem && fused_tma && c->world == 1) {
+            constexpr int TILE = (TY + 2) * (2 * TX + 4);
+            constexpr size_t stage = (size_t)(TILE * 8 + 127) / 128 * 128;
+            constexpr size_t smem = 2 * 4 * stage;
+            static bool opted = false;
+            if (!opted) {
+                ATK_CUDA_CHECK(cudaFuncSetAttribute(stencil7_cg_fused_tma_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)smem));
+                opted = true;
+            }
+            const CUtensorMap tm_r = make_tensor_map<TX, TY>(fa.r), tm_p0 = make_tensor_map<TX, TY>(fa.P0),
+                              tm_p1 = make_tensor_map<TX, TY>(fa.P1);
+            stencil7_cg_fused_tma_kernel<TX, TY><<<grid, block, smem, c->stream>>>(tm_r, tm_p0, tm_p1, g, fa, k_lo, k_hi, kcc,
+                                                                                   c->d_partials, partial_base, c->d_tickets + 5,
+                                                                                   dot_out, is_final ? 1 : 0);
+        } else if (vec && fsmem) {
             constexpr size_t smem = fused_smem_bytes<TX, TY>();
             stencil7_cg_fused_smem_kernel<TX, TY><<<grid, block, smem, c->stream>>>(g, fa, k_lo, k_hi, kcc, c->d_partials,
                                                                                     partial_base, c->d_tickets + 5, dot_out,
@@ -2344,6 +2573,7 @@ Operator* make_stencil7(Context* ctx, int nx, int ny, int nz, double cx, double 
     if (const char* e = std::getenv("ATK_FUSED_TILE")) S->ftile = std::atoi(e);
     if (const char* e = std::getenv("ATK_FUSED_SMEM")) S->fsmem = std::atoi(e) != 0;
     if (const char* e = std::getenv("ATK_STENCIL_TMA")) S->use_tma = std::atoi(e) != 0;
+    if (const char* e = std::getenv("ATK_FUSED_TMA")) S->fused_tma = std::atoi(e) != 0;
     try {
         if (ctx->world > 1) {
             ATK_CUDA_CHECK(cudaMalloc(&S->nccl_halo_lo, sizeof(double) * (size_t)plane));
