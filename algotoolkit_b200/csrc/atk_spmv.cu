@@ -627,6 +627,96 @@ __global__ void __launch_bounds__(kStreamBlock) csr_stream2_spmv_kernel(int n_bl
     }
 }
 
+// CSR-stream, third form (default for the CSR format): the staging of the second form made WARP-private.  A warp owns 32
+// consecutive rows: it copies their entries (values + column indices, one contiguous range of the CSR arrays) into its own
+// slice of shared memory with 16-byte cp.async, waits for its own copies (__syncwarp, no block barrier anywhere), then
+// every lane walks its row through shared memory (row starts an odd stride apart: no bank conflicts on stencil-like rows)
+// and gathers x for the same tap position of 32 consecutive rows at a time - a few sectors per request.  Warps run ahead of
+// one another freely, up to 64 per SM, so the DRAM latency of one warp's stream hides behind the gathers of the others.
+// Products are added from 0.0 in ascending column order in registers: the CSC matvec's exact sequence per row.
+// CAP = entries a warp can stage; a 32-row group with more entries is walked lane by lane straight from global memory.
+constexpr int kWarpStreamWarps = 8;
+template <int CAP, bool DOT>
+__global__ void __launch_bounds__(kWarpStreamWarps * 32) csr_warp_stream_spmv_kernel(int n_rows, int64_t nnz,
+                                                                                   const int* __restrict__ row_ptr,
+                                                                                   const int* __restrict__ csr_col,
+                                                                                   const double* __restrict__ csr_val,
+                                                                                   const double* __restrict__ x, double* __restrict__ y,
+                                                                                   double* partials, unsigned* ticket, double* dot_out,
+                                                                                   const int* skip_flag) {
+    if (skip_flag && *skip_flag) return;
+    extern __shared__ __align__(16) double smem3[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* sv = smem3 + (size_t)warp * (CAP + 4);
+    int* sc = reinterpret_cast<int*>(smem3 + (size_t)kWarpStreamWarps * (CAP + 4)) + (size_t)warp * (CAP + 4);
+    const int n_groups = (n_rows + 31) >> 5;
+    const int total_warps = gridDim.x * kWarpStreamWarps;
+    const int64_t nnz4 = nnz & ~(int64_t)3;
+    double dacc = 0.0;
+    constexpr int U = 8;
+    for (int grp = blockIdx.x * kWarpStreamWarps + warp; grp < n_groups; grp += total_warps) {
+        const int r = (grp << 5) + lane;
+        const int k0 = row_ptr[min(r, n_rows)], k1 = row_ptr[min(r + 1, n_rows)];
+        const int e0 = __shfl_sync(0xffffffffu, k0, 0), e1 = __shfl_sync(0xffffffffu, k1, 31);
+        double acc = 0.0;
+        if (e1 - (e0 & ~3) <= CAP + 4 - 4) {
+            const int e0a = e0 & ~3;
+            const int n4 = (e1 - e0a + 3) >> 2;
+            for (int q = lane; q < n4; q += 32) {
+                const int64_t idx = (int64_t)e0a + 4 * q;
+                if (idx + 4 <= nnz4) {
+                    cp_async16_g2s(sc + 4 * q, csr_col + idx);
+                    cp_async16_g2s(sv + 4 * q, csr_val + idx);
+                    cp_async16_g2s(sv + 4 * q + 2, csr_val + idx + 2);
+                } else {
+                    for (int u = 0; u < 4; ++u)
+                        if (idx + u < nnz) {
+                            sc[4 * q + u] = csr_col[idx + u];
+                            sv[4 * q + u] = csr_val[idx + u];
+                        }
+                }
+            }
+            asm volatile("cp.async.commit_group;\n" ::);
+            asm volatile("cp.async.wait_group 0;\n" ::);
+            __syncwarp();
+            for (int kb = k0 - e0a; kb < k1 - e0a; kb += U) {
+                int c[U];
+                double v[U], xv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool in = kb + u < k1 - e0a;
+                    c[u] = in ? sc[kb + u] : -1;
+                    v[u] = in ? sv[kb + u] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) xv[u] = x[c[u] < 0 ? 0 : c[u]];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {  // ascending column order; exact-zero x entries contribute nothing (SparseObj.hpp:141)
+                    const double t = add_rn(acc, mul_rn(v[u], xv[u]));
+                    acc = (c[u] >= 0 && xv[u] != 0.0) ? t : acc;
+                }
+            }
+            __syncwarp();  // the slice is restaged by the next trip
+        } else {
+            for (int k = k0; k < k1; ++k) {
+                const double xv = x[csr_col[k]];
+                const double t = add_rn(acc, mul_rn(csr_val[k], xv));
+                acc = xv != 0.0 ? t : acc;
+            }
+        }
+        if (r < n_rows) {
+            y[r] = acc;
+            if constexpr (DOT) dacc = add_rn(dacc, mul_rn(x[r], acc));
+        }
+    }
+    if constexpr (DOT) {
+        double total;
+        if (grid_sum_last_block<kWarpStreamWarps * 32>(dacc, partials, ticket, &total)) {
+            if (linear_thread_id() == 0) *dot_out = total;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ the operator
 struct AssembledMatrix : public Operator {
     int n_rows = 0;
@@ -712,6 +802,32 @@ struct AssembledMatrix : public Operator {
             ATK_CUDA_CHECK(cudaGetLastError());
             if (dot) allgather_slot(c, dot_slot, c->stream);
             return;
+        } else if (stream_blocks > 0 && !std::getenv("ATK_CSR_STREAM_V1") && !std::getenv("ATK_CSR_STREAM_V2")) {
+            // warp-private staging: CAP from the mean row length (a group of 32 rows must fit with ~15 % to spare)
+            const double per_group = n_rows > 0 ? 32.0 * (double)nnz / n_rows * 1.15 : 0.0;
+            const int cap_sel = per_group <= 256 ? 256 : per_group <= 512 ? 512 : per_group <= 1024 ? 1024 : 2048;
+            const bool dot = dot_slot >= 0;
+            auto go = [&](auto kern, int cap_v) {
+                const size_t smem = (size_t)kWarpStreamWarps * (cap_v + 4) * (sizeof(double) + sizeof(int));
+                ATK_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int per_sm = 1;
+                ATK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpStreamWarps * 32, smem));
+                const int groups = (n_rows + 31) / 32;
+                const int g = std::max(1, std::min((groups + kWarpStreamWarps - 1) / kWarpStreamWarps, c->sm_count * std::max(per_sm, 1)));
+                kern<<<g, kWarpStreamWarps * 32, smem, c->stream>>>(n_rows, nnz, row_ptr, csr_col, csr_val, x, y,
+                                                                    dot ? c->d_partials : nullptr, dot ? c->d_tickets + 1 : nullptr,
+                                                                    dot ? dot_out : nullptr, skip_flag);
+            };
+#define ATK_WS(CAPV) \
+    if (dot) go(csr_warp_stream_spmv_kernel<CAPV, true>, CAPV); \
+    else go(csr_warp_stream_spmv_kernel<CAPV, false>, CAPV);
+            switch (cap_sel) {
+                case 256: ATK_WS(256) break;
+                case 512: ATK_WS(512) break;
+                case 1024: ATK_WS(1024) break;
+                default: ATK_WS(2048) break;
+            }
+#undef ATK_WS
         } else if (stream_blocks > 0 && !std::getenv("ATK_CSR_STREAM_V1")) {
             const int g = std::min(stream_blocks, c->sm_count * 2);  // two CTAs of 130 KB per SM, persistent over the runs
             constexpr size_t smem = 2 * (sizeof(double) * (kStream2Cap + 4) + sizeof(int) * (kStream2Cap + 4 + kStream2Rows + 4));
