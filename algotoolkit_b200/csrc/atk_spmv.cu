@@ -495,139 +495,8 @@ __global__ void __launch_bounds__(kStreamBlock) csr_stream_spmv_kernel(int n_blo
     }
 }
 
-// CSR-stream, second form (default): the MATRIX entries of the row run are staged in shared memory instead of the products.
-// Phase 1 copies the run's values and column indices global -> shared with 16-byte cp.async (aligned superset of the run,
-// nothing passes through registers, fully coalesced); phase 2 is thread-per-row: consecutive threads walk consecutive rows
-// through shared memory (row starts are an odd stride apart for stencil-like rows: no bank conflicts) and gather x for the
-// SAME tap position of 32 consecutive rows at a time - consecutive or near-consecutive addresses, a few sectors per warp
-// request, which is what the thread-per-entry form above lacks (~7 scattered sectors per request, LSU-bound at 53 % of
-// peak).  The row's products are added from 0.0 in ascending column order in registers: the CSC matvec's exact sequence.
-constexpr int kStream2Cap = 4096;   // entries per CTA and buffer: 32 KB of values + 16 KB of column indices
-constexpr int kStream2Rows = 1024;  // row pointers staged per buffer (rows of a run beyond that read theirs from global memory)
-__device__ __forceinline__ void cp_async16_g2s(void* smem, const void* gmem) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async4_g2s(void* smem, const void* gmem) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem));
-}
-// Two buffers: while the rows of one run are being summed, the entries (and row pointers) of the CTA's next run are already
-// on their way into the other buffer, so neither the DRAM latency of the stream nor the L2 latency of the gathers is exposed.
-template <bool DOT>
-__global__ void __launch_bounds__(kStreamBlock) csr_stream2_spmv_kernel(int n_blocks, int64_t nnz, const int* __restrict__ blk_row,
-                                                                        const int* __restrict__ row_ptr,
-                                                                        const int* __restrict__ csr_col,
-                                                                        const double* __restrict__ csr_val,
-                                                                        const double* __restrict__ x, double* __restrict__ y,
-                                                                        double* partials, unsigned* ticket, double* dot_out,
-                                                                        const int* skip_flag) {
-    if (skip_flag && *skip_flag) return;
-    constexpr int BUF_D = kStream2Cap + 4;                                   // doubles of values per buffer
-    constexpr int BUF_I = kStream2Cap + 4 + kStream2Rows + 4;                // ints per buffer: column indices, then row pointers
-    extern __shared__ __align__(16) double smem2[];
-    double* sv_base = smem2;                                                 // [2][BUF_D]
-    int* si_base = reinterpret_cast<int*>(smem2 + 2 * BUF_D);                // [2][BUF_I]
-    double dacc = 0.0;
-    const int64_t nnz4 = nnz & ~(int64_t)3;  // whole 16-byte chunks of column indices end here
-    // stage run `b` into buffer `buf` (no waiting)
-    auto stage = [&](int b, int buf) {
-        if (b < n_blocks) {
-            const int r0 = blk_row[b], r1 = blk_row[b + 1];
-            const int e0 = row_ptr[r0], e1 = row_ptr[r1];
-            const int e0a = e0 & ~3;
-            const int n4 = (e1 - e0a + 3) >> 2;  // chunks of four entries: 16 B of indices, 32 B of values
-            double* sv = sv_base + buf * BUF_D;
-            int* sc = si_base + buf * BUF_I;
-            int* sr = sc + kStream2Cap + 4;
-            for (int q = threadIdx.x; q < n4; q += kStreamBlock) {
-                const int64_t idx = (int64_t)e0a + 4 * q;
-                if (idx + 4 <= nnz4) {
-                    cp_async16_g2s(sc + 4 * q, csr_col + idx);
-                    cp_async16_g2s(sv + 4 * q, csr_val + idx);
-                    cp_async16_g2s(sv + 4 * q + 2, csr_val + idx + 2);
-                } else {
-                    for (int u = 0; u < 4; ++u)
-                        if (idx + u < nnz) {
-                            sc[4 * q + u] = csr_col[idx + u];
-                            sv[4 * q + u] = csr_val[idx + u];
-                        }
-                }
-            }
-            const int nr = min(r1 - r0 + 1, kStream2Rows);
-            for (int q = threadIdx.x; q < nr; q += kStreamBlock) cp_async4_g2s(sr + q, row_ptr + r0 + q);
-        }
-        asm volatile("cp.async.commit_group;\n" ::);
-    };
-    int b = blockIdx.x;
-    int buf = 0;
-    stage(b, 0);
-    for (; b < n_blocks; b += gridDim.x, buf ^= 1) {
-        stage(b + gridDim.x, buf ^ 1);
-        asm volatile("cp.async.wait_group 1;\n" ::);
-        __syncthreads();
-        const int r0 = blk_row[b], r1 = blk_row[b + 1];
-        const double* sv = sv_base + buf * BUF_D;
-        const int* sc = si_base + buf * BUF_I;
-        const int* sr = sc + kStream2Cap + 4;
-        const int e0a = sr[0] & ~3;
-        // two rows per thread and trip (rows r and r + blockDim), their gathers issued together: twice the loads in flight
-        for (int r = r0 + threadIdx.x; r < r1; r += 2 * kStreamBlock) {
-            constexpr int U = 8;
-            const int rB = r + kStreamBlock;
-            const bool hasB = rB < r1;
-            const int qa = r - r0, qb = rB - r0;
-            const int ka0 = (qa < kStream2Rows ? sr[qa] : row_ptr[r]) - e0a;
-            const int ka1 = (qa + 1 < kStream2Rows ? sr[qa + 1] : row_ptr[r + 1]) - e0a;
-            int kb0 = 0, kb1 = 0;
-            if (hasB) {
-                kb0 = (qb < kStream2Rows ? sr[qb] : row_ptr[rB]) - e0a;
-                kb1 = (qb + 1 < kStream2Rows ? sr[qb + 1] : row_ptr[rB + 1]) - e0a;
-            }
-            double accA = 0.0, accB = 0.0;
-            for (int off = 0; ka0 + off < ka1 || kb0 + off < kb1; off += U) {
-                int ca[U], cb[U];
-                double va[U], vb[U], xa[U], xb[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const bool ina = ka0 + off + u < ka1, inb = kb0 + off + u < kb1;
-                    ca[u] = ina ? sc[ka0 + off + u] : -1;
-                    va[u] = ina ? sv[ka0 + off + u] : 0.0;
-                    cb[u] = inb ? sc[kb0 + off + u] : -1;
-                    vb[u] = inb ? sv[kb0 + off + u] : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    xa[u] = x[ca[u] < 0 ? 0 : ca[u]];
-                    xb[u] = x[cb[u] < 0 ? 0 : cb[u]];
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {  // ascending column order; exact-zero x entries contribute nothing (SparseObj.hpp:141)
-                    const double ta = add_rn(accA, mul_rn(va[u], xa[u]));
-                    accA = (ca[u] >= 0 && xa[u] != 0.0) ? ta : accA;
-                    const double tb = add_rn(accB, mul_rn(vb[u], xb[u]));
-                    accB = (cb[u] >= 0 && xb[u] != 0.0) ? tb : accB;
-                }
-            }
-            y[r] = accA;
-            if (hasB) y[rB] = accB;
-            if constexpr (DOT) {
-                dacc = add_rn(dacc, mul_rn(x[r], accA));
-                if (hasB) dacc = add_rn(dacc, mul_rn(x[rB], accB));
-            }
-        }
-        __syncthreads();  // this buffer is refilled by the next trip's stage()
-    }
-    asm volatile("cp.async.wait_group 0;\n" ::);
-    if constexpr (DOT) {
-        double total;
-        if (grid_sum_last_block<kStreamBlock>(dacc, partials, ticket, &total)) {
-            if (linear_thread_id() == 0) *dot_out = total;
-        }
-    }
-}
-
-// CSR-stream, third form (default for the CSR format): the staging of the second form made WARP-private.  A warp owns 32
+// CSR-stream, second form (default for the CSR format): the MATRIX entries are staged in shared memory instead of the
+// products, and the staging is WARP-private.  A warp owns 32
 // consecutive rows: it copies their entries (values + column indices, one contiguous range of the CSR arrays) into its own
 // slice of shared memory with 16-byte cp.async, waits for its own copies (__syncwarp, no block barrier anywhere), then
 // every lane walks its row through shared memory (row starts an odd stride apart: no bank conflicts on stencil-like rows)
@@ -635,6 +504,10 @@ __global__ void __launch_bounds__(kStreamBlock) csr_stream2_spmv_kernel(int n_bl
 // one another freely, up to 64 per SM, so the DRAM latency of one warp's stream hides behind the gathers of the others.
 // Products are added from 0.0 in ascending column order in registers: the CSC matvec's exact sequence per row.
 // CAP = entries a warp can stage; a 32-row group with more entries is walked lane by lane straight from global memory.
+__device__ __forceinline__ void cp_async16_g2s(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
 constexpr int kWarpStreamWarps = 8;
 template <int CAP, bool DOT>
 __global__ void __launch_bounds__(kWarpStreamWarps * 32) csr_warp_stream_spmv_kernel(int n_rows, int64_t nnz,
@@ -802,7 +675,7 @@ struct AssembledMatrix : public Operator {
             ATK_CUDA_CHECK(cudaGetLastError());
             if (dot) allgather_slot(c, dot_slot, c->stream);
             return;
-        } else if (stream_blocks > 0 && !std::getenv("ATK_CSR_STREAM_V1") && !std::getenv("ATK_CSR_STREAM_V2")) {
+        } else if (stream_blocks > 0 && !std::getenv("ATK_CSR_STREAM_V1")) {
             // warp-private staging: CAP from the mean row length (a group of 32 rows must fit with ~15 % to spare)
             const double per_group = n_rows > 0 ? 32.0 * (double)nnz / n_rows * 1.15 : 0.0;
             const int cap_sel = per_group <= 256 ? 256 : per_group <= 512 ? 512 : per_group <= 1024 ? 1024 : 2048;
@@ -828,22 +701,6 @@ struct AssembledMatrix : public Operator {
                 default: ATK_WS(2048) break;
             }
 #undef ATK_WS
-        } else if (stream_blocks > 0 && !std::getenv("ATK_CSR_STREAM_V1")) {
-            const int g = std::min(stream_blocks, c->sm_count * 2);  // two CTAs of 130 KB per SM, persistent over the runs
-            constexpr size_t smem = 2 * (sizeof(double) * (kStream2Cap + 4) + sizeof(int) * (kStream2Cap + 4 + kStream2Rows + 4));
-            static bool opted_in = false;
-            if (!opted_in) {  // above the 48 KB default: raise the limit of both instantiations once
-                ATK_CUDA_CHECK(cudaFuncSetAttribute(csr_stream2_spmv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                ATK_CUDA_CHECK(cudaFuncSetAttribute(csr_stream2_spmv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                opted_in = true;
-            }
-            if (dot_slot >= 0)
-                csr_stream2_spmv_kernel<true><<<g, kStreamBlock, smem, c->stream>>>(stream_blocks, nnz, blk_row, row_ptr, csr_col,
-                                                                                  csr_val, x, y, c->d_partials, c->d_tickets + 1,
-                                                                                  dot_out, skip_flag);
-            else
-                csr_stream2_spmv_kernel<false><<<g, kStreamBlock, smem, c->stream>>>(stream_blocks, nnz, blk_row, row_ptr, csr_col,
-                                                                                   csr_val, x, y, nullptr, nullptr, nullptr, skip_flag);
         } else if (stream_blocks > 0) {
             const int g = std::min(stream_blocks, c->sm_count * 32);
             constexpr size_t smem = sizeof(double) * kStreamCap;

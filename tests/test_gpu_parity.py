@@ -823,9 +823,6 @@ def test_csr_stream_is_bit_exact_and_vector_kernel_still_covered(ctx, port, monk
     want = port.spmv(A, x)
     op = ctx.operator_from_csc(n_rows, n_cols, A.col_ptr, A.row_idx, A.vals, capi.FORMAT_CSR_VECTOR)
     assert np.array_equal(op.apply_numpy(x), want)  # warp-private staging of the matrix entries (default)
-    monkeypatch.setenv("ATK_CSR_STREAM_V2", "1")
-    assert np.array_equal(op.apply_numpy(x), want)  # CTA-wide staging of the matrix entries, two buffers
-    monkeypatch.delenv("ATK_CSR_STREAM_V2")
     monkeypatch.setenv("ATK_CSR_STREAM_V1", "1")
     assert np.array_equal(op.apply_numpy(x), want)  # entry-parallel form: products staged in shared memory
     monkeypatch.delenv("ATK_CSR_STREAM_V1")

@@ -12,8 +12,8 @@ ctx = capi.Context(0)
 peak = 6556.5
 for label, make in (("poisson256", lambda fmt: ctx.operator_poisson_assembled(256, 256, 256, *synthetic.poisson_coeffs(256, 256, 256), fmt)),
                     ("op27_128", lambda fmt: ctx.operator_stencil27_assembled(128, 128, 128, synthetic.stencil27_coefficients(), fmt))):
-    for variant, env in (("sell", {}), ("csr_warp_stream", {}), ("csr_stream_v2", {"ATK_CSR_STREAM_V2": "1"}), ("csr_stream_v1", {"ATK_CSR_STREAM_V1": "1"})):
-        for k in ("ATK_CSR_STREAM_V1", "ATK_CSR_STREAM_V2"):
+    for variant, env in (("sell", {}), ("csr_warp_stream", {}), ("csr_stream_v1", {"ATK_CSR_STREAM_V1": "1"})):
+        for k in ("ATK_CSR_STREAM_V1",):
             os.environ.pop(k, None)
         os.environ.update(env)
         op = make(capi.FORMAT_SELL if variant == "sell" else capi.FORMAT_CSR_VECTOR)
