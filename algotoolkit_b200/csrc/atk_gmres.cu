@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
             const double total = block_sum<BLOCK>(s);
             if (threadIdx.x < 32 && (int)threadIdx.x < a.world) {
                 const unsigned long long bits = (unsigned long long)__double_as_longlong(total);
-                const unsigned long long tag = (seq & 0xffffffffull) << 32;
+                const unsigned long long tag = ll_tag(seq) << 32;
                 unsigned long long* dst = ((int)threadIdx.x == a.rank ? a.ll : a.peer_ll[threadIdx.x]) + (size_t)(slot * kMaxRanks + a.rank) * 2;
                 st_relaxed_sys(dst, (bits & 0xffffffffull) | tag);
                 st_relaxed_sys(dst + 1, (bits >> 32) | tag);
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
         }
         if (threadIdx.x < 32 && (int)threadIdx.x < a.world) {
             const unsigned long long* src = a.ll + (size_t)(slot * kMaxRanks + threadIdx.x) * 2;
-            const unsigned long long tag = seq & 0xffffffffull;
+            const unsigned long long tag = ll_tag(seq);
             unsigned long long w0, w1;
             unsigned spins = 0;
             unsigned long long t0 = 0;

@@ -518,12 +518,15 @@ __device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned l
 // Producer: first warp of the CTA that finished last; lane q serves rank q.  Ordering of the HALO planes other CTAs
 // stored into the peers is given by the system-scope fence every CTA executes before it takes its ticket: those stores
 // are performed before the ticket is visible, hence before this function is even entered.
+// 32-bit tag of a sequence number: the top bit is always set, so a word that still holds its initial zeros can never
+// validate, whatever the sequence number (the low 31 bits wrap around freely; tags are only compared for equality).
+__device__ __forceinline__ unsigned long long ll_tag(unsigned long long seq) { return 0x80000000ull | (seq & 0x7fffffffull); }
 __device__ __forceinline__ void publish_partial_warp(unsigned long long* const* peer_ll, int world, int rank, int slot,
                                                      double value, unsigned long long seq) {
     const int lane = threadIdx.x & 31;
     if (lane < world) {
         const unsigned long long bits = (unsigned long long)__double_as_longlong(value);
-        const unsigned long long tag = (seq & 0xffffffffull) << 32;
+        const unsigned long long tag = ll_tag(seq) << 32;
         unsigned long long* dst = peer_ll[lane] + (size_t)(slot * kMaxRanks + rank) * 2;
         st_relaxed_sys(dst, (bits & 0xffffffffull) | tag);
         st_relaxed_sys(dst + 1, (bits >> 32) | tag);
@@ -548,7 +551,7 @@ __device__ __forceinline__ double peer_wait_sum(const unsigned long long* ll, in
         const int lane = linear_thread_id();
         if (lane < world) {
             const unsigned long long* src = ll + (size_t)(slot * kMaxRanks + lane) * 2;
-            const unsigned long long tag = seq & 0xffffffffull;
+            const unsigned long long tag = ll_tag(seq);
             unsigned long long w0, w1;
             unsigned spins = 0;
             unsigned long long t0 = 0;

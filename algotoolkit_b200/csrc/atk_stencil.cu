@@ -1332,6 +1332,12 @@ struct PersistArgs {
     double* nb_hi_p_lo[2];
     unsigned long long* stamps;   // optional globaltimer stamps: [0] after the start-up sums, then one per reduction
     int stamp_cap;
+    // experiment knobs (ATK_PERSIST_POLL): 0 = every CTA polls the packed words of all ranks; 1 = only CTA 0 does, and
+    // republishes the finished sum in a LOCAL packed pair that the other CTAs poll (keeps the words the remote ranks
+    // store into free of local polling traffic); poll_sleep_ns > 0 backs the pollers off between attempts
+    int poll_mode;
+    unsigned poll_sleep_ns;
+    unsigned long long* bcast;    // [2 slots][2 words] local broadcast pair
 };
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
@@ -1405,17 +1411,48 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
             if (tid < 32 && tid < a.world) {
                 if (dist) __threadfence_system();
                 const unsigned long long bits = (unsigned long long)__double_as_longlong(total);
-                const unsigned long long tag = (seq & 0xffffffffull) << 32;
+                const unsigned long long tag = ll_tag(seq) << 32;
                 unsigned long long* dst = (tid == a.rank ? a.ll : a.peer_ll[tid]) + (size_t)(slot * kMaxRanks + a.rank) * 2;
                 st_relaxed_sys(dst, (bits & 0xffffffffull) | tag);
                 st_relaxed_sys(dst + 1, (bits >> 32) | tag);
             }
         }
+        if (a.poll_mode == 1 && bid != 0) {
+            // CTA 0 gathers the ranks' sums (below) and republishes the total locally: poll that pair only
+            if (tid == 0) {
+                const unsigned long long* src = a.bcast + (size_t)slot * 2;
+                const unsigned long long tag = ll_tag(seq);
+                unsigned long long w0, w1;
+                unsigned spins = 0;
+                unsigned long long t0 = 0;
+                for (;;) {
+                    w0 = ld_acquire_sys(src);
+                    w1 = ld_acquire_sys(src + 1);
+                    if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
+                    if (a.poll_sleep_ns) __nanosleep(a.poll_sleep_ns);
+                    if ((++spins & 0xfffu) == 0) {
+                        const unsigned long long now = global_timer_ns();
+                        if (t0 == 0) t0 = now;
+                        if (now - t0 > kPeerWaitNs || *reinterpret_cast<volatile int*>(&st->peer_timeout)) {
+                            st->peer_timeout = 1;
+                            s_abort = 1;
+                            break;
+                        }
+                    }
+                }
+                rank_vals[0] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+            }
+            __syncthreads();
+            const double s = rank_vals[0];
+            aborted = s_abort != 0;
+            __syncthreads();
+            return s;
+        }
         // every CTA: wait for all ranks' words of this phase (local memory), lane q polls rank q
         if (tid < 32) {
             if (tid < a.world) {
                 const unsigned long long* src = a.ll + (size_t)(slot * kMaxRanks + tid) * 2;
-                const unsigned long long tag = seq & 0xffffffffull;
+                const unsigned long long tag = ll_tag(seq);
                 unsigned long long w0, w1;
                 unsigned spins = 0;
                 unsigned long long t0 = 0;
@@ -1424,8 +1461,10 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
                     w0 = ld_acquire_sys(src);
                     w1 = ld_acquire_sys(src + 1);
                     if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
+                    if (a.poll_sleep_ns) __nanosleep(a.poll_sleep_ns);
                     // a word two or more phases AHEAD of this rank would mean a peer overwrote a value nobody here has read
-                    ATK_DEVICE_ASSERT((unsigned)((w0 >> 32) - tag) >= 0x80000000u || (unsigned)((w0 >> 32) - tag) == 0u || (w0 >> 32) == 0ull);
+                    ATK_DEVICE_ASSERT((w0 >> 32) == 0ull || (((unsigned)((w0 >> 32) - tag)) & 0x7fffffffu) == 0u ||
+                                      (((unsigned)((w0 >> 32) - tag)) & 0x7fffffffu) >= 0x40000000u);
                     if ((++spins & 0xfffu) == 0) {
                         const unsigned long long now = global_timer_ns();
                         if (t0 == 0) t0 = now;
@@ -1444,6 +1483,13 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
         double s = rank_vals[0];
         for (int q = 1; q < a.world; ++q) s = add_rn(s, rank_vals[q]);
         aborted = s_abort != 0;
+        if (a.poll_mode == 1 && tid == 0) {  // (CTA 0) republish the total for the other CTAs of this GPU
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(s);
+            const unsigned long long tag = ll_tag(seq) << 32;
+            __threadfence();
+            st_relaxed_sys(a.bcast + (size_t)slot * 2, (bits & 0xffffffffull) | tag);
+            st_relaxed_sys(a.bcast + (size_t)slot * 2 + 1, (bits >> 32) | tag);
+        }
         __syncthreads();  // rank_vals is rewritten by the next reduction
         return s;
     };
@@ -1841,7 +1887,7 @@ struct Stencil7 : public Operator {
         self->ps_chunks = (g.nz_loc + self->ps_kc - 1) / self->ps_kc;
         const int64_t items = tiles * self->ps_chunks;
         const int grid = (int)std::min(g_max, items);
-        if (cudaMalloc(&self->ps_part, sizeof(double) * ((size_t)grid + 2)) != cudaSuccess) {
+        if (cudaMalloc(&self->ps_part, sizeof(double) * ((size_t)grid + 8)) != cudaSuccess) {
             cudaGetLastError();
             return 0;
         }
@@ -1890,6 +1936,11 @@ struct Stencil7 : public Operator {
         }
         pa.stamps = stamps;
         pa.stamp_cap = stamp_cap;
+        pa.poll_mode = 0;
+        pa.poll_sleep_ns = 0;
+        if (const char* e = std::getenv("ATK_PERSIST_POLL")) pa.poll_mode = std::atoi(e) == 1 ? 1 : 0;
+        if (const char* e = std::getenv("ATK_PERSIST_POLL_SLEEP")) pa.poll_sleep_ns = (unsigned)std::max(0, std::atoi(e));
+        pa.bcast = pa.arrive + 2;  // [2 slots][2 words] behind the arrival counter
         ATK_CUDA_CHECK(cudaMemsetAsync(pa.arrive, 0, sizeof(unsigned long long), c->stream));
         void* kargs[] = {&pa};
         ATK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)cg_persistent_kernel<TX, TY>, dim3((unsigned)ps_grid), dim3(TX, TY, 1), kargs,
@@ -1941,9 +1992,14 @@ struct Stencil7 : public Operator {
         const cuuint64_t strides[2] = {(cuuint64_t)g.nx * 8u, (cuuint64_t)g.nx * (cuuint64_t)g.ny * 8u};
         const cuuint32_t box[3] = {(cuuint32_t)(2 * TX + 4), (cuuint32_t)(TY + 2), 1u};
         const cuuint32_t estr[3] = {1u, 1u, 1u};
+        CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;  // ATK_TMA_L2PROMO: 0 none, 1 64 B, 2 128 B, 3 256 B
+        if (const char* e = std::getenv("ATK_TMA_L2PROMO")) {
+            const int v = std::atoi(e);
+            promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                  : v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+        }
         const CUresult rc = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         ATK_REQUIRE(rc == CUDA_SUCCESS, ATK_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)rc) + ")");
         return tm;
     }
