@@ -1332,12 +1332,6 @@ struct PersistArgs {
     double* nb_hi_p_lo[2];
     unsigned long long* stamps;   // optional globaltimer stamps: [0] after the start-up sums, then one per reduction
     int stamp_cap;
-    // experiment knobs (ATK_PERSIST_POLL): 0 = every CTA polls the packed words of all ranks; 1 = only CTA 0 does, and
-    // republishes the finished sum in a LOCAL packed pair that the other CTAs poll (keeps the words the remote ranks
-    // store into free of local polling traffic); poll_sleep_ns > 0 backs the pollers off between attempts
-    int poll_mode;
-    unsigned poll_sleep_ns;
-    unsigned long long* bcast;    // [2 slots][2 words] local broadcast pair
 };
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
@@ -1417,37 +1411,6 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
                 st_relaxed_sys(dst + 1, (bits >> 32) | tag);
             }
         }
-        if (a.poll_mode == 1 && bid != 0) {
-            // CTA 0 gathers the ranks' sums (below) and republishes the total locally: poll that pair only
-            if (tid == 0) {
-                const unsigned long long* src = a.bcast + (size_t)slot * 2;
-                const unsigned long long tag = ll_tag(seq);
-                unsigned long long w0, w1;
-                unsigned spins = 0;
-                unsigned long long t0 = 0;
-                for (;;) {
-                    w0 = ld_acquire_sys(src);
-                    w1 = ld_acquire_sys(src + 1);
-                    if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
-                    if (a.poll_sleep_ns) __nanosleep(a.poll_sleep_ns);
-                    if ((++spins & 0xfffu) == 0) {
-                        const unsigned long long now = global_timer_ns();
-                        if (t0 == 0) t0 = now;
-                        if (now - t0 > kPeerWaitNs || *reinterpret_cast<volatile int*>(&st->peer_timeout)) {
-                            st->peer_timeout = 1;
-                            s_abort = 1;
-                            break;
-                        }
-                    }
-                }
-                rank_vals[0] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
-            }
-            __syncthreads();
-            const double s = rank_vals[0];
-            aborted = s_abort != 0;
-            __syncthreads();
-            return s;
-        }
         // every CTA: wait for all ranks' words of this phase (local memory), lane q polls rank q
         if (tid < 32) {
             if (tid < a.world) {
@@ -1461,7 +1424,6 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
                     w0 = ld_acquire_sys(src);
                     w1 = ld_acquire_sys(src + 1);
                     if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
-                    if (a.poll_sleep_ns) __nanosleep(a.poll_sleep_ns);
                     // a word two or more phases AHEAD of this rank would mean a peer overwrote a value nobody here has read
                     ATK_DEVICE_ASSERT((w0 >> 32) == 0ull || (((unsigned)((w0 >> 32) - tag)) & 0x7fffffffu) == 0u ||
                                       (((unsigned)((w0 >> 32) - tag)) & 0x7fffffffu) >= 0x40000000u);
@@ -1483,13 +1445,6 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
         double s = rank_vals[0];
         for (int q = 1; q < a.world; ++q) s = add_rn(s, rank_vals[q]);
         aborted = s_abort != 0;
-        if (a.poll_mode == 1 && tid == 0) {  // (CTA 0) republish the total for the other CTAs of this GPU
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(s);
-            const unsigned long long tag = ll_tag(seq) << 32;
-            __threadfence();
-            st_relaxed_sys(a.bcast + (size_t)slot * 2, (bits & 0xffffffffull) | tag);
-            st_relaxed_sys(a.bcast + (size_t)slot * 2 + 1, (bits >> 32) | tag);
-        }
         __syncthreads();  // rank_vals is rewritten by the next reduction
         return s;
     };
@@ -1936,11 +1891,6 @@ struct Stencil7 : public Operator {
         }
         pa.stamps = stamps;
         pa.stamp_cap = stamp_cap;
-        pa.poll_mode = 0;
-        pa.poll_sleep_ns = 0;
-        if (const char* e = std::getenv("ATK_PERSIST_POLL")) pa.poll_mode = std::atoi(e) == 1 ? 1 : 0;
-        if (const char* e = std::getenv("ATK_PERSIST_POLL_SLEEP")) pa.poll_sleep_ns = (unsigned)std::max(0, std::atoi(e));
-        pa.bcast = pa.arrive + 2;  // [2 slots][2 words] behind the arrival counter
         ATK_CUDA_CHECK(cudaMemsetAsync(pa.arrive, 0, sizeof(unsigned long long), c->stream));
         void* kargs[] = {&pa};
         ATK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)cg_persistent_kernel<TX, TY>, dim3((unsigned)ps_grid), dim3(TX, TY, 1), kargs,

@@ -122,3 +122,22 @@ def test_header_is_plain_c_and_a_c_program_links(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     status = int(r.stdout.split()[0])
     assert status in (0, 4), r.stdout  # ATK_OK on a GPU box, ATK_ERR_CUDA without a device - never a crash, never a CPU path
+
+
+def test_hot_kernels_do_not_spill():
+    """The fused CG kernels run at a fixed register budget (7 CTAs per SM); code added to them has twice pushed ptxas into
+    spilling inside the plane loop, which costs 30 % of the iteration without failing any parity test.  The build log
+    (-Xptxas -v) must show at most a few bytes of spills for them."""
+    import re
+
+    from algotoolkit_b200 import build as atk_build
+
+    atk_build.build()
+    log = open(os.path.join(atk_build.OBJ, "atk_stencil.cu.log")).read()
+    seen = 0
+    for kernel in ("cg_persistent_kernelILi32ELi4E", "stencil7_cg_fused_smem_kernelILi32ELi4E", "stencil7_smem_kernelILi32ELi4ELb0ELb0E"):
+        m = re.search(kernel + r".*?(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", log, re.S)
+        assert m, f"{kernel} not found in the ptxas log"
+        assert int(m.group(2)) <= 16 and int(m.group(3)) <= 16, (kernel, m.groups())
+        seen += 1
+    assert seen == 3
