@@ -45,17 +45,20 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, checked: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, checked: bool = False, profile: bool = False) -> str:
     """checked=True builds libatk_cuda_checked.so with -DATK_CHECKED (device-side assertions on tile / halo indices and on
     the peer protocols' sequence numbers); ATK_LIB=checked makes capi load it."""
     global OBJ, LIB
     if checked:
         OBJ = os.path.join(HERE, "build_checked")
         LIB = os.path.join(HERE, "libatk_cuda_checked.so")
+    elif profile:  # -DATK_REDUCE_PROFILE: %globaltimer stamps at the five stations of every in-kernel reduction
+        OBJ = os.path.join(HERE, "build_profile")
+        LIB = os.path.join(HERE, "libatk_cuda_profile.so")
     else:
         OBJ = os.path.join(HERE, "build")
         LIB = os.path.join(HERE, "libatk_cuda.so")
-    flags = NVCC_FLAGS + (["-DATK_CHECKED"] if checked else [])
+    flags = NVCC_FLAGS + (["-DATK_CHECKED"] if checked else []) + (["-DATK_REDUCE_PROFILE"] if profile else [])
     os.makedirs(OBJ, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(INCLUDE, "atk_cuda.h"))
@@ -95,5 +98,6 @@ def build(force: bool = False, verbose: bool = False, checked: bool = False) -> 
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, checked="--checked" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, checked="--checked" in sys.argv,
+                 profile="--profile" in sys.argv)
     print(path)

@@ -508,7 +508,11 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
         unsigned long long* d_stamps = nullptr;
         int stamp_cap = 0;
         if (persistent && info->time_kernels) {
+#ifdef ATK_REDUCE_PROFILE
+            stamp_cap = 5 * (2 * std::min(max_iter, 1 << 12) + 2) + 1;  // five stations per reduction (profile build)
+#else
             stamp_cap = 2 * std::min(max_iter, 1 << 15) + 1;
+#endif
             d_stamps = static_cast<unsigned long long*>(ctx->ws_alloc(sizeof(unsigned long long) * ((size_t)stamp_cap + 1)));
             ATK_CUDA_CHECK(cudaMemsetAsync(d_stamps, 0, sizeof(unsigned long long) * ((size_t)stamp_cap + 1), st));
         }
@@ -581,10 +585,20 @@ void cg_solve(Context* ctx, Operator* op, const double* b, double* x, double* r,
         float ms = 0.f;
         ATK_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1));
         info->kernel_ms[0] = info->kernel_ms[1] = info->kernel_ms[2] = 0.f;
+#ifdef ATK_REDUCE_PROFILE
+        if (!h_stamps.empty() && info->rs_trace && info->trace_capacity > 0) {
+            // profile build: the raw station stamps (ns since the first one) go back through rs_trace, five per reduction,
+            // starting with the two start-up reductions; tools/latency_breakdown.py turns them into averages
+            const unsigned long long t0s = h_stamps[1];
+            for (int q = 0; q < info->trace_capacity && q + 1 < stamp_cap; ++q)
+                info->rs_trace[q] = h_stamps[(size_t)q + 1] ? (double)(h_stamps[(size_t)q + 1] - t0s) : -1.0;
+        }
+#else
         if (!h_stamps.empty()) {  // [0] end of start-up, [1+2i] after p.Ap of iteration i, [2+2i] after its r.r
             const int cnt = (int)h_stamps[(size_t)stamp_cap];
             for (int q = 0; q + 1 < cnt; ++q) info->kernel_ms[q & 1] += (float)((double)(h_stamps[(size_t)q + 1] - h_stamps[(size_t)q]) * 1e-6);
         }
+#endif
         for (size_t q = 0; q + 3 < kev.size(); q += 4)
             for (int c = 0; c < 3; ++c) {
                 float t = 0.f;

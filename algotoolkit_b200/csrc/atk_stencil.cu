@@ -1368,13 +1368,28 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
     if (tid == 0) s_abort = 0;
 
     auto stamp = [&]() {
+#ifndef ATK_REDUCE_PROFILE
         if (a.stamps && bid == 0 && tid == 0 && n_stamps < a.stamp_cap) a.stamps[n_stamps] = global_timer_ns();
+#endif
         ++n_stamps;
     };
     // grid-wide and cross-GPU sum of one value per thread; every thread of every rank returns the same bits
+#ifdef ATK_REDUCE_PROFILE
+    // profile build only (python -m algotoolkit_b200.build --profile): CTA 0 stamps the five stations of every reduction -
+    // own arrival, all CTAs arrived, rank sum published, all ranks' words seen, resume - at stamps[1 + 5*(phase-1) + k]
+    auto rstamp = [&](int k) {
+        if (a.stamps && bid == 0 && tid == 0) {
+            const long long idx = 1 + 5 * ((long long)phase - 1) + k;
+            if (idx < a.stamp_cap) a.stamps[idx] = global_timer_ns();
+        }
+    };
+#else
+    auto rstamp = [&](int) {};
+#endif
     auto reduce = [&](double v) -> double {
         const double bs = block_sum<NT>(v);
         ++phase;
+        rstamp(0);
         const int slot = (int)(phase & 1ull);
         const unsigned long long seq = a.epoch + phase;
         if (tid == 0) {
@@ -1401,6 +1416,7 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
                 __threadfence();
             }
             __syncthreads();
+            rstamp(1);
             const double total = partials_sum<NT>(a.partials, G);
             if (tid < 32 && tid < a.world) {
                 if (dist) __threadfence_system();
@@ -1410,6 +1426,7 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
                 st_relaxed_sys(dst, (bits & 0xffffffffull) | tag);
                 st_relaxed_sys(dst + 1, (bits >> 32) | tag);
             }
+            rstamp(2);
         }
         // every CTA: wait for all ranks' words of this phase (local memory), lane q polls rank q
         if (tid < 32) {
@@ -1442,10 +1459,12 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
             }
         }
         __syncthreads();
+        rstamp(3);
         double s = rank_vals[0];
         for (int q = 1; q < a.world; ++q) s = add_rn(s, rank_vals[q]);
         aborted = s_abort != 0;
         __syncthreads();  // rank_vals is rewritten by the next reduction
+        rstamp(4);
         return s;
     };
 
