@@ -60,12 +60,13 @@ def run():
 run()  # warm-up
 st, info = run()
 # reductions: 0, 1 = start-up sums (r.r, b.b); then per iteration: p.Ap (after phase A), r.r (after phase B)
-st = st[2:2 + 2 * iters]
+done = min(iters, info.iterations)  # the |pAp| < 1e-12 exit may end the loop early on small grids
+st = st[2:2 + 2 * done]
 A, B = st[0::2], st[1::2]
 seg = lambda R: [float(np.mean(R[:, k + 1] - R[:, k])) * 1e-3 for k in range(4)]
 phaseA = float(np.mean(A[1:, 0] - B[:-1, 4])) * 1e-3   # station 4 of the previous r.r reduction -> station 0 of this p.Ap reduction
 phaseB = float(np.mean(B[:, 0] - A[:, 4])) * 1e-3
-line = (f"rank {rank}/{world} grid {g}^3 ({info.device_ms / iters * 1e3:.1f} us/iteration over {iters}): "
+line = (f"rank {rank}/{world} grid {g}^3 ({info.device_ms / max(done, 1) * 1e3:.1f} us/iteration over {done}): "
         f"phase A compute {phaseA:7.1f} us | p.Ap reduction: arrive-spread {seg(A)[0]:5.1f}  sum+publish {seg(A)[1]:5.1f}  remote-wait {seg(A)[2]:5.1f}  resume {seg(A)[3]:4.1f} us || "
         f"phase B compute {phaseB:7.1f} us | r.r reduction: arrive-spread {seg(B)[0]:5.1f}  sum+publish {seg(B)[1]:5.1f}  remote-wait {seg(B)[2]:5.1f}  resume {seg(B)[3]:4.1f} us")
 if world > 1:
