@@ -102,23 +102,6 @@ void exchange_halo(Context* ctx, const double* first_plane, const double* last_p
     nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd");
 }
 
-void exchange_ranges(Context* ctx, const double* to_prev, size_t n_to_prev, const double* to_next, size_t n_to_next,
-                     double* from_prev, size_t n_from_prev, double* from_next, size_t n_from_next, cudaStream_t stream) {
-    if (ctx->world == 1) return;
-    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
-    const int lo = ctx->rank - 1, hi = ctx->rank + 1;
-    nccl_check(g_nccl.GroupStart(), "ncclGroupStart");
-    if (lo >= 0) {
-        if (n_to_prev) nccl_check(g_nccl.Send(to_prev, n_to_prev, ncclDouble, lo, comm, stream), "ncclSend");
-        if (n_from_prev) nccl_check(g_nccl.Recv(from_prev, n_from_prev, ncclDouble, lo, comm, stream), "ncclRecv");
-    }
-    if (hi < ctx->world) {
-        if (n_to_next) nccl_check(g_nccl.Send(to_next, n_to_next, ncclDouble, hi, comm, stream), "ncclSend");
-        if (n_from_next) nccl_check(g_nccl.Recv(from_next, n_from_next, ncclDouble, hi, comm, stream), "ncclRecv");
-    }
-    nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd");
-}
-
 void allgather_host_bytes(Context* ctx, const void* send, void* recv, size_t bytes) {
     if (ctx->world == 1) {
         std::memcpy(recv, send, bytes);

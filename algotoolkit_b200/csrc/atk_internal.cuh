@@ -176,10 +176,6 @@ void host_free_pinned(void* p);
 void host_numa_query(const void* p, int* buffer_node, int* device_node);
 // Collective all-gather of `bytes` host bytes per rank (setup-time helper, goes through NCCL).
 void allgather_host_bytes(Context* ctx, const void* send, void* recv, size_t bytes);
-// Neighbour exchange with independent counts (row-block partitioned assembled operators): send `to_prev` / `to_next`
-// to ranks rank-1 / rank+1 and receive `from_prev` / `from_next` from them; a count of 0 skips that transfer.
-void exchange_ranges(Context* ctx, const double* to_prev, size_t n_to_prev, const double* to_next, size_t n_to_next,
-                     double* from_prev, size_t n_from_prev, double* from_next, size_t n_from_next, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------ peer-memory halo exchange
 // Neighbour exchange of an operator apply without NCCL (distributed contexts with Context::p2p): every rank exports one
