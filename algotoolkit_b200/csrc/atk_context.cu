@@ -306,12 +306,6 @@ void PeerHalo::wait() {
 
 // ------------------------------------------------------------------------------------------ PeerGather
 namespace {
-struct GatherTable {
-    double* dst[kMaxRanks];               // where destination d's entries go (null: nothing to send to that partner)
-    int begin[kMaxRanks + 1];             // destination d serves send_idx[begin[d] .. begin[d+1])
-    unsigned long long* flag[kMaxRanks];  // flag word to release per partner (null: none)
-    int n_dst;
-};
 __global__ void __launch_bounds__(256) gather_push_kernel(const double* __restrict__ x, const int* __restrict__ idx, GatherTable tb,
                                                           unsigned long long seq, unsigned* ticket, int release) {
     const int total = tb.begin[tb.n_dst];
@@ -330,10 +324,6 @@ __global__ void __launch_bounds__(256) gather_push_kernel(const double* __restri
         }
     }
 }
-struct WaitTable {
-    const unsigned long long* flag[kMaxRanks];
-    int n;
-};
 __global__ void gather_wait_kernel(WaitTable wt, unsigned long long seq) {
     const int lane = threadIdx.x;
     if (lane < wt.n) {
@@ -447,6 +437,35 @@ void PeerGather::release() {
     peer_ready = false;
 }
 
+bool PeerGather::begin_inline(GatherTable* tb, WaitTable* wt, unsigned long long* seq_out, const double** ext) {
+    Context* c = ctx;
+    const char* comm_env = std::getenv("ATK_COMM");
+    if (!(peer_ready && !(comm_env && std::string(comm_env) == "nccl") && !c->capturing())) return false;
+    last_was_peer = true;
+    ++seq;
+    const size_t par = (size_t)(seq & 1);
+    tb->n_dst = (int)partners.size();
+    int pos = 0;
+    tb->begin[0] = 0;
+    // d_send_idx is grouped by destination RANK; the partners are in ascending rank order, and ranks that are no
+    // partners have nothing to receive, so walking the partners in order walks d_send_idx in order
+    for (int d = 0; d < tb->n_dst; ++d) {
+        const int p = partners[(size_t)d];
+        ATK_REQUIRE(send_off[(size_t)p] == pos, ATK_ERR_RUNTIME, "internal: send list order");
+        double* pa = peer_arena[(size_t)p];
+        tb->dst[d] = send_count[(size_t)p] > 0 ? pa + par * peer_n_ext[(size_t)p] + off_in_peer[(size_t)p] : nullptr;
+        tb->flag[d] = reinterpret_cast<unsigned long long*>(pa + flag_offset(peer_n_ext[(size_t)p])) + c->rank;
+        pos += send_count[(size_t)p];
+        tb->begin[d + 1] = pos;
+    }
+    wt->n = (int)partners.size();
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(arena + flag_offset((size_t)n_ext));
+    for (int d = 0; d < wt->n; ++d) wt->flag[d] = flags + partners[(size_t)d];
+    *seq_out = seq;
+    *ext = arena + par * (size_t)n_ext;
+    return true;
+}
+
 const double* PeerGather::begin(const double* x) {
     Context* c = ctx;
     const char* comm_env = std::getenv("ATK_COMM");
@@ -457,27 +476,13 @@ const double* PeerGather::begin(const double* x) {
     GatherTable tb;
     const double* result = nullptr;
     if (peer) {
-        ++seq;
-        const size_t par = (size_t)(seq & 1);
-        tb.n_dst = (int)partners.size();
-        int pos = 0;
-        tb.begin[0] = 0;
-        // d_send_idx is grouped by destination RANK; the partners are in ascending rank order, and ranks that are no
-        // partners have nothing to receive, so walking the partners in order walks d_send_idx in order
-        for (int d = 0; d < tb.n_dst; ++d) {
-            const int p = partners[(size_t)d];
-            ATK_REQUIRE(send_off[(size_t)p] == pos, ATK_ERR_RUNTIME, "internal: send list order");
-            double* pa = peer_arena[(size_t)p];
-            tb.dst[d] = send_count[(size_t)p] > 0 ? pa + par * peer_n_ext[(size_t)p] + off_in_peer[(size_t)p] : nullptr;
-            tb.flag[d] = reinterpret_cast<unsigned long long*>(pa + flag_offset(peer_n_ext[(size_t)p])) + c->rank;
-            pos += send_count[(size_t)p];
-            tb.begin[d + 1] = pos;
-        }
+        WaitTable wt_unused;
+        unsigned long long seq_now = 0;
+        begin_inline(&tb, &wt_unused, &seq_now, &result);
         const int grid = std::max(1, std::min((n_send + 255) / 256, 128));
         gather_push_kernel<<<grid, 256, 0, c->comm_stream>>>(x, d_send_idx, tb, seq, d_ticket, 1);
         ATK_CUDA_CHECK(cudaGetLastError());
         count_launch(c);
-        result = arena + par * (size_t)n_ext;
     } else {
         tb.n_dst = 1;
         tb.dst[0] = d_pack;

@@ -229,6 +229,16 @@ struct PeerHalo {
 //              write-after-read argument of PeerHalo holds pairwise);
 //   NCCL mode: packs them and exchanges the packed ranges with grouped ncclSend / ncclRecv (also while a CUDA graph is
 //              being captured).
+struct GatherTable {
+    double* dst[kMaxRanks];               // where destination d's entries go (null: nothing to send to that partner)
+    int begin[kMaxRanks + 1];             // destination d serves send_idx[begin[d] .. begin[d+1])
+    unsigned long long* flag[kMaxRanks];  // flag word to release per partner (null: none)
+    int n_dst;
+};
+struct WaitTable {
+    const unsigned long long* flag[kMaxRanks];
+    int n;
+};
 struct PeerGather {
     Context* ctx = nullptr;
     int n_ext = 0;                          // external entries this rank receives per apply
@@ -257,6 +267,10 @@ struct PeerGather {
     // entries of THIS apply arrive in (valid for the kernels launched after wait())
     const double* begin(const double* x);
     void wait();
+    // For operators whose own kernel gathers, stores, releases and waits (single-launch apply): true when the peer path can
+    // be taken for the apply that starts now.  Starts it (parity flips) and fills the tables of its stores and waits;
+    // *ext = the buffer its external entries arrive in.  d_ticket is free for that kernel's arrival counter.
+    bool begin_inline(GatherTable* tb, WaitTable* wt, unsigned long long* seq_out, const double** ext);
 };
 
 // ------------------------------------------------------------------------------------------ fused CG state
@@ -489,6 +503,19 @@ __device__ __forceinline__ bool last_block_done(unsigned* ticket) {
     }
     __syncthreads();
     return is_last_e;
+}
+
+// The same among the first `nb` blocks of a launch only (the others never call it).
+__device__ __forceinline__ bool last_block_done_among(unsigned* ticket, unsigned nb) {
+    __shared__ bool is_last_a;
+    __syncthreads();
+    if (linear_thread_id() == 0) {
+        __threadfence();
+        const unsigned t = atomicInc(ticket, nb - 1);
+        is_last_a = (t == nb - 1);
+    }
+    __syncthreads();
+    return is_last_a;
 }
 
 // ---- peer signalling primitives ----

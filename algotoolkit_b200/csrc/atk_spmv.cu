@@ -242,21 +242,79 @@ struct DistX {
     int h_lo;
     int n_mid;
 };
-template <bool DOT, bool DIST>
+// PUSH (distributed contexts in peer-memory mode): the whole apply in ONE launch.  The first `n_push` CTAs start by gathering
+// the x entries the other ranks need and storing them straight into their receive buffers (NVLink), fence, and the last
+// of them releases the apply's sequence number into every partner's flag word; every warp then walks the slices that
+// need no external entry first and waits on the LOCAL flags only before its first slice that does.  The grid never
+// exceeds the resident capacity, so the pushing CTAs of every rank are running before anybody waits.
+struct SellPush {
+    GatherTable tb;
+    WaitTable wt;
+    const int* send_idx = nullptr;
+    unsigned* ticket = nullptr;
+    unsigned long long seq = 0;
+    int n_push = 0;
+    int s_int_begin = 0, s_int_end = 0;
+};
+template <bool DOT, bool DIST, bool PUSH = false>
 __global__ void __launch_bounds__(kReduceBlock) sell_spmv_kernel(int n_rows, int n_slices, const int* __restrict__ wscan,
                                                                  const int* __restrict__ sell_col,
                                                                  const double* __restrict__ sell_val,
                                                                  const int* __restrict__ perm, const double* __restrict__ x,
                                                                  double* __restrict__ y, double* partials, unsigned* ticket,
                                                                  double* dot_out, const int* skip_flag, DistX dx, int s_begin,
-                                                                 int s_end, int partial_base, int is_final) {
+                                                                 int s_end, int partial_base, int is_final,
+                                                                 SellPush sp = SellPush()) {
     if (skip_flag && *skip_flag) return;
     const int lane = threadIdx.x & 31;
     const int warp0 = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int nwarps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
     double dacc = 0.0;
     constexpr int U = 8;  // entries of a row handled per batch: all 2U matrix loads are issued together, then all U gathers
-    for (int s = s_begin + warp0; s < s_end; s += nwarps) {
+    if constexpr (PUSH) {
+        if ((int)blockIdx.x < sp.n_push) {
+            const int total = sp.tb.begin[sp.tb.n_dst];
+            for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += sp.n_push * blockDim.x) {
+                int d = 0;
+                while (t >= sp.tb.begin[d + 1]) ++d;
+                sp.tb.dst[d][t - sp.tb.begin[d]] = x[sp.send_idx[t]];
+            }
+            __threadfence_system();
+            if (last_block_done_among(sp.ticket, (unsigned)sp.n_push)) {
+                if ((int)threadIdx.x < sp.tb.n_dst && sp.tb.flag[threadIdx.x]) {
+                    __threadfence_system();
+                    st_release_sys(sp.tb.flag[threadIdx.x], sp.seq);
+                }
+            }
+        }
+    }
+    const int n_int = PUSH ? sp.s_int_end - sp.s_int_begin : 0;
+    bool waited = false;
+    for (int t = s_begin + warp0; t < s_end; t += nwarps) {
+        int s = t;
+        if constexpr (PUSH) {  // logical order: slices without external entries, then the lower ones, then the upper ones
+            if (t < n_int) {
+                s = sp.s_int_begin + t;
+            } else {
+                if (!waited) {
+                    if (lane < sp.wt.n) {
+                        unsigned spins = 0;
+                        unsigned long long t0 = 0;
+                        while (ld_acquire_sys(sp.wt.flag[lane]) < sp.seq) {
+                            if ((++spins & 0xfffu) == 0) {
+                                const unsigned long long now = global_timer_ns();
+                                if (t0 == 0) t0 = now;
+                                if (now - t0 > kPeerWaitNs) asm volatile("trap;");  // a partner died or fell out of step
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    waited = true;
+                }
+                const int u = t - n_int;
+                s = u < sp.s_int_begin ? u : sp.s_int_end + (u - sp.s_int_begin);
+            }
+        }
         const int w0 = wscan[s], w = wscan[s + 1] - w0;
         const int64_t off = (int64_t)w0 * kSliceRows + lane;
         double acc = 0.0;
@@ -286,9 +344,9 @@ __global__ void __launch_bounds__(kReduceBlock) sell_spmv_kernel(int n_rows, int
                 acc = (c[u] >= 0 && xv[u] != 0.0) ? t : acc;
             }
         }
-        const int t = s * kSliceRows + lane;
-        if (t < n_rows) {
-            const int r = perm ? perm[t] : t;
+        const int tr = s * kSliceRows + lane;
+        if (tr < n_rows) {
+            const int r = perm ? perm[tr] : tr;
             y[r] = acc;
             if constexpr (DOT) dacc = add_rn(dacc, mul_rn(x[r], acc));
         }
@@ -639,10 +697,44 @@ struct AssembledMatrix : public Operator {
         double* dot_out = dot_slot >= 0 ? c->slot(dot_slot) + c->rank : nullptr;
         const int grid = c->sm_count * 8;
         if (format == ATK_FORMAT_SELL) {
+            const bool dot = dot_slot >= 0;
+            if (dist && !std::getenv("ATK_APPLY_SPLIT")) {
+                // peer mode: ONE launch gathers and stores for the partners, computes, and waits where it must
+                SellPush sp;
+                const double* ext_in = nullptr;
+                if (pg.begin_inline(&sp.tb, &sp.wt, &sp.seq, &ext_in)) {
+                    sp.send_idx = pg.d_send_idx;
+                    sp.ticket = pg.d_ticket;
+                    sp.s_int_begin = s_int_begin;
+                    sp.s_int_end = s_int_end;
+                    static int per_sm_dot = 0, per_sm_plain = 0;
+                    int& per_sm = dot ? per_sm_dot : per_sm_plain;
+                    if (per_sm == 0) {
+                        if (dot) ATK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sell_spmv_kernel<true, true, true>, kReduceBlock, 0));
+                        else ATK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sell_spmv_kernel<false, true, true>, kReduceBlock, 0));
+                        per_sm = std::max(per_sm, 1);
+                    }
+                    const int cap_g = std::min(grid, per_sm * c->sm_count);  // every CTA resident: pushers run before anybody waits
+                    const int g = (int)std::max<int64_t>(1, std::min<int64_t>(cap_g, ((int64_t)n_slices * 32 + kReduceBlock - 1) / kReduceBlock));
+                    sp.n_push = std::max(1, std::min(g, (pg.n_send + 2 * kReduceBlock - 1) / (2 * kReduceBlock)));
+                    const DistX dxi{nullptr, ext_in, 0, n_rows};
+                    if (dot)
+                        sell_spmv_kernel<true, true, true><<<g, kReduceBlock, 0, c->stream>>>(n_rows, n_slices, wscan, sell_col, sell_val, perm, x, y,
+                                                                                              c->d_partials, c->d_tickets + 1, dot_out, skip_flag,
+                                                                                              dxi, 0, n_slices, 0, 1, sp);
+                    else
+                        sell_spmv_kernel<false, true, true><<<g, kReduceBlock, 0, c->stream>>>(n_rows, n_slices, wscan, sell_col, sell_val, perm, x, y,
+                                                                                               nullptr, nullptr, nullptr, skip_flag, dxi, 0,
+                                                                                               n_slices, 0, 1, sp);
+                    ATK_CUDA_CHECK(cudaGetLastError());
+                    count_launch(c);
+                    if (dot) allgather_slot(c, dot_slot, c->stream);
+                    return;
+                }
+            }
             // distributed: the owners start sending the external entries of this apply (communication stream)
             const double* ext = dist ? pg.begin(x) : nullptr;
             const DistX dx{nullptr, ext, 0, n_rows};
-            const bool dot = dot_slot >= 0;
             int pbase = 0;
             // (measured at 2 GPUs, 256^3: the persistent grid of the interior piece fills every SM, so the one-CTA transfer
             // kernel mostly runs after it - 0.173 ms per apply against 0.176 ms without the split; shrinking the grid to

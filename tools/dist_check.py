@@ -129,6 +129,11 @@ os.environ["ATK_COMM"] = "nccl"
 yg_nccl = gather(opg.apply_numpy(xg[g0:g1]))
 os.environ.pop("ATK_COMM")
 yg2 = gather(opg.apply_numpy(xg[g0:g1]))  # and back to peer stores: the sequence numbers of the two modes are independent
+os.environ["ATK_APPLY_SPLIT"] = "1"        # three-piece form: push kernel on the communication stream, wait kernel, pieces
+yg3 = gather(opg.apply_numpy(xg[g0:g1]))
+y_split = gather(op.apply_numpy(xin[op.row_begin: op.row_begin + op.n_rows_local]))
+os.environ.pop("ATK_APPLY_SPLIT")
+yg4 = gather(opg.apply_numpy(xg[g0:g1]))
 os.environ["ATK_CG_FUSED"] = "0"
 resg = ctx.cg_solve_host(opg, bg[g0:g1], 8)
 xgs = gather(resg["x"])
@@ -190,6 +195,9 @@ if rank == 0:
     print("general sparsity, whole-matrix entry, apply bit-exact (peer stores / NCCL / peer again):", np.array_equal(yg, yg_ref),
           np.array_equal(yg_nccl, yg_ref), np.array_equal(yg2, yg_ref), " row-slice entry:", np.array_equal(ys, yg_ref))
     ok &= np.array_equal(yg, yg_ref) and np.array_equal(yg_nccl, yg_ref) and np.array_equal(yg2, yg_ref) and np.array_equal(ys, yg_ref)
+    print("three-piece apply (ATK_APPLY_SPLIT=1) bit-exact: general", np.array_equal(yg3, yg_ref), "stencil", np.array_equal(y_split, y_ref),
+          " single launch again:", np.array_equal(yg4, yg_ref))
+    ok &= np.array_equal(yg3, yg_ref) and np.array_equal(y_split, y_ref) and np.array_equal(yg4, yg_ref)
     orag = P.cg(Ag, bg, 8)
     exg = np.linalg.norm(xgs - orag["x"]) / np.linalg.norm(orag["x"])
     print(f"CG on the general distributed operator: iters {resg['iters']} (oracle {orag['iters']}) relerr x {exg:.2e}")
