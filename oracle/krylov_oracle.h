@@ -107,6 +107,14 @@ int orc_gmres_solve_precond(int n, const int* col_ptr, const int* row_idx, const
                             int n_x, int max_iter, int krylov_dim, double tol, double* resid, int resid_cap, int* n_resid,
                             int* status, int* last_kry_update);
 
+/* ILU(0): the reference's elimination (loops and drop rules of ILU.hpp:21-81) restricted to the positions A stores - no
+ * fill-in.  The reference itself has no such factorisation; where its full elimination creates no fill-in the two agree
+ * bit for bit.  LU is a dense column-major n x n array like orc_ilu_compute's; orc_ilu_solve / orc_ilu_factors apply. */
+int orc_ilu0_compute(int n, const int* col_ptr, const int* row_idx, const double* vals, double* LU);
+int orc_gmres_solve_precond_ilu0(int n, const int* col_ptr, const int* row_idx, const double* vals, const double* b, double* x,
+                                 int n_x, int max_iter, int krylov_dim, double tol, double* resid, int resid_cap, int* n_resid,
+                                 int* status, int* last_kry_update);
+
 /* ---- "next" rows: compositions of the same kernels ---- */
 /* GradientDescent::solve (src/LinearAlgebra/Solver/IterSolver.hpp:23-44): steepest descent with the residual-norm loop
  * condition and the change-norm early exit.  x in/out; iters = iterations whose update was applied. */

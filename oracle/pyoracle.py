@@ -108,6 +108,8 @@ class Port:
         L.orc_ilu_solve.argtypes = [C.c_int, _dp, _dp, _dp]
         L.orc_ilu_factors.argtypes = [C.c_int, _dp, _dp, _dp]
         L.orc_gmres_solve_precond.argtypes = L.orc_gmres_solve.argtypes
+        L.orc_ilu0_compute.argtypes = L.orc_ilu_compute.argtypes
+        L.orc_gmres_solve_precond_ilu0.argtypes = L.orc_gmres_solve.argtypes
         L.orc_arnoldi.argtypes = [C.c_int, _ip, _ip, _dp, _dp, C.c_int, _dp, C.c_double, _ip]
 
     # -- vectors
@@ -278,6 +280,29 @@ class Port:
         if rc == 2:
             raise RuntimeError("Matrix is numerically singular")
         return LU.T.copy()
+
+    def ilu0_compute(self, A):
+        """ILU(0): the reference's elimination restricted to the stored positions of A (no fill-in); same layout as ilu_compute."""
+        n = A.n_rows
+        if A.n_rows != A.n_cols:
+            raise ValueError("Matrix must be square for ILU factorization")
+        LU = np.zeros((n, n))
+        rc = self.L.orc_ilu0_compute(n, _i(A.col_ptr), _i(A.row_idx), _d(A.vals), _d(LU))
+        if rc == 2:
+            raise RuntimeError("Matrix is numerically singular")
+        return LU.T.copy()
+
+    def gmres_precond_ilu0(self, A, b, x0, max_iter, krylov_dim, tol):
+        b, x = _f64(b), _f64(x0).copy()
+        cap = max_iter + 2
+        resid = np.zeros(cap)
+        nres, status, kry = C.c_int(0), C.c_int(0), C.c_int(0)
+        rc = self.L.orc_gmres_solve_precond_ilu0(A.n_rows, _i(A.col_ptr), _i(A.row_idx), _d(A.vals), _d(b), _d(x), x.size,
+                                                 max_iter, krylov_dim, tol, _d(resid), cap, C.byref(nres), C.byref(status),
+                                                 C.byref(kry))
+        if rc == 1:
+            raise ValueError("invalid argument")
+        return dict(x=x, resid=resid[: nres.value].copy(), status=status.value, rc=rc, kry_update=kry.value)
 
     def ilu_solve(self, LU, b):
         LUc = np.ascontiguousarray(np.asarray(LU, np.float64).T)
