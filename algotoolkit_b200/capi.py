@@ -84,7 +84,7 @@ EXPORTS = [
     "atk_operator_destroy",
     "atk_operator_shape", "atk_operator_row_range", "atk_operator_export_csr", "atk_operator_apply", "atk_cg_solve",
     "atk_cg_solve_host", "atk_gmres_solve", "atk_gmres_solve_host", "atk_gd_solve", "atk_gd_solve_host", "atk_arnoldi",
-    "atk_arnoldi_host", "atk_ilu_compute", "atk_ilu_solve", "atk_ilu_solve_host", "atk_ilu_export",
+    "atk_arnoldi_host", "atk_ilu_compute", "atk_ilu0_compute", "atk_ilu_solve", "atk_ilu_solve_host", "atk_ilu_export",
     "atk_preconditioner_destroy", "atk_gmres_solve_precond", "atk_gmres_solve_precond_host",
 ]
 
@@ -154,6 +154,7 @@ def load():
     sig["atk_arnoldi"] = [_vp, _vp, _vp, i64, C.c_int, _dp, C.c_double, _ip]
     sig["atk_arnoldi_host"] = sig["atk_arnoldi"]
     sig["atk_ilu_compute"] = [_vp, i64, i64, i64, _vp, _vp, _vp, C.POINTER(_vp)]
+    sig["atk_ilu0_compute"] = sig["atk_ilu_compute"]
     sig["atk_ilu_solve"] = [_vp, _vp, i64, _vp, _vp]
     sig["atk_ilu_solve_host"] = [_vp, _vp, i64, _vp, _vp]
     sig["atk_ilu_export"] = [_vp, _vp, _vp]
@@ -460,6 +461,16 @@ class Context:
         h = _vp()
         _check(self.L.atk_ilu_compute(self.h, n_rows, n_cols, vals.size, _np_ptr(col_ptr), _np_ptr(row_idx), _np_ptr(vals),
                                       C.byref(h)))
+        return IluPreconditioner(self, h, n_rows)
+
+    def ilu0_compute(self, n_rows, n_cols, col_ptr, row_idx, vals) -> "IluPreconditioner":
+        """Sparse ILU(0) (no fill-in, level-scheduled) on finished CSC arrays; same handle type as ilu_compute."""
+        col_ptr = np.ascontiguousarray(col_ptr, np.int32)
+        row_idx = np.ascontiguousarray(row_idx, np.int32)
+        vals = np.ascontiguousarray(vals, np.float64)
+        h = _vp()
+        _check(self.L.atk_ilu0_compute(self.h, n_rows, n_cols, vals.size, _np_ptr(col_ptr), _np_ptr(row_idx), _np_ptr(vals),
+                                       C.byref(h)))
         return IluPreconditioner(self, h, n_rows)
 
     def gmres_solve_host(self, op: Operator, b, x0, max_iter: int, krylov_dim: int, tol: float, ortho=GMRES_MGS,

@@ -388,6 +388,16 @@ int atk_ilu_compute(atk_context_t ctx, int64_t n_rows, int64_t n_cols, int64_t n
         *out = new atk_preconditioner{pc};
     });
 }
+int atk_ilu0_compute(atk_context_t ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* col_ptr,
+                     const int32_t* row_idx, const double* vals, atk_preconditioner_t* out) {
+    return guarded([&] {
+        atk::Context* c = C(ctx);
+        ATK_REQUIRE(out, ATK_ERR_INVALID_ARGUMENT, "null pointer");
+        *out = nullptr;
+        atk::Preconditioner* pc = atk::make_ilu0(c, n_rows, n_cols, nnz, col_ptr, row_idx, vals);
+        *out = new atk_preconditioner{pc};
+    });
+}
 int atk_ilu_solve(atk_context_t ctx, atk_preconditioner_t pc, int64_t n, const double* b, double* x) {
     return guarded([&] {
         atk::Context* c = C(ctx);

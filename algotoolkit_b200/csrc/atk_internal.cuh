@@ -331,6 +331,8 @@ struct Operator {
     virtual void set_peer_mode(bool) {}
     virtual void peer_r_targets(double** lo, double** hi, int64_t* plane_elems) const { *lo = *hi = nullptr; *plane_elems = 0; }
     virtual void initial_halo_exchange(const double* /*r*/, const double* /*p*/) {}
+    // device CSR arrays (ascending columns inside a row) of an assembled operator; false when there are none
+    virtual bool device_csr(const int** /*row_ptr*/, const int** /*col*/, const double** /*val*/) const { return false; }
     virtual bool has_csr() const { return false; }
     virtual void export_csr(int*, int*, double*) const { throw Error(ATK_ERR_INVALID_ARGUMENT, "operator has no CSR arrays"); }
 };
@@ -374,6 +376,9 @@ struct Preconditioner {
 };
 Preconditioner* make_ilu(Context* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* col_ptr, const int32_t* row_idx,
                          const double* vals);
+// sparse ILU(0) (the reference's elimination restricted to the pattern of A) with level-scheduled solves: atk_ilu0.cu
+Preconditioner* make_ilu0(Context* ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* col_ptr, const int32_t* row_idx,
+                          const double* vals);
 void gmres_solve(Context* ctx, Operator* op, Preconditioner* pc, const double* b, double* x, int64_t n_x, int max_iter,
                  int krylov_dim, double tol, atk_gmres_ortho ortho, atk_gmres_callback cb, void* user, atk_gmres_info* info);
 

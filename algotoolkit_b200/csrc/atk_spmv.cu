@@ -680,6 +680,13 @@ struct AssembledMatrix : public Operator {
         pg.release();
     }
     bool has_csr() const override { return true; }
+    bool device_csr(const int** rp, const int** ci, const double** v) const override {
+        if (dist) return false;  // distributed blocks number their columns locally
+        *rp = row_ptr;
+        *ci = csr_col;
+        *v = csr_val;
+        return true;
+    }
     void export_csr(int* h_row_ptr, int* h_col, double* h_val) const override {
         ATK_CUDA_CHECK(cudaMemcpy(h_row_ptr, row_ptr, sizeof(int) * ((size_t)n_rows + 1), cudaMemcpyDeviceToHost));
         if (nnz > 0) {

@@ -294,6 +294,15 @@ int atk_arnoldi_host(atk_context_t ctx, atk_operator_t op, double* Q, int64_t ld
 typedef struct atk_preconditioner* atk_preconditioner_t;
 int atk_ilu_compute(atk_context_t ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* col_ptr,
                     const int32_t* row_idx, const double* vals, atk_preconditioner_t* out);
+/* Sparse ILU(0) - what SURVEY 8(f) rank 4 names as the next step: the SAME elimination (loops and 1e-12 drop rules of
+ * ILU.hpp:21-81) restricted to the positions A stores, i.e. without fill-in, for systems of any size; level-scheduled
+ * factorisation (one launch per level) and triangular solves (one cooperative launch for both sweeps, a grid barrier per
+ * level), every sum in ascending column order.  The reference has no such factorisation; on a matrix whose full
+ * elimination creates no fill-in (tridiagonal ...) the factors and solves are bit-identical to atk_ilu_compute / the
+ * reference.  The handle works with atk_ilu_solve[_host], atk_ilu_export and atk_gmres_solve_precond[_host].  Same errors
+ * as atk_ilu_compute (a missing diagonal entry counts as a zero pivot).  Single-GPU contexts. */
+int atk_ilu0_compute(atk_context_t ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* col_ptr,
+                     const int32_t* row_idx, const double* vals, atk_preconditioner_t* out);
 int atk_ilu_solve(atk_context_t ctx, atk_preconditioner_t pc, int64_t n, const double* b, double* x);      /* device */
 int atk_ilu_solve_host(atk_context_t ctx, atk_preconditioner_t pc, int64_t n, const double* b, double* x); /* host */
 int atk_ilu_export(atk_preconditioner_t pc, double* L, double* U);

@@ -105,7 +105,147 @@ def test_oracle_vs_reference_live(port, ref):
         f["free"]()
 
 
+# ------------------------------------------------------------------------------------------------ ILU(0) (CPU)
+def _no_fill_matrices(port, rng):
+    """Matrices whose full elimination creates no fill-in: there ILU(0) must be the reference's ILU bit for bit."""
+    out = []
+    n = 57  # tridiagonal
+    rows = np.concatenate([np.arange(n), np.arange(1, n), np.arange(n - 1)])
+    cols = np.concatenate([np.arange(n), np.arange(n - 1), np.arange(1, n)])
+    vals = np.concatenate([4.0 + rng.random(n), -1.0 - rng.random(n - 1), -1.0 - rng.random(n - 1)])
+    out.append(("tridiagonal", port.csc_from_triplets(n, n, rows, cols, vals)))
+    m, k = 9, 4  # block diagonal with dense blocks
+    D = np.zeros((m * k, m * k))
+    for q in range(m):
+        B = rng.standard_normal((k, k))
+        B[np.arange(k), np.arange(k)] = np.abs(B).sum(1) + 1.0
+        D[q * k:(q + 1) * k, q * k:(q + 1) * k] = B
+    c, r = np.nonzero(D.T)
+    out.append(("block_diagonal", port.csc_from_triplets(m * k, m * k, r, c, D[r, c])))
+    n = 40  # "arrow pointing down-right": dense last row and column, diagonal elsewhere
+    D = np.diag(3.0 + rng.random(n))
+    D[-1, :] = rng.standard_normal(n)
+    D[:, -1] = rng.standard_normal(n)
+    D[-1, -1] = 50.0
+    c, r = np.nonzero(D.T)
+    out.append(("arrow", port.csc_from_triplets(n, n, r, c, D[r, c])))
+    return out
+
+
+def test_ilu0_restatement_equals_reference_where_no_fill_occurs(port, ref):
+    """The reference has no sparse ILU(0); what pins the restatement is that on matrices without fill-in it must give
+    the reference's own factors, solves and preconditioned GMRES bit for bit."""
+    rng = np.random.default_rng(3)
+    for name, A in _no_fill_matrices(port, rng):
+        n = A.n_rows
+        M = ref.mat_from_csc(A)
+        f = ref.ilu(M)
+        LU0 = port.ilu0_compute(A)
+        assert np.array_equal(LU0, port.ilu_compute(A)), name
+        L0, U0 = port.ilu_factors(LU0)
+        assert np.array_equal(L0, f["L"]) and np.array_equal(U0, f["U"]), name
+        b = rng.standard_normal(n)
+        assert np.array_equal(port.ilu_solve(LU0, b), f["solve"](b)), name
+        rhs = port.spmv(A, port.u01_array(5, n))
+        g0 = port.gmres_precond_ilu0(A, rhs, np.zeros(n), 2, 6, 1e-12)
+        gr = ref.gmres_precond(M, rhs, np.zeros(n), 2, 6, 1e-12)
+        assert np.array_equal(g0["x"], gr["x"]) and g0["status"] == gr["status"], name
+        f["free"]()
+
+
+def test_ilu0_restatement_drops_fill(port):
+    """With fill-in the two factorisations differ, ILU(0) keeps A's pattern, and L*U reproduces A on that pattern."""
+    A = port.poisson_csc(5, 5, 5)
+    LU0, LU = port.ilu0_compute(A), port.ilu_compute(A)
+    assert not np.array_equal(LU0, LU)
+    dense = A.to_scipy().toarray()
+    assert not (LU0[dense == 0.0] != 0.0).any()
+    L0, U0 = port.ilu_factors(LU0)
+    prod = L0 @ U0
+    assert np.allclose(prod[dense != 0.0], dense[dense != 0.0], rtol=1e-12, atol=1e-12)
+    with pytest.raises(RuntimeError, match="numerically singular"):
+        port.ilu0_compute(port.csc_from_triplets(3, 3, [0, 1, 2, 2], [0, 1, 0, 1], [1.0, 1.0, 1.0, 1.0]))  # no (2,2) entry
+
+
 # ------------------------------------------------------------------------------------------------ device (GPU)
+def _ilu0_cases(port):
+    rng = np.random.default_rng(8)
+    cases = _no_fill_matrices(port, rng)
+    cases.append(("poisson_6", port.poisson_csc(6, 6, 6)))
+    cases.append(("op27_5", port.op27_csc(5, 5, 5)))
+    n = 300
+    D = np.where(rng.random((n, n)) < 0.03, rng.standard_normal((n, n)), 0.0)
+    D[np.arange(n), np.arange(n)] = np.abs(D).sum(1) + 1.0
+    D[17, :17] = 1e-13  # multipliers below the 1e-12 threshold: left in place, their row update skipped
+    c, r = np.nonzero(D.T)
+    cases.append(("random_300", port.csc_from_triplets(n, n, r, c, D[r, c])))
+    return cases
+
+
+@pytest.mark.gpu
+def test_device_ilu0_factors_solves_and_gmres_are_bit_exact(ctx, port):
+    """Level-scheduled sparse ILU(0) on the device against the dense restatement with a pattern mask: factors, solves
+    (every row sums in ascending column order, whatever the reduction mode) and - with reference-ordered dot products -
+    the preconditioned GMRES are bit-identical."""
+    from algotoolkit_b200 import capi
+
+    rng = np.random.default_rng(1)
+    for name, A in _ilu0_cases(port):
+        n = A.n_rows
+        pc = ctx.ilu0_compute(n, n, A.col_ptr, A.row_idx, A.vals)
+        LU0 = port.ilu0_compute(A)
+        Lw, Uw = port.ilu_factors(LU0)
+        Lf, Uf = pc.factors()
+        assert np.array_equal(Lf, Lw) and np.array_equal(Uf, Uw), name
+        b = rng.standard_normal(n)
+        assert np.array_equal(pc.solve_host(b), port.ilu_solve(LU0, b)), name
+        rhs = port.spmv(A, port.u01_array(777, n))
+        op = ctx.operator_from_csc(n, n, A.col_ptr, A.row_idx, A.vals)
+        K = min(n, 10)
+        want = port.gmres_precond_ilu0(A, rhs, np.zeros(n), 3, K, 1e-10)
+        tree = ctx.gmres_solve_host(op, rhs, np.zeros(n), 3, K, 1e-10, precond=pc)
+        assert tree["status"] == want["status"] and np.allclose(tree["resid"], want["resid"], rtol=1e-8, atol=1e-12), name
+        ctx.set_reduction(capi.REDUCE_SEQUENTIAL)
+        try:
+            seq = ctx.gmres_solve_host(op, rhs, np.zeros(n), 3, K, 1e-10, precond=pc)
+        finally:
+            ctx.set_reduction(capi.REDUCE_TREE)
+        assert np.array_equal(seq["x"], want["x"]) and list(seq["resid"]) == list(want["resid"]), name
+        op.destroy()
+        pc.destroy()
+
+
+@pytest.mark.gpu
+def test_device_ilu0_errors_and_large_system(ctx, port):
+    with pytest.raises(RuntimeError, match="numerically singular"):  # a missing diagonal entry is a zero pivot
+        ctx.ilu0_compute(3, 3, *(lambda A: (A.col_ptr, A.row_idx, A.vals))(port.csc_from_triplets(3, 3, [0, 1, 2, 2], [0, 1, 0, 1], [1.0] * 4)))
+    with pytest.raises(ValueError, match="square"):
+        ctx.ilu0_compute(3, 4, np.zeros(5, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    # a system the dense elimination cannot hold (n = 262144 > 13500): ILU(0)-preconditioned GMRES on the 27-point operator
+    from algotoolkit_b200 import synthetic
+
+    g = 64
+    A = port.op27_csc(g, g, g)
+    n = A.n_rows
+    with pytest.raises(ValueError):
+        ctx.ilu_compute(n, n, A.col_ptr, A.row_idx, A.vals)
+    pc = ctx.ilu0_compute(n, n, A.col_ptr, A.row_idx, A.vals)
+    op = ctx.operator_from_csc(n, n, A.col_ptr, A.row_idx, A.vals)
+    x_ext = synthetic.u01_array(777, 0, n)
+    b = op.apply_numpy(x_ext)
+    plain = ctx.gmres_solve_host(op, b, np.zeros(n), 1, 20, 1e-6)
+    prec = ctx.gmres_solve_host(op, b, np.zeros(n), 1, 20, 1e-6, precond=pc)
+    true_res = np.linalg.norm(b - op.apply_numpy(prec["x"]))
+    assert true_res < 0.05 * np.linalg.norm(b - op.apply_numpy(plain["x"]))  # the preconditioner earns its keep
+    assert relerr(prec["x"], x_ext) < 1e-6
+    # M^-1 applied to A*z gives back roughly z, exactly L*U*w = A*z on the level-scheduled sweeps' own terms
+    z = np.random.default_rng(2).standard_normal(n)
+    w = pc.solve_host(op.apply_numpy(z))
+    assert relerr(w, z) < 0.2
+    op.destroy()
+    pc.destroy()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CASES)
 def test_device_ilu_and_preconditioned_gmres(ctx, port, gilu, name):
