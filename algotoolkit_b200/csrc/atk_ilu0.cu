@@ -106,6 +106,7 @@ struct Ilu0SolveArgs {
 constexpr int kIlu0Block = 256;
 __global__ void __launch_bounds__(kIlu0Block) ilu0_solve_kernel(Ilu0SolveArgs a) {
     if (a.skip_flag && *a.skip_flag) return;
+    constexpr int U = 8;
     unsigned target = 0;
     const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
     for (int lvl = 0; lvl < a.n_llev; ++lvl) {  // L y = b
@@ -113,11 +114,23 @@ __global__ void __launch_bounds__(kIlu0Block) ilu0_solve_kernel(Ilu0SolveArgs a)
             const int i = a.lrows[t];
             double sum = 0.0;
             const int di = a.diag[i];
-            for (int p = a.row_ptr[i]; p < di; ++p) {
-                const double v = a.val[p];
-                if (fabs(v) > kEps) sum = add_rn(sum, mul_rn(v, __ldcg(a.y + a.col[p])));
+            const double bi = a.b[i];
+            for (int p = a.row_ptr[i]; p < di; p += U) {  // U entries at a time: all their loads in flight before the ordered adds
+                int c[U];
+                double v[U], yv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool in = p + u < di;
+                    c[u] = in ? a.col[p + u] : i;
+                    v[u] = in ? a.val[p + u] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) yv[u] = __ldcg(a.y + c[u]);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (fabs(v[u]) > kEps) sum = add_rn(sum, mul_rn(v[u], yv[u]));
             }
-            __stcg(a.y + i, sub_rn(a.b[i], sum));
+            __stcg(a.y + i, sub_rn(bi, sum));
         }
         coop_grid_barrier(a.bar, target);
     }
@@ -125,13 +138,25 @@ __global__ void __launch_bounds__(kIlu0Block) ilu0_solve_kernel(Ilu0SolveArgs a)
         for (int t = a.uptr[lvl] + gt; t < a.uptr[lvl + 1]; t += gs) {
             const int i = a.urows[t];
             double sum = 0.0;
-            const int di = a.diag[i];
-            for (int p = di + 1; p < a.row_ptr[i + 1]; ++p) {
-                const double v = a.val[p];
-                if (fabs(v) > kEps) sum = add_rn(sum, mul_rn(v, __ldcg(a.x + a.col[p])));
-            }
+            const int di = a.diag[i], r1 = a.row_ptr[i + 1];
             const double d = a.val[di];
-            __stcg(a.x + i, __ddiv_rn(sub_rn(__ldcg(a.y + i), sum), fabs(d) > kEps ? d : 0.0));
+            const double yi = __ldcg(a.y + i);
+            for (int p = di + 1; p < r1; p += U) {
+                int c[U];
+                double v[U], xv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool in = p + u < r1;
+                    c[u] = in ? a.col[p + u] : i;
+                    v[u] = in ? a.val[p + u] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) xv[u] = v[u] != 0.0 ? __ldcg(a.x + c[u]) : 0.0;  // (x[i] itself is not written yet)
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (fabs(v[u]) > kEps) sum = add_rn(sum, mul_rn(v[u], xv[u]));
+            }
+            __stcg(a.x + i, __ddiv_rn(sub_rn(yi, sum), fabs(d) > kEps ? d : 0.0));
         }
         coop_grid_barrier(a.bar, target);
     }
