@@ -1332,7 +1332,6 @@ struct PersistArgs {
     double* nb_hi_p_lo[2];
     unsigned long long* stamps;   // optional globaltimer stamps: [0] after the start-up sums, then one per reduction
     int stamp_cap;
-    unsigned* xq;                 // XQ variant: next chunk of the active x update
 };
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
@@ -1340,48 +1339,7 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 }
 __device__ __forceinline__ double2 ldcg2(const double* p) { return __ldcg(reinterpret_cast<const double2*>(p)); }
 
-// One chunk of the queued x update (XQ variant below): every thread of the CTA calls it; returns false once the queue is empty.
-template <int NT>
-__device__ __noinline__ bool persist_x_try(double* __restrict__ x, const double* __restrict__ p, double alpha, int64_t n2,
-                                           unsigned* queue, int tid) {
-    constexpr int XCH = 8 * NT;  // element pairs per chunk
-    __shared__ int s_chunk;
-    const int n_chunks = (int)((n2 + XCH - 1) / XCH);
-    if (tid == 0) s_chunk = (int)atomicAdd(queue, 1u);
-    __syncthreads();
-    const int c = s_chunk;
-    __syncthreads();
-    if (c >= n_chunks) return false;
-    const int64_t e0 = (int64_t)c * XCH + tid;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        double2 xv[4], pv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t e = e0 + (int64_t)(h * 4 + u) * NT;
-            if (e < n2) {
-                xv[u] = ldcg2(x + 2 * e);
-                pv[u] = ldcg2(p + 2 * e);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t e = e0 + (int64_t)(h * 4 + u) * NT;
-            if (e < n2) {
-                xv[u].x = add_rn(xv[u].x, mul_rn(pv[u].x, alpha));  // x = x + p*alpha (ConjugateGradient.hpp:60)
-                xv[u].y = add_rn(xv[u].y, mul_rn(pv[u].y, alpha));
-                *reinterpret_cast<double2*>(x + 2 * e) = xv[u];
-            }
-        }
-    }
-    return true;
-}
-
-// XQ (ATK_PERSIST_XQ=1, experiment): the deferred update x += alpha*p leaves phase A and becomes a QUEUE of small chunks that
-// any CTA takes - while it waits for the other CTAs and ranks in the r.r reduction, and, for whatever is left, at the end of
-// phase A (work stealing absorbs that phase's CTA imbalance).  One update is active at a time and it is complete before the
-// next p.Ap reduction is passed, so every element still receives x = x + p*alpha once per iteration, in iteration order.
-template <int TX, int TY, bool XQ = false>
+template <int TX, int TY>
 __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a) {
     constexpr int DEPTH = 4;
     constexpr int W = 2 * TX + 4;
@@ -1416,12 +1374,6 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
         ++n_stamps;
     };
     // grid-wide and cross-GPU sum of one value per thread; every thread of every rank returns the same bits
-    // ---- XQ: the queue of x-update chunks (persist_x_try is a real function call: its registers stay out of the plane loop)
-    __shared__ int s_ready;
-    bool x_active = false;
-    double x_alpha = 0.0;
-    const double* x_p = nullptr;
-    auto x_try = [&]() -> bool { return persist_x_try<NT>(a.x, x_p, x_alpha, n2, a.xq, tid); };
 #ifdef ATK_REDUCE_PROFILE
     // profile build only (python -m algotoolkit_b200.build --profile): CTA 0 stamps the five stations of every reduction -
     // own arrival, all CTAs arrived, rank sum published, all ranks' words seen, resume - at stamps[1 + 5*(phase-1) + k]
@@ -1434,7 +1386,7 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
 #else
     auto rstamp = [&](int) {};
 #endif
-    auto reduce = [&](double v, bool work = false, bool reset_queue = false) -> double {
+    auto reduce = [&](double v) -> double {
         const double bs = block_sum<NT>(v);
         ++phase;
         rstamp(0);
@@ -1466,12 +1418,6 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
             __syncthreads();
             rstamp(1);
             const double total = partials_sum<NT>(a.partials, G);
-            if constexpr (XQ) {
-                if (reset_queue && tid == 0) {  // every CTA has drained the previous update: the queue restarts for the next one
-                    *a.xq = 0u;
-                    __threadfence();
-                }
-            }
             if (tid < 32 && tid < a.world) {
                 if (dist) __threadfence_system();
                 const unsigned long long bits = (unsigned long long)__double_as_longlong(total);
@@ -1482,49 +1428,8 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
             }
             rstamp(2);
         }
-        bool polled = false;
-        if constexpr (XQ) {
-            if (work && x_active) {
-                // wait for all ranks' words AND use the time: one poll round, then one chunk of the x update, until the words are there
-                unsigned rounds = 0;
-                unsigned long long t0 = 0;
-                for (;;) {
-                    if (tid < 32) {
-                        bool ok = true;
-                        unsigned long long w0 = 0, w1 = 0;
-                        if (tid < a.world) {
-                            const unsigned long long* src = a.ll + (size_t)(slot * kMaxRanks + tid) * 2;
-                            const unsigned long long tag = ll_tag(seq);
-                            w0 = ld_acquire_sys(src);
-                            w1 = ld_acquire_sys(src + 1);
-                            ok = (w0 >> 32) == tag && (w1 >> 32) == tag;
-                        }
-                        ok = __all_sync(0xffffffffu, ok);
-                        if (ok && tid < a.world) rank_vals[tid] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
-                        if (tid == 0) {
-                            if (!ok && (++rounds & 0xfffu) == 0) {
-                                const unsigned long long now = global_timer_ns();
-                                if (t0 == 0) t0 = now;
-                                if (now - t0 > kPeerWaitNs || *reinterpret_cast<volatile int*>(&st->peer_timeout)) {
-                                    st->peer_timeout = 1;
-                                    s_abort = 1;
-                                    ok = true;
-                                }
-                            }
-                            s_ready = ok ? 1 : 0;
-                        }
-                    }
-                    __syncthreads();
-                    const int ready = s_ready;
-                    __syncthreads();  // s_ready is rewritten in the next round
-                    if (ready) break;
-                    (void)x_try();
-                }
-                polled = true;
-            }
-        }
         // every CTA: wait for all ranks' words of this phase (local memory), lane q polls rank q
-        if (!polled && tid < 32) {
+        if (tid < 32) {
             if (tid < a.world) {
                 const unsigned long long* src = a.ll + (size_t)(slot * kMaxRanks + tid) * 2;
                 const unsigned long long tag = ll_tag(seq);
@@ -1666,9 +1571,7 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
                 issue_plane(kb + 1);
                 issue_plane(kb + 2);
                 double2 xv = zero2;
-                if constexpr (!XQ) {
-                    if (active && !first) xv = ldcg2(a.x + (int64_t)kb * sxy + row);
-                }
+                if (active && !first) xv = ldcg2(a.x + (int64_t)kb * sxy + row);
                 cp_async_wait<2>();
                 __syncthreads();
                 double2 pnA = zero2, pnB = zero2, pnC = zero2, poB = zero2;
@@ -1684,9 +1587,7 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
                     __syncthreads();
                     issue_plane(k + 3);
                     double2 xn = zero2;
-                    if constexpr (!XQ) {
-                        if (active && !first && k + 1 < ke) xn = ldcg2(a.x + idx + sxy);
-                    }
+                    if (active && !first && k + 1 < ke) xn = ldcg2(a.x + idx + sxy);
                     if (active) {
                         const int so = ((k - kb + 1) & (DEPTH - 1)) * STAGE, sn = ((k - kb + 2) & (DEPTH - 1)) * STAGE;
                         const double* rs = ring_r + so + centre;
@@ -1724,12 +1625,10 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
                         }
                         dacc = add_rn(dacc, mul_rn(pnB.x, out.x));
                         dacc = add_rn(dacc, mul_rn(pnB.y, out.y));
-                        if constexpr (!XQ) {
-                            if (!first) {
-                                xv.x = add_rn(xv.x, mul_rn(poB.x, alpha));  // x = x + p*alpha of the previous iteration (:60)
-                                xv.y = add_rn(xv.y, mul_rn(poB.y, alpha));
-                                *reinterpret_cast<double2*>(a.x + idx) = xv;
-                            }
+                        if (!first) {
+                            xv.x = add_rn(xv.x, mul_rn(poB.x, alpha));  // x = x + p*alpha of the previous iteration (:60)
+                            xv.y = add_rn(xv.y, mul_rn(poB.y, alpha));
+                            *reinterpret_cast<double2*>(a.x + idx) = xv;
                         }
                         pnA = pnB;
                         pnB = pnC;
@@ -1740,13 +1639,7 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
                 cp_async_wait<0>();
                 __syncthreads();  // the ring is free for the next item
             }
-            if constexpr (XQ) {  // whatever is left of the previous iteration's x update: shared out among the CTAs that are done
-                if (x_active) {
-                    while (x_try()) {}
-                    x_active = false;
-                }
-            }
-            const double pAp = reduce(dacc, false, true);  // :51
+            const double pAp = reduce(dacc);  // :51
             stamp();
             if (aborted) break;
             last_pAp = pAp;
@@ -1756,11 +1649,6 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
                 break;
             }
             alpha = __ddiv_rn(rs_old, pAp);  // :58
-            if constexpr (XQ) {  // x = x + p*alpha (:60) opens as a queue: p of this iteration is complete in pd
-                x_active = true;
-                x_alpha = alpha;
-                x_p = pd;
-            }
             // ================================================================ phase B (KB): r = r - Ap*alpha ; r.r
             double acc0 = 0.0, acc1 = 0.0;
             {
@@ -1799,18 +1687,12 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
                 }
                 for (; i < n2; i += stride) one(i, ldcg2(a.r + at(i)), ldcg2(a.Ap + at(i)));
             }
-            const double rs_new = reduce(add_rn(acc0, acc1), true);  // :63 (XQ: the wait is spent on chunks of the x update)
+            const double rs_new = reduce(add_rn(acc0, acc1));  // :63
             stamp();
             if (aborted) break;
             beta = __ddiv_rn(rs_new, rs_old);
             if (bid == 0 && tid == 0 && a.rs_trace && it < a.trace_cap) a.rs_trace[it] = rs_new;
             rs_old = rs_new;  // :80
-        }
-    }
-    if constexpr (XQ) {  // the last x update must be complete before KF overwrites the p it reads (the caller's p may be that buffer)
-        if (x_active && !aborted) {
-            while (x_try()) {}
-            (void)reduce(0.0);
         }
     }
     // ---- KF: bring the caller's x and p to the reference's state
@@ -1823,12 +1705,10 @@ __global__ void __launch_bounds__(TX* TY, 7) cg_persistent_kernel(PersistArgs a)
         } else {  // the last iteration still owes x = x + p*alpha (:60) and p = r + p*beta (:79)
             for (int64_t i = t_lin; i < n2; i += stride) {
                 const double2 pv = ldcg2(pc + 2 * i), rv = ldcg2(a.r + 2 * i);
-                if constexpr (!XQ) {
-                    double2 xv = ldcg2(a.x + 2 * i);
-                    xv.x = add_rn(xv.x, mul_rn(pv.x, alpha));
-                    xv.y = add_rn(xv.y, mul_rn(pv.y, alpha));
-                    *reinterpret_cast<double2*>(a.x + 2 * i) = xv;
-                }
+                double2 xv = ldcg2(a.x + 2 * i);
+                xv.x = add_rn(xv.x, mul_rn(pv.x, alpha));
+                xv.y = add_rn(xv.y, mul_rn(pv.y, alpha));
+                *reinterpret_cast<double2*>(a.x + 2 * i) = xv;
                 *reinterpret_cast<double2*>(a.P0 + 2 * i) = make_double2(add_rn(rv.x, mul_rn(pv.x, beta)), add_rn(rv.y, mul_rn(pv.y, beta)));
             }
         }
@@ -1948,7 +1828,7 @@ struct Stencil7 : public Operator {
         int coop = 0, per_sm = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
         if (!coop) return 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_kernel<TX, TY, false>, TX * TY, fused_smem_bytes<TX, TY>()) !=
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_kernel<TX, TY>, TX * TY, fused_smem_bytes<TX, TY>()) !=
                 cudaSuccess || per_sm < 1)
             return 0;
         const int64_t g_max = (int64_t)per_sm * ctx->sm_count;
@@ -2030,20 +1910,10 @@ struct Stencil7 : public Operator {
         }
         pa.stamps = stamps;
         pa.stamp_cap = stamp_cap;
-        pa.xq = reinterpret_cast<unsigned*>(pa.arrive + 2);
-        ATK_CUDA_CHECK(cudaMemsetAsync(pa.arrive, 0, 4 * sizeof(unsigned long long), c->stream));
+        ATK_CUDA_CHECK(cudaMemsetAsync(pa.arrive, 0, sizeof(unsigned long long), c->stream));
         void* kargs[] = {&pa};
-        const char* xq_env = std::getenv("ATK_PERSIST_XQ");
-        const bool xq = xq_env && xq_env[0] == '1';
-        int grid = ps_grid;
-        if (xq) {  // the variant may hold fewer CTAs per SM: never launch more than are resident
-            int per_sm = 0;
-            ATK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_persistent_kernel<TX, TY, true>, TX * TY,
-                                                                         fused_smem_bytes<TX, TY>()));
-            grid = std::min(grid, std::max(per_sm, 1) * c->sm_count);
-        }
-        ATK_CUDA_CHECK(cudaLaunchCooperativeKernel(xq ? (void*)cg_persistent_kernel<TX, TY, true> : (void*)cg_persistent_kernel<TX, TY, false>,
-                                                   dim3((unsigned)grid), dim3(TX, TY, 1), kargs, fused_smem_bytes<TX, TY>(), c->stream));
+        ATK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)cg_persistent_kernel<TX, TY>, dim3((unsigned)ps_grid), dim3(TX, TY, 1), kargs,
+                                                   fused_smem_bytes<TX, TY>(), c->stream));
         count_launch(c);
     }
     bool peer_mode = false;  // set by the CG driver for the duration of a solve (all ranks agree)

@@ -334,15 +334,13 @@ def test_cg_fixed_work_and_continuation(ctx, port, golden, cg_loop):
     assert relerr(bb["x"], ora2["x"]) < REL and relerr(bb["x"], r50["x"]) < REL
 
 
-@pytest.mark.parametrize("xq", ["0", "1"])
 @pytest.mark.parametrize("dims,split", [((96, 70, 40), None), ((64, 8, 130), None), ((130, 36, 24), "3"), ((32, 4, 9), None)])
-def test_cg_persistent_loop(ctx, port, dims, split, xq, monkeypatch):
+def test_cg_persistent_loop(ctx, port, dims, split, monkeypatch):
     """The one-launch persistent loop on grids with partial tiles, several z-chunks per tile and more items than CTAs:
     it must be the path taken (info.persistent), agree with the oracle per iteration (traces), honour the exit, the
     zero right-hand side and the continuation semantics, and report phase times."""
     monkeypatch.setenv("ATK_CG_ONCHIP", "0")
     monkeypatch.setenv("ATK_CG_PERSISTENT", "1")
-    monkeypatch.setenv("ATK_PERSIST_XQ", xq)  # "1": the deferred x update as a queue of chunks worked off in the reduction waits
     if split:
         monkeypatch.setenv("ATK_PERSIST_SPLIT", split)
     nx, ny, nz = dims

@@ -42,14 +42,12 @@ ok = True
 results = {}
 # "1": fused, persistent one-launch loop (peer memory); "graph": fused two-kernel CUDA-graph loop (peer memory);
 # "0": generic three-kernel loop over NCCL
-for fused in ("1", "xq", "graph", "0"):
+for fused in ("1", "graph", "0"):
     os.environ["ATK_CG_FUSED"] = "0" if fused == "0" else "1"
     os.environ["ATK_CG_PERSISTENT"] = "0" if fused == "graph" else "1"
-    os.environ["ATK_PERSIST_XQ"] = "1" if fused == "xq" else "0"  # persistent loop with the x update as a work queue
     res = ctx.cg_solve_host(op, b_loc, iters, trace=True)
     results[fused] = (gather(res["x"]), gather(res["r"]), gather(res["p"]), res)
 os.environ["ATK_CG_PERSISTENT"] = "1"
-os.environ["ATK_PERSIST_XQ"] = "0"
 # a second fused solve on the same context (sequence-number epochs must advance), continuing from the first state
 os.environ["ATK_CG_FUSED"] = "1"
 x1, r1, p1, _ = [results["1"][q] for q in range(4)]
@@ -58,17 +56,15 @@ res2 = ctx.cg_solve_host(op, b_loc, 7, state=(x1[sl], r1[sl], p1[sl]))
 x_cont = gather(res2["x"])
 # latency floor of one iteration on this (small) grid, warm, per communication mode
 lat = {}
-for mode in ("persistent", "persistent_xq", "peer", "nccl"):
+for mode in ("persistent", "peer", "nccl"):
     os.environ["ATK_CG_FUSED"] = "1"
     os.environ["ATK_CG_FORCE_NCCL"] = "1" if mode == "nccl" else "0"
-    os.environ["ATK_CG_PERSISTENT"] = "1" if mode.startswith("persistent") else "0"
-    os.environ["ATK_PERSIST_XQ"] = "1" if mode == "persistent_xq" else "0"
+    os.environ["ATK_CG_PERSISTENT"] = "1" if mode == "persistent" else "0"
     for rep in range(2):
         rr = ctx.cg_solve_host(op, b_loc, 200)
     lat[mode] = (rr["device_ms"] / max(rr["iters"], 1) * 1e3, rr["peer"], rr["iters"])
 os.environ["ATK_CG_FORCE_NCCL"] = "0"
 os.environ["ATK_CG_PERSISTENT"] = "1"
-os.environ["ATK_PERSIST_XQ"] = "0"
 # plain operator apply with halo exchange
 xin = np.random.default_rng(3).standard_normal(nx * ny * nz)
 y_loc = op.apply_numpy(xin[op.row_begin: op.row_begin + op.n_rows_local])
@@ -184,7 +180,7 @@ if rank == 0:
         print(f"fused={fused}: iters {res['iters']} (oracle {ora['iters']}) fusedflag {res['fused']} peer {res['peer']} persistent {res['persistent']}  relerr x {ex:.2e} r {er:.2e} p {ep:.2e} "
               f"launches {res['kernel_launches']} ms {res['device_ms']:.2f}")
         ok &= res["iters"] == ora["iters"] and ex < 1e-10 and er < 1e-8 and ep < 1e-8
-        ok &= res["persistent"] == (fused in ("1", "xq"))
+        ok &= res["persistent"] == (fused == "1")
     print("assembled Poisson (SELL, row blocks) apply bit-exact:", np.array_equal(ya, y_ref),
           " 27-point assembled:", np.array_equal(y27a, P.spmv(A27, xin)))
     ok &= np.array_equal(ya, y_ref) and np.array_equal(y27a, P.spmv(A27, xin))
