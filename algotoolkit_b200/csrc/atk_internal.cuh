@@ -1,13 +1,16 @@
 // atk_internal.cuh -- shared declarations of libatk_cuda.so (not part of the public ABI).
 //
 // Layout of the library:
-//   atk_context.cu   context, streams, scratch, memory entry points, NCCL (dlopen'ed lazily)
+//   atk_context.cu   context, streams, scratch, memory entry points, NCCL (dlopen'ed lazily), peer-memory exchanges
+//                    (PeerHalo, PeerGather), NUMA-local pinned host buffers
 //   atk_vector.cu    VectorObj kernels: dot / nrm2 / scale / div / add / sub / axpy
 //   atk_spmv.cu      CSC -> CSR -> SELL-32 conversion on the device, SELL and CSR-vector SpMV
 //   atk_stencil.cu   matrix-free 7-point Poisson operator (+ fused p.Ap), device-side assembly
 //   atk_cg.cu        ConjugateGrad::solve device loop
 //   atk_gmres.cu     GMRES::solve device loop
 //   atk_ilu.cu       ILUPreconditioner (dense-in-disguise elimination + triangular sweeps) for GMRES::enablePreconditioner
+//   atk_ilu0.cu      sparse ILU(0) (the same elimination restricted to A's pattern), level-scheduled factorisation / solves
+//   atk_gd.cu        GradientDescent::solve device loop
 //   atk_api.cu       extern "C" wrappers (exceptions -> status codes)
 #pragma once
 

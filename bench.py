@@ -344,7 +344,6 @@ def run_ours(args):
         pass
     t_it = dev_ms * 1e-3 / args.steps
     iter_gbs = iter_bytes_per_row * N / t_it / 1e9 / world      # bytes this formulation must move, per GPU
-    iter_gbs_88 = 88.0 * N / t_it / 1e9 / world                 # SURVEY 8(d) three-kernel figure, for comparison
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -371,7 +370,6 @@ def run_ours(args):
                      "iteration_bytes_per_row": iter_bytes_per_row,
                      "iteration_achieved_gbs_per_gpu": iter_gbs, "iteration_frac": iter_gbs / peak,
                      "iteration_frac_of_8TBs": iter_gbs / 8000.0,
-                     "iteration_88B_equivalent_gbs_per_gpu": iter_gbs_88, "iteration_88B_equivalent_frac_of_8TBs": iter_gbs_88 / 8000.0,
                      "per_kernel": per_kernel},
         "rs_final": res["rs"],
     }
