@@ -36,7 +36,9 @@ struct NvtxRange {
     NvtxRange(const NvtxRange&) = delete;
     NvtxRange& operator=(const NvtxRange&) = delete;
 };
-#define ATK_NVTX(name) ::atk::NvtxRange atk_nvtx_range_##__LINE__(name)
+#define ATK_NVTX_CAT2(a, b) a##b
+#define ATK_NVTX_CAT(a, b) ATK_NVTX_CAT2(a, b)
+#define ATK_NVTX(name) ::atk::NvtxRange ATK_NVTX_CAT(atk_nvtx_range_, __LINE__)(name)
 
 // Checked build (python -m algotoolkit_b200.build --checked -> libatk_cuda_checked.so, ATK_LIB=checked selects it): device-side
 // assertions on tile / halo indices and on the sequence numbers of the peer protocols; a violation prints and traps.

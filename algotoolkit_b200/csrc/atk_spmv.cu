@@ -672,6 +672,7 @@ struct AssembledMatrix : public Operator {
     bool dist = false;
     PeerGather pg;
     std::vector<int> ext_cols_host;      // global column of every external entry (for export)
+    int push_per_sm_dot = 0, push_per_sm_plain = 0;  // resident CTAs per SM of the single-launch apply (evaluated once)
     int s_int_begin = 0, s_int_end = 0;  // slices whose rows touch no external entry: they run while the exchange is in flight
 
     ~AssembledMatrix() override {
@@ -714,8 +715,7 @@ struct AssembledMatrix : public Operator {
                     sp.ticket = pg.d_ticket;
                     sp.s_int_begin = s_int_begin;
                     sp.s_int_end = s_int_end;
-                    static int per_sm_dot = 0, per_sm_plain = 0;
-                    int& per_sm = dot ? per_sm_dot : per_sm_plain;
+                    int& per_sm = dot ? push_per_sm_dot : push_per_sm_plain;  // per operator (= per device)
                     if (per_sm == 0) {
                         if (dot) ATK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sell_spmv_kernel<true, true, true>, kReduceBlock, 0));
                         else ATK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sell_spmv_kernel<false, true, true>, kReduceBlock, 0));

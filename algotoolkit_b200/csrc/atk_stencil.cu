@@ -1991,12 +1991,9 @@ struct Stencil7 : public Operator {
             constexpr int TILE = (TY + 2) * (2 * TX + 4);
             constexpr size_t stage = (size_t)(TILE * 8 + 127) / 128 * 128;
             constexpr size_t smem = 2 * 4 * stage;
-            static bool opted = false;
-            if (!opted) {
-                ATK_CUDA_CHECK(cudaFuncSetAttribute(stencil7_cg_fused_tma_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    (int)smem));
-                opted = true;
-            }
+            // (the limit is per function AND per device: set on every launch - it is cheap and a solve captures KA once)
+            ATK_CUDA_CHECK(cudaFuncSetAttribute(stencil7_cg_fused_tma_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem));
             const CUtensorMap tm_r = make_tensor_map<TX, TY>(fa.r), tm_p0 = make_tensor_map<TX, TY>(fa.P0),
                               tm_p1 = make_tensor_map<TX, TY>(fa.P1);
             stencil7_cg_fused_tma_kernel<TX, TY><<<grid, block, smem, c->stream>>>(tm_r, tm_p0, tm_p1, g, fa, k_lo, k_hi, kcc,
