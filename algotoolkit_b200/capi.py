@@ -16,6 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # ATK_LIB=profile loads the build with reduction-station stamps (python -m algotoolkit_b200.build --profile)
 LIB_PATH = os.path.join(_HERE, {"checked": "libatk_cuda_checked.so", "profile": "libatk_cuda_profile.so"}.get(
     os.environ.get("ATK_LIB", ""), "libatk_cuda.so"))
+if os.environ.get("ATK_LIB_PATH"):  # A/B runs against another build of the same ABI
+    LIB_PATH = os.environ["ATK_LIB_PATH"]
 
 ATK_OK, ATK_ERR_INVALID_ARGUMENT, ATK_ERR_RUNTIME, ATK_ERR_OUT_OF_RANGE, ATK_ERR_CUDA, ATK_ERR_NCCL, ATK_ERR_NOMEM = range(7)
 REDUCE_TREE, REDUCE_SEQUENTIAL = 0, 1

@@ -240,6 +240,83 @@ __device__ __forceinline__ double sequential_sum(int64_t len, double* stage, dou
     return *bcast;
 }
 
+// h from a per-thread partial: fixed block tree, then (several CTAs) barrier + fixed-order sum of the CTA partials; on
+// distributed contexts the rank sums cross NVLink as packed words (see MgsArgs).  Ends with a block-wide barrier.
+// (Measured and rejected: every CTA leaving its sum as a packed {half | tag} word pair and every CTA polling all 148
+// pairs - no fence, no atomic - is SLOWER, 10.4 vs 6.7 us per projection at 2.1 M rows: 22 k polling threads on 19
+// cache lines; profiles/r02_mgs_step.txt.)
+template <int BLOCK>
+__device__ __forceinline__ double mgs_finish_tree(const MgsArgs& a, double acc, int i, unsigned& target, double* rank_vals) {
+    const unsigned G = gridDim.x;
+    const double bs = block_sum<BLOCK>(acc);
+    if (G == 1 && a.world == 1) return bs;
+    double* part = a.partials + (size_t)(i & 1) * G;
+    if (a.world == 1) {
+        if (threadIdx.x == 0) part[blockIdx.x] = bs;
+        grid_barrier(a.bar, target);
+        double s = 0.0;
+        for (unsigned q = threadIdx.x; q < G; q += BLOCK) s = add_rn(s, __ldcg(part + q));
+        return block_sum<BLOCK>(s);
+    }
+    // ---- distributed: arrive, CTA 0 publishes the rank's sum to every rank, everyone polls its local words
+    const int slot = kMgsLlSlot + (i & 1);
+    const unsigned long long seq = a.seq_base + (unsigned long long)i + 1ull;
+    target += G;
+    if (threadIdx.x == 0) {
+        __stcg(part + blockIdx.x, bs);
+        __threadfence();
+        atomicAdd(a.bar, 1u);
+    }
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) {
+            unsigned spins = 0;
+            unsigned long long t0 = 0;
+            while (*reinterpret_cast<volatile unsigned*>(a.bar) < target) {
+                if ((++spins & 0xfffu) == 0) {
+                    const unsigned long long now = global_timer_ns();
+                    if (t0 == 0) t0 = now;
+                    if (now - t0 > kPeerWaitNs) asm volatile("trap;");
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        double s = 0.0;
+        for (unsigned q = threadIdx.x; q < G; q += BLOCK) s = add_rn(s, __ldcg(part + q));
+        const double total = block_sum<BLOCK>(s);
+        if (threadIdx.x < 32 && (int)threadIdx.x < a.world) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(total);
+            const unsigned long long tag = ll_tag(seq) << 32;
+            unsigned long long* dst = ((int)threadIdx.x == a.rank ? a.ll : a.peer_ll[threadIdx.x]) + (size_t)(slot * kMaxRanks + a.rank) * 2;
+            st_relaxed_sys(dst, (bits & 0xffffffffull) | tag);
+            st_relaxed_sys(dst + 1, (bits >> 32) | tag);
+        }
+    }
+    if (threadIdx.x < 32 && (int)threadIdx.x < a.world) {
+        const unsigned long long* src = a.ll + (size_t)(slot * kMaxRanks + threadIdx.x) * 2;
+        const unsigned long long tag = ll_tag(seq);
+        unsigned long long w0, w1;
+        unsigned spins = 0;
+        unsigned long long t0 = 0;
+        for (;;) {
+            w0 = ld_relaxed_sys(src);
+            w1 = ld_relaxed_sys(src + 1);
+            if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
+            if ((++spins & 0xfffu) == 0) {
+                const unsigned long long now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                if (now - t0 > kPeerWaitNs) asm volatile("trap;");  // a rank died or fell out of step: fail loudly
+            }
+        }
+        rank_vals[threadIdx.x] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    }
+    __syncthreads();
+    double h = rank_vals[0];
+    for (int q = 1; q < a.world; ++q) h = add_rn(h, rank_vals[q]);
+    __syncthreads();  // rank_vals is rewritten by the next projection
+    return h;
+}
+
 constexpr int kMgsRegRows = 8;  // rows per thread the register variant can hold
 
 // REG = true (slices of at most 8*BLOCK rows): the thread's rows of w and of the current V column live in registers,
@@ -255,79 +332,8 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
     const int64_t c0 = (int64_t)blockIdx.x * a.chunk;
     const int64_t len = max((int64_t)0, min(a.chunk, a.n - c0));
     unsigned target = 0;
-    const unsigned G = gridDim.x;
-
-    // h from a per-thread partial: fixed block tree, then (several CTAs) barrier + fixed-order sum of the CTA partials
     __shared__ double rank_vals[kMaxRanks];
-    auto finish_tree = [&](double acc, int i) -> double {
-        const double bs = block_sum<BLOCK>(acc);
-        if (G == 1 && a.world == 1) return bs;
-        double* part = a.partials + (size_t)(i & 1) * G;
-        if (a.world == 1) {
-            if (threadIdx.x == 0) part[blockIdx.x] = bs;
-            grid_barrier(a.bar, target);
-            double s = 0.0;
-            for (unsigned q = threadIdx.x; q < G; q += BLOCK) s = add_rn(s, __ldcg(part + q));
-            return block_sum<BLOCK>(s);
-        }
-        // ---- distributed: arrive, CTA 0 publishes the rank's sum to every rank, everyone polls its local words
-        const int slot = kMgsLlSlot + (i & 1);
-        const unsigned long long seq = a.seq_base + (unsigned long long)i + 1ull;
-        target += G;
-        if (threadIdx.x == 0) {
-            __stcg(part + blockIdx.x, bs);
-            __threadfence();
-            atomicAdd(a.bar, 1u);
-        }
-        if (blockIdx.x == 0) {
-            if (threadIdx.x == 0) {
-                unsigned spins = 0;
-                unsigned long long t0 = 0;
-                while (*reinterpret_cast<volatile unsigned*>(a.bar) < target) {
-                    if ((++spins & 0xfffu) == 0) {
-                        const unsigned long long now = global_timer_ns();
-                        if (t0 == 0) t0 = now;
-                        if (now - t0 > kPeerWaitNs) asm volatile("trap;");
-                    }
-                }
-                __threadfence();
-            }
-            __syncthreads();
-            double s = 0.0;
-            for (unsigned q = threadIdx.x; q < G; q += BLOCK) s = add_rn(s, __ldcg(part + q));
-            const double total = block_sum<BLOCK>(s);
-            if (threadIdx.x < 32 && (int)threadIdx.x < a.world) {
-                const unsigned long long bits = (unsigned long long)__double_as_longlong(total);
-                const unsigned long long tag = ll_tag(seq) << 32;
-                unsigned long long* dst = ((int)threadIdx.x == a.rank ? a.ll : a.peer_ll[threadIdx.x]) + (size_t)(slot * kMaxRanks + a.rank) * 2;
-                st_relaxed_sys(dst, (bits & 0xffffffffull) | tag);
-                st_relaxed_sys(dst + 1, (bits >> 32) | tag);
-            }
-        }
-        if (threadIdx.x < 32 && (int)threadIdx.x < a.world) {
-            const unsigned long long* src = a.ll + (size_t)(slot * kMaxRanks + threadIdx.x) * 2;
-            const unsigned long long tag = ll_tag(seq);
-            unsigned long long w0, w1;
-            unsigned spins = 0;
-            unsigned long long t0 = 0;
-            for (;;) {
-                w0 = ld_relaxed_sys(src);
-                w1 = ld_relaxed_sys(src + 1);
-                if ((w0 >> 32) == tag && (w1 >> 32) == tag) break;
-                if ((++spins & 0xfffu) == 0) {
-                    const unsigned long long now = global_timer_ns();
-                    if (t0 == 0) t0 = now;
-                    if (now - t0 > kPeerWaitNs) asm volatile("trap;");  // a rank died or fell out of step: fail loudly
-                }
-            }
-            rank_vals[threadIdx.x] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
-        }
-        __syncthreads();
-        double h = rank_vals[0];
-        for (int q = 1; q < a.world; ++q) h = add_rn(h, rank_vals[q]);
-        __syncthreads();  // rank_vals is rewritten by the next projection
-        return h;
-    };
+    auto finish_tree = [&](double acc, int i) -> double { return mgs_finish_tree<BLOCK>(a, acc, i, target, rank_vals); };
 
     if constexpr (REG) {
         double wr[kMgsRegRows], vc[kMgsRegRows], vn[kMgsRegRows];
@@ -444,16 +450,20 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
                     const double2 z2 = make_double2(0.0, 0.0);
                     auto ldp = [&](int64_t e) -> double2 { return vp ? __ldcg(reinterpret_cast<const double2*>(vp) + e) : z2; };
                     auto ldc = [&](int64_t e) -> double2 { return vc ? __ldcs(reinterpret_cast<const double2*>(vc) + e) : z2; };
-                    int64_t e = threadIdx.x;
-                    for (; e + 3 * BLOCK < len2; e += 4 * BLOCK) {
-                        const double2 p0 = ldp(e), p1 = ldp(e + BLOCK), p2 = ldp(e + 2 * BLOCK), p3 = ldp(e + 3 * BLOCK);
-                        const double2 q0 = ldc(e), q1 = ldc(e + BLOCK), q2 = ldc(e + 2 * BLOCK), q3 = ldc(e + 3 * BLOCK);
-                        one(e, p0, q0);
-                        one(e + BLOCK, p1, q1);
-                        one(e + 2 * BLOCK, p2, q2);
-                        one(e + 3 * BLOCK, p3, q3);
+                    // eight entries per thread and trip, predicated: sixteen 16-byte loads in flight before anything is
+                    // consumed, and the last trip is as wide as the first (a 14 k-row slice is one or two trips)
+                    for (int64_t e = threadIdx.x; e < len2; e += 8 * BLOCK) {
+                        double2 pp[8], qq[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const bool in = e + (int64_t)u * BLOCK < len2;
+                            pp[u] = in ? ldp(e + u * BLOCK) : z2;
+                            qq[u] = in ? ldc(e + u * BLOCK) : z2;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            if (e + (int64_t)u * BLOCK < len2) one(e + u * BLOCK, pp[u], qq[u]);
                     }
-                    for (; e < len2; e += BLOCK) one(e, ldp(e), ldc(e));
                     acc = add_rn(acc, acc1);
                     if ((len & 1) && threadIdx.x == 0) {
                         const int64_t t = len - 1;
@@ -497,6 +507,104 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
     }
 }
 
+// RING variant (slices of 8*BLOCK < rows <= 28*BLOCK whose TWO column slices fit in shared memory - the 14 170-row slices of
+// a 2.1 M-row rank, i.e. BASELINE config 5 on 8 GPUs): the thread's rows of w live in REGISTERS for the whole step and the
+// columns arrive through a two-deep shared-memory ring filled by cp.async (16 bytes per request, L2 only).  Column i+1 is
+// requested by each thread for its own entries the moment pass i has consumed the buffer it replaces, so it travels
+// HBM -> shared memory while the reduction of projection i is in flight, and a pass reads shared memory only: no global
+// load latency and no second (L2) read of a column on the critical path.  Every ring entry is written (cp.async) and read
+// by the same thread, so the only block-wide barriers are those of the reductions.
+constexpr int kMgsRingSlots = 14;  // 16-byte slots per thread
+template <int BLOCK, int S>
+__global__ void __launch_bounds__(BLOCK) arnoldi_mgs_ring_kernel(MgsArgs a) {
+    extern __shared__ __align__(16) double wsm[];  // two column slices of a.chunk doubles
+    __shared__ double rank_vals[kMaxRanks];
+    if (a.stop && *reinterpret_cast<volatile int*>(a.stop)) return;
+    const int64_t c0 = (int64_t)blockIdx.x * a.chunk;
+    const int64_t len = max((int64_t)0, min(a.chunk, a.n - c0));
+    unsigned target = 0;
+    // entries of slot u that exist: 2, 1 (the last row of an odd slice) or 0
+    auto slot_rows = [&](int u) -> int {
+        const int64_t e = 2 * ((int64_t)threadIdx.x + (int64_t)u * BLOCK);
+        return e + 1 < len ? 2 : (e < len ? 1 : 0);
+    };
+    auto request = [&](int col) {
+        const double* src = a.V + (int64_t)col * a.ldv + c0;
+        const unsigned dst0 = (unsigned)__cvta_generic_to_shared(wsm + (size_t)(col & 1) * a.chunk);
+#pragma unroll
+        for (int u = 0; u < S; ++u) {
+            const int rows = slot_rows(u);
+            const int64_t e = 2 * ((int64_t)threadIdx.x + (int64_t)u * BLOCK);
+            if (rows) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (unsigned)(e * 8)), "l"(src + e), "r"(rows * 8) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (a.j > 0) request(0);
+    if (a.j > 1) request(1);
+    double2 wr[S];
+#pragma unroll
+    for (int u = 0; u < S; ++u) {
+        const int rows = slot_rows(u);
+        const int64_t e = 2 * ((int64_t)threadIdx.x + (int64_t)u * BLOCK);
+        wr[u] = make_double2(0.0, 0.0);
+        if (rows == 2) wr[u] = *reinterpret_cast<const double2*>(a.w + c0 + e);
+        else if (rows == 1) wr[u].x = a.w[c0 + e];
+    }
+    double hprev = 0.0;
+    for (int i = 0; i <= a.j; ++i) {
+        if (i < a.j) {
+            if (i == 0 && a.j > 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        const double2* bp = reinterpret_cast<const double2*>(wsm + (size_t)((i + 1) & 1) * a.chunk);  // column i-1
+        const double2* bc = reinterpret_cast<const double2*>(wsm + (size_t)(i & 1) * a.chunk);        // column i
+        double acc = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int u = 0; u < S; ++u) {
+            const int rows = slot_rows(u);
+            if (rows == 0) continue;
+            const int64_t sl = (int64_t)threadIdx.x + (int64_t)u * BLOCK;
+            double2 wv = wr[u];
+            if (i > 0) {                                                   // update of projection i-1   (:76)
+                const double2 pv = bp[sl];
+                wv.x = sub_rn(wv.x, mul_rn(pv.x, hprev));
+                if (rows == 2) wv.y = sub_rn(wv.y, mul_rn(pv.y, hprev));
+                wr[u] = wv;
+            }
+            if (i < a.j) {                                                 // products of projection i   (:75)
+                const double2 cv = bc[sl];
+                acc = add_rn(acc, mul_rn(cv.x, wv.x));
+                if (rows == 2) acc1 = add_rn(acc1, mul_rn(cv.y, wv.y));
+            } else {                                                       // ||w||^2                     (:79)
+                acc = add_rn(acc, mul_rn(wv.x, wv.x));
+                if (rows == 2) acc1 = add_rn(acc1, mul_rn(wv.y, wv.y));
+            }
+        }
+        acc = add_rn(acc, acc1);
+        if (i >= 1 && i + 1 < a.j) request(i + 1);  // into the buffer column i-1 just left
+        const double h = mgs_finish_tree<BLOCK>(a, acc, i, target, rank_vals);
+        if (i < a.j) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) a.h_out[i] = h;  // H(i,j)
+            hprev = h;
+        } else {
+            const double nrm = sqrt(h);
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                a.h_out[a.j] = nrm;
+                if (a.stop && (nrm == 0.0 || nrm < a.skip_below)) { a.stop[1] = a.j; a.stop[0] = 1; }
+            }
+            if (nrm != 0.0 && !(nrm < a.skip_below)) {
+#pragma unroll
+                for (int u = 0; u < S; ++u) {
+                    const int rows = slot_rows(u);
+                    const int64_t e = 2 * ((int64_t)threadIdx.x + (int64_t)u * BLOCK);
+                    if (rows == 2) *reinterpret_cast<double2*>(a.vnext + c0 + e) = make_double2(__ddiv_rn(wr[u].x, nrm), __ddiv_rn(wr[u].y, nrm));  // (:86)
+                    else if (rows == 1) a.vnext[c0 + e] = __ddiv_rn(wr[u].x, nrm);
+                }
+            }
+        }
+    }
+}
+
 using MgsKernel = void (*)(MgsArgs);
 inline MgsKernel mgs_kernel_for(int block, bool reg) {
     switch (block) {
@@ -513,8 +621,9 @@ struct PersistentMgs {
     bool usable = false;
     int grid = 1, block = 512;
     MgsKernel kernel = nullptr;
+    MgsKernel ring_kernel = nullptr;  // w in registers + cp.async column ring, when the slice allows it (else nullptr)
     int64_t chunk = 0;
-    size_t smem = 0;
+    size_t smem = 0, ring_smem = 0;
     unsigned* d_bar = nullptr;
     double* d_part = nullptr;
     int n_bars = 0;
@@ -558,6 +667,21 @@ struct PersistentMgs {
         int coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
         if (!coop) return false;
+        if (!seq && !reg && block == 512 && rows <= (int64_t)2 * kMgsRingSlots * 512 && !std::getenv("ATK_MGS_NO_RING")) {
+            MgsKernel rk = arnoldi_mgs_ring_kernel<512, kMgsRingSlots>;
+            const size_t rsm = sizeof(double) * 2 * (size_t)c;
+            cudaFuncAttributes rfa;
+            ATK_CUDA_CHECK(cudaFuncGetAttributes(&rfa, rk));
+            if (rsm + rfa.sharedSizeBytes <= (size_t)max_smem) {
+                ATK_CUDA_CHECK(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - (int)rfa.sharedSizeBytes));
+                int rper = 0;
+                ATK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rper, rk, 512, rsm));
+                if (rper >= 1 && g <= rper * ctx->sm_count) {
+                    ring_kernel = rk;
+                    ring_smem = rsm;
+                }
+            }
+        }
         grid = g;
         chunk = c;
         smem = sm;
@@ -574,7 +698,11 @@ struct PersistentMgs {
                    skip_below, stop, ctx->world, ctx->rank, ctx->d_ll, ctx->d_peer_ll, ctx->epoch};
         if (ctx->world > 1) ctx->epoch += (unsigned long long)ncols + 2ull;  // same advance on every rank
         void* kargs[] = {&ma};
-        ATK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)kernel, dim3(grid), dim3(block), kargs, smem, ctx->stream));
+        // the ring variant moves 16-byte pieces: every column slice, w and V_next must start on a 16-byte boundary
+        const bool ring = ring_kernel && (ldv & 1) == 0 && (chunk & 1) == 0 &&
+                          ((reinterpret_cast<uintptr_t>(V) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(vnext)) & 15u) == 0;
+        ATK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)(ring ? ring_kernel : kernel), dim3(grid), dim3(block), kargs,
+                                                   ring ? ring_smem : smem, ctx->stream));
         count_launch(ctx);
     }
 };

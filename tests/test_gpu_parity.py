@@ -783,13 +783,18 @@ def test_gmres_op27_larger_systems_vs_reference(ctx, port, key):
         assert digest(seq["x"]) == g["x_sha256"] and list(seq["resid"]) == g["resid"]
 
 
-@pytest.mark.parametrize("dims", [(96, 96, 96), (95, 97, 96)])
-def test_gmres_persistent_step_with_w_in_shared_memory(ctx, dims, monkeypatch):
-    """Slices above 4096 rows per CTA keep w in shared memory and fuse the update of projection i-1 with the products of
-    projection i (16-byte accesses when the column stride is even, scalar otherwise): must agree with the per-projection
-    kernels and with the batched form to 1e-10."""
+@pytest.mark.parametrize("dims,ring", [((96, 96, 96), True), ((96, 96, 96), False), ((95, 97, 96), True), ((95, 97, 95), False),
+                                       ((128, 128, 127), True)])
+def test_gmres_persistent_step_with_w_in_shared_memory(ctx, dims, ring, monkeypatch):
+    """Slices above 4096 rows per CTA: (ring) w in registers and the columns in a two-deep cp.async ring in shared memory
+    (slices up to 14 336 rows, even column stride - 128x128x127 is 14 060 rows per CTA, next to the limit), or (no ring:
+    ATK_MGS_NO_RING, or an odd column stride as in 95x97x95) w in shared memory with the update of projection i-1 fused
+    into the products of projection i, 16-byte accesses when the stride is even and scalar otherwise.  Must agree with the
+    per-projection kernels and with the batched form to 1e-10."""
     from algotoolkit_b200 import synthetic
 
+    if not ring:
+        monkeypatch.setenv("ATK_MGS_NO_RING", "1")
     nx, ny, nz = dims
     rows = nx * ny * nz
     op = ctx.operator_stencil27(nx, ny, nz, synthetic.stencil27_coefficients())
