@@ -510,9 +510,9 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
 // RING variant (slices of 8*BLOCK < rows <= 28*BLOCK whose TWO column slices fit in shared memory - the 14 170-row slices of
 // a 2.1 M-row rank, i.e. BASELINE config 5 on 8 GPUs): the thread's rows of w live in REGISTERS for the whole step and the
 // columns arrive through a two-deep shared-memory ring filled by cp.async (16 bytes per request, L2 only).  Column i+1 is
-// requested by each thread for its own entries the moment pass i has consumed the buffer it replaces, so it travels
-// HBM -> shared memory while the reduction of projection i is in flight, and a pass reads shared memory only: no global
-// load latency and no second (L2) read of a column on the critical path.  Every ring entry is written (cp.async) and read
+// requested by each thread, entry by entry, the moment pass i has read the entry it replaces (of column i-1), so it
+// travels HBM -> shared memory while pass i and the reduction of projection i are in flight, and a pass reads shared
+// memory only: no global load latency and no second (L2) read of a column on the critical path.  Every ring entry is written (cp.async) and read
 // by the same thread, so the only block-wide barriers are those of the reductions.
 constexpr int kMgsRingSlots = 14;  // 16-byte slots per thread
 template <int BLOCK, int S>
@@ -528,15 +528,16 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_ring_kernel(MgsArgs a) {
         const int64_t e = 2 * ((int64_t)threadIdx.x + (int64_t)u * BLOCK);
         return e + 1 < len ? 2 : (e < len ? 1 : 0);
     };
+    auto request_slot = [&](int col, int u) {
+        const int rows = slot_rows(u);
+        const int64_t e = 2 * ((int64_t)threadIdx.x + (int64_t)u * BLOCK);
+        const double* src = a.V + (int64_t)col * a.ldv + c0 + e;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(wsm + (size_t)(col & 1) * a.chunk + e);
+        if (rows) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(rows * 8) : "memory");
+    };
     auto request = [&](int col) {
-        const double* src = a.V + (int64_t)col * a.ldv + c0;
-        const unsigned dst0 = (unsigned)__cvta_generic_to_shared(wsm + (size_t)(col & 1) * a.chunk);
 #pragma unroll
-        for (int u = 0; u < S; ++u) {
-            const int rows = slot_rows(u);
-            const int64_t e = 2 * ((int64_t)threadIdx.x + (int64_t)u * BLOCK);
-            if (rows) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (unsigned)(e * 8)), "l"(src + e), "r"(rows * 8) : "memory");
-        }
+        for (int u = 0; u < S; ++u) request_slot(col, u);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if (a.j > 0) request(0);
@@ -558,6 +559,10 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_ring_kernel(MgsArgs a) {
         }
         const double2* bp = reinterpret_cast<const double2*>(wsm + (size_t)((i + 1) & 1) * a.chunk);  // column i-1
         const double2* bc = reinterpret_cast<const double2*>(wsm + (size_t)(i & 1) * a.chunk);        // column i
+        // Column i+1 goes into the buffer column i-1 is leaving, and each slot is requested the moment this thread has read
+        // it - not after the pass: the HBM fetch of a column (2.6 us of bandwidth plus latency) then has the pass AND the
+        // reduction to hide behind (6.74 -> 5.49 us per projection).  A prefetch of column i+2 into L2 on top: slower (5.90).
+        const bool refill = i >= 1 && i + 1 < a.j;
         double acc = 0.0, acc1 = 0.0;
 #pragma unroll
         for (int u = 0; u < S; ++u) {
@@ -570,6 +575,7 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_ring_kernel(MgsArgs a) {
                 wv.x = sub_rn(wv.x, mul_rn(pv.x, hprev));
                 if (rows == 2) wv.y = sub_rn(wv.y, mul_rn(pv.y, hprev));
                 wr[u] = wv;
+                if (refill) request_slot(i + 1, u);
             }
             if (i < a.j) {                                                 // products of projection i   (:75)
                 const double2 cv = bc[sl];
@@ -581,7 +587,7 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_ring_kernel(MgsArgs a) {
             }
         }
         acc = add_rn(acc, acc1);
-        if (i >= 1 && i + 1 < a.j) request(i + 1);  // into the buffer column i-1 just left
+        if (refill) asm volatile("cp.async.commit_group;" ::: "memory");
         const double h = mgs_finish_tree<BLOCK>(a, acc, i, target, rank_vals);
         if (i < a.j) {
             if (blockIdx.x == 0 && threadIdx.x == 0) a.h_out[i] = h;  // H(i,j)

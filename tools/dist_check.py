@@ -80,6 +80,21 @@ g27 = ctx.gmres_solve_host(op27, b27_loc, np.zeros(op27.n_rows_local), 2, 20, 1e
 x27 = gather(g27["x"])
 g27b = ctx.gmres_solve_host(op27, b27_loc, np.zeros(op27.n_rows_local), 2, 20, 1e-6, ortho=capi.GMRES_MGS_BATCHED)
 x27b = gather(g27b["x"])
+# the same at slices of 4428 rows per CTA (128 x 128 x 40*world): the Arnoldi step runs as the cp.async-ring kernel (w in
+# registers); checked against the shared-memory step kernel and the batched form (no CPU oracle at 0.65 M rows per rank)
+opr = ctx.operator_stencil27(128, 128, 40 * world, coef)
+br_loc = opr.apply_numpy(synthetic.u01_array(778, opr.row_begin, opr.n_rows_local))
+g_ring = ctx.gmres_solve_host(opr, br_loc, np.zeros(opr.n_rows_local), 2, 20, 1e-6)
+os.environ["ATK_MGS_NO_RING"] = "1"
+g_smem = ctx.gmres_solve_host(opr, br_loc, np.zeros(opr.n_rows_local), 2, 20, 1e-6)
+del os.environ["ATK_MGS_NO_RING"]
+g_bat = ctx.gmres_solve_host(opr, br_loc, np.zeros(opr.n_rows_local), 2, 20, 1e-6, ortho=capi.GMRES_MGS_BATCHED)
+ring_ok = g_ring["kernel_launches"] < 2 * (20 * 3 + 20)
+for other in (g_smem, g_bat):
+    ring_ok = ring_ok and np.allclose(g_ring["resid"], other["resid"], rtol=1e-10, atol=0.0)
+    ring_ok = ring_ok and np.linalg.norm(g_ring["x"] - other["x"]) <= 1e-10 * np.linalg.norm(other["x"])
+ring_flags = gather(np.array([1.0 if ring_ok else 0.0]))
+ring_ms = (g_ring["device_ms"], g_smem["device_ms"], g_bat["device_ms"])
 # assembled operators partitioned by row blocks (SELL on the local rows, neighbour ranges exchanged per apply)
 opa = ctx.operator_poisson_assembled(nx, ny, nz, cx, cy, cz, capi.FORMAT_SELL)
 assert (opa.row_begin, opa.n_rows_local) == (op.row_begin, op.n_rows_local)
@@ -173,6 +188,9 @@ if rank == 0:
     e27b = np.linalg.norm(x27b - o27["x"]) / np.linalg.norm(o27["x"])
     print(f"  batched MGS: relerr x {e27b:.2e}  ms {g27b['device_ms']:.2f} vs {g27['device_ms']:.2f} (per-projection path)")
     ok &= e27b < 1e-10 and np.allclose(g27b["resid"], o27["resid"], rtol=1e-10)
+    print(f"GMRES(20) x2 at 128x128x{40 * world}, ring step kernel vs shared-memory step kernel vs batched: agree on every rank "
+          f"{bool(ring_flags.min() == 1.0)}  ms {ring_ms[0]:.2f} / {ring_ms[1]:.2f} / {ring_ms[2]:.2f}  resid {g_ring['resid'].tolist()}")
+    ok &= bool(ring_flags.min() == 1.0)
     for fused, (x, r, p, res) in results.items():
         ex = np.linalg.norm(x - ora["x"]) / np.linalg.norm(ora["x"])
         er = np.linalg.norm(r - ora["r"]) / np.linalg.norm(ora["r"])
