@@ -207,6 +207,7 @@ struct MgsArgs {
     unsigned long long* ll;               // local packed words
     unsigned long long* const* peer_ll;   // every rank's packed words as mapped here
     unsigned long long seq_base;          // this launch uses sequence numbers seq_base + 1 .. seq_base + j + 1
+    unsigned long long* stamps;           // profile build (ATK_REDUCE_PROFILE): [gridDim.x][4] + [gridDim.x][3] summed clocks, else nullptr
 };
 constexpr int kMgsLlSlot = 2;  // packed-word slots 2 and 3 (0 and 1 belong to the CG loops)
 
@@ -246,17 +247,27 @@ __device__ __forceinline__ double sequential_sum(int64_t len, double* stage, dou
 // pairs - no fence, no atomic - is SLOWER, 10.4 vs 6.7 us per projection at 2.1 M rows: 22 k polling threads on 19
 // cache lines; profiles/r02_mgs_step.txt.)
 template <int BLOCK>
-__device__ __forceinline__ double mgs_finish_tree(const MgsArgs& a, double acc, int i, unsigned& target, double* rank_vals) {
+__device__ __forceinline__ double mgs_finish_tree(const MgsArgs& a, double acc, int i, unsigned& target, double* rank_vals, long long* prof = nullptr) {
+#ifdef ATK_REDUCE_PROFILE
+    long long pl = clock64();
+    auto station = [&](int k) { if (prof) { const long long now = clock64(); prof[k] += now - pl; pl = now; } };
+#else
+    auto station = [](int) {};
+#endif
     const unsigned G = gridDim.x;
     const double bs = block_sum<BLOCK>(acc);
+    station(0);  // block tree (includes waiting for the CTA's slowest warp)
     if (G == 1 && a.world == 1) return bs;
     double* part = a.partials + (size_t)(i & 1) * G;
     if (a.world == 1) {
         if (threadIdx.x == 0) part[blockIdx.x] = bs;
         grid_barrier(a.bar, target);
+        station(1);  // store, fence, arrive, wait for the last CTA
         double s = 0.0;
         for (unsigned q = threadIdx.x; q < G; q += BLOCK) s = add_rn(s, __ldcg(part + q));
-        return block_sum<BLOCK>(s);
+        const double tot = block_sum<BLOCK>(s);
+        station(2);  // the partials and the second block tree
+        return tot;
     }
     // ---- distributed: arrive, CTA 0 publishes the rank's sum to every rank, everyone polls its local words
     const int slot = kMgsLlSlot + (i & 1);
@@ -521,74 +532,120 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_ring_kernel(MgsArgs a) {
     __shared__ double rank_vals[kMaxRanks];
     if (a.stop && *reinterpret_cast<volatile int*>(a.stop)) return;
     const int64_t c0 = (int64_t)blockIdx.x * a.chunk;
-    const int64_t len = max((int64_t)0, min(a.chunk, a.n - c0));
+    const int64_t len = max((int64_t)0, min(a.chunk, a.n - c0));  // even: the launcher takes this kernel for even n only
     unsigned target = 0;
-    // entries of slot u that exist: 2, 1 (the last row of an odd slice) or 0
-    auto slot_rows = [&](int u) -> int {
-        const int64_t e = 2 * ((int64_t)threadIdx.x + (int64_t)u * BLOCK);
-        return e + 1 < len ? 2 : (e < len ? 1 : 0);
-    };
-    auto request_slot = [&](int col, int u) {
-        const int rows = slot_rows(u);
-        const int64_t e = 2 * ((int64_t)threadIdx.x + (int64_t)u * BLOCK);
-        const double* src = a.V + (int64_t)col * a.ldv + c0 + e;
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(wsm + (size_t)(col & 1) * a.chunk + e);
-        if (rows) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(rows * 8) : "memory");
-    };
-    auto request = [&](int col) {
+    // Slot u of this thread is the 16-byte entry threadIdx.x + u*BLOCK of the slice.  Which slots exist is one bit mask,
+    // and every address below is a per-thread base plus a compile-time multiple of BLOCK: the pass is bounded by
+    // instruction issue (16 warps, 14 slots each), so nothing is recomputed per slot.
+    const int len2 = (int)(len >> 1);
+    unsigned full = 0;
 #pragma unroll
-        for (int u = 0; u < S; ++u) request_slot(col, u);
+    for (int u = 0; u < S; ++u) full |= ((int)threadIdx.x + u * BLOCK < len2) ? (1u << u) : 0u;
+    const double2* const buf0 = reinterpret_cast<const double2*>(wsm) + threadIdx.x;            // columns 0, 2, 4, ...
+    const double2* const buf1 = reinterpret_cast<const double2*>(wsm + a.chunk) + threadIdx.x;  // columns 1, 3, 5, ...
+    const unsigned sb0 = (unsigned)__cvta_generic_to_shared(buf0), sb1 = (unsigned)__cvta_generic_to_shared(buf1);
+    const double2* const vcol = reinterpret_cast<const double2*>(a.V + c0) + threadIdx.x;
+    const int64_t ldv2 = a.ldv >> 1;  // column stride in 16-byte entries
+    auto request = [&](int col) {
+        const double2* src = vcol + (int64_t)col * ldv2;
+        const unsigned dst = (col & 1) ? sb1 : sb0;
+#pragma unroll
+        for (int u = 0; u < S; ++u)
+            if (full & (1u << u)) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + u * BLOCK * 16), "l"(src + u * BLOCK) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if (a.j > 0) request(0);
     if (a.j > 1) request(1);
     double2 wr[S];
+    {
+        const double2* w2 = reinterpret_cast<const double2*>(a.w + c0) + threadIdx.x;
 #pragma unroll
-    for (int u = 0; u < S; ++u) {
-        const int rows = slot_rows(u);
-        const int64_t e = 2 * ((int64_t)threadIdx.x + (int64_t)u * BLOCK);
-        wr[u] = make_double2(0.0, 0.0);
-        if (rows == 2) wr[u] = *reinterpret_cast<const double2*>(a.w + c0 + e);
-        else if (rows == 1) wr[u].x = a.w[c0 + e];
+        for (int u = 0; u < S; ++u) wr[u] = (full & (1u << u)) ? w2[u * BLOCK] : make_double2(0.0, 0.0);
     }
     double hprev = 0.0;
+#ifdef ATK_REDUCE_PROFILE
+    long long pt_wait = 0, pt_pass = 0, pt_red = 0;  // thread 0's clocks: waiting for the column, the pass, the reduction
+    long long pt_sta[3] = {0, 0, 0};                 // ... and inside the reduction: block tree / arrive + wait / partials + tree
+#endif
     for (int i = 0; i <= a.j; ++i) {
+#ifdef ATK_REDUCE_PROFILE
+        const long long pc0 = clock64();
+#endif
         if (i < a.j) {
             if (i == 0 && a.j > 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        const double2* bp = reinterpret_cast<const double2*>(wsm + (size_t)((i + 1) & 1) * a.chunk);  // column i-1
-        const double2* bc = reinterpret_cast<const double2*>(wsm + (size_t)(i & 1) * a.chunk);        // column i
+#ifdef ATK_REDUCE_PROFILE
+        const long long pc1 = clock64();
+#endif
+        const double2* const bp = (i & 1) ? buf0 : buf1;  // column i-1
+        const double2* const bc = (i & 1) ? buf1 : buf0;  // column i
         // Column i+1 goes into the buffer column i-1 is leaving, and each slot is requested the moment this thread has read
         // it - not after the pass: the HBM fetch of a column (2.6 us of bandwidth plus latency) then has the pass AND the
         // reduction to hide behind (6.74 -> 5.49 us per projection).  A prefetch of column i+2 into L2 on top: slower (5.90).
         const bool refill = i >= 1 && i + 1 < a.j;
+        const double2* const nsrc = vcol + (int64_t)(i + 1) * ldv2;
+        const unsigned ndst = (i & 1) ? sb0 : sb1;
         double acc = 0.0, acc1 = 0.0;
+        if (i == 0 && a.j > 0) {                                           // products of projection 0   (:75)
 #pragma unroll
-        for (int u = 0; u < S; ++u) {
-            const int rows = slot_rows(u);
-            if (rows == 0) continue;
-            const int64_t sl = (int64_t)threadIdx.x + (int64_t)u * BLOCK;
-            double2 wv = wr[u];
-            if (i > 0) {                                                   // update of projection i-1   (:76)
-                const double2 pv = bp[sl];
-                wv.x = sub_rn(wv.x, mul_rn(pv.x, hprev));
-                if (rows == 2) wv.y = sub_rn(wv.y, mul_rn(pv.y, hprev));
-                wr[u] = wv;
-                if (refill) request_slot(i + 1, u);
-            }
-            if (i < a.j) {                                                 // products of projection i   (:75)
-                const double2 cv = bc[sl];
-                acc = add_rn(acc, mul_rn(cv.x, wv.x));
-                if (rows == 2) acc1 = add_rn(acc1, mul_rn(cv.y, wv.y));
-            } else {                                                       // ||w||^2                     (:79)
-                acc = add_rn(acc, mul_rn(wv.x, wv.x));
-                if (rows == 2) acc1 = add_rn(acc1, mul_rn(wv.y, wv.y));
-            }
+            for (int u = 0; u < S; ++u)
+                if (full & (1u << u)) {
+                    const double2 cv = bc[u * BLOCK];
+                    acc = add_rn(acc, mul_rn(cv.x, wr[u].x));
+                    acc1 = add_rn(acc1, mul_rn(cv.y, wr[u].y));
+                }
+        } else if (i < a.j) {                                              // update of projection i-1 (:76), products of i (:75)
+#pragma unroll
+            for (int u = 0; u < S; ++u)
+                if (full & (1u << u)) {
+                    const double2 pv = bp[u * BLOCK];
+                    const double2 cv = bc[u * BLOCK];
+                    if (refill) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ndst + u * BLOCK * 16), "l"(nsrc + u * BLOCK) : "memory");
+                    double2 wv = wr[u];
+                    wv.x = sub_rn(wv.x, mul_rn(pv.x, hprev));
+                    wv.y = sub_rn(wv.y, mul_rn(pv.y, hprev));
+                    wr[u] = wv;
+                    acc = add_rn(acc, mul_rn(cv.x, wv.x));
+                    acc1 = add_rn(acc1, mul_rn(cv.y, wv.y));
+                }
+        } else {                                                           // last update (none when j == 0), ||w||^2   (:79)
+#pragma unroll
+            for (int u = 0; u < S; ++u)
+                if (full & (1u << u)) {
+                    double2 wv = wr[u];
+                    if (i > 0) {
+                        const double2 pv = bp[u * BLOCK];
+                        wv.x = sub_rn(wv.x, mul_rn(pv.x, hprev));
+                        wv.y = sub_rn(wv.y, mul_rn(pv.y, hprev));
+                        wr[u] = wv;
+                    }
+                    acc = add_rn(acc, mul_rn(wv.x, wv.x));
+                    acc1 = add_rn(acc1, mul_rn(wv.y, wv.y));
+                }
         }
         acc = add_rn(acc, acc1);
         if (refill) asm volatile("cp.async.commit_group;" ::: "memory");
+#ifdef ATK_REDUCE_PROFILE
+        const long long pc2 = clock64();
+#endif
+#ifdef ATK_REDUCE_PROFILE
+        const double h = mgs_finish_tree<BLOCK>(a, acc, i, target, rank_vals, pt_sta);
+#else
         const double h = mgs_finish_tree<BLOCK>(a, acc, i, target, rank_vals);
+#endif
+#ifdef ATK_REDUCE_PROFILE
+        pt_wait += pc1 - pc0;
+        pt_pass += pc2 - pc1;
+        pt_red += clock64() - pc2;
+        if (i == a.j && threadIdx.x == 0 && a.stamps) {
+            atomicAdd(a.stamps + 4 * blockIdx.x + 0, (unsigned long long)pt_wait);
+            atomicAdd(a.stamps + 4 * blockIdx.x + 1, (unsigned long long)pt_pass);
+            atomicAdd(a.stamps + 4 * blockIdx.x + 2, (unsigned long long)pt_red);
+            atomicAdd(a.stamps + 4 * blockIdx.x + 3, (unsigned long long)(a.j + 1));
+            for (int k = 0; k < 3; ++k) atomicAdd(a.stamps + 4 * gridDim.x + 3 * blockIdx.x + k, (unsigned long long)pt_sta[k]);
+        }
+#endif
         if (i < a.j) {
             if (blockIdx.x == 0 && threadIdx.x == 0) a.h_out[i] = h;  // H(i,j)
             hprev = h;
@@ -599,13 +656,10 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_ring_kernel(MgsArgs a) {
                 if (a.stop && (nrm == 0.0 || nrm < a.skip_below)) { a.stop[1] = a.j; a.stop[0] = 1; }
             }
             if (nrm != 0.0 && !(nrm < a.skip_below)) {
+                double2* vn = reinterpret_cast<double2*>(a.vnext + c0) + threadIdx.x;
 #pragma unroll
-                for (int u = 0; u < S; ++u) {
-                    const int rows = slot_rows(u);
-                    const int64_t e = 2 * ((int64_t)threadIdx.x + (int64_t)u * BLOCK);
-                    if (rows == 2) *reinterpret_cast<double2*>(a.vnext + c0 + e) = make_double2(__ddiv_rn(wr[u].x, nrm), __ddiv_rn(wr[u].y, nrm));  // (:86)
-                    else if (rows == 1) a.vnext[c0 + e] = __ddiv_rn(wr[u].x, nrm);
-                }
+                for (int u = 0; u < S; ++u)
+                    if (full & (1u << u)) vn[u * BLOCK] = make_double2(__ddiv_rn(wr[u].x, nrm), __ddiv_rn(wr[u].y, nrm));  // (:86)
             }
         }
     }
@@ -632,10 +686,29 @@ struct PersistentMgs {
     size_t smem = 0, ring_smem = 0;
     unsigned* d_bar = nullptr;
     double* d_part = nullptr;
+    unsigned long long* d_stamps = nullptr;  // profile build only
     int n_bars = 0;
     ~PersistentMgs() {
+#ifdef ATK_REDUCE_PROFILE
+        if (d_stamps && ring_kernel) {  // thread 0 of every CTA: clocks per projection spent waiting for the column / in the pass / in the reduction
+            std::vector<unsigned long long> h((size_t)grid * 7);
+            if (cudaMemcpy(h.data(), d_stamps, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess && h[3]) {
+                const char* name[6] = {"column wait", "pass", "reduction", " block tree", " arrive+wait", " partials"};
+                for (int k = 0; k < 6; ++k) {
+                    double lo = 1e300, hi = 0, sum = 0;
+                    for (int c = 0; c < grid; ++c) {
+                        const double v = (double)(k < 3 ? h[(size_t)c * 4 + k] : h[(size_t)grid * 4 + (size_t)c * 3 + (k - 3)]) / (double)h[(size_t)c * 4 + 3];
+                        lo = std::min(lo, v), hi = std::max(hi, v), sum += v;
+                    }
+                    std::fprintf(stderr, "[atk mgs ring] %-12s clocks per projection over %d CTAs: min %.0f mean %.0f max %.0f (CTA 0: %.0f)\n", name[k], grid, lo,
+                                 sum / grid, hi, (double)(k < 3 ? h[k] : h[(size_t)grid * 4 + (k - 3)]) / (double)h[3]);
+                }
+            }
+        }
+#endif
         cudaFree(d_bar);
         cudaFree(d_part);
+        cudaFree(d_stamps);
     }
     void setup(Context* ctx, int64_t n, int max_steps) {
         int mine = try_setup(ctx, n, max_steps) ? 1 : 0;
@@ -694,6 +767,10 @@ struct PersistentMgs {
         n_bars = max_steps + 1;
         ATK_CUDA_CHECK(cudaMalloc(&d_bar, sizeof(unsigned) * (size_t)n_bars));
         ATK_CUDA_CHECK(cudaMalloc(&d_part, sizeof(double) * 2 * (size_t)g));
+#ifdef ATK_REDUCE_PROFILE
+        ATK_CUDA_CHECK(cudaMalloc(&d_stamps, sizeof(unsigned long long) * 7 * (size_t)g));
+        ATK_CUDA_CHECK(cudaMemset(d_stamps, 0, sizeof(unsigned long long) * 7 * (size_t)g));
+#endif
         return true;
     }
     void reset_barriers(cudaStream_t st) { ATK_CUDA_CHECK(cudaMemsetAsync(d_bar, 0, sizeof(unsigned) * (size_t)n_bars, st)); }
@@ -701,11 +778,11 @@ struct PersistentMgs {
     void launch(Context* ctx, int64_t n, int ncols, int step, const double* V, int64_t ldv, const double* w, double* vnext,
                 double* h_out, double skip_below, int* stop = nullptr) {
         MgsArgs ma{n, ncols, V, ldv, w, vnext, h_out, d_part, d_bar + step, chunk, ctx->reduction == ATK_REDUCE_SEQUENTIAL ? 1 : 0,
-                   skip_below, stop, ctx->world, ctx->rank, ctx->d_ll, ctx->d_peer_ll, ctx->epoch};
+                   skip_below, stop, ctx->world, ctx->rank, ctx->d_ll, ctx->d_peer_ll, ctx->epoch, d_stamps};
         if (ctx->world > 1) ctx->epoch += (unsigned long long)ncols + 2ull;  // same advance on every rank
         void* kargs[] = {&ma};
         // the ring variant moves 16-byte pieces: every column slice, w and V_next must start on a 16-byte boundary
-        const bool ring = ring_kernel && (ldv & 1) == 0 && (chunk & 1) == 0 &&
+        const bool ring = ring_kernel && (n & 1) == 0 && (ldv & 1) == 0 && (chunk & 1) == 0 &&
                           ((reinterpret_cast<uintptr_t>(V) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(vnext)) & 15u) == 0;
         ATK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)(ring ? ring_kernel : kernel), dim3(grid), dim3(block), kargs,
                                                    ring ? ring_smem : smem, ctx->stream));
