@@ -211,20 +211,6 @@ struct MgsArgs {
 };
 constexpr int kMgsLlSlot = 2;  // packed-word slots 2 and 3 (0 and 1 belong to the CG loops)
 
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
-    __syncthreads();
-    if (gridDim.x > 1) {
-        if (threadIdx.x == 0) {
-            target += gridDim.x;
-            __threadfence();
-            atomicAdd(counter, 1u);
-            while (*reinterpret_cast<volatile unsigned*>(counter) < target) {}
-            __threadfence();
-        }
-        __syncthreads();
-    }
-}
-
 // Strictly ordered sum (single CTA, ATK_REDUCE_SEQUENTIAL): all threads write the rounded products of the whole slice
 // into `stage`, one barrier, thread 0 adds them in index order from 0.0 (= std::inner_product), result broadcast.
 template <typename F>
@@ -243,11 +229,23 @@ __device__ __forceinline__ double sequential_sum(int64_t len, double* stage, dou
 
 // h from a per-thread partial: fixed block tree, then (several CTAs) barrier + fixed-order sum of the CTA partials; on
 // distributed contexts the rank sums cross NVLink as packed words (see MgsArgs).  Ends with a block-wide barrier.
-// (Measured and rejected: every CTA leaving its sum as a packed {half | tag} word pair and every CTA polling all 148
-// pairs - no fence, no atomic - is SLOWER, 10.4 vs 6.7 us per projection at 2.1 M rows: 22 k polling threads on 19
-// cache lines; profiles/r02_mgs_step.txt.)
-template <int BLOCK>
-__device__ __forceinline__ double mgs_finish_tree(const MgsArgs& a, double acc, int i, unsigned& target, double* rank_vals, long long* prof = nullptr) {
+// (Measured and rejected, profiles/r02_mgs_step.txt: every CTA leaving its sum as a packed {half | tag} word pair and every
+// CTA polling all 148 pairs - no fence, no atomic, one L2 round trip less - is SLOWER at 2.1 M rows, with one thread per
+// pair (10.4 vs 6.7 us per projection) and with one warp and 16-byte loads (5.46 vs 4.77); so is CTA 0 gathering the
+// pairs and handing the total back as a pair (6.73 vs 6.74).)
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+struct MgsNoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+// `after_arrive` runs on every thread once this CTA's sum has been handed over (before the wait for the others): the ring
+// kernel parks there the cp.async requests of the arriving warp, so that its fence does not wait for column data.
+template <int BLOCK, typename Hook = MgsNoHook>
+__device__ __forceinline__ double mgs_finish_tree(const MgsArgs& a, double acc, int i, unsigned& target, double* rank_vals, long long* prof = nullptr,
+                                                  Hook after_arrive = Hook()) {
 #ifdef ATK_REDUCE_PROFILE
     long long pl = clock64();
     auto station = [&](int k) { if (prof) { const long long now = clock64(); prof[k] += now - pl; pl = now; } };
@@ -257,11 +255,23 @@ __device__ __forceinline__ double mgs_finish_tree(const MgsArgs& a, double acc, 
     const unsigned G = gridDim.x;
     const double bs = block_sum<BLOCK>(acc);
     station(0);  // block tree (includes waiting for the CTA's slowest warp)
-    if (G == 1 && a.world == 1) return bs;
+    if (G == 1 && a.world == 1) {
+        after_arrive();
+        return bs;
+    }
     double* part = a.partials + (size_t)(i & 1) * G;
     if (a.world == 1) {
-        if (threadIdx.x == 0) part[blockIdx.x] = bs;
-        grid_barrier(a.bar, target);
+        target += G;
+        if (threadIdx.x == 0) {
+            __stcg(part + blockIdx.x, bs);
+            __threadfence();
+            atomicAdd(a.bar, 1u);
+        }
+        after_arrive();
+        if (threadIdx.x == 0) {
+            while (ld_acquire_gpu(a.bar) < target) {}
+        }
+        __syncthreads();
         station(1);  // store, fence, arrive, wait for the last CTA
         double s = 0.0;
         for (unsigned q = threadIdx.x; q < G; q += BLOCK) s = add_rn(s, __ldcg(part + q));
@@ -278,6 +288,7 @@ __device__ __forceinline__ double mgs_finish_tree(const MgsArgs& a, double acc, 
         __threadfence();
         atomicAdd(a.bar, 1u);
     }
+    after_arrive();
     if (blockIdx.x == 0) {
         if (threadIdx.x == 0) {
             unsigned spins = 0;
@@ -582,8 +593,12 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_ring_kernel(MgsArgs a) {
         const double2* const bc = (i & 1) ? buf1 : buf0;  // column i
         // Column i+1 goes into the buffer column i-1 is leaving, and each slot is requested the moment this thread has read
         // it - not after the pass: the HBM fetch of a column (2.6 us of bandwidth plus latency) then has the pass AND the
-        // reduction to hide behind (6.74 -> 5.49 us per projection).  A prefetch of column i+2 into L2 on top: slower (5.90).
+        // reduction to hide behind (6.74 -> 5.49 us per projection).  A prefetch of column i+2 into L2 on top, after the pass
+        // or at its start: slower (5.90 / 5.27 vs 5.03).
         const bool refill = i >= 1 && i + 1 < a.j;
+        // ... except in the warp whose thread 0 hands over the CTA's sum: a fence waits for the thread's outstanding cp.async
+        // too, i.e. for HBM, so that warp sends its requests once the sum is on its way (after_arrive below)
+        const bool refill_now = refill && threadIdx.x >= 32;
         const double2* const nsrc = vcol + (int64_t)(i + 1) * ldv2;
         const unsigned ndst = (i & 1) ? sb0 : sb1;
         double acc = 0.0, acc1 = 0.0;
@@ -601,7 +616,7 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_ring_kernel(MgsArgs a) {
                 if (full & (1u << u)) {
                     const double2 pv = bp[u * BLOCK];
                     const double2 cv = bc[u * BLOCK];
-                    if (refill) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ndst + u * BLOCK * 16), "l"(nsrc + u * BLOCK) : "memory");
+                    if (refill_now) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ndst + u * BLOCK * 16), "l"(nsrc + u * BLOCK) : "memory");
                     double2 wv = wr[u];
                     wv.x = sub_rn(wv.x, mul_rn(pv.x, hprev));
                     wv.y = sub_rn(wv.y, mul_rn(pv.y, hprev));
@@ -625,14 +640,19 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_ring_kernel(MgsArgs a) {
                 }
         }
         acc = add_rn(acc, acc1);
-        if (refill) asm volatile("cp.async.commit_group;" ::: "memory");
+        auto late_refill = [&]() {
+            if (refill && !refill_now) {
+#pragma unroll
+                for (int u = 0; u < S; ++u)
+                    if (full & (1u << u)) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ndst + u * BLOCK * 16), "l"(nsrc + u * BLOCK) : "memory");
+            }
+            if (refill) asm volatile("cp.async.commit_group;" ::: "memory");
+        };
 #ifdef ATK_REDUCE_PROFILE
         const long long pc2 = clock64();
-#endif
-#ifdef ATK_REDUCE_PROFILE
-        const double h = mgs_finish_tree<BLOCK>(a, acc, i, target, rank_vals, pt_sta);
+        const double h = mgs_finish_tree<BLOCK>(a, acc, i, target, rank_vals, pt_sta, late_refill);
 #else
-        const double h = mgs_finish_tree<BLOCK>(a, acc, i, target, rank_vals);
+        const double h = mgs_finish_tree<BLOCK>(a, acc, i, target, rank_vals, nullptr, late_refill);
 #endif
 #ifdef ATK_REDUCE_PROFILE
         pt_wait += pc1 - pc0;
