@@ -470,8 +470,23 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
                         acc1 = add_rn(acc1, vc ? mul_rn(cv.y, wv.y) : mul_rn(wv.y, wv.y));
                     };
                     const double2 z2 = make_double2(0.0, 0.0);
-                    auto ldp = [&](int64_t e) -> double2 { return vp ? __ldcg(reinterpret_cast<const double2*>(vp) + e) : z2; };
-                    auto ldc = [&](int64_t e) -> double2 { return vc ? __ldcs(reinterpret_cast<const double2*>(vc) + e) : z2; };
+                    // L2 priorities follow the reuse: column i is read again by the next pass (as the update column), so its
+                    // lines are kept (evict_last, like the prefetch below that brings them in); column i-1 is read for the
+                    // last time here (evict_first).  With the default / streaming hints three 33 MB column slices thrash
+                    // the L2 at 4 M rows per GPU and the "second read from L2" comes from HBM.
+                    unsigned long long pol_first, pol_last;
+                    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+                    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+                    auto ldp = [&](int64_t e) -> double2 {
+                        double2 v = z2;
+                        if (vp) asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(reinterpret_cast<const double2*>(vp) + e), "l"(pol_first));
+                        return v;
+                    };
+                    auto ldc = [&](int64_t e) -> double2 {
+                        double2 v = z2;
+                        if (vc) asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(reinterpret_cast<const double2*>(vc) + e), "l"(pol_last));
+                        return v;
+                    };
                     // eight entries per thread and trip, predicated: sixteen 16-byte loads in flight before anything is
                     // consumed, and the last trip is as wide as the first (a 14 k-row slice is one or two trips)
                     for (int64_t e = threadIdx.x; e < len2; e += 8 * BLOCK) {
@@ -509,7 +524,7 @@ __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
                 if (i + 1 < a.j) {  // the next column's slice starts its way from HBM into L2 while the sum is in flight
                     const char* nx = reinterpret_cast<const char*>(a.V + (int64_t)(i + 1) * a.ldv + c0);
                     for (int64_t o = (int64_t)threadIdx.x * 128; o < len * 8; o += (int64_t)BLOCK * 128)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + o));
+                        asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(nx + o));
                 }
                 const double h = finish_tree(acc, i);
                 if (i < a.j) {
