@@ -179,10 +179,15 @@ __global__ void __launch_bounds__(kReduceBlock) multi_axmy_norm_kernel(int64_t n
 // ---- persistent Arnoldi-MGS step ----------------------------------------------------------------------------------
 // One cooperative launch performs the WHOLE projection loop of an Arnoldi step (GMRES.hpp:73-86):
 //     for i < j: h = V[i].w ; w = w - V[i]*h        then  ||w|| ; V[j+1] = w / ||w||
-// Each CTA owns a contiguous chunk of rows and keeps its slice of w in SHARED MEMORY for the whole step, so per
-// projection only V[i] streams in (8 B/row from HBM, the second pass hits L2) instead of the 40 B/row of separate dot and
-// axmy kernels, and the 2j kernel launches of the step collapse into one.  CTAs meet at one software grid barrier per
-// projection (cooperative launch guarantees co-residency); every CTA then adds the per-CTA partials in CTA order.
+// Each CTA owns a contiguous chunk of rows and keeps its slice of w ON CHIP for the whole step, so per projection only
+// V[i] streams in (8 B/row from HBM) instead of the 40 B/row of separate dot and axmy kernels, and the 2j kernel launches
+// of the step collapse into one.  Three variants by slice length (rows per CTA, 512 threads):
+//   <= 4 096          arnoldi_mgs_kernel<.., true>    w and the current column in registers, next column requested early
+//   <= 14 336         arnoldi_mgs_ring_kernel         w in registers, columns through a two-deep cp.async ring in smem
+//   <= ~28 k          arnoldi_mgs_kernel<.., false>   w in shared memory, every column read twice (second read from L2,
+//                                                     kept there by cache-hint policies)
+// CTAs meet at one software grid barrier per projection (cooperative launch guarantees co-residency); every CTA then adds
+// the per-CTA partials in CTA order.
 // With a single CTA (small n, e.g. bcsstk08) the barrier degenerates to __syncthreads; that configuration also
 // implements ATK_REDUCE_SEQUENTIAL (thread 0 adds the rounded products strictly in index order).
 struct MgsArgs {
@@ -343,7 +348,8 @@ constexpr int kMgsRegRows = 8;  // rows per thread the register variant can hold
 
 // REG = true (slices of at most 8*BLOCK rows): the thread's rows of w and of the current V column live in registers,
 // the next column is requested while the current one is being reduced, and nothing is re-read.
-// REG = false: the slice of w lives in shared memory and V[i] is streamed twice (the second pass hits L1/L2).
+// REG = false: the slice of w lives in shared memory and V[i] is read twice, by pass i for the products and by pass
+// i+1 for the update (from L2: see the cache-hint policies in the pass).
 template <int BLOCK, bool REG>
 __global__ void __launch_bounds__(BLOCK) arnoldi_mgs_kernel(MgsArgs a) {
     extern __shared__ __align__(16) double wsm[];  // REG: products [chunk] (sequential mode only); else w [chunk] (+ products)

@@ -141,3 +141,9 @@ def test_hot_kernels_do_not_spill():
         assert int(m.group(2)) <= 16 and int(m.group(3)) <= 16, (kernel, m.groups())
         seen += 1
     assert seen == 3
+    # the Arnoldi step kernels sit at the 128-register cap of a 512-thread CTA (w in registers / sixteen loads in flight)
+    glog = open(os.path.join(atk_build.OBJ, "atk_gmres.cu.log")).read()
+    for kernel in ("arnoldi_mgs_ring_kernelILi512ELi14E", "arnoldi_mgs_kernelILi512ELb0E", "arnoldi_mgs_kernelILi512ELb1E"):
+        m = re.search(kernel + r".*?(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", glog, re.S)
+        assert m, f"{kernel} not found in the ptxas log"
+        assert int(m.group(2)) == 0 and int(m.group(3)) == 0, (kernel, m.groups())
