@@ -47,6 +47,55 @@ __global__ void __launch_bounds__(256) mgs_axmy_kernel(int64_t n, const double* 
     for (int64_t i = t; i < n; i += stride) w[i] = sub_rn(w[i], mul_rn(v[i], h));
 }
 
+// Per-projection path, single GPU, tree sums: the update of projection i-1 and the products of projection i in ONE pass,
+//     w = w - v_prev * h_(i-1)   (h from the slot the previous launch left)  ;  partial sums of v_cur . w  (v_cur == nullptr: w . w)
+// 32 B/row and one launch per projection instead of 40 B/row and two (dot, then axmy).  Thread layout, accumulation order
+// and the grid-wide sum are those of dot_tree_kernel (atk_vector.cu), so with 16-byte-aligned columns (even n) h is
+// bit-identical to the unfused path.
+template <bool VEC2>
+__global__ void __launch_bounds__(kReduceBlock) mgs_axmy_dot_kernel(int64_t n, const double* __restrict__ v_prev, const double* __restrict__ v_cur,
+                                                                    double* __restrict__ w, const double* __restrict__ slot_prev,
+                                                                    double* __restrict__ h_out, double* partials, unsigned* ticket, double* out) {
+    const double h = __ldcg(slot_prev);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) *h_out = h;  // H(i-1, j)
+    double acc = 0.0;
+    if constexpr (VEC2) {
+        const int64_t n2 = n >> 1;
+        const double2* p2 = reinterpret_cast<const double2*>(v_prev);
+        const double2* c2 = reinterpret_cast<const double2*>(v_cur);
+        double2* w2 = reinterpret_cast<double2*>(w);
+        double acc1 = 0.0;
+        for (int64_t i = t; i < n2; i += stride) {
+            const double2 pv = p2[i];
+            double2 wv = w2[i];
+            wv.x = sub_rn(wv.x, mul_rn(pv.x, h));
+            wv.y = sub_rn(wv.y, mul_rn(pv.y, h));
+            w2[i] = wv;
+            const double2 cv = v_cur ? c2[i] : wv;
+            acc = add_rn(acc, mul_rn(cv.x, wv.x));
+            acc1 = add_rn(acc1, mul_rn(cv.y, wv.y));
+        }
+        acc = add_rn(acc, acc1);
+        if (t == 0 && (n & 1)) {
+            const double wv = sub_rn(w[n - 1], mul_rn(v_prev[n - 1], h));
+            w[n - 1] = wv;
+            acc = add_rn(acc, mul_rn(v_cur ? v_cur[n - 1] : wv, wv));
+        }
+    } else {
+        for (int64_t i = t; i < n; i += stride) {
+            const double wv = sub_rn(w[i], mul_rn(v_prev[i], h));
+            w[i] = wv;
+            acc = add_rn(acc, mul_rn(v_cur ? v_cur[i] : wv, wv));
+        }
+    }
+    double total;
+    if (grid_sum_last_block<kReduceBlock>(acc, partials, ticket, &total)) {
+        if (linear_thread_id() == 0) *out = total;
+    }
+}
+
 // out = w / sqrt(slot)  (V[j+1] = w / H(j+1,j), :86) - skipped when the norm is zero (the host raises the error).
 __global__ void __launch_bounds__(256) normalize_kernel(int64_t n, const double* __restrict__ w, double* __restrict__ out,
                                                         const double* __restrict__ slot, int world, double* __restrict__ norm_out,
@@ -892,6 +941,8 @@ void gmres_solve(Context* ctx, Operator* op, Preconditioner* pc, const double* b
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8));
         // batched MGS: per-CTA partials of the two multi-dots, the reduced [c | g] vector (all ranks), Gram matrix on the host
         const bool batched = ortho == ATK_GMRES_MGS_BATCHED;
+        // per-projection path on one GPU with tree sums: one fused update+products launch per projection (mgs_axmy_dot_kernel)
+        const bool fuse_dots = ctx->world == 1 && ctx->reduction != ATK_REDUCE_SEQUENTIAL && !std::getenv("ATK_GMRES_NO_FUSED_DOT");
         const int bd_blocks = (int)std::max<int64_t>(1, (n + kBdBlock * kBdRows - 1) / (kBdBlock * kBdRows));
         const int cg_len = 2 * (K + 1);
         double* h_cg = nullptr;  // pinned [world * cg_len]
@@ -1010,7 +1061,28 @@ void gmres_solve(Context* ctx, Operator* op, Preconditioner* pc, const double* b
                         } else {
                             op->apply(vj, w, -1, nullptr);  // :70
                         }
-                        if (ortho == ATK_GMRES_MGS) {
+                        bool norm_done = false;
+                        if (ortho == ATK_GMRES_MGS && fuse_dots && j > 0) {  // :73-79, update i-1 fused with the products of i
+                            launch_dot(ctx, n, V, w, kSlotH);
+                            double* const slot_h = ctx->slot(kSlotH);
+                            for (int i = 1; i <= j; ++i) {
+                                const double* vp = V + (size_t)(i - 1) * nn;
+                                const double* vc = i < j ? V + (size_t)i * nn : nullptr;  // last launch: w . w for the norm
+                                const bool vec = aligned16(vp) && aligned16(w) && (!vc || aligned16(vc));
+                                const int64_t work = vec ? (n + 1) / 2 : n;
+                                const int fgrid = (int)std::min<int64_t>(std::max<int64_t>((work + kReduceBlock - 1) / kReduceBlock, 1),
+                                                                         (int64_t)ctx->reduce_grid());
+                                double* out = i < j ? slot_h : ctx->slot(kSlotNorm);
+                                if (vec)
+                                    mgs_axmy_dot_kernel<true><<<fgrid, kReduceBlock, 0, st>>>(n, vp, vc, w, slot_h, d_h + (i - 1), ctx->d_partials,
+                                                                                              ctx->d_tickets + 0, out);
+                                else
+                                    mgs_axmy_dot_kernel<false><<<fgrid, kReduceBlock, 0, st>>>(n, vp, vc, w, slot_h, d_h + (i - 1), ctx->d_partials,
+                                                                                               ctx->d_tickets + 0, out);
+                                count_launch(ctx);
+                            }
+                            norm_done = true;
+                        } else if (ortho == ATK_GMRES_MGS) {
                             for (int i = 0; i < j; ++i) {  // :73-77
                                 const double* vi = V + (size_t)i * nn;
                                 launch_dot(ctx, n, vi, w, kSlotH);
@@ -1048,7 +1120,7 @@ void gmres_solve(Context* ctx, Operator* op, Preconditioner* pc, const double* b
                             count_launch(ctx);
                             allgather_slot(ctx, kSlotNorm, st);
                         }
-                        if (!(batched && j > 0)) launch_dot(ctx, n, w, w, kSlotNorm);  // :79 (the batched pass 2 already summed w.w)
+                        if (!(batched && j > 0) && !norm_done) launch_dot(ctx, n, w, w, kSlotNorm);  // :79 (the batched pass 2 already summed w.w)
                         normalize_kernel<<<grid, 256, 0, st>>>(n, w, V + (size_t)(j + 1) * nn, ctx->slot(kSlotNorm), ctx->world, d_h + j,
                                                                tol);  // :86 (skipped when the norm is 0 or below tol)
                         count_launch(ctx);

@@ -810,6 +810,34 @@ def test_gmres_persistent_step_with_w_in_shared_memory(ctx, dims, ring, monkeypa
     op.destroy()
 
 
+@pytest.mark.parametrize("dims", [(48, 48, 48), (41, 43, 45)])
+def test_gmres_fused_update_and_products_launch_is_bit_identical(ctx, dims, monkeypatch):
+    """Per-projection path on one GPU (what config 5 runs on at 16.7 M rows): one launch per projection applies the update of
+    projection i-1 and forms the products of projection i (mgs_axmy_dot_kernel, 32 B/row) instead of a dot and an axmy launch
+    (40 B/row).  Same thread layout and summation order as the dot kernel: with an even column stride (16-byte accesses in
+    both forms) the residual ladder and x must not change by one bit.  With an odd stride every other column is misaligned,
+    the dot kernel alternates between its 16-byte and its scalar layout while the fused launch (two columns at once) always
+    takes the scalar one: equal to 1e-10."""
+    from algotoolkit_b200 import synthetic
+
+    nx, ny, nz = dims
+    rows = nx * ny * nz
+    op = ctx.operator_stencil27(nx, ny, nz, synthetic.stencil27_coefficients())
+    b = op.apply_numpy(synthetic.u01_array(777, 0, rows))
+    monkeypatch.setenv("ATK_GMRES_NO_PERSISTENT", "1")
+    fused = ctx.gmres_solve_host(op, b, np.zeros(rows), 2, 30, 1e-6)
+    monkeypatch.setenv("ATK_GMRES_NO_FUSED_DOT", "1")
+    plain = ctx.gmres_solve_host(op, b, np.zeros(rows), 2, 30, 1e-6)
+    assert fused["kernel_launches"] < plain["kernel_launches"] - 2 * 300  # 30*29/2 projections per restart: one launch each instead of two
+    if rows % 2 == 0:
+        assert list(fused["resid"]) == list(plain["resid"])
+        assert digest(fused["x"]) == digest(plain["x"])
+    else:
+        assert np.allclose(fused["resid"], plain["resid"], rtol=REL, atol=0.0)
+        assert relerr(fused["x"], plain["x"]) < REL
+    op.destroy()
+
+
 # ------------------------------------------------------------------------------------------------ CSR format kernels
 def test_csr_stream_is_bit_exact_and_vector_kernel_still_covered(ctx, port, monkeypatch):
     """CSR format: short rows -> CSR-stream (per-row ascending sums: bit-identical to the CSC matvec, empty rows, rows

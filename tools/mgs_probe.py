@@ -1,6 +1,6 @@
 """Persistent Arnoldi-MGS step: GMRES(K), one restart, on the 27-point operator at grid^3, exact MGS (persistent step kernel)
 and batched MGS; seconds per restart and microseconds per projection (operator applies included).
-    python tools/mgs_probe.py [grid=128] [K=300]              one GPU; 128^3 = the per-GPU slice of BASELINE config 5 on 8 GPUs
+    python tools/mgs_probe.py [grid=128] [K=300] [reps=2] [exact|batched]   one GPU; 128^3 = the per-GPU slice of BASELINE config 5 on 8 GPUs
     tools/run_dist.sh 8 tools/mgs_probe.py 256 300             BASELINE config 5 itself, z-slabs over 8 GPUs"""
 import os
 import sys
@@ -12,6 +12,8 @@ from algotoolkit_b200 import capi, synthetic
 
 g = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 300
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2          # the last repetition is reported
+only = sys.argv[4] if len(sys.argv) > 4 else ""              # "exact" or "batched": that mode only
 world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
 if world > 1:
     import torch
@@ -31,7 +33,9 @@ op = ctx.operator_stencil27(g, g, g, synthetic.stencil27_coefficients())
 n = op.n_rows_local
 b = op.apply_numpy(synthetic.u01_array(777, op.row_begin, n))
 for name, ortho in (("exact_mgs", capi.GMRES_MGS), ("batched_mgs", capi.GMRES_MGS_BATCHED)):
-    for rep in range(2):
+    if only and not name.startswith(only):
+        continue
+    for rep in range(reps):
         r = ctx.gmres_solve_host(op, b, np.zeros(n), 1, K, 1e-6, ortho=ortho)
     ms = r["device_ms"]
     if world > 1:
