@@ -47,16 +47,16 @@ __global__ void __launch_bounds__(256) mgs_axmy_kernel(int64_t n, const double* 
     for (int64_t i = t; i < n; i += stride) w[i] = sub_rn(w[i], mul_rn(v[i], h));
 }
 
-// Per-projection path, single GPU, tree sums: the update of projection i-1 and the products of projection i in ONE pass,
+// Per-projection path, tree sums: the update of projection i-1 and the products of projection i in ONE pass,
 //     w = w - v_prev * h_(i-1)   (h from the slot the previous launch left)  ;  partial sums of v_cur . w  (v_cur == nullptr: w . w)
 // 32 B/row and one launch per projection instead of 40 B/row and two (dot, then axmy).  Thread layout, accumulation order
 // and the grid-wide sum are those of dot_tree_kernel (atk_vector.cu), so with 16-byte-aligned columns (even n) h is
 // bit-identical to the unfused path.
 template <bool VEC2>
 __global__ void __launch_bounds__(kReduceBlock) mgs_axmy_dot_kernel(int64_t n, const double* __restrict__ v_prev, const double* __restrict__ v_cur,
-                                                                    double* __restrict__ w, const double* __restrict__ slot_prev,
+                                                                    double* __restrict__ w, const double* __restrict__ slot_prev, int world,
                                                                     double* __restrict__ h_out, double* partials, unsigned* ticket, double* out) {
-    const double h = __ldcg(slot_prev);
+    const double h = slot_sum(slot_prev, world);  // every rank's share of h_(i-1), added in rank order
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t == 0) *h_out = h;  // H(i-1, j)
@@ -941,8 +941,8 @@ void gmres_solve(Context* ctx, Operator* op, Preconditioner* pc, const double* b
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8));
         // batched MGS: per-CTA partials of the two multi-dots, the reduced [c | g] vector (all ranks), Gram matrix on the host
         const bool batched = ortho == ATK_GMRES_MGS_BATCHED;
-        // per-projection path on one GPU with tree sums: one fused update+products launch per projection (mgs_axmy_dot_kernel)
-        const bool fuse_dots = ctx->world == 1 && ctx->reduction != ATK_REDUCE_SEQUENTIAL && !std::getenv("ATK_GMRES_NO_FUSED_DOT");
+        // per-projection path with tree sums: one fused update+products launch per projection (mgs_axmy_dot_kernel)
+        const bool fuse_dots = ctx->reduction != ATK_REDUCE_SEQUENTIAL && !std::getenv("ATK_GMRES_NO_FUSED_DOT");
         const int bd_blocks = (int)std::max<int64_t>(1, (n + kBdBlock * kBdRows - 1) / (kBdBlock * kBdRows));
         const int cg_len = 2 * (K + 1);
         double* h_cg = nullptr;  // pinned [world * cg_len]
@@ -1072,14 +1072,18 @@ void gmres_solve(Context* ctx, Operator* op, Preconditioner* pc, const double* b
                                 const int64_t work = vec ? (n + 1) / 2 : n;
                                 const int fgrid = (int)std::min<int64_t>(std::max<int64_t>((work + kReduceBlock - 1) / kReduceBlock, 1),
                                                                          (int64_t)ctx->reduce_grid());
-                                double* out = i < j ? slot_h : ctx->slot(kSlotNorm);
+                                const int out_slot = i < j ? kSlotH : kSlotNorm;
+                                double* out = ctx->slot(out_slot) + ctx->rank;
                                 if (vec)
-                                    mgs_axmy_dot_kernel<true><<<fgrid, kReduceBlock, 0, st>>>(n, vp, vc, w, slot_h, d_h + (i - 1), ctx->d_partials,
-                                                                                              ctx->d_tickets + 0, out);
+                                    mgs_axmy_dot_kernel<true><<<fgrid, kReduceBlock, 0, st>>>(n, vp, vc, w, slot_h, ctx->world, d_h + (i - 1),
+                                                                                              ctx->d_partials, ctx->d_tickets + 0, out);
                                 else
-                                    mgs_axmy_dot_kernel<false><<<fgrid, kReduceBlock, 0, st>>>(n, vp, vc, w, slot_h, d_h + (i - 1), ctx->d_partials,
-                                                                                               ctx->d_tickets + 0, out);
+                                    mgs_axmy_dot_kernel<false><<<fgrid, kReduceBlock, 0, st>>>(n, vp, vc, w, slot_h, ctx->world, d_h + (i - 1),
+                                                                                               ctx->d_partials, ctx->d_tickets + 0, out);
                                 count_launch(ctx);
+                                // distributed: the same all-gather as after a dot launch.  It runs in stream order on every rank,
+                                // so a rank's slot array is rewritten only after its own launch i has read h_(i-1) from it.
+                                allgather_slot(ctx, out_slot, st);
                             }
                             norm_done = true;
                         } else if (ortho == ATK_GMRES_MGS) {

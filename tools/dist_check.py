@@ -80,6 +80,14 @@ g27 = ctx.gmres_solve_host(op27, b27_loc, np.zeros(op27.n_rows_local), 2, 20, 1e
 x27 = gather(g27["x"])
 g27b = ctx.gmres_solve_host(op27, b27_loc, np.zeros(op27.n_rows_local), 2, 20, 1e-6, ortho=capi.GMRES_MGS_BATCHED)
 x27b = gather(g27b["x"])
+# the per-projection path (what slices too large for the chip run on): fused update+products launch + all-gather per
+# projection, and the dot / all-gather / axmy form it replaces
+os.environ["ATK_GMRES_NO_PERSISTENT"] = "1"
+g27p = ctx.gmres_solve_host(op27, b27_loc, np.zeros(op27.n_rows_local), 2, 20, 1e-6)
+os.environ["ATK_GMRES_NO_FUSED_DOT"] = "1"
+g27u = ctx.gmres_solve_host(op27, b27_loc, np.zeros(op27.n_rows_local), 2, 20, 1e-6)
+del os.environ["ATK_GMRES_NO_FUSED_DOT"], os.environ["ATK_GMRES_NO_PERSISTENT"]
+x27p, x27u = gather(g27p["x"]), gather(g27u["x"])
 # the same at slices of 4428 rows per CTA (128 x 128 x 40*world): the Arnoldi step runs as the cp.async-ring kernel (w in
 # registers); checked against the shared-memory step kernel and the batched form (no CPU oracle at 0.65 M rows per rank)
 opr = ctx.operator_stencil27(128, 128, 40 * world, coef)
@@ -188,6 +196,11 @@ if rank == 0:
     e27b = np.linalg.norm(x27b - o27["x"]) / np.linalg.norm(o27["x"])
     print(f"  batched MGS: relerr x {e27b:.2e}  ms {g27b['device_ms']:.2f} vs {g27['device_ms']:.2f} (per-projection path)")
     ok &= e27b < 1e-10 and np.allclose(g27b["resid"], o27["resid"], rtol=1e-10)
+    e27p = np.linalg.norm(x27p - o27["x"]) / np.linalg.norm(o27["x"])
+    e27u = np.linalg.norm(x27u - o27["x"]) / np.linalg.norm(o27["x"])
+    print(f"  per-projection path: fused launch relerr x {e27p:.2e} ({g27p['kernel_launches']} launches), dot + axmy {e27u:.2e} "
+          f"({g27u['kernel_launches']} launches)")
+    ok &= e27p < 1e-10 and e27u < 1e-10 and np.allclose(g27p["resid"], o27["resid"], rtol=1e-10) and g27p["kernel_launches"] < g27u["kernel_launches"]
     print(f"GMRES(20) x2 at 128x128x{40 * world}, ring step kernel vs shared-memory step kernel vs batched: agree on every rank "
           f"{bool(ring_flags.min() == 1.0)}  ms {ring_ms[0]:.2f} / {ring_ms[1]:.2f} / {ring_ms[2]:.2f}  resid {g_ring['resid'].tolist()}")
     ok &= bool(ring_flags.min() == 1.0)
